@@ -1,0 +1,173 @@
+/*
+ * lapper_b200.h -- C ABI of liblapper_b200.so: a B200 (sm_100a) batched interval-overlap engine
+ * that is a drop-in for the query path of the Rust crate rust-lapper 1.3.0.
+ *
+ * The reference has no FFI layer; its boundary is the public Rust API of `Lapper<I,T>`
+ * (/root/reference/src/lib.rs:182-680).  Each entry point below names the reference item it
+ * replaces.  A Rust shim (`extern "C"` block), the C++ facade
+ * (include/lapper_b200.hpp) and the Python/ctypes mirror (rust_lapper_b200/lapper.py) bind
+ * exactly these symbols.
+ *
+ * Conventions
+ *  - Coordinates are I = u32 (the reference bench's `Interval<u32, bool>`,
+ *    benches/lapper_benchmark.rs:13).  Intervals and queries are half-open [start, stop).
+ *  - The payload `val: T` never crosses the ABI: the library returns POSITIONS in the sorted
+ *    interval vector (`lapper.intervals`, src/lib.rs:112) plus `perm` (sorted position -> input
+ *    position, stable on ties like Vec::sort, src/lib.rs:201), so the caller indexes its own vals.
+ *  - Every function returns an int status (LAPPER_OK == 0).  Nothing throws or aborts across the
+ *    ABI; lapper_last_error() gives a thread-local message for the last failing call.
+ *  - `_dev` variants take DEVICE pointers and a cudaStream_t (passed as void*), enqueue on that
+ *    stream and do not synchronise unless stated.  The other variants take HOST pointers (pinned
+ *    host memory gives full PCIe speed; pageable works) and return when outputs are complete.
+ *  - Inputs are borrowed for the duration of the call; outputs are caller-allocated.
+ *  - Threading: concurrent calls that take `const lapper_t*` may run from several host threads on
+ *    one handle (the reference's shared `&Lapper`, src/lib.rs:7, :643-645); functions taking a
+ *    non-const handle need exclusive access (the reference's `&mut self`).
+ *  - There is no CPU fallback: without a CUDA device every build call fails with
+ *    LAPPER_ERR_NO_DEVICE.
+ */
+#ifndef LAPPER_B200_H
+#define LAPPER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LAPPER_OK 0
+#define LAPPER_ERR_INVALID_ARG 1
+#define LAPPER_ERR_CUDA 2
+#define LAPPER_ERR_OOM 3
+#define LAPPER_ERR_PRECONDITION 4 /* input violates start <= stop where the closed form needs it */
+#define LAPPER_ERR_NO_DEVICE 5
+
+/* lapper_build_u32_ex flags */
+#define LAPPER_BUILD_DEFAULT 0u
+#define LAPPER_BUILD_NO_BUCKETS 1u    /* search the sorted arrays directly (sampled keys in smem) */
+#define LAPPER_BUILD_FORCE_BUCKETS 2u /* build the bucket-rank table even for tiny sets */
+#define LAPPER_BUILD_SHIFT(k) ((((uint32_t)(k)) + 1u) << 8) /* force bucket width 2^k, 0 <= k <= 13 */
+
+typedef struct lapper lapper_t;               /* Lapper<u32, T>              src/lib.rs:102-123 */
+typedef struct lapper_result lapper_result_t; /* a batch of IterFind outputs src/lib.rs:682-718 */
+typedef struct lapper_group lapper_group_t;   /* one replica per GPU, queries sharded            */
+
+int lapper_version(void);
+const char *lapper_last_error(void);
+int lapper_device_count(int *count_out);
+
+/* ---- Lapper::new (src/lib.rs:196-236): stable sort by (start, stop), sorted starts, sorted stops,
+ *      max_len.  Built on `device` by a radix sort + reductions.  n may be 0. */
+int lapper_build_u32(const uint32_t *starts, const uint32_t *stops, uint64_t n, int device, lapper_t **out);
+int lapper_build_u32_ex(const uint32_t *starts, const uint32_t *stops, uint64_t n, int device, uint32_t flags,
+                        lapper_t **out);
+/* inputs already on `device`; enqueued on `stream`, synchronises it before returning */
+int lapper_build_u32_dev(const uint32_t *d_starts, const uint32_t *d_stops, uint64_t n, int device, uint32_t flags,
+                         void *stream, lapper_t **out);
+void lapper_free(lapper_t *l);
+
+/* ---- accessors: Lapper::len/is_empty (src/lib.rs:284-299) and the fields of src/lib.rs:111-122 */
+uint64_t lapper_len(const lapper_t *l);
+uint32_t lapper_max_len(const lapper_t *l);
+int lapper_overlaps_merged(const lapper_t *l);
+int lapper_has_inverted(const lapper_t *l); /* 1 if some interval has stop < start */
+int lapper_device(const lapper_t *l);
+uint32_t lapper_bucket_shift(const lapper_t *l);  /* 0xFFFFFFFF when no bucket table is in use */
+uint64_t lapper_index_bytes(const lapper_t *l);   /* device bytes held by the handle */
+/* `intervals` in sorted order as SoA + perm; any pointer may be NULL.  After merge_overlaps perm is
+ * the input position of each run's first interval (whose val the reference keeps, src/lib.rs:385-389). */
+int lapper_get_intervals(const lapper_t *l, uint32_t *starts_out, uint32_t *stops_out, uint32_t *perm_out);
+int lapper_get_starts(const lapper_t *l, uint32_t *out); /* private `starts`, src/lib.rs:114 */
+int lapper_get_stops(const lapper_t *l, uint32_t *out);  /* private `stops` (sorted), src/lib.rs:116 */
+
+/* Borrowed device pointers, valid until lapper_free / lapper_merge_overlaps. */
+typedef struct {
+    const uint32_t *starts;       /* sorted starts == intervals[i].start */
+    const uint32_t *stops_by_iv;  /* intervals[i].stop */
+    const uint32_t *stops_sorted; /* sorted stops */
+    const uint32_t *perm;         /* sorted position -> input position */
+    const uint32_t *prefix_max;   /* max(stops_by_iv[0..=i]) */
+    uint64_t n;
+} lapper_dev_view;
+int lapper_get_dev_view(const lapper_t *l, lapper_dev_view *out);
+
+/* ---- Lapper::count (src/lib.rs:610-618), batched.  counts_out[j] == lapper.count(q_start[j],
+ *      q_stop[j]) as the release-mode `usize` (it wraps exactly where the reference wraps). */
+int lapper_count_batch_u32(const lapper_t *l, const uint32_t *q_start, const uint32_t *q_stop, uint64_t nq,
+                           uint64_t *counts_out);
+/* low 32 bits of the same value (exact whenever the reference does not wrap) */
+int lapper_count_batch_u32_c32(const lapper_t *l, const uint32_t *q_start, const uint32_t *q_stop, uint64_t nq,
+                               uint32_t *counts_out);
+int lapper_count_batch_u32_dev(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop, uint64_t nq,
+                               uint32_t *d_counts_out, void *stream);
+int lapper_count_batch_u32_dev64(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop, uint64_t nq,
+                                 uint64_t *d_counts_out, void *stream);
+
+/* ---- Lapper::find + IterFind::next (src/lib.rs:628-639, :695-718), batched, CSR output:
+ *      indices[offsets[j] .. offsets[j+1]) are the positions (in `intervals`) that
+ *      lapper.find(q_start[j], q_stop[j]) yields, in iterator order.  Lapper::seek
+ *      (src/lib.rs:656-679) yields the same sequence for start-sorted queries; no cursor crosses
+ *      the ABI (lapper_seek_cursor below gives the reference's cursor value where a shim wants it). */
+int lapper_find_batch_u32(const lapper_t *l, const uint32_t *q_start, const uint32_t *q_stop, uint64_t nq,
+                          lapper_result_t **out);
+/* same, queries already on the device (enqueued on `stream`, synchronised before returning) */
+int lapper_find_batch_u32_devq(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop, uint64_t nq,
+                               void *stream, lapper_result_t **out);
+uint64_t lapper_result_nq(const lapper_result_t *r);
+uint64_t lapper_result_total(const lapper_result_t *r);
+/* host copies; either pointer may be NULL.  offsets_out has nq+1 entries, indices_out total entries */
+int lapper_result_copy(const lapper_result_t *r, uint64_t *offsets_out, uint32_t *indices_out);
+int lapper_result_dev(const lapper_result_t *r, const uint64_t **d_offsets, const uint32_t **d_indices);
+void lapper_result_free(lapper_result_t *r);
+
+/* two-phase, caller-allocated device buffers: phase 1 writes d_offsets[nq+1] and returns the total
+ * (synchronises `stream`); phase 2 fills d_indices[total]. */
+int lapper_find_batch_offsets_u32_dev(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop,
+                                      uint64_t nq, uint64_t *d_offsets, uint64_t *total_out, void *stream);
+int lapper_find_batch_fill_u32_dev(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop,
+                                   uint64_t nq, const uint64_t *d_offsets, uint32_t *d_indices, void *stream);
+
+/* Lapper::seek's cursor update (src/lib.rs:658-671) for one query, so a host shim can keep the
+ * reference's `&mut usize` protocol: *cursor is updated exactly as the reference updates it. */
+int lapper_seek_cursor(const lapper_t *l, uint32_t start, uint64_t *cursor);
+
+/* ---- Lapper::merge_overlaps (src/lib.rs:361-416): prefix-max scan, run heads, compaction; rebuilds
+ *      starts / stops / max_len; sets overlaps_merged iff the lapper is non-empty.
+ *      LAPPER_ERR_PRECONDITION if some interval has stop < start. */
+int lapper_merge_overlaps(lapper_t *l);
+/* ---- Lapper::cov / set_cov (src/lib.rs:310-350) */
+int lapper_cov(const lapper_t *l, uint32_t *cov_out);
+int lapper_set_cov(lapper_t *l, uint32_t *cov_out);
+/* ---- Lapper::union_and_intersect / intersect / union (src/lib.rs:512-559) */
+int lapper_union_and_intersect(const lapper_t *a, const lapper_t *b, uint32_t *union_out, uint32_t *intersect_out);
+
+/* frees buffers the library malloc'ed for the caller (lapper_group_find_batch_u32) */
+void lapper_host_free(void *p);
+
+/* ---- multi-GPU, single process: the index is replicated (peer copies over NVLink), queries are
+ *      sharded contiguously: device g owns queries [g*nq/G, (g+1)*nq/G).  No data-path collective
+ *      for count; find rebases per-shard CSR offsets by the shard totals. */
+int lapper_replicate(const lapper_t *l, const int *devices, int g, lapper_group_t **out);
+void lapper_group_free(lapper_group_t *grp);
+int lapper_group_size(const lapper_group_t *grp);
+const lapper_t *lapper_group_replica(const lapper_group_t *grp, int i);
+int lapper_group_count_batch_u32(const lapper_group_t *grp, const uint32_t *q_start, const uint32_t *q_stop,
+                                 uint64_t nq, uint64_t *counts_out);
+int lapper_group_find_batch_u32(const lapper_group_t *grp, const uint32_t *q_start, const uint32_t *q_stop,
+                                uint64_t nq, uint64_t *offsets_out /* nq+1 */, uint32_t **indices_out /* lapper_host_free */,
+                                uint64_t *total_out);
+
+/* ---- index import/export for one-process-per-GPU deployments (torch.distributed broadcast of the
+ *      built arrays): build a handle from already-sorted device arrays without re-sorting. */
+int lapper_from_sorted_dev(const uint32_t *d_starts, const uint32_t *d_stops_by_iv, const uint32_t *d_stops_sorted,
+                           const uint32_t *d_perm, uint64_t n, int overlaps_merged, int device, uint32_t flags,
+                           void *stream, lapper_t **out);
+
+/* pinned host memory helpers (cudaHostAlloc / cudaFreeHost) for callers that want full-speed copies */
+int lapper_host_alloc_pinned(uint64_t bytes, void **out);
+void lapper_host_free_pinned(void *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,239 @@
+// build.cu -- index build: Lapper::new (/root/reference/src/lib.rs:196-236) on the device.
+//
+//   sort by (start, stop), stable   -> LSD radix sort of the 64-bit key (start << 32) | stop with
+//                                      the input position as payload (src/lib.rs:145-157, :201)
+//   starts / stops                  -> unzip of the sorted keys; stops sorted on their own (:203-216)
+//   max_len                         -> max(stop (-) start) reduction, checked_sub -> 0 (:218-227)
+//   + prefix_max, + the BITS bucket sectors described in index.cuh (new; the reference searches
+//     the sorted vectors directly).
+#include <cub/device/device_radix_sort.cuh>
+
+#include "index.cuh"
+
+#ifdef THRUST_CUB_WRAPPED_NAMESPACE
+namespace cubns = THRUST_CUB_WRAPPED_NAMESPACE::cub;  // private copy of CUB: no symbol clashes with torch's
+#else
+namespace cubns = cub;
+#endif
+
+namespace lap {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__global__ void pack_keys_kernel(const uint32_t *__restrict__ s, const uint32_t *__restrict__ e, uint64_t n,
+                                 uint64_t *__restrict__ keys, uint32_t *__restrict__ pos) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = ((uint64_t)s[i] << 32) | (uint64_t)e[i];
+    pos[i] = (uint32_t)i;
+}
+
+__global__ void unpack_keys_kernel(const uint64_t *__restrict__ keys, uint64_t n, uint32_t *__restrict__ s,
+                                   uint32_t *__restrict__ e) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t k = keys[i];
+    s[i] = (uint32_t)(k >> 32);
+    e[i] = (uint32_t)k;
+}
+
+struct BuildStats {
+    uint32_t max_len;
+    uint32_t inverted;
+};
+
+// max_len = max over intervals of stop.checked_sub(start).unwrap_or(0)   (src/lib.rs:218-227)
+__global__ void stats_kernel(const uint32_t *__restrict__ s, const uint32_t *__restrict__ e, uint64_t n,
+                             BuildStats *__restrict__ out) {
+    uint32_t mx = 0, inv = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t a = s[i], b = e[i];
+        mx = max(mx, b >= a ? b - a : 0u);
+        inv |= (b < a);
+    }
+    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
+    inv = __reduce_or_sync(0xFFFFFFFFu, inv);
+    if ((threadIdx.x & 31) == 0) {
+        if (mx) atomicMax(&out->max_len, mx);
+        if (inv) atomicOr(&out->inverted, 1u);
+    }
+}
+
+// One thread per bucket: four coherent bisections (neighbouring buckets walk the same path) and
+// one 32-byte sector store.
+__global__ void fill_buckets_kernel(const uint32_t *__restrict__ S, const uint32_t *__restrict__ E, uint32_t n,
+                                    uint32_t shift, uint64_t nb, Sector *__restrict__ buckets) {
+    uint64_t B = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (B > nb) return;
+    Sector sec;
+    const uint32_t width = 1u << shift;
+    const uint32_t mask = width - 1u;
+    const uint32_t empty = 0x8000u | width;
+    if (B == nb) {  // sentinel: every key is below it
+        sec.w[0] = n;
+        sec.w[1] = n;
+#pragma unroll
+        for (int j = 2; j < 8; j++) sec.w[j] = empty * 0x10001u;
+        buckets[B] = sec;
+        return;
+    }
+    const uint64_t base = B << shift;
+    const uint64_t next = base + width;
+    const uint32_t rs = lower_bound_u32(S, 0, n, (uint32_t)base);
+    const uint32_t re_lo = lower_bound_u32(E, 0, n, (uint32_t)base);
+    const uint32_t rs_next = next > 0xFFFFFFFFull ? n : lower_bound_u32(S, rs, n, (uint32_t)next);
+    const uint32_t re_hi = next > 0xFFFFFFFFull ? n : lower_bound_u32(E, re_lo, n, (uint32_t)next);
+    const uint32_t ns = rs_next - rs, ne = re_hi - re_lo;
+    sec.w[0] = rs;
+    sec.w[1] = re_hi;
+    if (ns + ne > kBucketLanes) {
+#pragma unroll
+        for (int j = 2; j < 8; j++) sec.w[j] = 0xFFFFFFFFu;
+    } else {
+        uint32_t lanes[kBucketLanes];
+#pragma unroll
+        for (uint32_t j = 0; j < kBucketLanes; j++) {
+            uint32_t v = empty;
+            if (j < ns)
+                v = 0x8000u | (S[rs + j] & mask);
+            else if (j < ns + ne)
+                v = 0x8000u | (width + (E[re_lo + (j - ns)] & mask));
+            lanes[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 6; j++) sec.w[2 + j] = lanes[2 * j] | (lanes[2 * j + 1] << 16);
+    }
+    buckets[B] = sec;
+}
+
+template <typename T>
+T *dev_alloc(uint64_t count, uint64_t &bytes) {
+    T *p = nullptr;
+    uint64_t b = (count ? count : 1) * sizeof(T);
+    LAPPER_CUDA_CHECK(cudaMalloc((void **)&p, b));
+    bytes += b;
+    return p;
+}
+
+uint32_t grid_for(uint64_t n) { return (uint32_t)div_up(n ? n : 1, kThreads); }
+
+// Pick the bucket width: about six keys (starts + stops) per 12-lane sector keeps the overflow
+// rate of a Poisson load under 2%, and at the cfg-2 shape (10 M intervals over 3.1 G) that is
+// shift 10 -> 3.0 M sectors = 97 MB, which fits the 126 MB L2.
+bool choose_shift(uint64_t n, uint32_t max_coord, uint32_t flags, uint32_t &shift_out) {
+    if (flags & LAPPER_BUILD_NO_BUCKETS) return false;
+    const uint32_t forced = (flags >> 8) & 0xFFu;
+    if (forced) {
+        shift_out = forced - 1u;
+        LAPPER_REQUIRE(shift_out <= kMaxBucketShift, "LAPPER_BUILD_SHIFT: shift must be <= 13");
+        return true;
+    }
+    const bool force = (flags & LAPPER_BUILD_FORCE_BUCKETS) != 0;
+    if (n < 4096 && !force) return false;
+    const uint64_t target = (2 * n) / 6 > 1024 ? (2 * n) / 6 : 1024;
+    uint32_t k = 0;
+    while (k < kMaxBucketShift && ((uint64_t)(max_coord >> k) + 1) > target) k++;
+    const uint64_t nb = (uint64_t)(max_coord >> k) + 1;
+    if (!force) {
+        if (nb > 64 * n) return false;      // very sparse: the table would dwarf the index
+        if (2 * n > 24 * nb) return false;  // very dense: nearly every sector would overflow
+    }
+    shift_out = k;
+    return true;
+}
+
+}  // namespace
+
+void free_index(DeviceIndex &ix) {
+    cudaFree(ix.starts);
+    cudaFree(ix.stops_by_iv);
+    cudaFree(ix.stops_sorted);
+    cudaFree(ix.perm);
+    cudaFree(ix.prefix_max);
+    cudaFree(ix.buckets);
+    ix = DeviceIndex();
+}
+
+void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stream) {
+    const uint64_t n = ix.n;
+    ix.max_len = 0;
+    ix.has_inverted = false;
+    ix.max_coord = 0;
+    ix.shift = 0xFFFFFFFFu;
+    ix.nbuckets = 0;
+    if (n == 0) return;
+
+    Scratch<BuildStats> d_stats(1, stream);
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(d_stats.p, 0, sizeof(BuildStats), stream));
+    uint32_t g = (uint32_t)std::min<uint64_t>(div_up(n, kThreads), 148 * 16);
+    stats_kernel<<<g, kThreads, 0, stream>>>(ix.starts, ix.stops_by_iv, n, d_stats.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+
+    ix.prefix_max = dev_alloc<uint32_t>(n, ix.bytes);
+    launch_prefix_max(ix.stops_by_iv, ix.prefix_max, n, stream);
+
+    BuildStats st;
+    uint32_t last_start = 0, last_stop = 0;
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&st, d_stats.p, sizeof(st), cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&last_start, ix.starts + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&last_stop, ix.stops_sorted + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    ix.max_len = st.max_len;
+    ix.has_inverted = st.inverted != 0;
+    ix.max_coord = std::max(last_start, last_stop);
+
+    uint32_t shift = 0;
+    if (choose_shift(n, ix.max_coord, flags, shift)) {
+        ix.shift = shift;
+        ix.nbuckets = (uint64_t)(ix.max_coord >> shift) + 1;
+        ix.buckets = dev_alloc<Sector>(ix.nbuckets + 1, ix.bytes);
+        fill_buckets_kernel<<<grid_for(ix.nbuckets + 1), kThreads, 0, stream>>>(
+            ix.starts, ix.stops_sorted, (uint32_t)n, shift, ix.nbuckets, ix.buckets);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
+}
+
+void build_index_from_unsorted(DeviceIndex &ix, const uint32_t *d_starts, const uint32_t *d_stops, uint64_t n,
+                               uint32_t flags, cudaStream_t stream) {
+    LAPPER_REQUIRE(n < 0xFFFFFFF0ull, "lapper_build: n must be < 2^32 - 16 (positions are u32)");
+    ix = DeviceIndex();
+    ix.n = n;
+    if (n == 0) {
+        finish_index_from_sorted(ix, flags, stream);
+        return;
+    }
+    try {
+        ix.starts = dev_alloc<uint32_t>(n, ix.bytes);
+        ix.stops_by_iv = dev_alloc<uint32_t>(n, ix.bytes);
+        ix.stops_sorted = dev_alloc<uint32_t>(n, ix.bytes);
+        ix.perm = dev_alloc<uint32_t>(n, ix.bytes);
+        {
+            Scratch<uint64_t> keys_in(n, stream), keys_out(n, stream);
+            Scratch<uint32_t> pos_in(n, stream);
+            pack_keys_kernel<<<grid_for(n), kThreads, 0, stream>>>(d_starts, d_stops, n, keys_in.p, pos_in.p);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+            // LSD radix sort: stable, so equal (start, stop) keep input order like Vec::sort.
+            size_t tmp_pairs = 0, tmp_keys = 0;
+            LAPPER_CUDA_CHECK(cubns::DeviceRadixSort::SortPairs(nullptr, tmp_pairs, keys_in.p, keys_out.p, pos_in.p,
+                                                              ix.perm, n, 0, 64, stream));
+            LAPPER_CUDA_CHECK(cubns::DeviceRadixSort::SortKeys(nullptr, tmp_keys, d_stops, ix.stops_sorted, n, 0, 32,
+                                                             stream));
+            Scratch<uint8_t> tmp(std::max(tmp_pairs, tmp_keys), stream);
+            LAPPER_CUDA_CHECK(cubns::DeviceRadixSort::SortPairs(tmp.p, tmp_pairs, keys_in.p, keys_out.p, pos_in.p,
+                                                              ix.perm, n, 0, 64, stream));
+            unpack_keys_kernel<<<grid_for(n), kThreads, 0, stream>>>(keys_out.p, n, ix.starts, ix.stops_by_iv);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+            LAPPER_CUDA_CHECK(cubns::DeviceRadixSort::SortKeys(tmp.p, tmp_keys, d_stops, ix.stops_sorted, n, 0, 32,
+                                                             stream));
+        }
+        finish_index_from_sorted(ix, flags, stream);
+    } catch (...) {
+        free_index(ix);
+        throw;
+    }
+}
+
+}  // namespace lap

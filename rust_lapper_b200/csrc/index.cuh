@@ -1,0 +1,105 @@
+// index.cuh -- the device-resident index behind a lapper_t, and the launchers each .cu exports.
+//
+// HBM layout (all u32, SoA; the reference's AoS Vec<Interval<I,T>> is a CPU artefact):
+//   starts[n]        intervals[i].start, i in sorted (start, stop) order      (src/lib.rs:112,114)
+//   stops_by_iv[n]   intervals[i].stop                                        (src/lib.rs:112)
+//   stops_sorted[n]  the reference's private sorted `stops`                   (src/lib.rs:116)
+//   perm[n]          sorted position -> input position (stable on ties)
+//   prefix_max[n]    max(stops_by_iv[0..=i]); drives find's window, merge_overlaps and cov
+//   buckets[nb+1]    32-byte BITS sectors, see below
+#pragma once
+
+#include <atomic>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace lap {
+
+// ---- BITS bucket sector -------------------------------------------------------------------------
+// Bucket B covers coordinates [B << shift, (B+1) << shift).  One 32-byte sector (one LDG.E.256,
+// one L2 sector, one L1 wavefront) answers both halves of BITS count for a query whose start and
+// stop fall in the bucket:
+//   w[0]      rs    = #starts        <  (B << shift)
+//   w[1]      re_hi = #sorted stops  <  ((B+1) << shift)
+//   w[2..7]   12 x 16-bit lanes, each with guard bit 15 set:
+//               a start s in the bucket  ->  0x8000 | (s & mask)
+//               a stop  e in the bucket  ->  0x8000 | (2^shift + (e & mask))
+//               empty lane               ->  0x8000 | 2^shift
+//   lower_bound(starts, b) = rs    + #{lane value <  (b & mask)}
+//   upper_bound(stops,  a) = re_hi - #{lane value >= 2^shift + (a & mask) + 1}
+// Both lane counts are one packed 16-bit subtract per word: (0x8000|v) - x keeps bit 15 iff v >= x
+// and never borrows across lanes because x <= 2^(shift+1) <= 0x4000.  shift <= 13.
+// A bucket holding more than 12 keys stores 0xFFFF in every lane (overflow marker); such a query
+// bisects starts[rs, rs_next) / stops_sorted[re_lo, re_hi) instead.  Bucket nb is a sentinel
+// (rs = re_hi = n, empty) for coordinates beyond the last key.
+constexpr uint32_t kBucketLanes = 12;
+constexpr uint32_t kMaxBucketShift = 13;
+constexpr uint32_t kLaneGuard = 0x80008000u;
+
+struct DeviceIndex {
+    uint64_t n = 0;
+    uint32_t *starts = nullptr;
+    uint32_t *stops_by_iv = nullptr;
+    uint32_t *stops_sorted = nullptr;
+    uint32_t *perm = nullptr;
+    uint32_t *prefix_max = nullptr;
+    Sector *buckets = nullptr;
+    uint64_t nbuckets = 0;  // real buckets; the array has nbuckets + 1 sectors
+    uint32_t shift = 0xFFFFFFFFu;
+    uint32_t max_len = 0;
+    uint32_t max_coord = 0;
+    bool has_inverted = false;
+    uint64_t bytes = 0;
+};
+
+}  // namespace lap
+
+// The opaque handle of the C ABI.
+struct lapper {
+    int device = 0;
+    lap::DeviceIndex ix;
+    bool overlaps_merged = false;
+    bool cov_is_some = false;
+    uint32_t cov = 0;
+    uint32_t build_flags = 0;
+};
+
+struct lapper_result {
+    int device = 0;
+    uint64_t nq = 0;
+    uint64_t total = 0;
+    uint64_t *d_offsets = nullptr;
+    uint32_t *d_indices = nullptr;
+};
+
+namespace lap {
+
+// build.cu ---------------------------------------------------------------------------------------
+// Sort (start, stop) pairs (stable, by (start, stop)) and derive every array of DeviceIndex.
+void build_index_from_unsorted(DeviceIndex &ix, const uint32_t *d_starts, const uint32_t *d_stops, uint64_t n,
+                               uint32_t flags, cudaStream_t stream);
+// Arrays already sorted (import / after merge_overlaps).  Takes ownership of the four arrays.
+void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stream);
+void free_index(DeviceIndex &ix);
+
+// query.cu ---------------------------------------------------------------------------------------
+void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, uint32_t *d_out32,
+                  uint64_t *d_out64, cudaStream_t stream);
+// writes d_offsets[nq+1]; returns total hits (synchronises the stream)
+uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
+                             uint64_t *d_offsets, cudaStream_t stream);
+void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
+                      const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream);
+
+// setops.cu --------------------------------------------------------------------------------------
+// inclusive prefix max of `in` (n elements) into `out`
+void launch_prefix_max(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream);
+uint32_t compute_cov(const DeviceIndex &ix, cudaStream_t stream);
+// merged (start, stop, head perm) arrays; returns m.  Outputs are cudaMalloc'ed (m may be 0).
+uint64_t compute_merged(const DeviceIndex &ix, uint32_t **m_starts, uint32_t **m_stops, uint32_t **m_perm,
+                        cudaStream_t stream);
+// measure of (union of a) intersected with (union of b), wrapping u32
+uint32_t compute_intersect_measure(const DeviceIndex &a, const DeviceIndex &b, cudaStream_t stream);
+
+}  // namespace lap

@@ -1,0 +1,493 @@
+// query.cu -- the batched query path: Lapper::count and Lapper::find on the device.
+//
+//   count(a, b) = lower_bound(starts, b) - upper_bound(stops_sorted, a)       (src/lib.rs:611-618;
+//                 `start + 1` there turns bsearch_seq's "<" into "<=", :614), wrapping like usize.
+//   find(a, b)  = ascending i in [lower_bound(starts, a (-) max_len), lower_bound(starts, b))
+//                 with stops_by_iv[i] > a                                      (src/lib.rs:629-639, :704-717)
+//
+// The reference walks each search with ~24 dependent cache misses (bsearch_seq_ref, :448-466).
+// Here a query normally costs ONE 32-byte sector (index.cuh) fetched with one LDG.E.256; the sorted
+// arrays are touched only for overflowing buckets.  Without a bucket table (tiny or degenerate
+// sets) the kernels bisect the sorted arrays under a sampled-key directory held in shared memory.
+#include "index.cuh"
+
+namespace lap {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kQPT = 4;  // queries per thread: four independent sector gathers in flight
+
+struct BucketView {
+    const Sector *buckets;
+    const uint32_t *S;
+    const uint32_t *E;
+    uint32_t n;
+    uint32_t shift;
+    uint32_t nb;  // index of the sentinel bucket
+};
+
+// number of 16-bit lanes (of the 12 in w[2..7]) whose value is >= x; x2 = x replicated in both halves
+__device__ __forceinline__ uint32_t lanes_ge(const Sector &s, uint32_t x2) {
+    const uint32_t t0 = s.w[2] - x2, t1 = s.w[3] - x2, t2 = s.w[4] - x2;
+    const uint32_t t3 = s.w[5] - x2, t4 = s.w[6] - x2, t5 = s.w[7] - x2;
+    // gather the guard bits (bit 15 of every lane) of two words into the MSBs of four bytes
+    const uint32_t p01 = __byte_perm(t0, t1, 0x7531);
+    const uint32_t p23 = __byte_perm(t2, t3, 0x7531);
+    const uint32_t p45 = __byte_perm(t4, t5, 0x7531);
+    const uint32_t m = (p01 & 0x80808080u) | ((p23 & 0x80808080u) >> 1) | ((p45 & 0x80808080u) >> 2);
+    return __popc(m);
+}
+
+__device__ __forceinline__ bool sector_overflow(const Sector &s) { return s.w[7] == 0xFFFFFFFFu; }
+
+// lower_bound(starts, key) given the sector of key's bucket
+__device__ __forceinline__ uint32_t lb_from_sector(const BucketView &v, const Sector &s, uint32_t bucket,
+                                                   uint32_t key) {
+    if (__builtin_expect(sector_overflow(s), 0)) {
+        const uint32_t rs_next = __ldg(reinterpret_cast<const uint32_t *>(v.buckets + bucket + 1));
+        return lower_bound_u32(v.S, s.w[0], rs_next, key);
+    }
+    const uint32_t mask = (1u << v.shift) - 1u;
+    return s.w[0] + kBucketLanes - lanes_ge(s, (key & mask) * 0x10001u);
+}
+
+// upper_bound(stops_sorted, key) given the sector of key's bucket
+__device__ __forceinline__ uint32_t ub_from_sector(const BucketView &v, const Sector &s, uint32_t bucket,
+                                                   uint32_t key) {
+    if (__builtin_expect(sector_overflow(s), 0)) {
+        const uint32_t re_lo = bucket ? __ldg(reinterpret_cast<const uint32_t *>(v.buckets + bucket - 1) + 1) : 0u;
+        return upper_bound_u32(v.E, re_lo, s.w[1], key);
+    }
+    const uint32_t width = 1u << v.shift;
+    return s.w[1] - lanes_ge(s, (width + (key & (width - 1u)) + 1u) * 0x10001u);
+}
+
+__device__ __forceinline__ uint32_t bucket_of(const BucketView &v, uint32_t x) { return min(x >> v.shift, v.nb); }
+
+// Lapper::count for one query from its sector(s).
+__device__ __forceinline__ void bits_count(const BucketView &v, uint32_t a, uint32_t b, const Sector &sb,
+                                           uint32_t bb, const Sector &sa, uint32_t ba, uint32_t &lb, uint32_t &ub) {
+    lb = lb_from_sector(v, sb, bb, b);
+    ub = ub_from_sector(v, sa, ba, a);
+    // src/lib.rs:614: `start + one` wraps to 0 when start == u32::MAX, so `first` is 0 there.
+    if (a == 0xFFFFFFFFu) ub = 0;
+}
+
+template <bool kOut64>
+__device__ __forceinline__ void store_count(uint32_t *o32, uint64_t *o64, uint64_t j, uint32_t lb, uint32_t ub) {
+    // len - first - (len - last) in wrapping usize == last - first (mod 2^64)
+    if (kOut64)
+        st_stream_u64(o64 + j, (uint64_t)lb - (uint64_t)ub);
+    else
+        st_stream_u32(o32 + j, lb - ub);
+}
+
+// ---- count, bucket path.  Each thread owns kQPT consecutive queries: coalesced 16-byte loads of
+// starts/stops, then up to 2*kQPT independent sector gathers, then one 16-byte store.
+template <bool kOut64, bool kVec>
+__global__ void __launch_bounds__(kThreads) count_bucket_kernel(BucketView v, const uint32_t *__restrict__ qs,
+                                                                const uint32_t *__restrict__ qe, uint64_t nq,
+                                                                uint32_t *__restrict__ o32,
+                                                                uint64_t *__restrict__ o64) {
+    const uint64_t ntiles = div_up(nq, kQPT);
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles;
+         t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t j0 = t * kQPT;
+        uint32_t a[kQPT], b[kQPT];
+        const bool full = j0 + kQPT <= nq;
+        if (kVec && full) {
+            const uint4 va = ld_stream_v4(qs + j0), vb = ld_stream_v4(qe + j0);
+            a[0] = va.x, a[1] = va.y, a[2] = va.z, a[3] = va.w;
+            b[0] = vb.x, b[1] = vb.y, b[2] = vb.z, b[3] = vb.w;
+        } else {
+#pragma unroll
+            for (int k = 0; k < kQPT; k++) {
+                const bool ok = j0 + k < nq;
+                a[k] = ok ? ld_stream_u32(qs + j0 + k) : 0u;
+                b[k] = ok ? ld_stream_u32(qe + j0 + k) : 0u;
+            }
+        }
+        uint32_t ba[kQPT], bb[kQPT];
+        Sector sb[kQPT];
+#pragma unroll
+        for (int k = 0; k < kQPT; k++) {
+            ba[k] = bucket_of(v, a[k]);
+            bb[k] = bucket_of(v, b[k]);
+            sb[k] = ld_sector_cached(v.buckets + bb[k]);
+        }
+        uint32_t lb[kQPT], ub[kQPT];
+#pragma unroll
+        for (int k = 0; k < kQPT; k++) {
+            if (ba[k] == bb[k]) {
+                bits_count(v, a[k], b[k], sb[k], bb[k], sb[k], bb[k], lb[k], ub[k]);
+            } else {
+                const Sector sa = ld_sector_cached(v.buckets + ba[k]);
+                bits_count(v, a[k], b[k], sb[k], bb[k], sa, ba[k], lb[k], ub[k]);
+            }
+        }
+        if (kVec && full && !kOut64) {
+            st_stream_v4(o32 + j0, make_uint4(lb[0] - ub[0], lb[1] - ub[1], lb[2] - ub[2], lb[3] - ub[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < kQPT; k++)
+                if (j0 + k < nq) store_count<kOut64>(o32, o64, j0 + k, lb[k], ub[k]);
+        }
+    }
+}
+
+// ---- count, direct path: bisect the sorted arrays under a sampled-key directory in shared memory
+// (every 2^dshift-th key; the top levels of both searches never leave the SM).
+constexpr uint32_t kDirSlots = 2048;
+
+struct PlainView {
+    const uint32_t *S;
+    const uint32_t *E;
+    uint32_t n;
+    uint32_t dshift;  // directory stride = 2^dshift
+    uint32_t nsamp;   // ceil(n / stride) <= kDirSlots
+};
+
+__device__ __forceinline__ uint32_t dir_count_lt(const uint32_t *dir, uint32_t key) {
+    // #directory keys < key; dir is padded with 0xFFFFFFFF up to kDirSlots (a power of two)
+    uint32_t pos = 0;
+#pragma unroll
+    for (uint32_t step = kDirSlots >> 1; step > 0; step >>= 1) pos += (dir[pos + step - 1] < key) ? step : 0u;
+    return pos + (dir[pos] < key ? 1u : 0u);
+}
+__device__ __forceinline__ uint32_t dir_count_le(const uint32_t *dir, uint32_t nsamp, uint32_t key) {
+    uint32_t lo = 0, hi = nsamp;  // padding equals 0xFFFFFFFF and must not count when key == 0xFFFFFFFF
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (dir[mid] <= key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t plain_lb(const PlainView &v, const uint32_t *dirS, uint32_t key) {
+    const uint32_t j = min(dir_count_lt(dirS, key), v.nsamp);
+    const uint32_t lo = j ? (j - 1) << v.dshift : 0u;
+    const uint32_t hi = min(j << v.dshift, v.n);
+    return lower_bound_u32(v.S, lo, hi, key);
+}
+__device__ __forceinline__ uint32_t plain_ub(const PlainView &v, const uint32_t *dirE, uint32_t key) {
+    const uint32_t j = dir_count_le(dirE, v.nsamp, key);
+    const uint32_t lo = j ? (j - 1) << v.dshift : 0u;
+    const uint32_t hi = min(j << v.dshift, v.n);
+    return upper_bound_u32(v.E, lo, hi, key);
+}
+
+template <bool kOut64>
+__global__ void __launch_bounds__(kThreads) count_plain_kernel(PlainView v, const uint32_t *__restrict__ qs,
+                                                               const uint32_t *__restrict__ qe, uint64_t nq,
+                                                               uint32_t *__restrict__ o32,
+                                                               uint64_t *__restrict__ o64) {
+    __shared__ uint32_t dirS[kDirSlots];
+    __shared__ uint32_t dirE[kDirSlots];
+    for (uint32_t i = threadIdx.x; i < kDirSlots; i += blockDim.x) {
+        const bool ok = i < v.nsamp;
+        dirS[i] = ok ? __ldg(v.S + ((uint64_t)i << v.dshift)) : 0xFFFFFFFFu;
+        dirE[i] = ok ? __ldg(v.E + ((uint64_t)i << v.dshift)) : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = ld_stream_u32(qs + j), b = ld_stream_u32(qe + j);
+        const uint32_t lb = v.n ? plain_lb(v, dirS, b) : 0u;
+        uint32_t ub = v.n ? plain_ub(v, dirE, a) : 0u;
+        if (a == 0xFFFFFFFFu) ub = 0;  // src/lib.rs:614 wrap
+        store_count<kOut64>(o32, o64, j, lb, ub);
+    }
+}
+
+// ------------------------------------------------------------------------------------- find
+// A generic per-thread rank helper (bucket table when present, plain bisection otherwise).
+struct FindView {
+    BucketView bv;
+    bool has_buckets;
+    const uint32_t *S;
+    const uint32_t *Eiv;  // stops paired with S
+    const uint32_t *E;    // sorted stops
+    uint32_t n;
+    uint32_t max_len;
+    bool has_inverted;
+};
+
+__device__ __forceinline__ uint32_t rank_lb_starts(const FindView &f, uint32_t key) {
+    if (f.has_buckets) {
+        const uint32_t bk = bucket_of(f.bv, key);
+        const Sector s = ld_sector_cached(f.bv.buckets + bk);
+        return lb_from_sector(f.bv, s, bk, key);
+    }
+    return lower_bound_u32(f.S, 0, f.n, key);
+}
+__device__ __forceinline__ uint32_t rank_ub_stops(const FindView &f, uint32_t key) {
+    if (f.has_buckets) {
+        const uint32_t bk = bucket_of(f.bv, key);
+        const Sector s = ld_sector_cached(f.bv.buckets + bk);
+        return ub_from_sector(f.bv, s, bk, key);
+    }
+    return upper_bound_u32(f.E, 0, f.n, key);
+}
+
+// IterFind's scan window (src/lib.rs:632-635 start offset, :712-713 early break):
+// [lower_bound(starts, a (-) max_len), lower_bound(starts, b)).
+__device__ __forceinline__ void find_window(const FindView &f, uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi) {
+    hi = rank_lb_starts(f, b);
+    lo = rank_lb_starts(f, a >= f.max_len ? a - f.max_len : 0u);
+}
+
+// number of positions find(a, b) yields
+__device__ __forceinline__ uint32_t find_count_one(const FindView &f, uint32_t a, uint32_t b) {
+    if (f.n == 0) return 0;
+    if (a < b && !f.has_inverted) {
+        // |find| == count when every interval has start <= stop and the query is non-empty
+        // (SURVEY Appendix A.4); a == u32::MAX cannot happen here because a < b.
+        return rank_lb_starts(f, b) - rank_ub_stops(f, a);
+    }
+    uint32_t lo, hi;
+    find_window(f, a, b, lo, hi);
+    uint32_t c = 0;
+    for (uint32_t i = lo; i < hi; i++) c += (__ldg(f.Eiv + i) > a);
+    return c;
+}
+
+constexpr int kFindQPT = 4;
+constexpr int kFindTile = kThreads * kFindQPT;
+
+__device__ __forceinline__ uint64_t block_reduce_sum_u64(uint64_t v, uint64_t *smem /* 8 */) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, o);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) smem[w] = v;
+    __syncthreads();
+    uint64_t r = 0;
+    if (threadIdx.x < 32) {
+        r = threadIdx.x < (kThreads / 32) ? smem[threadIdx.x] : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xFFFFFFFFu, r, o);
+    }
+    return r;  // valid in thread 0
+}
+
+// pass 1: per-query hit counts (thread t of a tile owns queries t*4..t*4+3) and per-tile sums
+__global__ void __launch_bounds__(kThreads) find_count_kernel(FindView f, const uint32_t *__restrict__ qs,
+                                                              const uint32_t *__restrict__ qe, uint64_t nq,
+                                                              uint32_t *__restrict__ counts,
+                                                              uint64_t *__restrict__ tile_sums) {
+    __shared__ uint64_t red[8];
+    const uint64_t base = (uint64_t)blockIdx.x * kFindTile + (uint64_t)threadIdx.x * kFindQPT;
+    uint64_t local = 0;
+#pragma unroll
+    for (int k = 0; k < kFindQPT; k++) {
+        const uint64_t j = base + k;
+        if (j < nq) {
+            const uint32_t c = find_count_one(f, ld_stream_u32(qs + j), ld_stream_u32(qe + j));
+            counts[j] = c;
+            local += c;
+        }
+    }
+    const uint64_t s = block_reduce_sum_u64(local, red);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
+}
+
+// pass 2: exclusive scan of the tile sums (one block; ntiles ~ nq / 1024)
+__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(uint64_t *__restrict__ tile_sums, uint64_t ntiles,
+                                                              uint64_t *__restrict__ total_out) {
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (uint64_t base = 0; base < ntiles; base += 1024) {
+        const uint64_t i = base + threadIdx.x;
+        const uint64_t x = i < ntiles ? tile_sums[i] : 0;
+        uint64_t inc = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            uint64_t t = warp_tot[lane], ti = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, ti, o);
+                if (lane >= o) ti += y;
+            }
+            warp_tot[lane] = ti - t;  // exclusive
+        }
+        __syncthreads();
+        const uint64_t carry = carry_s;
+        const uint64_t excl = carry + warp_tot[w] + inc - x;
+        if (i < ntiles) tile_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_s = excl + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+// pass 3: offsets[j] = tile base + exclusive scan of the tile's counts
+__global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t *__restrict__ counts,
+                                                                 const uint64_t *__restrict__ tile_base, uint64_t nq,
+                                                                 uint64_t *__restrict__ offsets) {
+    __shared__ uint64_t warp_tot[kThreads / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kFindTile + (uint64_t)threadIdx.x * kFindQPT;
+    uint32_t c[kFindQPT];
+    uint64_t local = 0;
+#pragma unroll
+    for (int k = 0; k < kFindQPT; k++) {
+        c[k] = base + k < nq ? counts[base + k] : 0u;
+        local += c[k];
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    uint64_t wbase = 0;
+#pragma unroll
+    for (int i = 0; i < kThreads / 32; i++) wbase += (i < w) ? warp_tot[i] : 0;
+    uint64_t run = tile_base[blockIdx.x] + wbase + inc - local;
+#pragma unroll
+    for (int k = 0; k < kFindQPT; k++) {
+        if (base + k < nq) offsets[base + k] = run;
+        run += c[k];
+    }
+}
+
+// emit: one thread per query walks its window and writes the hit positions in ascending order
+__global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const uint32_t *__restrict__ qs,
+                                                             const uint32_t *__restrict__ qe, uint64_t nq,
+                                                             const uint64_t *__restrict__ offsets,
+                                                             uint32_t *__restrict__ indices) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t o0 = offsets[j], o1 = offsets[j + 1];
+        if (o1 == o0) continue;
+        const uint32_t a = ld_stream_u32(qs + j), b = ld_stream_u32(qe + j);
+        uint32_t lo, hi;
+        find_window(f, a, b, lo, hi);
+        uint32_t *out = indices + o0;
+        uint64_t room = o1 - o0;
+        for (uint32_t i = lo; i < hi && room; i++) {
+            if (__ldg(f.Eiv + i) > a) {
+                *out++ = i;
+                room--;
+            }
+        }
+    }
+}
+
+BucketView make_bucket_view(const DeviceIndex &ix) {
+    BucketView v;
+    v.buckets = ix.buckets;
+    v.S = ix.starts;
+    v.E = ix.stops_sorted;
+    v.n = (uint32_t)ix.n;
+    v.shift = ix.shift;
+    v.nb = (uint32_t)ix.nbuckets;
+    return v;
+}
+
+FindView make_find_view(const DeviceIndex &ix) {
+    FindView f;
+    f.has_buckets = ix.buckets != nullptr;
+    f.bv = make_bucket_view(ix);
+    f.S = ix.starts;
+    f.Eiv = ix.stops_by_iv;
+    f.E = ix.stops_sorted;
+    f.n = (uint32_t)ix.n;
+    f.max_len = ix.max_len;
+    f.has_inverted = ix.has_inverted;
+    return f;
+}
+
+uint32_t capped_grid(uint64_t work_items, int per_block, int waves) {
+    uint64_t g = div_up(work_items ? work_items : 1, per_block);
+    const uint64_t cap = 148ull * waves;
+    return (uint32_t)(g < cap ? g : cap);
+}
+
+}  // namespace
+
+void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, uint32_t *d_out32,
+                  uint64_t *d_out64, cudaStream_t stream) {
+    if (nq == 0) return;
+    const bool out64 = d_out64 != nullptr;
+    if (ix.buckets) {
+        const BucketView v = make_bucket_view(ix);
+        const bool vec = ((reinterpret_cast<uintptr_t>(d_qs) | reinterpret_cast<uintptr_t>(d_qe) |
+                           reinterpret_cast<uintptr_t>(d_out32)) & 15u) == 0;
+        // 148 SMs x 8 resident CTAs of 256 threads, grid-stride over 4-query tiles
+        const uint32_t grid = capped_grid(div_up(nq, kQPT), kThreads, 8 * 4);
+        if (out64) {
+            if (vec)
+                count_bucket_kernel<true, true><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, nullptr, d_out64);
+            else
+                count_bucket_kernel<true, false><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, nullptr, d_out64);
+        } else {
+            if (vec)
+                count_bucket_kernel<false, true><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, d_out32, nullptr);
+            else
+                count_bucket_kernel<false, false><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, d_out32, nullptr);
+        }
+    } else {
+        PlainView v;
+        v.S = ix.starts;
+        v.E = ix.stops_sorted;
+        v.n = (uint32_t)ix.n;
+        v.dshift = 0;
+        while (div_up(ix.n, 1ull << v.dshift) > kDirSlots) v.dshift++;
+        v.nsamp = (uint32_t)div_up(ix.n, 1ull << v.dshift);
+        const uint32_t grid = capped_grid(nq, kThreads, 8);
+        if (out64)
+            count_plain_kernel<true><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, nullptr, d_out64);
+        else
+            count_plain_kernel<false><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, d_out32, nullptr);
+    }
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+}
+
+uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
+                             uint64_t *d_offsets, cudaStream_t stream) {
+    if (nq == 0) {
+        LAPPER_CUDA_CHECK(cudaMemsetAsync(d_offsets, 0, sizeof(uint64_t), stream));
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    const FindView f = make_find_view(ix);
+    const uint64_t ntiles = div_up(nq, kFindTile);
+    LAPPER_REQUIRE(ntiles < 0x7FFFFFFFull, "find_batch: too many queries in one call");
+    Scratch<uint32_t> counts(nq, stream);
+    Scratch<uint64_t> tile_sums(ntiles, stream);
+    find_count_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    scan_tile_sums_kernel<<<1, 1024, 0, stream>>>(tile_sums.p, ntiles, d_offsets + nq);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    write_offsets_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(counts.p, tile_sums.p, nq, d_offsets);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    uint64_t total = 0;
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return total;
+}
+
+void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
+                      const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream) {
+    if (nq == 0 || ix.n == 0) return;
+    const FindView f = make_find_view(ix);
+    const uint32_t grid = capped_grid(nq, kThreads, 8 * 8);
+    find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+}
+
+}  // namespace lap

@@ -1,0 +1,194 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle on identical seeded inputs:
+bit-exact counts, CSR offsets and positions; merge / cov / union_and_intersect; seek cursors."""
+import numpy as np
+import pytest
+
+import reference_suite as rs
+
+pytestmark = pytest.mark.gpu
+
+FLAGS = {"auto": 0, "plain": 1, "shift4": (4 + 1) << 8, "shift13": (13 + 1) << 8}
+
+
+def _both(oracle, s, e, flags=0):
+    from rust_lapper_b200 import Lapper
+
+    return Lapper(starts=s, stops=e, flags=flags), oracle.OracleLapper(starts=s, stops=e)
+
+
+def _assert_same_queries(gpu, cpu, qs, qe):
+    assert np.array_equal(gpu.count_batch(qs, qe), cpu.count_batch(qs, qe))
+    assert np.array_equal(gpu.count_batch_c32(qs, qe), cpu.count_batch(qs, qe).astype(np.uint32))
+    go, gi = gpu.find_batch(qs, qe)
+    co, ci = cpu.find_batch(qs, qe)
+    assert np.array_equal(go, co)
+    assert np.array_equal(gi, ci)
+
+
+@pytest.mark.parametrize("flags", list(FLAGS))
+@pytest.mark.parametrize("seed", range(3))
+def test_random_small(oracle, seed, flags):
+    rng = np.random.default_rng(seed)
+    for _ in range(12):
+        n = int(rng.integers(1, 400))
+        universe = int(rng.choice([50, 3000, 10**6, 4 * 10**9]))
+        max_len = int(rng.choice([0, 5, 200, universe // 3]))
+        nq = int(rng.integers(1, 700))
+        s, e, qs, qe = rs.random_case(rng, n, min(universe, 0xFFFFFFFF - 1), max_len, nq,
+                                      int(rng.choice([0, 1, 100, universe // 2])))
+        gpu, cpu = _both(oracle, s, e, FLAGS[flags])
+        assert len(gpu) == len(cpu) and gpu.max_len == cpu.max_len
+        gs, ge, gp = gpu.intervals_soa()
+        cs, ce, cv = cpu.intervals_soa()
+        assert np.array_equal(gs, cs) and np.array_equal(ge, ce) and np.array_equal(gp, cv)
+        assert np.array_equal(gpu.starts, cpu.starts) and np.array_equal(gpu.stops, cpu.stops)
+        _assert_same_queries(gpu, cpu, qs, qe)
+
+
+@pytest.mark.parametrize("flags", ["auto", "plain"])
+def test_inverted_intervals_and_queries(oracle, flags):
+    rng = np.random.default_rng(11)
+    n, nq = 300, 2000
+    s = rng.integers(0, 5000, n).astype(np.uint32)
+    e = rng.integers(0, 5000, n).astype(np.uint32)  # about half inverted
+    qs = rng.integers(0, 5200, nq).astype(np.uint32)
+    qe = rng.integers(0, 5200, nq).astype(np.uint32)
+    gpu, cpu = _both(oracle, s, e, FLAGS[flags])
+    assert gpu.max_len == cpu.max_len
+    _assert_same_queries(gpu, cpu, qs, qe)
+
+
+def test_extreme_coordinates(oracle):
+    X = 0xFFFFFFFF
+    s = np.array([0, 0, X - 5, X, X - 1, 7, X], dtype=np.uint32)
+    e = np.array([X, 0, X, X, X, 7, X - 1], dtype=np.uint32)
+    vals = [0, 1, 5, 7, X - 6, X - 5, X - 1, X]
+    qs, qe = np.meshgrid(vals, vals)
+    qs, qe = qs.ravel().astype(np.uint32), qe.ravel().astype(np.uint32)
+    for flags in (0, 1, 2, 2 | ((13 + 1) << 8)):
+        gpu, cpu = _both(oracle, s, e, flags)
+        _assert_same_queries(gpu, cpu, qs, qe)
+
+
+def test_empty_and_ragged(oracle):
+    from rust_lapper_b200 import Lapper
+
+    gpu = Lapper([])
+    assert len(gpu) == 0 and gpu.max_len == 0
+    assert gpu.count_batch([1, 2, 3], [4, 5, 6]).tolist() == [0, 0, 0]
+    off, idx = gpu.find_batch([1, 2, 3], [4, 5, 6])
+    assert off.tolist() == [0, 0, 0, 0] and idx.size == 0
+    one = Lapper([(10, 20)])
+    assert one.count_batch([], []).size == 0
+    off, idx = one.find_batch([], [])
+    assert off.tolist() == [0] and idx.size == 0
+    # ragged batch sizes around the 4-query / 1024-query tiles
+    rng = np.random.default_rng(5)
+    s, e, _, _ = rs.random_case(rng, 5000, 10**6, 3000, 1, 1)
+    gpu, cpu = _both(oracle, s, e)
+    for nq in (1, 2, 3, 4, 5, 255, 1023, 1024, 1025, 4099):
+        _, _, qs, qe = rs.random_case(rng, 1, 10**6, 3000, nq, 500)
+        _assert_same_queries(gpu, cpu, qs, qe)
+        # unaligned device pointers take the scalar path: offset the host view by one element
+        _assert_same_queries(gpu, cpu, qs[1:], qe[1:])
+
+
+@pytest.mark.parametrize("name", ["cfg2_uniform", "cfg3_gene_exon", "cfg4_pathological", "cfg1b_criterion", "dense"])
+def test_seeded_configs_medium(oracle, name):
+    """The BASELINE.json shapes at sizes the oracle finishes in seconds (same generators as bench.py)."""
+    from rust_lapper_b200 import synth
+
+    U = synth.GRCH38
+    if name == "cfg2_uniform":
+        s, e = synth.intervals_uniform(42, 200_000, U // 50, 50, 5000)
+        qs, qe = synth.queries_fixed_len(43, 300_000, U // 50, 150)
+    elif name == "cfg3_gene_exon":
+        s, e = synth.intervals_gene_exon(44, 200_000, U // 50)
+        qs, qe = synth.queries_sorted_fixed_len(45, 300_000, U // 50, 150)
+    elif name == "cfg4_pathological":
+        s, e = synth.intervals_pathological(46, 20_000, U)
+        qs, qe = synth.queries_fixed_len(47, 2_000, U, 150)
+    elif name == "cfg1b_criterion":  # benches/lapper_benchmark.rs:34-43: n = 1000, U = 1e8, len 500..80000
+        s, e = synth.intervals_uniform(7, 1000, 100_000_000, 500, 79_999)
+        qs, qe = synth.queries_fixed_len(8, 1000, 1_000_000_000, 1)
+        qs, qe = np.concatenate([qs, s]), np.concatenate([qe, e])
+    else:  # far more keys than coordinates: every bucket overflows
+        s, e = synth.intervals_uniform(9, 100_000, 3000, 0, 40)
+        qs, qe = synth.queries_fixed_len(10, 50_000, 3100, 7)
+    gpu, cpu = _both(oracle, s, e)
+    _assert_same_queries(gpu, cpu, qs, qe)
+    assert gpu.cov() == cpu.cov()
+
+
+def test_bakeoff_readme_shape(oracle):
+    """cfg 1a (README.md:51-61) scaled to 5,000 intervals: A-vs-A and A-vs-B, find == count, u64 offsets."""
+    from rust_lapper_b200 import synth
+
+    (sa, ea), (sb, eb) = synth.bakeoff_sets(1, 2, 5000, 100_000)
+    gpu, cpu = _both(oracle, sa, ea)
+    for qs, qe in ((sa, ea), (sb, eb)):
+        _assert_same_queries(gpu, cpu, qs, qe)
+        off, _ = gpu.find_batch(qs, qe)
+        assert int(off[-1]) == int(gpu.count_batch(qs, qe).sum())
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_merge_cov_union(oracle, seed):
+    rng = np.random.default_rng(300 + seed)
+    for _ in range(10):
+        n, m = int(rng.integers(1, 3000)), int(rng.integers(1, 3000))
+        U = int(rng.choice([500, 100_000]))
+        s, e, qs, qe = rs.random_case(rng, n, U, int(rng.choice([0, 4, 60])), 500, 30)
+        s2, e2, _, _ = rs.random_case(rng, m, U, int(rng.choice([0, 4, 60])), 1, 1)
+        A, cA = _both(oracle, s, e)
+        B, cB = _both(oracle, s2, e2)
+        assert A.cov() == cA.cov()
+        assert A.union_and_intersect(B) == cA.union_and_intersect(cB)
+        assert B.union_and_intersect(A) == cB.union_and_intersect(cA)
+        A.merge_overlaps()
+        cA.merge_overlaps()
+        assert A.overlaps_merged and len(A) == len(cA) and A.max_len == cA.max_len
+        gs, ge, gp = A.intervals_soa()
+        cs, ce, cv = cA.intervals_soa()
+        assert np.array_equal(gs, cs) and np.array_equal(ge, ce) and np.array_equal(gp, cv)
+        assert np.array_equal(A.starts, cA.starts) and np.array_equal(A.stops, cA.stops)
+        assert A.cov() == cA.cov()
+        _assert_same_queries(A, cA, qs, qe)
+        assert A.union_and_intersect(B) == cA.union_and_intersect(cB)  # mixed flags
+        B.merge_overlaps()
+        cB.merge_overlaps()
+        B.set_cov()
+        cB.set_cov()
+        assert A.union_and_intersect(B) == cA.union_and_intersect(cB)  # both merged
+        A.merge_overlaps()  # idempotent
+        assert np.array_equal(A.intervals_soa()[0], cs)
+
+
+def test_merge_large_and_precondition(oracle):
+    from rust_lapper_b200 import Lapper, LapperError, _ffi, synth
+
+    s, e = synth.intervals_uniform(3, 300_000, 20_000_000, 0, 120)
+    A, cA = _both(oracle, s, e)
+    assert A.cov() == cA.cov()
+    A.merge_overlaps()
+    cA.merge_overlaps()
+    assert np.array_equal(A.intervals_soa()[0], cA.intervals_soa()[0])
+    assert np.array_equal(A.intervals_soa()[1], cA.intervals_soa()[1])
+    assert np.array_equal(A.intervals_soa()[2], cA.intervals_soa()[2])
+    bad = Lapper([(10, 5), (1, 2)])
+    with pytest.raises(LapperError) as ei:
+        bad.merge_overlaps()
+    assert ei.value.code == _ffi.ERR_PRECONDITION
+
+
+def test_seek_cursor_protocol(oracle):
+    rng = np.random.default_rng(21)
+    s, e, qs, qe = rs.random_case(rng, 300, 20_000, 900, 120, 200)
+    gpu, cpu = _both(oracle, s, e)
+    # sorted queries: seek == find; unsorted: whatever the reference does with its cursor
+    for order in (np.argsort(qs, kind="stable"), np.arange(qs.size)):
+        cg, cc = [0], [0]
+        for j in order:
+            a, b = int(qs[j]), int(qe[j])
+            assert gpu.seek_idx(a, b, cg) == cpu.seek_idx(a, b, cc)
+            assert cg == cc
