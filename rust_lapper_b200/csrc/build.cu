@@ -126,8 +126,11 @@ bool choose_shift(uint64_t n, uint32_t max_coord, uint32_t flags, uint32_t &shif
     if (flags & LAPPER_BUILD_NO_BUCKETS) return false;
     const uint32_t forced = (flags >> 8) & 0xFFu;
     if (forced) {
-        shift_out = forced - 1u;
-        LAPPER_REQUIRE(shift_out <= kMaxBucketShift, "LAPPER_BUILD_SHIFT: shift must be <= 13");
+        uint32_t k = forced - 1u;
+        LAPPER_REQUIRE(k <= kMaxBucketShift, "LAPPER_BUILD_SHIFT: shift must be <= 13");
+        // a forced width never makes the table larger than 2^26 sectors (2 GB); widen it instead
+        while (k < kMaxBucketShift && ((uint64_t)(max_coord >> k) + 1) > (1ull << 26)) k++;
+        shift_out = k;
         return true;
     }
     const bool force = (flags & LAPPER_BUILD_FORCE_BUCKETS) != 0;

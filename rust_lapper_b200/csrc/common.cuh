@@ -132,6 +132,15 @@ __device__ __forceinline__ void st_stream_u64(void *p, uint64_t v) {
     asm volatile("st.global.cs.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+
+// 256-bit streaming accesses: eight u32 per lane, read or written once (no L1 allocation)
+__device__ __forceinline__ Sector ld_stream_v8(const void *p) { return ld_sector_stream(p); }
+__device__ __forceinline__ void st_stream_v8(void *p, const Sector &v) {
+    asm volatile("st.global.L1::no_allocate.v8.u32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v.w[0]), "r"(v.w[1]),
+                 "r"(v.w[2]), "r"(v.w[3]), "r"(v.w[4]), "r"(v.w[5]), "r"(v.w[6]), "r"(v.w[7])
+                 : "memory");
+}
+
 // lower_bound over a sorted u32 range [lo, hi): first index whose element is >= key.
 __device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi,
                                                     uint32_t key) {

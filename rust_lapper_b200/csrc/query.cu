@@ -9,6 +9,8 @@
 // Here a query normally costs ONE 32-byte sector (index.cuh) fetched with one LDG.E.256; the sorted
 // arrays are touched only for overflowing buckets.  Without a bucket table (tiny or degenerate
 // sets) the kernels bisect the sorted arrays under a sampled-key directory held in shared memory.
+#include <algorithm>
+
 #include "index.cuh"
 
 namespace lap {
@@ -16,7 +18,8 @@ namespace lap {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kQPT = 4;  // queries per thread: four independent sector gathers in flight
+constexpr int kQPT = 8;                   // queries per thread: eight independent sector gathers in flight
+constexpr int kTileQ = kThreads * kQPT;   // queries per CTA tile
 
 struct BucketView {
     const Sector *buckets;
@@ -27,29 +30,65 @@ struct BucketView {
     uint32_t nb;  // index of the sentinel bucket
 };
 
-// number of 16-bit lanes (of the 12 in w[2..7]) whose value is >= x; x2 = x replicated in both halves
-__device__ __forceinline__ uint32_t lanes_ge(const Sector &s, uint32_t x2) {
-    const uint32_t t0 = s.w[2] - x2, t1 = s.w[3] - x2, t2 = s.w[4] - x2;
-    const uint32_t t3 = s.w[5] - x2, t4 = s.w[6] - x2, t5 = s.w[7] - x2;
-    // gather the guard bits (bit 15 of every lane) of two words into the MSBs of four bytes
-    const uint32_t p01 = __byte_perm(t0, t1, 0x7531);
-    const uint32_t p23 = __byte_perm(t2, t3, 0x7531);
-    const uint32_t p45 = __byte_perm(t4, t5, 0x7531);
-    const uint32_t m = (p01 & 0x80808080u) | ((p23 & 0x80808080u) >> 1) | ((p45 & 0x80808080u) >> 2);
-    return __popc(m);
+// bytes 1 and 3 of t0 and of t1 (the high byte of every 16-bit lane), each replaced by its sign bit
+// replicated: 0xFF where the lane's guard bit survived the subtraction, 0x00 where it did not
+__device__ __forceinline__ uint32_t guard_bytes(uint32_t t0, uint32_t t1) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(r) : "r"(t0), "r"(t1));
+    return r;
+}
+
+// acc - #{16-bit lanes of w[2..7] whose value is >= x}; x2 = x replicated in both halves.
+// One packed subtract per word, one PRMT per two words, one IDP.4A (bytes are 0 or -1) per PRMT.
+__device__ __forceinline__ int sub_lanes_ge(const Sector &s, uint32_t x2, int acc) {
+    acc = __dp4a((int)guard_bytes(s.w[2] - x2, s.w[3] - x2), 0x01010101, acc);
+    acc = __dp4a((int)guard_bytes(s.w[4] - x2, s.w[5] - x2), 0x01010101, acc);
+    acc = __dp4a((int)guard_bytes(s.w[6] - x2, s.w[7] - x2), 0x01010101, acc);
+    return acc;
 }
 
 __device__ __forceinline__ bool sector_overflow(const Sector &s) { return s.w[7] == 0xFFFFFFFFu; }
+
+// lower_bound / upper_bound inside one overflowing bucket's slice of a sorted array: bisect down to a
+// short range, then count it with independent (not dependent) loads -- one memory round trip
+__device__ __forceinline__ uint32_t count_lt_range(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi,
+                                                   uint32_t key) {
+    while (hi - lo > 32) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(a + mid) < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    uint32_t c = lo;
+#pragma unroll 8
+    for (uint32_t i = lo; i < hi; i++) c += (__ldg(a + i) < key);
+    return c;
+}
+__device__ __forceinline__ uint32_t count_le_range(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi,
+                                                   uint32_t key) {
+    while (hi - lo > 32) {
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(a + mid) <= key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    uint32_t c = lo;
+#pragma unroll 8
+    for (uint32_t i = lo; i < hi; i++) c += (__ldg(a + i) <= key);
+    return c;
+}
 
 // lower_bound(starts, key) given the sector of key's bucket
 __device__ __forceinline__ uint32_t lb_from_sector(const BucketView &v, const Sector &s, uint32_t bucket,
                                                    uint32_t key) {
     if (__builtin_expect(sector_overflow(s), 0)) {
         const uint32_t rs_next = __ldg(reinterpret_cast<const uint32_t *>(v.buckets + bucket + 1));
-        return lower_bound_u32(v.S, s.w[0], rs_next, key);
+        return count_lt_range(v.S, s.w[0], rs_next, key);
     }
     const uint32_t mask = (1u << v.shift) - 1u;
-    return s.w[0] + kBucketLanes - lanes_ge(s, (key & mask) * 0x10001u);
+    return s.w[0] + kBucketLanes + (uint32_t)sub_lanes_ge(s, (key & mask) * 0x10001u, 0);
 }
 
 // upper_bound(stops_sorted, key) given the sector of key's bucket
@@ -57,19 +96,26 @@ __device__ __forceinline__ uint32_t ub_from_sector(const BucketView &v, const Se
                                                    uint32_t key) {
     if (__builtin_expect(sector_overflow(s), 0)) {
         const uint32_t re_lo = bucket ? __ldg(reinterpret_cast<const uint32_t *>(v.buckets + bucket - 1) + 1) : 0u;
-        return upper_bound_u32(v.E, re_lo, s.w[1], key);
+        return count_le_range(v.E, re_lo, s.w[1], key);
     }
     const uint32_t width = 1u << v.shift;
-    return s.w[1] - lanes_ge(s, (width + (key & (width - 1u)) + 1u) * 0x10001u);
+    return s.w[1] + (uint32_t)sub_lanes_ge(s, (width + (key & (width - 1u)) + 1u) * 0x10001u, 0);
 }
 
 __device__ __forceinline__ uint32_t bucket_of(const BucketView &v, uint32_t x) { return min(x >> v.shift, v.nb); }
 
-// Lapper::count for one query from its sector(s).
-__device__ __forceinline__ void bits_count(const BucketView &v, uint32_t a, uint32_t b, const Sector &sb,
-                                           uint32_t bb, const Sector &sa, uint32_t ba, uint32_t &lb, uint32_t &ub) {
+// Lapper::count for one query, any case (overflowing buckets bisect the sorted arrays)
+__device__ __forceinline__ void bits_count_slow(const BucketView &v, uint32_t a, uint32_t b, uint32_t &lb,
+                                                uint32_t &ub) {
+    const uint32_t bb = bucket_of(v, b), ba = bucket_of(v, a);
+    const Sector sb = ld_sector_cached(v.buckets + bb);
     lb = lb_from_sector(v, sb, bb, b);
-    ub = ub_from_sector(v, sa, ba, a);
+    if (ba == bb) {
+        ub = ub_from_sector(v, sb, bb, a);
+    } else {
+        const Sector sa = ld_sector_cached(v.buckets + ba);
+        ub = ub_from_sector(v, sa, ba, a);
+    }
     // src/lib.rs:614: `start + one` wraps to 0 when start == u32::MAX, so `first` is 0 there.
     if (a == 0xFFFFFFFFu) ub = 0;
 }
@@ -83,56 +129,139 @@ __device__ __forceinline__ void store_count(uint32_t *o32, uint64_t *o64, uint64
         st_stream_u32(o32 + j, lb - ub);
 }
 
-// ---- count, bucket path.  Each thread owns kQPT consecutive queries: coalesced 16-byte loads of
-// starts/stops, then up to 2*kQPT independent sector gathers, then one 16-byte store.
-template <bool kOut64, bool kVec>
-__global__ void __launch_bounds__(kThreads) count_bucket_kernel(BucketView v, const uint32_t *__restrict__ qs,
-                                                                const uint32_t *__restrict__ qe, uint64_t nq,
-                                                                uint32_t *__restrict__ o32,
-                                                                uint64_t *__restrict__ o64) {
-    const uint64_t ntiles = div_up(nq, kQPT);
-    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles;
-         t += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t j0 = t * kQPT;
-        uint32_t a[kQPT], b[kQPT];
-        const bool full = j0 + kQPT <= nq;
-        if (kVec && full) {
-            const uint4 va = ld_stream_v4(qs + j0), vb = ld_stream_v4(qe + j0);
-            a[0] = va.x, a[1] = va.y, a[2] = va.z, a[3] = va.w;
-            b[0] = vb.x, b[1] = vb.y, b[2] = vb.z, b[3] = vb.w;
-        } else {
-#pragma unroll
-            for (int k = 0; k < kQPT; k++) {
-                const bool ok = j0 + k < nq;
-                a[k] = ok ? ld_stream_u32(qs + j0 + k) : 0u;
-                b[k] = ok ? ld_stream_u32(qe + j0 + k) : 0u;
-            }
-        }
+// ---- count, bucket path, full tiles.  Persistent CTAs walk tiles of 2048 queries; each thread owns
+// eight consecutive queries: two 256-bit loads (starts, stops), eight independent sector gathers
+// (LDG.E.256), a second predicated round for the ~15 % of queries whose start falls in another
+// bucket than their stop, one 256-bit store.  Queries that meet an overflowing bucket are NOT
+// resolved in line (that would serialise a divergent search behind every warp): their index goes to
+// a per-warp shared-memory queue, and whenever a warp has 32 of them it resolves them one per lane.
+// No CTA barrier anywhere in the loop.
+constexpr int kWarps = kThreads / 32;
+constexpr int kWQCap = 32 + 32 * kQPT;  // leftovers below one drain + one full iteration of deferrals
+
+template <bool kOut64>
+__device__ __forceinline__ void count_deferred(const BucketView &v, const uint32_t *__restrict__ qs,
+                                               const uint32_t *__restrict__ qe, uint64_t base, uint32_t rel,
+                                               uint32_t *__restrict__ o32, uint64_t *__restrict__ o64) {
+    const uint64_t j = base + rel;
+    uint32_t lb, ub;
+    bits_count_slow(v, __ldg(qs + j), __ldg(qe + j), lb, ub);
+    store_count<kOut64>(o32, o64, j, lb, ub);
+}
+
+template <bool kOut64>
+__global__ void __launch_bounds__(kThreads, 2) count_bucket_kernel(BucketView v, const uint32_t *__restrict__ qs,
+                                                                   const uint32_t *__restrict__ qe, uint64_t ntiles,
+                                                                   uint32_t *__restrict__ o32,
+                                                                   uint64_t *__restrict__ o64) {
+    __shared__ uint32_t wqueue[kWarps][kWQCap];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t *const wq = wqueue[warp];
+    uint32_t wq_n = 0;  // warp-uniform
+    const uint32_t width = 1u << v.shift, mask = width - 1u;
+    // queue entries are query indices relative to the first tile of this CTA's walk (fits 32 bits:
+    // launch_count never hands one launch more than 2^32 - 1 queries)
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t j0 = tile * kTileQ + (uint64_t)threadIdx.x * kQPT;
+        const Sector qa = ld_stream_v8(qs + j0), qb = ld_stream_v8(qe + j0);
         uint32_t ba[kQPT], bb[kQPT];
-        Sector sb[kQPT];
+        Sector sec[kQPT];
 #pragma unroll
         for (int k = 0; k < kQPT; k++) {
-            ba[k] = bucket_of(v, a[k]);
-            bb[k] = bucket_of(v, b[k]);
-            sb[k] = ld_sector_cached(v.buckets + bb[k]);
+            ba[k] = bucket_of(v, qa.w[k]);
+            bb[k] = bucket_of(v, qb.w[k]);
+            sec[k] = ld_sector_cached(v.buckets + bb[k]);
         }
-        uint32_t lb[kQPT], ub[kQPT];
+        uint32_t res[kQPT];
+        uint32_t defer = 0, second = 0;
 #pragma unroll
         for (int k = 0; k < kQPT; k++) {
+            const uint32_t a = qa.w[k], b = qb.w[k];
+            // lower_bound(starts, b) = rs + 12 - #{lanes >= low(b)}
+            int acc = (int)(sec[k].w[0] + kBucketLanes);
+            acc = sub_lanes_ge(sec[k], (b & mask) * 0x10001u, acc);
+            defer |= (uint32_t)sector_overflow(sec[k]) << k;
             if (ba[k] == bb[k]) {
-                bits_count(v, a[k], b[k], sb[k], bb[k], sb[k], bb[k], lb[k], ub[k]);
+                // upper_bound(stops, a) = re_hi - #{lanes >= 2^shift + low(a) + 1}; count = lb - ub
+                int ub = sub_lanes_ge(sec[k], (width + (a & mask) + 1u) * 0x10001u, (int)sec[k].w[1]);
+                if (a == 0xFFFFFFFFu) ub = 0;  // src/lib.rs:614 wrap
+                res[k] = (uint32_t)(acc - ub);
             } else {
-                const Sector sa = ld_sector_cached(v.buckets + ba[k]);
-                bits_count(v, a[k], b[k], sb[k], bb[k], sa, ba[k], lb[k], ub[k]);
+                res[k] = (uint32_t)acc;
+                second |= 1u << k;
             }
         }
-        if (kVec && full && !kOut64) {
-            st_stream_v4(o32 + j0, make_uint4(lb[0] - ub[0], lb[1] - ub[1], lb[2] - ub[2], lb[3] - ub[3]));
-        } else {
+        if (second) {
 #pragma unroll
             for (int k = 0; k < kQPT; k++)
-                if (j0 + k < nq) store_count<kOut64>(o32, o64, j0 + k, lb[k], ub[k]);
+                if (second & (1u << k)) sec[k] = ld_sector_cached(v.buckets + ba[k]);
+#pragma unroll
+            for (int k = 0; k < kQPT; k++)
+                if (second & (1u << k)) {
+                    const uint32_t a = qa.w[k];
+                    int ub = sub_lanes_ge(sec[k], (width + (a & mask) + 1u) * 0x10001u, (int)sec[k].w[1]);
+                    if (a == 0xFFFFFFFFu) ub = 0;
+                    res[k] -= (uint32_t)ub;
+                    defer |= (uint32_t)sector_overflow(sec[k]) << k;
+                }
         }
+        if (kOut64) {
+#pragma unroll
+            for (int k = 0; k < kQPT; k += 4) {
+                // a negative difference only arises from an inverted query or interval; it must widen the
+                // way usize wraps, which needs lb and ub separately -> such queries take the deferred path
+                Sector o;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    o.w[2 * q] = res[k + q];
+                    o.w[2 * q + 1] = 0;
+                    defer |= (uint32_t)((int32_t)res[k + q] < 0) << (k + q);
+                }
+                st_stream_v8(o64 + j0 + k, o);
+            }
+        } else {
+            Sector o;
+#pragma unroll
+            for (int k = 0; k < kQPT; k++) o.w[k] = res[k];
+            st_stream_v8(o32 + j0, o);
+        }
+        // ---- enqueue this iteration's deferred queries (ballot-free: exclusive scan of per-lane counts)
+        const uint32_t mine = __popc(defer);
+        if (__any_sync(0xFFFFFFFFu, mine != 0)) {
+            uint32_t inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            uint32_t slot = wq_n + inc - mine;
+            const uint32_t rel0 = (uint32_t)(j0 - (uint64_t)blockIdx.x * kTileQ);
+#pragma unroll
+            for (int k = 0; k < kQPT; k++)
+                if (defer & (1u << k)) wq[slot++] = rel0 + k;
+            wq_n += total;
+            __syncwarp();  // queue visible to the warp; also orders the vector store above before the drain's stores
+            while (wq_n >= 32) {
+                wq_n -= 32;
+                count_deferred<kOut64>(v, qs, qe, (uint64_t)blockIdx.x * kTileQ, wq[wq_n + lane], o32, o64);
+            }
+            __syncwarp();
+        }
+    }
+    if (lane < wq_n) count_deferred<kOut64>(v, qs, qe, (uint64_t)blockIdx.x * kTileQ, wq[lane], o32, o64);
+}
+
+// ---- count, bucket path, any alignment / ragged tail: one query per thread
+template <bool kOut64>
+__global__ void __launch_bounds__(kThreads) count_bucket_tail_kernel(BucketView v, const uint32_t *__restrict__ qs,
+                                                                     const uint32_t *__restrict__ qe, uint64_t nq,
+                                                                     uint32_t *__restrict__ o32,
+                                                                     uint64_t *__restrict__ o64) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t lb, ub;
+        bits_count_slow(v, ld_stream_u32(qs + j), ld_stream_u32(qe + j), lb, ub);
+        store_count<kOut64>(o32, o64, j, lb, ub);
     }
 }
 
@@ -422,23 +551,40 @@ uint32_t capped_grid(uint64_t work_items, int per_block, int waves) {
 void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, uint32_t *d_out32,
                   uint64_t *d_out64, cudaStream_t stream) {
     if (nq == 0) return;
+    constexpr uint64_t kMaxPerLaunch = 1ull << 31;  // deferred-queue entries are 32-bit relative indices
+    if (nq > kMaxPerLaunch) {
+        for (uint64_t done = 0; done < nq; done += kMaxPerLaunch) {
+            const uint64_t m = std::min(kMaxPerLaunch, nq - done);
+            launch_count(ix, d_qs + done, d_qe + done, m, d_out32 ? d_out32 + done : nullptr,
+                         d_out64 ? d_out64 + done : nullptr, stream);
+        }
+        return;
+    }
     const bool out64 = d_out64 != nullptr;
     if (ix.buckets) {
         const BucketView v = make_bucket_view(ix);
-        const bool vec = ((reinterpret_cast<uintptr_t>(d_qs) | reinterpret_cast<uintptr_t>(d_qe) |
-                           reinterpret_cast<uintptr_t>(d_out32)) & 15u) == 0;
-        // 148 SMs x 8 resident CTAs of 256 threads, grid-stride over 4-query tiles
-        const uint32_t grid = capped_grid(div_up(nq, kQPT), kThreads, 8 * 4);
-        if (out64) {
-            if (vec)
-                count_bucket_kernel<true, true><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, nullptr, d_out64);
+        const void *out = out64 ? (const void *)d_out64 : (const void *)d_out32;
+        const bool aligned = ((reinterpret_cast<uintptr_t>(d_qs) | reinterpret_cast<uintptr_t>(d_qe) |
+                               reinterpret_cast<uintptr_t>(out)) & 31u) == 0;
+        const uint64_t ntiles = aligned ? nq / kTileQ : 0;
+        if (ntiles) {
+            // persistent: 148 SMs x 2 resident CTAs (128 registers x 256 threads each)
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, 148 * 2);
+            if (out64)
+                count_bucket_kernel<true><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, ntiles, nullptr, d_out64);
             else
-                count_bucket_kernel<true, false><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, nullptr, d_out64);
-        } else {
-            if (vec)
-                count_bucket_kernel<false, true><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, d_out32, nullptr);
+                count_bucket_kernel<false><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, ntiles, d_out32, nullptr);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+        }
+        const uint64_t done = ntiles * kTileQ, rest = nq - done;
+        if (rest) {
+            const uint32_t grid = capped_grid(rest, kThreads, 16);
+            if (out64)
+                count_bucket_tail_kernel<true><<<grid, kThreads, 0, stream>>>(v, d_qs + done, d_qe + done, rest, nullptr,
+                                                                              d_out64 + done);
             else
-                count_bucket_kernel<false, false><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, d_out32, nullptr);
+                count_bucket_tail_kernel<false><<<grid, kThreads, 0, stream>>>(v, d_qs + done, d_qe + done, rest,
+                                                                               d_out32 + done, nullptr);
         }
     } else {
         PlainView v;

@@ -1,0 +1,92 @@
+// Microbenchmark: random 32-byte sector gathers (LDG.E.256) from a table of a given size, as a function
+// of table size, independent loads in flight per thread and occupancy.  Sets the hardware ceiling for the
+// bucket-sector count kernel.  nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o mb_gather mb_gather.cu
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cuda_runtime.h>
+
+struct __align__(32) Sector { uint32_t w[8]; };
+
+__device__ __forceinline__ Sector ld256(const void* p) {
+    Sector r;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]), "=r"(r.w[7]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t mix(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return (uint32_t)((x ^ (x >> 31)) >> 32);
+}
+
+// each thread performs `iters` rounds of K independent gathers; also streams `stream_bytes_per_gather` optional
+template <int K, bool STREAM>
+__global__ void gather_kernel(const Sector* __restrict__ table, uint32_t nsect, int iters, uint32_t* __restrict__ out,
+                              const uint4* __restrict__ stream_in, uint32_t* __restrict__ stream_out) {
+    const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
+    uint32_t acc = 0;
+    for (int it = 0; it < iters; it++) {
+        const uint64_t q0 = ((uint64_t)it * nthreads + tid) * K;
+        uint32_t extra = 0;
+        if (STREAM) {  // 8 B in per gather (coalesced), like the query arrays
+            const uint4* p = stream_in + q0 * 8 / 16;
+#pragma unroll
+            for (int k = 0; k < K / 2; k++) { uint4 v = __ldcs(p + k); extra += v.x ^ v.y ^ v.z ^ v.w; }
+        }
+        Sector s[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            uint32_t idx = (uint32_t)(((uint64_t)mix(q0 + k) * nsect) >> 32);
+            s[k] = ld256(table + idx);
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) acc += s[k].w[0] + s[k].w[7];
+        acc += extra;
+        if (STREAM) {
+#pragma unroll
+            for (int k = 0; k < K; k++) __stcs(stream_out + q0 + k, acc + k);
+        }
+    }
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+template <int K, bool STREAM>
+float run(const Sector* table, uint32_t nsect, uint64_t total_gathers, int threads, int blocks, uint32_t* out,
+          const uint4* sin, uint32_t* sout) {
+    int iters = (int)(total_gathers / ((uint64_t)threads * blocks * K));
+    if (iters < 1) iters = 1;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    gather_kernel<K, STREAM><<<blocks, threads>>>(table, nsect, iters, out, sin, sout);
+    cudaEventRecord(a);
+    for (int r = 0; r < 3; r++) gather_kernel<K, STREAM><<<blocks, threads>>>(table, nsect, iters, out, sin, sout);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b); ms /= 3;
+    double g = (double)iters * threads * blocks * K;
+    printf("K=%d stream=%d threads=%d blocks=%d : %.3f ms  %.1f Ggather/s  %.1f GB/s(sector bytes)\n", K, (int)STREAM, threads, blocks, ms,
+           g / ms * 1e-6, g * 32 / ms * 1e-6);
+    return ms;
+}
+
+int main(int argc, char** argv) {
+    const uint64_t total = 100000000ull;
+    uint32_t* out; cudaMalloc(&out, 4);
+    uint4* sin; uint32_t* sout; cudaMalloc(&sin, total * 8 + 4096); cudaMalloc(&sout, total * 4 + 4096);
+    cudaMemset(sin, 1, total * 8);
+    double sizes_mb[] = {12, 24, 48, 64, 80, 97, 194, 485};
+    for (double mb : sizes_mb) {
+        uint32_t nsect = (uint32_t)(mb * 1e6 / 32);
+        Sector* table; cudaMalloc(&table, (size_t)nsect * 32); cudaMemset(table, 1, (size_t)nsect * 32);
+        printf("== table %.0f MB (%u sectors)\n", mb, nsect);
+        for (int occ : {2, 4, 8}) {
+            int blocks = 148 * occ;
+            run<1, false>(table, nsect, total, 256, blocks, out, sin, sout);
+            run<4, false>(table, nsect, total, 256, blocks, out, sin, sout);
+            run<8, false>(table, nsect, total, 256, blocks, out, sin, sout);
+            run<4, true>(table, nsect, total, 256, blocks, out, sin, sout);
+            run<8, true>(table, nsect, total, 256, blocks, out, sin, sout);
+        }
+        cudaFree(table);
+    }
+    return 0;
+}

@@ -1,0 +1,33 @@
+"""Profiling driver: one cfg-2 index, a few count_batch launches on random and on start-sorted
+queries (device-resident).  Run plain first, then under ncu (see profiles/README.md)."""
+import ctypes as C
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rust_lapper_b200 import _ffi, synth  # noqa: E402
+
+n = int(os.environ.get("N_IV", 10_000_000))
+nq = int(os.environ.get("NQ", 100_000_000))
+reps = int(os.environ.get("REPS", 3))
+dev = torch.device("cuda", 0)
+lib = _ffi.lib()
+s, e = synth.intervals_uniform(42, n, synth.GRCH38, 50, 5000, device=dev)
+sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+h = C.c_void_p(0)
+_ffi.check(lib.lapper_build_u32_dev(C.c_void_p(s.data_ptr()), C.c_void_p(e.data_ptr()), n, 0, 0, sp, C.byref(h)))
+out = torch.empty(nq, dtype=torch.int32, device=dev)
+for name, (qs, qe) in (("random", synth.queries_fixed_len(43, nq, synth.GRCH38, 150, device=dev)),
+                       ("sorted", synth.queries_sorted_fixed_len(45, nq, synth.GRCH38, 150, device=dev))):
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        _ffi.check(lib.lapper_count_batch_u32_dev(h, C.c_void_p(qs.data_ptr()), C.c_void_p(qe.data_ptr()), nq,
+                                                  C.c_void_p(out.data_ptr()), sp))
+    b.record()
+    torch.cuda.synchronize()
+    print(f"{name}: {a.elapsed_time(b) / reps:.3f} ms per launch, checksum {int(out.to(torch.int64).sum())}")
+lib.lapper_free(h)
