@@ -8,6 +8,8 @@
 //     the sorted vectors directly).
 #include <cub/device/device_radix_sort.cuh>
 
+#include <algorithm>
+
 #include "index.cuh"
 
 #ifdef THRUST_CUB_WRAPPED_NAMESPACE
@@ -108,6 +110,53 @@ __global__ void fill_buckets_kernel(const uint32_t *__restrict__ S, const uint32
     buckets[B] = sec;
 }
 
+struct LenHist {
+    unsigned long long count[33];
+    uint32_t maxlen[33];
+};
+
+// histogram of interval lengths by bit length (bin 0 = length 0 or inverted) + the longest per bin
+__global__ void len_hist_kernel(const uint32_t *__restrict__ s, const uint32_t *__restrict__ e, uint64_t n,
+                                LenHist *__restrict__ out) {
+    __shared__ uint32_t cnt[33];
+    __shared__ uint32_t mx[33];
+    for (int i = threadIdx.x; i < 33; i += blockDim.x) cnt[i] = 0, mx[i] = 0;
+    __syncthreads();
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = s[i], b = e[i];
+        const uint32_t len = b > a ? b - a : 0u;
+        const uint32_t bin = len ? 32u - __clz(len) : 0u;
+        atomicAdd(&cnt[bin], 1u);
+        atomicMax(&mx[bin], len);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 33; i += blockDim.x) {
+        if (cnt[i]) {
+            atomicAdd(&out->count[i], (unsigned long long)cnt[i]);
+            atomicMax(&out->maxlen[i], mx[i]);
+        }
+    }
+}
+
+// rank of each bucket's first coordinate in every class (one uint4 per bucket)
+__global__ void fill_class_dir_kernel(const uint32_t *__restrict__ cs, uint32_t off0, uint32_t n0, uint32_t off1,
+                                      uint32_t n1, uint32_t off2, uint32_t n2, uint32_t off3, uint32_t n3,
+                                      uint32_t shift, uint64_t nb, uint4 *__restrict__ dir) {
+    const uint64_t B = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (B > nb) return;
+    uint4 r;
+    if (B == nb) {
+        r = make_uint4(n0, n1, n2, n3);
+    } else {
+        const uint32_t base = (uint32_t)(B << shift);
+        r.x = lower_bound_u32(cs + off0, 0, n0, base);
+        r.y = lower_bound_u32(cs + off1, 0, n1, base);
+        r.z = lower_bound_u32(cs + off2, 0, n2, base);
+        r.w = lower_bound_u32(cs + off3, 0, n3, base);
+    }
+    dir[B] = r;
+}
+
 template <typename T>
 T *dev_alloc(uint64_t count, uint64_t &bytes) {
     T *p = nullptr;
@@ -147,9 +196,104 @@ bool choose_shift(uint64_t n, uint32_t max_coord, uint32_t flags, uint32_t &shif
     return true;
 }
 
+// Choose up to kMaxClasses contiguous groups of length bins minimising the expected number of
+// interval slots find() has to look at per query: sum_c n_c * (maxlen_c + q) / span + kappa per class
+// (each class costs two directory lookups).  33 bins, a tiny DP on the host.
+void choose_classes(const LenHist &h, uint64_t span, uint8_t class_of_bin[33], uint32_t &ncls, uint32_t cls_n[4],
+                    uint32_t cls_maxlen[4]) {
+    const double kQueryLen = 256.0, kKappa = 12.0;
+    int bins[33], nbins = 0;
+    for (int b = 0; b < 33; b++)
+        if (h.count[b]) bins[nbins++] = b;
+    auto group_cost = [&](int i, int j) {  // bins[i..j]
+        double cnt = 0, mx = 0;
+        for (int k = i; k <= j; k++) {
+            cnt += (double)h.count[bins[k]];
+            mx = std::max(mx, (double)h.maxlen[bins[k]]);
+        }
+        return cnt * (mx + kQueryLen) / (double)std::max<uint64_t>(span, 1) + kKappa;
+    };
+    const int G = (int)kMaxClasses;
+    double f[5][34];
+    int cut[5][34];
+    for (int g = 0; g <= G; g++)
+        for (int j = 0; j <= nbins; j++) f[g][j] = 1e300, cut[g][j] = -1;
+    f[0][0] = 0;
+    for (int g = 1; g <= G; g++)
+        for (int j = 1; j <= nbins; j++)
+            for (int i = g - 1; i < j; i++) {
+                if (f[g - 1][i] >= 1e299) continue;
+                const double c = f[g - 1][i] + group_cost(i, j - 1);
+                if (c < f[g][j]) f[g][j] = c, cut[g][j] = i;
+            }
+    int best_g = 1;
+    for (int g = 1; g <= G && g <= nbins; g++)
+        if (f[g][nbins] < f[best_g][nbins]) best_g = g;
+    for (int b = 0; b < 33; b++) class_of_bin[b] = 0;
+    for (int c = 0; c < 4; c++) cls_n[c] = 0, cls_maxlen[c] = 0;
+    ncls = (uint32_t)best_g;
+    int j = nbins;
+    for (int g = best_g; g >= 1; g--) {
+        const int i = cut[g][j];
+        for (int k = i; k < j; k++) {
+            class_of_bin[bins[k]] = (uint8_t)(g - 1);
+            cls_n[g - 1] += (uint32_t)h.count[bins[k]];
+            cls_maxlen[g - 1] = std::max(cls_maxlen[g - 1], h.maxlen[bins[k]]);
+        }
+        j = i;
+    }
+    // empty bins between / beyond the groups: attach to the next class above so every bin maps somewhere valid
+    int last = 0;
+    for (int b = 0; b < 33; b++) {
+        if (h.count[b]) last = class_of_bin[b];
+        else class_of_bin[b] = (uint8_t)last;
+    }
+}
+
+void build_find_classes(DeviceIndex &ix, cudaStream_t stream) {
+    const uint64_t n = ix.n;
+    Scratch<LenHist> d_hist(1, stream);
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(d_hist.p, 0, sizeof(LenHist), stream));
+    const uint32_t g = (uint32_t)std::min<uint64_t>(div_up(n, kThreads), 148 * 8);
+    len_hist_kernel<<<g, kThreads, 0, stream>>>(ix.starts, ix.stops_by_iv, n, d_hist.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    LenHist h;
+    uint32_t first_start = 0, last_start = 0;
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&h, d_hist.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&first_start, ix.starts, 4, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&last_start, ix.starts + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    uint8_t class_of_bin[33];
+    choose_classes(h, (uint64_t)last_start - first_start + 1, class_of_bin, ix.ncls, ix.cls_n, ix.cls_maxlen);
+    uint32_t off = 0;
+    for (uint32_t c = 0; c < 4; c++) {
+        ix.cls_off[c] = off;
+        off += ix.cls_n[c];
+    }
+    ix.cls_starts = dev_alloc<uint32_t>(n, ix.bytes);
+    ix.cls_stops = dev_alloc<uint32_t>(n, ix.bytes);
+    ix.cls_gidx = dev_alloc<uint32_t>(n, ix.bytes);
+    launch_class_partition(ix, class_of_bin, stream);
+    // directory: about one bucket per six intervals, at least 2^4 coordinates wide
+    uint32_t k = 0;
+    const uint64_t target = std::max<uint64_t>(n / 6, 1024);
+    while (k < 31 && ((uint64_t)(last_start >> k) + 1) > target) k++;
+    ix.cls_shift = k;
+    ix.cls_nb = (uint64_t)(last_start >> k) + 1;
+    ix.cls_dir = dev_alloc<uint4>(ix.cls_nb + 1, ix.bytes);
+    fill_class_dir_kernel<<<grid_for(ix.cls_nb + 1), kThreads, 0, stream>>>(
+        ix.cls_starts, ix.cls_off[0], ix.cls_n[0], ix.cls_off[1], ix.cls_n[1], ix.cls_off[2], ix.cls_n[2], ix.cls_off[3],
+        ix.cls_n[3], k, ix.cls_nb, ix.cls_dir);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+}
+
 }  // namespace
 
 void free_index(DeviceIndex &ix) {
+    cudaFree(ix.cls_starts);
+    cudaFree(ix.cls_stops);
+    cudaFree(ix.cls_gidx);
+    cudaFree(ix.cls_dir);
     cudaFree(ix.starts);
     cudaFree(ix.stops_by_iv);
     cudaFree(ix.stops_sorted);
@@ -166,6 +310,7 @@ void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stre
     ix.max_coord = 0;
     ix.shift = 0xFFFFFFFFu;
     ix.nbuckets = 0;
+    ix.ncls = 0;
     if (n == 0) return;
 
     Scratch<BuildStats> d_stats(1, stream);
@@ -186,6 +331,8 @@ void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stre
     ix.max_len = st.max_len;
     ix.has_inverted = st.inverted != 0;
     ix.max_coord = std::max(last_start, last_stop);
+
+    build_find_classes(ix, stream);
 
     uint32_t shift = 0;
     if (choose_shift(n, ix.max_coord, flags, shift)) {

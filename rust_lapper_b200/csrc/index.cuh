@@ -51,7 +51,26 @@ struct DeviceIndex {
     uint32_t max_coord = 0;
     bool has_inverted = false;
     uint64_t bytes = 0;
+
+    // ---- find: length classes (build.cu::build_find_classes).  The sorted intervals are split,
+    // order-preserving, into up to kMaxClasses groups by length; class c occupies
+    // [cls_off[c], cls_off[c] + cls_n[c]) of cls_starts / cls_stops / cls_gidx (gidx = position in the
+    // global sorted order).  Inside a class no interval is longer than cls_maxlen[c], so
+    // find(a, b) only has to look at starts in [a - cls_maxlen[c], b) of that class -- a window that is
+    // short for the short classes and dense in hits for the long ones.  cls_dir[B] holds, for the
+    // coordinate bucket B (width 2^cls_shift), the rank of B's first coordinate in each class.
+    uint32_t ncls = 0;
+    uint32_t cls_off[4] = {0, 0, 0, 0};
+    uint32_t cls_n[4] = {0, 0, 0, 0};
+    uint32_t cls_maxlen[4] = {0, 0, 0, 0};
+    uint32_t *cls_starts = nullptr;
+    uint32_t *cls_stops = nullptr;
+    uint32_t *cls_gidx = nullptr;
+    uint4 *cls_dir = nullptr;  // cls_nb + 1 entries
+    uint32_t cls_shift = 0;
+    uint64_t cls_nb = 0;
 };
+constexpr uint32_t kMaxClasses = 4;
 
 }  // namespace lap
 
@@ -93,6 +112,8 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
                       const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream);
 
 // setops.cu --------------------------------------------------------------------------------------
+// order-preserving split of the sorted intervals into length classes (fills ix.cls_starts/stops/gidx)
+void launch_class_partition(DeviceIndex &ix, const uint8_t *class_of_bin /* host, 33 entries */, cudaStream_t stream);
 // inclusive prefix max of `in` (n elements) into `out`
 void launch_prefix_max(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream);
 uint32_t compute_cov(const DeviceIndex &ix, cudaStream_t stream);

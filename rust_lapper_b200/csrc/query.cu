@@ -332,7 +332,13 @@ __global__ void __launch_bounds__(kThreads) count_plain_kernel(PlainView v, cons
 }
 
 // ------------------------------------------------------------------------------------- find
-// A generic per-thread rank helper (bucket table when present, plain bisection otherwise).
+// find(a, b) = ascending i with start_i < b and stop_i > a (src/lib.rs:704-717; the start offset
+// :632-635 and the early break :712-713 only prune).  The reference scans one window
+// [lower_bound(a - max_len), lower_bound(b)) of the whole sorted vector, which a single long interval
+// stretches to everything before b (src/lib.rs:36-47).  Here the sorted vector is also kept split by
+// length class (index.cuh): per class the window is [lower_bound_c(a - maxlen_c), lower_bound_c(b)),
+// the class hit streams are ascending in global position, and a per-query k-way merge emits them in
+// exactly the reference's order.
 struct FindView {
     BucketView bv;
     bool has_buckets;
@@ -342,6 +348,12 @@ struct FindView {
     uint32_t n;
     uint32_t max_len;
     bool has_inverted;
+    // length classes
+    uint32_t ncls;
+    uint32_t cls_off[4], cls_n[4], cls_maxlen[4];
+    const uint32_t *cs, *ce, *cg;
+    const uint4 *dir;
+    uint32_t cls_shift, cls_nb;
 };
 
 __device__ __forceinline__ uint32_t rank_lb_starts(const FindView &f, uint32_t key) {
@@ -361,14 +373,41 @@ __device__ __forceinline__ uint32_t rank_ub_stops(const FindView &f, uint32_t ke
     return upper_bound_u32(f.E, 0, f.n, key);
 }
 
-// IterFind's scan window (src/lib.rs:632-635 start offset, :712-713 early break):
-// [lower_bound(starts, a (-) max_len), lower_bound(starts, b)).
-__device__ __forceinline__ void find_window(const FindView &f, uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi) {
-    hi = rank_lb_starts(f, b);
-    lo = rank_lb_starts(f, a >= f.max_len ? a - f.max_len : 0u);
+__device__ __forceinline__ uint32_t dir_get(const uint4 &d, int c) { return c == 0 ? d.x : c == 1 ? d.y : c == 2 ? d.z : d.w; }
+
+// lower_bound of `key` among the starts of class c: directory rank, then a short forward walk
+__device__ __forceinline__ uint32_t class_lb(const FindView &f, int c, uint32_t key) {
+    const uint32_t B = min(key >> f.cls_shift, f.cls_nb);
+    const uint4 d0 = __ldg(f.dir + B);
+    uint32_t r = dir_get(d0, c);
+    if (B < f.cls_nb) {
+        const uint32_t hi = dir_get(__ldg(f.dir + B + 1), c);
+        const uint32_t *cs = f.cs + f.cls_off[c];
+        if (hi - r > 16) return lower_bound_u32(cs, r, hi, key);
+        while (r < hi && __ldg(cs + r) < key) r++;
+    }
+    return r;
 }
 
-// number of positions find(a, b) yields
+// per-class scan windows of one query; returns the class-relative [lo, hi)
+__device__ __forceinline__ void class_window(const FindView &f, int c, uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi) {
+    hi = class_lb(f, c, b);
+    lo = class_lb(f, c, a >= f.cls_maxlen[c] ? a - f.cls_maxlen[c] : 0u);
+    if (lo > hi) lo = hi;
+}
+
+// number of positions find(a, b) yields, by the predicate (any input)
+__device__ __forceinline__ uint32_t find_count_scan(const FindView &f, uint32_t a, uint32_t b) {
+    uint32_t total = 0;
+    for (int c = 0; c < (int)f.ncls; c++) {
+        uint32_t lo, hi;
+        class_window(f, c, a, b, lo, hi);
+        const uint32_t *ce = f.ce + f.cls_off[c];
+        for (uint32_t i = lo; i < hi; i++) total += (__ldg(ce + i) > a);
+    }
+    return total;
+}
+
 __device__ __forceinline__ uint32_t find_count_one(const FindView &f, uint32_t a, uint32_t b) {
     if (f.n == 0) return 0;
     if (a < b && !f.has_inverted) {
@@ -376,11 +415,7 @@ __device__ __forceinline__ uint32_t find_count_one(const FindView &f, uint32_t a
         // (SURVEY Appendix A.4); a == u32::MAX cannot happen here because a < b.
         return rank_lb_starts(f, b) - rank_ub_stops(f, a);
     }
-    uint32_t lo, hi;
-    find_window(f, a, b, lo, hi);
-    uint32_t c = 0;
-    for (uint32_t i = lo; i < hi; i++) c += (__ldg(f.Eiv + i) > a);
-    return c;
+    return find_count_scan(f, a, b);
 }
 
 constexpr int kFindQPT = 4;
@@ -401,7 +436,10 @@ __device__ __forceinline__ uint64_t block_reduce_sum_u64(uint64_t v, uint64_t *s
     return r;  // valid in thread 0
 }
 
-// pass 1: per-query hit counts (thread t of a tile owns queries t*4..t*4+3) and per-tile sums
+// pass 1: per-query hit counts (thread t of a tile owns queries t*4..t*4+3) and per-tile sums.
+// kHaveCounts: `counts` already holds the BITS count of every query (the fast count kernel ran);
+// only queries outside its validity (a >= b) are recounted by the predicate.
+template <bool kHaveCounts>
 __global__ void __launch_bounds__(kThreads) find_count_kernel(FindView f, const uint32_t *__restrict__ qs,
                                                               const uint32_t *__restrict__ qe, uint64_t nq,
                                                               uint32_t *__restrict__ counts,
@@ -413,8 +451,18 @@ __global__ void __launch_bounds__(kThreads) find_count_kernel(FindView f, const 
     for (int k = 0; k < kFindQPT; k++) {
         const uint64_t j = base + k;
         if (j < nq) {
-            const uint32_t c = find_count_one(f, ld_stream_u32(qs + j), ld_stream_u32(qe + j));
-            counts[j] = c;
+            const uint32_t a = ld_stream_u32(qs + j), b = ld_stream_u32(qe + j);
+            uint32_t c;
+            if (kHaveCounts) {
+                c = counts[j];
+                if (!(a < b)) {
+                    c = find_count_scan(f, a, b);
+                    counts[j] = c;
+                }
+            } else {
+                c = find_count_one(f, a, b);
+                counts[j] = c;
+            }
             local += c;
         }
     }
@@ -494,24 +542,105 @@ __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t 
     }
 }
 
-// emit: one thread per query walks its window and writes the hit positions in ascending order
+// ---- emit.  One query per lane; a warp's 32 consecutive queries own one contiguous slice of the
+// CSR `indices` array, so each lane writes its hits into a per-warp shared-memory stage at
+// (offset - warp base) and the warp then copies the stage out with fully coalesced stores.  Slices
+// that do not fit the stage are written straight to global memory (warp-uniform choice).
+constexpr int kEmitStage = 1536;  // u32 slots per warp: 6 KB, 48 KB per CTA
+
+struct ClassCursor {
+    uint32_t cur, end, g;
+};
+
+__device__ __forceinline__ void cursor_settle(const FindView &f, int c, ClassCursor &k, uint32_t a) {
+    // advance to the next interval of the class whose stop is beyond the query start
+    const uint32_t *ce = f.ce + f.cls_off[c];
+    while (k.cur < k.end && __ldg(ce + k.cur) <= a) k.cur++;
+    k.g = k.cur < k.end ? __ldg(f.cg + f.cls_off[c] + k.cur) : 0xFFFFFFFFu;
+}
+
+template <typename Out>
+__device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, uint32_t b, Out out, uint64_t room) {
+    if (f.ncls == 1) {  // single class: its positions are the global positions
+        uint32_t lo, hi;
+        class_window(f, 0, a, b, lo, hi);
+        for (uint32_t i = lo; i < hi && room; i++)
+            if (__ldg(f.ce + i) > a) {
+                out.put(i);
+                room--;
+            }
+        return;
+    }
+    ClassCursor k[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        k[c].cur = k[c].end = 0;
+        k[c].g = 0xFFFFFFFFu;
+        if (c < (int)f.ncls) {
+            class_window(f, c, a, b, k[c].cur, k[c].end);
+            cursor_settle(f, c, k[c], a);
+        }
+    }
+    while (room) {
+        // smallest global position among the class heads
+        const uint32_t m01 = min(k[0].g, k[1].g), m23 = min(k[2].g, k[3].g);
+        const uint32_t m = min(m01, m23);
+        if (m == 0xFFFFFFFFu) break;
+        out.put(m);
+        room--;
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+            if (k[c].g == m) {
+                k[c].cur++;
+                cursor_settle(f, c, k[c], a);
+            }
+    }
+}
+
+struct OutGlobal {
+    uint32_t *p;
+    __device__ __forceinline__ void put(uint32_t v) { *p++ = v; }
+};
+struct OutShared {
+    uint32_t *p;
+    __device__ __forceinline__ void put(uint32_t v) { *p++ = v; }
+};
+
 __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const uint32_t *__restrict__ qs,
                                                              const uint32_t *__restrict__ qe, uint64_t nq,
                                                              const uint64_t *__restrict__ offsets,
                                                              uint32_t *__restrict__ indices) {
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t o0 = offsets[j], o1 = offsets[j + 1];
-        if (o1 == o0) continue;
-        const uint32_t a = ld_stream_u32(qs + j), b = ld_stream_u32(qe + j);
-        uint32_t lo, hi;
-        find_window(f, a, b, lo, hi);
-        uint32_t *out = indices + o0;
-        uint64_t room = o1 - o0;
-        for (uint32_t i = lo; i < hi && room; i++) {
-            if (__ldg(f.Eiv + i) > a) {
-                *out++ = i;
-                room--;
-            }
+    __shared__ uint32_t stage_all[kThreads / 32][kEmitStage];
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t *const stage = stage_all[threadIdx.x >> 5];
+    const uint64_t nwarps = (uint64_t)gridDim.x * (kThreads / 32);
+    const uint64_t nchunks = div_up(nq, 32);
+    for (uint64_t chunk = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); chunk < nchunks; chunk += nwarps) {
+        const uint64_t j = chunk * 32 + lane;
+        const bool live = j < nq;
+        const uint64_t o0 = live ? offsets[j] : 0;
+        // offsets[j + 1] is the next lane's o0; the last live lane reads it
+        uint64_t o1 = __shfl_down_sync(0xFFFFFFFFu, o0, 1);
+        const bool last = live && (lane == 31 || j + 1 == nq);
+        if (last) o1 = offsets[j + 1];
+        if (!live) o1 = 0;
+        const uint64_t wbase = __shfl_sync(0xFFFFFFFFu, o0, 0);
+        const uint32_t last_lane = 31u - __clz(__ballot_sync(0xFFFFFFFFu, live));
+        const uint64_t wend = __shfl_sync(0xFFFFFFFFu, o1, last_lane);
+        const uint64_t wtotal = wend - wbase;
+        if (wtotal == 0) continue;
+        uint32_t a = 0, b = 0;
+        if (live && o1 > o0) {
+            a = ld_stream_u32(qs + j);
+            b = ld_stream_u32(qe + j);
+        }
+        if (wtotal <= kEmitStage) {
+            if (live && o1 > o0) emit_one_query(f, a, b, OutShared{stage + (o0 - wbase)}, o1 - o0);
+            __syncwarp();
+            for (uint32_t i = lane; i < (uint32_t)wtotal; i += 32) indices[wbase + i] = stage[i];
+            __syncwarp();
+        } else {
+            if (live && o1 > o0) emit_one_query(f, a, b, OutGlobal{indices + o0}, o1 - o0);
         }
     }
 }
@@ -537,6 +666,18 @@ FindView make_find_view(const DeviceIndex &ix) {
     f.n = (uint32_t)ix.n;
     f.max_len = ix.max_len;
     f.has_inverted = ix.has_inverted;
+    f.ncls = ix.ncls;
+    for (int c = 0; c < 4; c++) {
+        f.cls_off[c] = ix.cls_off[c];
+        f.cls_n[c] = ix.cls_n[c];
+        f.cls_maxlen[c] = ix.cls_maxlen[c];
+    }
+    f.cs = ix.cls_starts;
+    f.ce = ix.cls_stops;
+    f.cg = ix.cls_gidx;
+    f.dir = ix.cls_dir;
+    f.cls_shift = ix.cls_shift;
+    f.cls_nb = (uint32_t)ix.cls_nb;
     return f;
 }
 
@@ -615,7 +756,18 @@ uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const 
     LAPPER_REQUIRE(ntiles < 0x7FFFFFFFull, "find_batch: too many queries in one call");
     Scratch<uint32_t> counts(nq, stream);
     Scratch<uint64_t> tile_sums(ntiles, stream);
-    find_count_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
+    if (ix.n == 0) {
+        LAPPER_CUDA_CHECK(cudaMemsetAsync(d_offsets, 0, (nq + 1) * sizeof(uint64_t), stream));
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return 0;
+    }
+    if (!ix.has_inverted) {
+        // every interval has start <= stop: the BITS count IS the number of hits for non-empty queries
+        launch_count(ix, d_qs, d_qe, nq, counts.p, nullptr, stream);
+        find_count_kernel<true><<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
+    } else {
+        find_count_kernel<false><<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
+    }
     LAPPER_CUDA_CHECK(cudaGetLastError());
     scan_tile_sums_kernel<<<1, 1024, 0, stream>>>(tile_sums.p, ntiles, d_offsets + nq);
     LAPPER_CUDA_CHECK(cudaGetLastError());
@@ -631,7 +783,7 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
                       const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream) {
     if (nq == 0 || ix.n == 0) return;
     const FindView f = make_find_view(ix);
-    const uint32_t grid = capped_grid(nq, kThreads, 8 * 8);
+    const uint32_t grid = capped_grid(nq, kThreads, 4 * 8);
     find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices);
     LAPPER_CUDA_CHECK(cudaGetLastError());
 }

@@ -43,6 +43,34 @@ struct RunLength {  // lengths of already-merged runs
     __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return e[i] - s[i]; }
 };
 
+// length bin of an interval: 0 for length 0 (or inverted, checked_sub -> 0), else its bit length
+__device__ __forceinline__ uint32_t len_bin(uint32_t s, uint32_t e) { return e > s ? 32u - __clz(e - s) : 0u; }
+
+struct ClassTable {
+    uint8_t of_bin[36];
+};
+struct ClassFlag {  // 1 where the interval belongs to class c
+    const uint32_t *S;
+    const uint32_t *E;
+    ClassTable t;
+    uint32_t c;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return t.of_bin[len_bin(S[i], E[i])] == c ? 1u : 0u; }
+};
+struct ClassSink {
+    const uint32_t *S;
+    const uint32_t *E;
+    uint32_t off;
+    uint32_t *cs, *ce, *cg;
+    __device__ __forceinline__ void operator()(uint64_t i, uint32_t flag, uint32_t inclusive) const {
+        if (flag) {
+            const uint32_t pos = off + inclusive - 1u;
+            cs[pos] = S[i];
+            ce[pos] = E[i];
+            cg[pos] = (uint32_t)i;
+        }
+    }
+};
+
 template <typename Op>
 __device__ __forceinline__ uint32_t block_scan_inclusive(uint32_t x, Op op, uint32_t *warp_tot, uint32_t &block_total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -236,6 +264,17 @@ struct DevArrays {
 };
 
 }  // namespace
+
+void launch_class_partition(DeviceIndex &ix, const uint8_t *class_of_bin, cudaStream_t stream) {
+    ClassTable t;
+    for (int b = 0; b < 36; b++) t.of_bin[b] = b < 33 ? class_of_bin[b] : 0;
+    for (uint32_t c = 0; c < ix.ncls; c++) {
+        if (ix.cls_n[c] == 0) continue;
+        scan3<AddOp>(ClassFlag{ix.starts, ix.stops_by_iv, t, c}, ix.n,
+                     ClassSink{ix.starts, ix.stops_by_iv, ix.cls_off[c], ix.cls_starts, ix.cls_stops, ix.cls_gidx}, nullptr,
+                     stream);
+    }
+}
 
 void launch_prefix_max(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream) {
     scan3<MaxOp>(LoadArray{in}, n, StoreSink{out}, nullptr, stream);
