@@ -1,0 +1,134 @@
+//! UNVERIFIED: written without a Rust toolchain (none in the build image); never compiled.
+//!
+//! `Lapper<T>` with `I = u32` over the C ABI of `include/lapper_b200.h`: the same method names as
+//! rust-lapper 1.3.0 (`new`, `find`, `seek`, `count`, `merge_overlaps`, `cov`, `set_cov`,
+//! `union_and_intersect`) plus `count_batch` / `find_batch`.  `val: T` stays on the host; the engine
+//! returns positions into the sorted `intervals` vector and `perm` maps them to input positions.
+use std::os::raw::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct LapperHandle {
+    _private: [u8; 0],
+}
+#[repr(C)]
+pub struct LapperResult {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    fn lapper_last_error() -> *const c_char;
+    fn lapper_build_u32(starts: *const u32, stops: *const u32, n: u64, device: c_int, out: *mut *mut LapperHandle) -> c_int;
+    fn lapper_free(l: *mut LapperHandle);
+    fn lapper_len(l: *const LapperHandle) -> u64;
+    fn lapper_max_len(l: *const LapperHandle) -> u32;
+    fn lapper_overlaps_merged(l: *const LapperHandle) -> c_int;
+    fn lapper_get_intervals(l: *const LapperHandle, s: *mut u32, e: *mut u32, perm: *mut u32) -> c_int;
+    fn lapper_count_batch_u32(l: *const LapperHandle, qs: *const u32, qe: *const u32, nq: u64, out: *mut u64) -> c_int;
+    fn lapper_find_batch_u32(l: *const LapperHandle, qs: *const u32, qe: *const u32, nq: u64, out: *mut *mut LapperResult) -> c_int;
+    fn lapper_result_total(r: *const LapperResult) -> u64;
+    fn lapper_result_copy(r: *const LapperResult, offsets: *mut u64, indices: *mut u32) -> c_int;
+    fn lapper_result_free(r: *mut LapperResult);
+    fn lapper_seek_cursor(l: *const LapperHandle, start: u32, cursor: *mut u64) -> c_int;
+    fn lapper_merge_overlaps(l: *mut LapperHandle) -> c_int;
+    fn lapper_cov(l: *const LapperHandle, out: *mut u32) -> c_int;
+    fn lapper_set_cov(l: *mut LapperHandle, out: *mut u32) -> c_int;
+    fn lapper_union_and_intersect(a: *const LapperHandle, b: *const LapperHandle, u: *mut u32, i: *mut u32) -> c_int;
+}
+
+fn check(rc: c_int) {
+    if rc != 0 {
+        let msg = unsafe { std::ffi::CStr::from_ptr(lapper_last_error()) }.to_string_lossy().into_owned();
+        panic!("liblapper_b200 error {}: {}", rc, msg); // the reference's only failure mode is a panic too
+    }
+}
+
+#[derive(Debug, Clone, Eq)]
+pub struct Interval<T: Eq + Clone + Send + Sync> {
+    pub start: u32,
+    pub stop: u32,
+    pub val: T,
+}
+impl<T: Eq + Clone + Send + Sync> PartialEq for Interval<T> {
+    fn eq(&self, o: &Self) -> bool {
+        self.start == o.start && self.stop == o.stop
+    }
+}
+
+pub struct Lapper<T: Eq + Clone + Send + Sync> {
+    pub intervals: Vec<Interval<T>>,
+    input: Vec<Interval<T>>,
+    h: *mut LapperHandle,
+    _pin: *mut c_void,
+}
+unsafe impl<T: Eq + Clone + Send + Sync> Send for Lapper<T> {}
+unsafe impl<T: Eq + Clone + Send + Sync> Sync for Lapper<T> {} // const calls on one handle are thread-safe
+
+impl<T: Eq + Clone + Send + Sync> Lapper<T> {
+    pub fn new(intervals: Vec<Interval<T>>) -> Self {
+        let s: Vec<u32> = intervals.iter().map(|x| x.start).collect();
+        let e: Vec<u32> = intervals.iter().map(|x| x.stop).collect();
+        let mut h = std::ptr::null_mut();
+        check(unsafe { lapper_build_u32(s.as_ptr(), e.as_ptr(), s.len() as u64, 0, &mut h) });
+        let mut l = Lapper { intervals: vec![], input: intervals, h, _pin: std::ptr::null_mut() };
+        l.refresh();
+        l
+    }
+    fn refresh(&mut self) {
+        let n = unsafe { lapper_len(self.h) } as usize;
+        let (mut s, mut e, mut p) = (vec![0u32; n], vec![0u32; n], vec![0u32; n]);
+        check(unsafe { lapper_get_intervals(self.h, s.as_mut_ptr(), e.as_mut_ptr(), p.as_mut_ptr()) });
+        self.intervals = (0..n).map(|i| Interval { start: s[i], stop: e[i], val: self.input[p[i] as usize].val.clone() }).collect();
+    }
+    pub fn len(&self) -> usize { self.intervals.len() }
+    pub fn is_empty(&self) -> bool { self.intervals.is_empty() }
+    pub fn max_len(&self) -> u32 { unsafe { lapper_max_len(self.h) } }
+    pub fn overlaps_merged(&self) -> bool { unsafe { lapper_overlaps_merged(self.h) != 0 } }
+    pub fn iter(&self) -> std::slice::Iter<'_, Interval<T>> { self.intervals.iter() }
+
+    pub fn count_batch(&self, qs: &[u32], qe: &[u32]) -> Vec<u64> {
+        assert_eq!(qs.len(), qe.len());
+        let mut out = vec![0u64; qs.len()];
+        check(unsafe { lapper_count_batch_u32(self.h, qs.as_ptr(), qe.as_ptr(), qs.len() as u64, out.as_mut_ptr()) });
+        out
+    }
+    /// CSR: `indices[offsets[j]..offsets[j+1]]` are the positions `find(qs[j], qe[j])` yields, in order.
+    pub fn find_batch(&self, qs: &[u32], qe: &[u32]) -> (Vec<u64>, Vec<u32>) {
+        assert_eq!(qs.len(), qe.len());
+        let mut r = std::ptr::null_mut();
+        check(unsafe { lapper_find_batch_u32(self.h, qs.as_ptr(), qe.as_ptr(), qs.len() as u64, &mut r) });
+        let total = unsafe { lapper_result_total(r) } as usize;
+        let (mut off, mut idx) = (vec![0u64; qs.len() + 1], vec![0u32; total]);
+        let rc = unsafe { lapper_result_copy(r, off.as_mut_ptr(), idx.as_mut_ptr()) };
+        unsafe { lapper_result_free(r) };
+        check(rc);
+        (off, idx)
+    }
+    pub fn count(&self, start: u32, stop: u32) -> usize { self.count_batch(&[start], &[stop])[0] as usize }
+    pub fn find(&self, start: u32, stop: u32) -> impl Iterator<Item = &Interval<T>> {
+        let (_, idx) = self.find_batch(&[start], &[stop]);
+        idx.into_iter().map(move |i| &self.intervals[i as usize])
+    }
+    pub fn seek<'a>(&'a self, start: u32, stop: u32, cursor: &mut usize) -> impl Iterator<Item = &'a Interval<T>> {
+        let mut c = *cursor as u64;
+        check(unsafe { lapper_seek_cursor(self.h, start, &mut c) });
+        *cursor = c as usize;
+        let (_, idx) = self.find_batch(&[start], &[stop]);
+        idx.into_iter().filter(move |&i| i as u64 >= c).map(move |i| &self.intervals[i as usize])
+    }
+    pub fn merge_overlaps(&mut self) {
+        check(unsafe { lapper_merge_overlaps(self.h) });
+        self.refresh();
+    }
+    pub fn cov(&self) -> u32 { let mut c = 0; check(unsafe { lapper_cov(self.h, &mut c) }); c }
+    pub fn set_cov(&mut self) -> u32 { let mut c = 0; check(unsafe { lapper_set_cov(self.h, &mut c) }); c }
+    pub fn union_and_intersect(&self, other: &Self) -> (u32, u32) {
+        let (mut u, mut i) = (0, 0);
+        check(unsafe { lapper_union_and_intersect(self.h, other.h, &mut u, &mut i) });
+        (u, i)
+    }
+    pub fn intersect(&self, other: &Self) -> u32 { self.union_and_intersect(other).1 }
+    pub fn union(&self, other: &Self) -> u32 { self.union_and_intersect(other).0 }
+}
+impl<T: Eq + Clone + Send + Sync> Drop for Lapper<T> {
+    fn drop(&mut self) { unsafe { lapper_free(self.h) } }
+}

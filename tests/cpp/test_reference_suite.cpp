@@ -1,0 +1,147 @@
+// The reference's unit tests (/root/reference/src/lib.rs `mod tests`) restated against the C++ facade
+// include/lapper_b200.hpp -- they read like the originals.  Needs a B200 to run; compiles anywhere.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "lapper_b200.hpp"
+
+using lapper_b200::Interval;
+using lapper_b200::Lapper;
+typedef Interval<uint32_t> Iv;
+
+static int failures = 0;
+#define CHECK(cond)                                                      \
+    do {                                                                 \
+        if (!(cond)) {                                                   \
+            std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond); \
+            failures++;                                                  \
+        }                                                                \
+    } while (0)
+
+static std::vector<Iv> step_by(uint32_t lo, uint32_t hi, uint32_t step, uint32_t len) {
+    std::vector<Iv> v;
+    for (uint32_t x = lo; x < hi; x += step) v.push_back(Iv{x, x + len, 0});
+    return v;
+}
+static std::vector<Iv> nonoverlapping() { return step_by(0, 100, 20, 10); }  // :857-867
+static std::vector<Iv> overlapping() { return step_by(0, 100, 10, 15); }     // :869-879
+static std::vector<Iv> badlapper() {                                         // :881-895
+    return {{70, 120, 0}, {10, 15, 1}, {10, 15, 2}, {12, 15, 3}, {14, 16, 4}, {40, 45, 5},
+            {50, 55, 6},  {60, 65, 7}, {68, 71, 8}, {70, 75, 9}};
+}
+static bool same(const std::vector<const Iv *> &got, const std::vector<Iv> &want) {
+    if (got.size() != want.size()) return false;
+    for (size_t i = 0; i < got.size(); i++)
+        if (!(*got[i] == want[i])) return false;
+    return true;
+}
+
+int main() {
+    {  // test_query_stop_interval_start / test_query_start_interval_stop  :1023-1039
+        Lapper<uint32_t> lapper(nonoverlapping());
+        size_t cursor = 0;
+        CHECK(lapper.find(15, 20).empty());
+        CHECK(lapper.seek(15, 20, &cursor).empty());
+        CHECK(lapper.find(15, 20).size() == lapper.count(15, 20));
+        CHECK(lapper.find(30, 35).empty());
+        CHECK(lapper.find(30, 35).size() == lapper.count(30, 35));
+    }
+    {  // the four overlap shapes  :1043-1099
+        Lapper<uint32_t> lapper(nonoverlapping());
+        const uint32_t qs[4][2] = {{15, 25}, {25, 35}, {22, 27}, {15, 35}};
+        for (auto &q : qs) {
+            size_t cursor = 0;
+            const Iv expected{20, 30, 0};
+            CHECK(*lapper.find(q[0], q[1]).front() == expected);
+            CHECK(*lapper.seek(q[0], q[1], &cursor).front() == expected);
+            CHECK(lapper.find(q[0], q[1]).size() == lapper.count(q[0], q[1]));
+        }
+    }
+    {  // test_overlapping_intervals  :1102-1121
+        Lapper<uint32_t> lapper(overlapping());
+        size_t cursor = 0;
+        CHECK(same(lapper.find(8, 20), {{0, 15, 0}, {10, 25, 0}}));
+        CHECK(same(lapper.seek(8, 20, &cursor), {{0, 15, 0}, {10, 25, 0}}));
+        CHECK(lapper.count(8, 20) == 2);
+    }
+    {  // test_merge_overlaps  :1124-1138  (+ val of a run is the val of its first interval, :385-389)
+        Lapper<uint32_t> lapper(badlapper());
+        lapper.merge_overlaps();
+        const std::vector<Iv> expected = {{10, 16, 0}, {40, 45, 0}, {50, 55, 0}, {60, 65, 0}, {68, 120, 0}};
+        CHECK(lapper.intervals.size() == expected.size());
+        for (size_t i = 0; i < expected.size() && i < lapper.intervals.size(); i++) CHECK(lapper.intervals[i] == expected[i]);
+        CHECK(lapper.intervals[0].val == 1 && lapper.intervals[4].val == 8);
+        CHECK(lapper.overlaps_merged());
+    }
+    {  // test_merge_overlaps_find  :1143-1165
+        Lapper<uint32_t> lapper({{2, 3, 0}, {3, 4, 0}, {4, 6, 0}, {6, 7, 0}, {7, 8, 0}});
+        CHECK(same(lapper.find(7, 9), {{7, 8, 0}}));
+        lapper.merge_overlaps();
+        CHECK(same(lapper.find(7, 9), {{2, 8, 0}}));
+    }
+    {  // test_lapper_cov  :1168-1178
+        Lapper<uint32_t> lapper(badlapper());
+        const uint32_t before = lapper.cov();
+        lapper.merge_overlaps();
+        CHECK(before == lapper.cov() && before == 73);
+        Lapper<uint32_t> l2(nonoverlapping());
+        l2.set_cov();
+        CHECK(l2.cov() == 50);
+    }
+    {  // test_interval_intersects  :1181-1200
+        const Iv i1{70, 120, 0}, i2{10, 15, 0}, i3{10, 15, 0}, i4{12, 15, 0}, i5{14, 16, 0}, i6{40, 50, 0}, i7{50, 55, 0},
+            i8{60, 65, 0}, i9{68, 71, 0}, i10{70, 75, 0};
+        CHECK(i2.intersect(i3) == 5 && i2.intersect(i4) == 3 && i2.intersect(i5) == 1 && i9.intersect(i10) == 1);
+        CHECK(i7.intersect(i8) == 0 && i6.intersect(i7) == 0 && i1.intersect(i10) == 5);
+    }
+    {  // test_union_and_intersect  :1203-1240
+        Lapper<uint32_t> l1({{70, 120, 0}, {10, 15, 0}, {12, 15, 0}, {14, 16, 0}, {68, 71, 0}});
+        Lapper<uint32_t> l2({{10, 15, 0}, {40, 45, 0}, {50, 55, 0}, {60, 65, 0}, {70, 75, 0}});
+        CHECK(l1.union_and_intersect(l2) == std::make_pair(73u, 10u));
+        CHECK(l2.union_and_intersect(l1) == std::make_pair(73u, 10u));
+        l1.merge_overlaps();
+        l1.set_cov();
+        l2.merge_overlaps();
+        l2.set_cov();
+        CHECK(l1.union_and_intersect(l2) == std::make_pair(73u, 10u));
+        CHECK(l2.union_and_intersect(l1) == std::make_pair(73u, 10u));
+    }
+    {  // test_find_overlaps_in_large_intervals  :1243-1276
+        Lapper<uint32_t> lapper({{0, 8, 0}, {1, 10, 0}, {2, 5, 0}, {3, 8, 0}, {4, 7, 0}, {5, 8, 0}, {8, 8, 0}, {9, 11, 0},
+                                 {10, 13, 0}, {100, 200, 0}, {110, 120, 0}, {110, 124, 0}, {111, 160, 0}, {150, 200, 0}});
+        CHECK(same(lapper.find(8, 11), {{1, 10, 0}, {9, 11, 0}, {10, 13, 0}}));
+        CHECK(lapper.count(8, 11) == 3);
+        CHECK(same(lapper.find(145, 151), {{100, 200, 0}, {111, 160, 0}, {150, 200, 0}}));
+        CHECK(lapper.count(145, 151) == 3);
+    }
+    {  // test_seek_over_len  :1343-1353
+        Lapper<uint32_t> lapper(nonoverlapping()), single({{10, 35, 0}});
+        size_t cursor = 0;
+        size_t hits = 0;
+        for (const Iv &iv : lapper) hits += single.seek(iv.start, iv.stop, &cursor).size();
+        CHECK(hits == 1);
+    }
+    {  // test_find_over_behind_first_match  :1357-1363, test_bad_skips  :1368-1385
+        Lapper<uint32_t> lapper(badlapper());
+        CHECK(*lapper.find(50, 55).front() == (Iv{50, 55, 0}));
+        CHECK(lapper.find(50, 55).size() == lapper.count(50, 55));
+        Lapper<uint32_t> bad({{25264912, 25264986, 0}, {27273024, 27273065, 0}, {27440273, 27440318, 0},
+                              {27488033, 27488125, 0}, {27938410, 27938470, 0}, {27959118, 27959171, 0},
+                              {28866309, 33141404, 0}});
+        CHECK(same(bad.find(28974798, 33141355), {{28866309, 33141404, 0}}));
+        CHECK(bad.count(28974798, 33141355) == 1);
+    }
+    {  // doctests: count/find :603-627, seek :646-655, cov :303-309, examples/ex1.rs:104-121
+        Lapper<uint32_t> lapper(step_by(0, 100, 5, 2));
+        CHECK(lapper.count(5, 11) == 2 && lapper.find(5, 11).size() == 2);
+        size_t cursor = 0;
+        for (const Iv &iv : lapper) CHECK(lapper.seek(iv.start, iv.stop, &cursor).size() == 1);
+        CHECK(Lapper<uint32_t>(step_by(0, 20, 5, 10)).cov() == 25);
+        Lapper<uint32_t> ex(badlapper()), other({{5, 15, 0}, {48, 80, 0}});
+        ex.merge_overlaps();
+        CHECK(ex.union_and_intersect(other) == std::make_pair(88u, 27u));
+    }
+    std::printf(failures ? "%d FAILED\n" : "all reference tests passed (C++ facade)\n", failures);
+    return failures ? 1 : 0;
+}
