@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblapper_b200.so")
+# LAPPER_B200_LIB selects an alternative build of the same library (kernel A/B experiments only)
+LIB_PATH = os.environ.get("LAPPER_B200_LIB") or os.path.join(_HERE, "liblapper_b200.so")
 
 OK = 0
 ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_PRECONDITION, ERR_NO_DEVICE = 1, 2, 3, 4, 5

@@ -63,51 +63,120 @@ __global__ void stats_kernel(const uint32_t *__restrict__ s, const uint32_t *__r
     }
 }
 
-// One thread per bucket: four coherent bisections (neighbouring buckets walk the same path) and
-// one 32-byte sector store.
+// Lanes of one sector covering [base, base + w) with stop margin m, from the slices
+// S[rs, rs_next) and E[re_m, re_hi) of the sorted arrays (re_m = #stops < base - m).
+__device__ __forceinline__ void pack_lanes(Sector &sec, const uint32_t *__restrict__ S, const uint32_t *__restrict__ E,
+                                           uint64_t base, uint32_t w, uint32_t m, uint32_t rs, uint32_t ns,
+                                           uint32_t re_m, uint32_t ne) {
+    uint32_t lanes[kBucketLanes];
+#pragma unroll
+    for (uint32_t j = 0; j < kBucketLanes; j++) {
+        uint32_t v = 0x8000u | w;
+        if (j < ns)
+            v = 0x8000u | (uint32_t)((uint64_t)S[rs + j] - base);
+        else if (j < ns + ne)
+            v = 0x8000u | (w + (uint32_t)((uint64_t)E[re_m + (j - ns)] + m - base));
+        lanes[j] = v;
+    }
+#pragma unroll
+    for (int j = 0; j < 6; j++) sec.w[2 + j] = lanes[2 * j] | (lanes[2 * j + 1] << 16);
+}
+
+__device__ __forceinline__ uint32_t lb64(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi, uint64_t key) {
+    return key > 0xFFFFFFFFull ? hi : lower_bound_u32(a, lo, hi, (uint32_t)key);
+}
+
+// One thread per bucket: coherent bisections (neighbouring buckets walk the same path) and one
+// 32-byte sector store.  Overflowing buckets choose their refinement depth and reserve child sectors.
 __global__ void fill_buckets_kernel(const uint32_t *__restrict__ S, const uint32_t *__restrict__ E, uint32_t n,
-                                    uint32_t shift, uint64_t nb, Sector *__restrict__ buckets) {
-    uint64_t B = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                    uint32_t shift, uint32_t margin, uint64_t nb, Sector *__restrict__ buckets,
+                                    unsigned long long *__restrict__ pool_count) {
+    const uint64_t B = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (B > nb) return;
     Sector sec;
-    const uint32_t width = 1u << shift;
-    const uint32_t mask = width - 1u;
-    const uint32_t empty = 0x8000u | width;
+    const uint32_t w = 1u << shift;
     if (B == nb) {  // sentinel: every key is below it
         sec.w[0] = n;
         sec.w[1] = n;
 #pragma unroll
-        for (int j = 2; j < 8; j++) sec.w[j] = empty * 0x10001u;
+        for (int j = 2; j < 8; j++) sec.w[j] = (0x8000u | w) * 0x10001u;
         buckets[B] = sec;
         return;
     }
-    const uint64_t base = B << shift;
-    const uint64_t next = base + width;
-    const uint32_t rs = lower_bound_u32(S, 0, n, (uint32_t)base);
-    const uint32_t re_lo = lower_bound_u32(E, 0, n, (uint32_t)base);
-    const uint32_t rs_next = next > 0xFFFFFFFFull ? n : lower_bound_u32(S, rs, n, (uint32_t)next);
-    const uint32_t re_hi = next > 0xFFFFFFFFull ? n : lower_bound_u32(E, re_lo, n, (uint32_t)next);
-    const uint32_t ns = rs_next - rs, ne = re_hi - re_lo;
+    const uint64_t base = B << shift, next = base + w;
+    const uint64_t lo_m = base >= margin ? base - margin : 0;
+    const uint32_t rs = lb64(S, 0, n, base), rs_next = lb64(S, rs, n, next);
+    const uint32_t re_m = lb64(E, 0, n, lo_m), re_lo = lb64(E, re_m, n, base), re_hi = lb64(E, re_lo, n, next);
+    const uint32_t ns = rs_next - rs, ne = re_hi - re_m;
     sec.w[0] = rs;
     sec.w[1] = re_hi;
-    if (ns + ne > kBucketLanes) {
-#pragma unroll
-        for (int j = 2; j < 8; j++) sec.w[j] = 0xFFFFFFFFu;
-    } else {
-        uint32_t lanes[kBucketLanes];
-#pragma unroll
-        for (uint32_t j = 0; j < kBucketLanes; j++) {
-            uint32_t v = empty;
-            if (j < ns)
-                v = 0x8000u | (S[rs + j] & mask);
-            else if (j < ns + ne)
-                v = 0x8000u | (width + (E[re_lo + (j - ns)] & mask));
-            lanes[j] = v;
-        }
-#pragma unroll
-        for (int j = 0; j < 6; j++) sec.w[2 + j] = lanes[2 * j] | (lanes[2 * j + 1] << 16);
+    if (ns + ne <= kBucketLanes) {
+        // base - m may be negative for bucket 0: the lane offset uses the real margin, not the clamped one
+        pack_lanes(sec, S, E, base, w, margin, rs, ns, re_m, ne);
+        buckets[B] = sec;
+        return;
     }
+    // overflow: find the smallest depth j whose 2^j children all fit (own keys only, no margin);
+    // more children than keys would only waste sectors, so j is capped at ceil(log2(keys))
+    const uint32_t own = ns + (re_hi - re_lo);
+    uint32_t jmax = 0;
+    while ((1u << jmax) < own && jmax < shift) jmax++;
+    uint32_t j = 0;
+    for (uint32_t t = 1; t <= jmax; t++) {
+        const uint32_t cshift = shift - t;
+        uint32_t is = rs, ie = re_lo, worst = 0;
+        for (uint32_t c = 0; c < (1u << t); c++) {
+            const uint64_t cnext = base + ((uint64_t)(c + 1) << cshift);
+            uint32_t cnt = 0;
+            while (is < rs_next && (uint64_t)S[is] < cnext) is++, cnt++;
+            while (ie < re_hi && (uint64_t)E[ie] < cnext) ie++, cnt++;
+            worst = max(worst, cnt);
+        }
+        j = t;
+        if (worst <= kBucketLanes) break;
+    }
+    sec.w[2] = j ? (uint32_t)atomicAdd(pool_count, (unsigned long long)(1u << j)) : kNoChild;
+    sec.w[3] = j;
+    sec.w[4] = rs_next;
+    sec.w[5] = re_lo;
+    sec.w[6] = 0;
+    sec.w[7] = 0xFFFFFFFFu;
     buckets[B] = sec;
+}
+
+// Children of the overflowing buckets (one thread per parent; a parent has 2^j children, j small).
+__global__ void fill_children_kernel(const uint32_t *__restrict__ S, const uint32_t *__restrict__ E, uint32_t n,
+                                     uint32_t shift, uint64_t nb, const Sector *__restrict__ buckets,
+                                     Sector *__restrict__ pool) {
+    const uint64_t B = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (B >= nb) return;
+    const Sector par = buckets[B];
+    if (par.w[7] != 0xFFFFFFFFu || par.w[2] == kNoChild) return;
+    const uint32_t j = par.w[3], cshift = shift - j, cw = 1u << cshift;
+    const uint64_t base = B << shift;
+    uint32_t is = par.w[0], ie = par.w[5];
+    const uint32_t rs_end = par.w[4], re_end = par.w[1];
+    for (uint32_t c = 0; c < (1u << j); c++) {
+        const uint64_t cbase = base + ((uint64_t)c << cshift), cnext = cbase + cw;
+        const uint32_t rs = is, re_lo = ie;
+        while (is < rs_end && (uint64_t)S[is] < cnext) is++;
+        while (ie < re_end && (uint64_t)E[ie] < cnext) ie++;
+        Sector sec;
+        sec.w[0] = rs;
+        sec.w[1] = ie;
+        const uint32_t ns = is - rs, ne = ie - re_lo;
+        if (ns + ne <= kBucketLanes) {
+            pack_lanes(sec, S, E, cbase, cw, 0, rs, ns, re_lo, ne);
+        } else {  // still too many (equal coordinates): leaf, resolved against the sorted arrays
+            sec.w[2] = kNoChild;
+            sec.w[3] = 0;
+            sec.w[4] = is;
+            sec.w[5] = re_lo;
+            sec.w[6] = 0;
+            sec.w[7] = 0xFFFFFFFFu;
+        }
+        pool[par.w[2] + c] = sec;
+    }
 }
 
 struct LenHist {
@@ -184,7 +253,7 @@ bool choose_shift(uint64_t n, uint32_t max_coord, uint32_t flags, uint32_t &shif
     }
     const bool force = (flags & LAPPER_BUILD_FORCE_BUCKETS) != 0;
     if (n < 4096 && !force) return false;
-    const uint64_t target = (2 * n) / 6 > 1024 ? (2 * n) / 6 : 1024;
+    const uint64_t target = (2 * n) / 6 > 1024 ? (2 * n) / 6 : 1024;  // ~6.6 own keys + ~0.8 margin stops per sector
     uint32_t k = 0;
     while (k < kMaxBucketShift && ((uint64_t)(max_coord >> k) + 1) > target) k++;
     const uint64_t nb = (uint64_t)(max_coord >> k) + 1;
@@ -300,6 +369,7 @@ void free_index(DeviceIndex &ix) {
     cudaFree(ix.perm);
     cudaFree(ix.prefix_max);
     cudaFree(ix.buckets);
+    cudaFree(ix.pool);
     ix = DeviceIndex();
 }
 
@@ -310,6 +380,8 @@ void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stre
     ix.max_coord = 0;
     ix.shift = 0xFFFFFFFFu;
     ix.nbuckets = 0;
+    ix.npool = 0;
+    ix.margin = 0;
     ix.ncls = 0;
     if (n == 0) return;
 
@@ -337,11 +409,26 @@ void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stre
     uint32_t shift = 0;
     if (choose_shift(n, ix.max_coord, flags, shift)) {
         ix.shift = shift;
+        ix.margin = shift >= 2 ? (1u << shift) / 4 : 0;
         ix.nbuckets = (uint64_t)(ix.max_coord >> shift) + 1;
+        LAPPER_REQUIRE(ix.nbuckets < (1ull << 31), "bucket table too large");
         ix.buckets = dev_alloc<Sector>(ix.nbuckets + 1, ix.bytes);
+        Scratch<unsigned long long> d_pool_count(1, stream);
+        LAPPER_CUDA_CHECK(cudaMemsetAsync(d_pool_count.p, 0, 8, stream));
         fill_buckets_kernel<<<grid_for(ix.nbuckets + 1), kThreads, 0, stream>>>(
-            ix.starts, ix.stops_sorted, (uint32_t)n, shift, ix.nbuckets, ix.buckets);
+            ix.starts, ix.stops_sorted, (uint32_t)n, shift, ix.margin, ix.nbuckets, ix.buckets, d_pool_count.p);
         LAPPER_CUDA_CHECK(cudaGetLastError());
+        unsigned long long npool = 0;
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(&npool, d_pool_count.p, 8, cudaMemcpyDeviceToHost, stream));
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+        LAPPER_REQUIRE(npool < 0xFFFFFFFFull, "child sector pool too large");
+        ix.npool = npool;
+        if (npool) {
+            ix.pool = dev_alloc<Sector>(npool, ix.bytes);
+            fill_children_kernel<<<grid_for(ix.nbuckets), kThreads, 0, stream>>>(
+                ix.starts, ix.stops_sorted, (uint32_t)n, shift, ix.nbuckets, ix.buckets, ix.pool);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+        }
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
 }

@@ -133,6 +133,39 @@ __device__ __forceinline__ void st_stream_u64(void *p, uint64_t v) {
 }
 
 
+
+// ---- L2 residency control (createpolicy + per-access cache hints)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ Sector ld_sector_hint(const void *p, uint64_t pol) {
+    Sector r;
+    asm volatile("ld.global.nc.L2::cache_hint.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                 : "=r"(r.w[0]), "=r"(r.w[1]), "=r"(r.w[2]), "=r"(r.w[3]), "=r"(r.w[4]), "=r"(r.w[5]), "=r"(r.w[6]),
+                   "=r"(r.w[7])
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ uint4 ld_v4_hint(const void *p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ void st_v4_hint(void *p, uint4 v, uint64_t pol) {
+    asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x),
+                 "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol)
+                 : "memory");
+}
+
 // 256-bit streaming accesses: eight u32 per lane, read or written once (no L1 allocation)
 __device__ __forceinline__ Sector ld_stream_v8(const void *p) { return ld_sector_stream(p); }
 __device__ __forceinline__ void st_stream_v8(void *p, const Sector &v) {

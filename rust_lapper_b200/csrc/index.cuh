@@ -17,25 +17,28 @@
 namespace lap {
 
 // ---- BITS bucket sector -------------------------------------------------------------------------
-// Bucket B covers coordinates [B << shift, (B+1) << shift).  One 32-byte sector (one LDG.E.256,
-// one L2 sector, one L1 wavefront) answers both halves of BITS count for a query whose start and
-// stop fall in the bucket:
-//   w[0]      rs    = #starts        <  (B << shift)
-//   w[1]      re_hi = #sorted stops  <  ((B+1) << shift)
+// Bucket B covers coordinates [base, base + w), base = B << shift, w = 2^shift.  One 32-byte sector
+// (one LDG.E.256, one L2 sector, one L1 wavefront) answers both halves of BITS count for a query
+// whose stop falls in the bucket and whose start is not more than the margin m = w/4 below it:
+//   w[0]      rs    = #starts        <  base
+//   w[1]      re_hi = #sorted stops  <  base + w
 //   w[2..7]   12 x 16-bit lanes, each with guard bit 15 set:
-//               a start s in the bucket  ->  0x8000 | (s & mask)
-//               a stop  e in the bucket  ->  0x8000 | (2^shift + (e & mask))
-//               empty lane               ->  0x8000 | 2^shift
-//   lower_bound(starts, b) = rs    + #{lane value <  (b & mask)}
-//   upper_bound(stops,  a) = re_hi - #{lane value >= 2^shift + (a & mask) + 1}
-// Both lane counts are one packed 16-bit subtract per word: (0x8000|v) - x keeps bit 15 iff v >= x
-// and never borrows across lanes because x <= 2^(shift+1) <= 0x4000.  shift <= 13.
-// A bucket holding more than 12 keys stores 0xFFFF in every lane (overflow marker); such a query
-// bisects starts[rs, rs_next) / stops_sorted[re_lo, re_hi) instead.  Bucket nb is a sentinel
-// (rs = re_hi = n, empty) for coordinates beyond the last key.
+//               a start s in [base, base + w)       ->  0x8000 | (s - base)
+//               a stop  e in [base - m, base + w)   ->  0x8000 | (w + (e - base + m))
+//               empty lane                          ->  0x8000 | w
+//   lower_bound(starts, b) = rs    + 12 - #{lane >= b - base}            for b in the bucket
+//   upper_bound(stops,  a) = re_hi      - #{lane >= w + (a - base + m) + 1}  for a in [base - m, base + w)
+// Both lane counts are one packed 16-bit subtract per word: (0x8000|v) - x keeps bit 15 iff v >= x and
+// never borrows across lanes because x <= 2w + m + 1 < 0x8000 (shift <= 13).
+// A bucket whose lanes would hold more than 12 keys is marked (w[7] = 0xFFFFFFFF) and refined: w[2]
+// points at 2^w[3] child sectors in `pool`, each a sector of the same format for a 2^(shift - w[3])
+// wide slice of the bucket (margin 0); w[4] = #starts < base + w and w[5] = #stops < base bound the
+// bucket's slices of the sorted arrays for the rare child that still overflows (many equal
+// coordinates).  Sector nb is a sentinel (rs = re_hi = n, no lanes) for coordinates beyond the last key.
 constexpr uint32_t kBucketLanes = 12;
 constexpr uint32_t kMaxBucketShift = 13;
 constexpr uint32_t kLaneGuard = 0x80008000u;
+constexpr uint32_t kNoChild = 0xFFFFFFFFu;
 
 struct DeviceIndex {
     uint64_t n = 0;
@@ -46,6 +49,9 @@ struct DeviceIndex {
     uint32_t *prefix_max = nullptr;
     Sector *buckets = nullptr;
     uint64_t nbuckets = 0;  // real buckets; the array has nbuckets + 1 sectors
+    Sector *pool = nullptr;  // child sectors of overflowing buckets
+    uint64_t npool = 0;
+    uint32_t margin = 0;     // stops this far below a bucket are also in its lanes
     uint32_t shift = 0xFFFFFFFFu;
     uint32_t max_len = 0;
     uint32_t max_coord = 0;

@@ -10,6 +10,7 @@
 // arrays are touched only for overflowing buckets.  Without a bucket table (tiny or degenerate
 // sets) the kernels bisect the sorted arrays under a sampled-key directory held in shared memory.
 #include <algorithm>
+#include <cstdlib>
 
 #include "index.cuh"
 
@@ -17,8 +18,14 @@ namespace lap {
 
 namespace {
 
+#ifndef LAPPER_MIN_CTAS
+#define LAPPER_MIN_CTAS 3
+#endif
+#ifndef LAPPER_QPT
+#define LAPPER_QPT 4
+#endif
 constexpr int kThreads = 256;
-constexpr int kQPT = 8;                   // queries per thread: eight independent sector gathers in flight
+constexpr int kQPT = LAPPER_QPT;                   // queries per thread: eight independent sector gathers in flight
 constexpr int kTileQ = kThreads * kQPT;   // queries per CTA tile
 
 struct BucketView {
@@ -26,7 +33,9 @@ struct BucketView {
     const uint32_t *S;
     const uint32_t *E;
     uint32_t n;
+    const Sector *pool;
     uint32_t shift;
+    uint32_t margin;
     uint32_t nb;  // index of the sentinel bucket
 };
 
@@ -80,41 +89,53 @@ __device__ __forceinline__ uint32_t count_le_range(const uint32_t *__restrict__ 
     return c;
 }
 
-// lower_bound(starts, key) given the sector of key's bucket
-__device__ __forceinline__ uint32_t lb_from_sector(const BucketView &v, const Sector &s, uint32_t bucket,
-                                                   uint32_t key) {
-    if (__builtin_expect(sector_overflow(s), 0)) {
-        const uint32_t rs_next = __ldg(reinterpret_cast<const uint32_t *>(v.buckets + bucket + 1));
-        return count_lt_range(v.S, s.w[0], rs_next, key);
-    }
-    const uint32_t mask = (1u << v.shift) - 1u;
-    return s.w[0] + kBucketLanes + (uint32_t)sub_lanes_ge(s, (key & mask) * 0x10001u, 0);
+// lane counts of a (non-overflowing) sector of width w
+__device__ __forceinline__ uint32_t sector_lb(const Sector &s, uint32_t b_rel) {
+    return s.w[0] + kBucketLanes + (uint32_t)sub_lanes_ge(s, b_rel * 0x10001u, 0);
+}
+__device__ __forceinline__ uint32_t sector_ub(const Sector &s, uint32_t w, uint32_t a_rel_plus_margin) {
+    return s.w[1] + (uint32_t)sub_lanes_ge(s, (w + a_rel_plus_margin + 1u) * 0x10001u, 0);
 }
 
-// upper_bound(stops_sorted, key) given the sector of key's bucket
-__device__ __forceinline__ uint32_t ub_from_sector(const BucketView &v, const Sector &s, uint32_t bucket,
-                                                   uint32_t key) {
-    if (__builtin_expect(sector_overflow(s), 0)) {
-        const uint32_t re_lo = bucket ? __ldg(reinterpret_cast<const uint32_t *>(v.buckets + bucket - 1) + 1) : 0u;
-        return count_le_range(v.E, re_lo, s.w[1], key);
+// lower_bound(starts, key) from the sector of key's own bucket, following the refinement if any
+__device__ __forceinline__ uint32_t lb_from_sector(const BucketView &v, const Sector &s, uint32_t key) {
+    const uint32_t low = key & ((1u << v.shift) - 1u);
+    if (__builtin_expect(!sector_overflow(s), 1)) return sector_lb(s, low);
+    if (s.w[2] != kNoChild) {
+        const uint32_t cshift = v.shift - s.w[3];
+        const Sector c = ld_sector_cached(v.pool + s.w[2] + (low >> cshift));
+        if (!sector_overflow(c)) return sector_lb(c, low & ((1u << cshift) - 1u));
+        return count_lt_range(v.S, c.w[0], c.w[4], key);
     }
-    const uint32_t width = 1u << v.shift;
-    return s.w[1] + (uint32_t)sub_lanes_ge(s, (width + (key & (width - 1u)) + 1u) * 0x10001u, 0);
+    return count_lt_range(v.S, s.w[0], s.w[4], key);
+}
+
+// upper_bound(stops_sorted, key) from the sector of key's own bucket
+__device__ __forceinline__ uint32_t ub_from_sector(const BucketView &v, const Sector &s, uint32_t key) {
+    const uint32_t w = 1u << v.shift, low = key & (w - 1u);
+    if (__builtin_expect(!sector_overflow(s), 1)) return sector_ub(s, w, low + v.margin);
+    if (s.w[2] != kNoChild) {
+        const uint32_t cshift = v.shift - s.w[3];
+        const Sector c = ld_sector_cached(v.pool + s.w[2] + (low >> cshift));
+        if (!sector_overflow(c)) return sector_ub(c, 1u << cshift, low & ((1u << cshift) - 1u));
+        return count_le_range(v.E, c.w[5], c.w[1], key);
+    }
+    return count_le_range(v.E, s.w[5], s.w[1], key);
 }
 
 __device__ __forceinline__ uint32_t bucket_of(const BucketView &v, uint32_t x) { return min(x >> v.shift, v.nb); }
 
-// Lapper::count for one query, any case (overflowing buckets bisect the sorted arrays)
+// Lapper::count for one query, any case: each side from its own bucket
 __device__ __forceinline__ void bits_count_slow(const BucketView &v, uint32_t a, uint32_t b, uint32_t &lb,
                                                 uint32_t &ub) {
     const uint32_t bb = bucket_of(v, b), ba = bucket_of(v, a);
     const Sector sb = ld_sector_cached(v.buckets + bb);
-    lb = lb_from_sector(v, sb, bb, b);
+    lb = lb_from_sector(v, sb, b);
     if (ba == bb) {
-        ub = ub_from_sector(v, sb, bb, a);
+        ub = ub_from_sector(v, sb, a);
     } else {
         const Sector sa = ld_sector_cached(v.buckets + ba);
-        ub = ub_from_sector(v, sa, ba, a);
+        ub = ub_from_sector(v, sa, a);
     }
     // src/lib.rs:614: `start + one` wraps to 0 when start == u32::MAX, so `first` is 0 there.
     if (a == 0xFFFFFFFFu) ub = 0;
@@ -140,35 +161,58 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kWQCap = 32 + 32 * kQPT;  // leftovers below one drain + one full iteration of deferrals
 
 template <bool kOut64>
-__device__ __forceinline__ void count_deferred(const BucketView &v, const uint32_t *__restrict__ qs,
-                                               const uint32_t *__restrict__ qe, uint64_t base, uint32_t rel,
+__device__ __forceinline__ void count_deferred(const BucketView &v, uint64_t base, const uint32_t *entry,
                                                uint32_t *__restrict__ o32, uint64_t *__restrict__ o64) {
-    const uint64_t j = base + rel;
     uint32_t lb, ub;
-    bits_count_slow(v, __ldg(qs + j), __ldg(qe + j), lb, ub);
-    store_count<kOut64>(o32, o64, j, lb, ub);
+    bits_count_slow(v, entry[1], entry[2], lb, ub);
+    store_count<kOut64>(o32, o64, base + entry[0], lb, ub);
+}
+
+// at deferral time: pull the child sector an overflowing parent points at into L2, so that the
+// drain (which runs a few iterations later) finds it there
+__device__ __forceinline__ void prefetch_child(const BucketView &v, const Sector &par, uint32_t key) {
+    if (sector_overflow(par) && par.w[2] != kNoChild) {
+        const uint32_t low = key & ((1u << v.shift) - 1u);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(v.pool + par.w[2] + (low >> (v.shift - par.w[3]))));
+    }
+}
+
+// load the kQPT starts and stops this thread owns in tile `tile`
+__device__ __forceinline__ void load_queries(const uint32_t *__restrict__ qs, const uint32_t *__restrict__ qe,
+                                             uint64_t j0, Sector &qa, Sector &qb) {
+    if (kQPT == 8) {
+        qa = ld_stream_v8(qs + j0);
+        qb = ld_stream_v8(qe + j0);
+    } else {
+        const uint64_t pol = l2_policy_evict_first();  // streams must not push the table out of L2
+        const uint4 ta = ld_v4_hint(qs + j0, pol), tb = ld_v4_hint(qe + j0, pol);
+        qa.w[0] = ta.x, qa.w[1] = ta.y, qa.w[2] = ta.z, qa.w[3] = ta.w;
+        qb.w[0] = tb.x, qb.w[1] = tb.y, qb.w[2] = tb.z, qb.w[3] = tb.w;
+    }
 }
 
 template <bool kOut64>
-__global__ void __launch_bounds__(kThreads, 2) count_bucket_kernel(BucketView v, const uint32_t *__restrict__ qs,
+__global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel(BucketView v, const uint32_t *__restrict__ qs,
                                                                    const uint32_t *__restrict__ qe, uint64_t ntiles,
                                                                    uint32_t *__restrict__ o32,
                                                                    uint64_t *__restrict__ o64) {
-    __shared__ uint32_t wqueue[kWarps][kWQCap];
+    __shared__ uint32_t wqueue[kWarps][kWQCap * 3];  // (relative query index, start, stop) per entry
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t *const wq = wqueue[warp];
     uint32_t wq_n = 0;  // warp-uniform
     const uint32_t width = 1u << v.shift, mask = width - 1u;
-    // queue entries are query indices relative to the first tile of this CTA's walk (fits 32 bits:
-    // launch_count never hands one launch more than 2^32 - 1 queries)
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t j0 = tile * kTileQ + (uint64_t)threadIdx.x * kQPT;
-        const Sector qa = ld_stream_v8(qs + j0), qb = ld_stream_v8(qe + j0);
-        uint32_t ba[kQPT], bb[kQPT];
+        if (tile + gridDim.x < ntiles) {  // next tile's queries -> L2 while this one is counted
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(qs + j0 + (uint64_t)gridDim.x * kTileQ));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(qe + j0 + (uint64_t)gridDim.x * kTileQ));
+        }
+        Sector qa, qb;
+        load_queries(qs, qe, j0, qa, qb);
+        uint32_t bb[kQPT];
         Sector sec[kQPT];
 #pragma unroll
         for (int k = 0; k < kQPT; k++) {
-            ba[k] = bucket_of(v, qa.w[k]);
             bb[k] = bucket_of(v, qb.w[k]);
             sec[k] = ld_sector_cached(v.buckets + bb[k]);
         }
@@ -177,13 +221,17 @@ __global__ void __launch_bounds__(kThreads, 2) count_bucket_kernel(BucketView v,
 #pragma unroll
         for (int k = 0; k < kQPT; k++) {
             const uint32_t a = qa.w[k], b = qb.w[k];
-            // lower_bound(starts, b) = rs + 12 - #{lanes >= low(b)}
+            // lower_bound(starts, b) = rs + 12 - #{lanes >= b - base}
             int acc = (int)(sec[k].w[0] + kBucketLanes);
             acc = sub_lanes_ge(sec[k], (b & mask) * 0x10001u, acc);
-            defer |= (uint32_t)sector_overflow(sec[k]) << k;
-            if (ba[k] == bb[k]) {
-                // upper_bound(stops, a) = re_hi - #{lanes >= 2^shift + low(a) + 1}; count = lb - ub
-                int ub = sub_lanes_ge(sec[k], (width + (a & mask) + 1u) * 0x10001u, (int)sec[k].w[1]);
+            if (sector_overflow(sec[k])) {
+                defer |= 1u << k;
+                prefetch_child(v, sec[k], b);
+            }
+            // the same sector also answers the stop side when a lies in [base - margin, base + w)
+            const uint32_t a_rel = a - (bb[k] << v.shift) + v.margin;
+            if (a_rel < width + v.margin && (b >> v.shift) == bb[k]) {
+                int ub = sub_lanes_ge(sec[k], (width + a_rel + 1u) * 0x10001u, (int)sec[k].w[1]);
                 if (a == 0xFFFFFFFFu) ub = 0;  // src/lib.rs:614 wrap
                 res[k] = (uint32_t)(acc - ub);
             } else {
@@ -192,17 +240,21 @@ __global__ void __launch_bounds__(kThreads, 2) count_bucket_kernel(BucketView v,
             }
         }
         if (second) {
+            // start far below the stop's bucket (long or inverted query): its own bucket's sector
 #pragma unroll
             for (int k = 0; k < kQPT; k++)
-                if (second & (1u << k)) sec[k] = ld_sector_cached(v.buckets + ba[k]);
+                if (second & (1u << k)) sec[k] = ld_sector_cached(v.buckets + bucket_of(v, qa.w[k]));
 #pragma unroll
             for (int k = 0; k < kQPT; k++)
                 if (second & (1u << k)) {
                     const uint32_t a = qa.w[k];
-                    int ub = sub_lanes_ge(sec[k], (width + (a & mask) + 1u) * 0x10001u, (int)sec[k].w[1]);
+                    int ub = sub_lanes_ge(sec[k], (width + (a & mask) + v.margin + 1u) * 0x10001u, (int)sec[k].w[1]);
                     if (a == 0xFFFFFFFFu) ub = 0;
                     res[k] -= (uint32_t)ub;
-                    defer |= (uint32_t)sector_overflow(sec[k]) << k;
+                    if (sector_overflow(sec[k])) {
+                        defer |= 1u << k;
+                        prefetch_child(v, sec[k], a);
+                    }
                 }
         }
         if (kOut64) {
@@ -219,11 +271,13 @@ __global__ void __launch_bounds__(kThreads, 2) count_bucket_kernel(BucketView v,
                 }
                 st_stream_v8(o64 + j0 + k, o);
             }
-        } else {
+        } else if (kQPT == 8) {
             Sector o;
 #pragma unroll
             for (int k = 0; k < kQPT; k++) o.w[k] = res[k];
             st_stream_v8(o32 + j0, o);
+        } else {
+            st_v4_hint(o32 + j0, make_uint4(res[0], res[1], res[2], res[3]), l2_policy_evict_first());
         }
         // ---- enqueue this iteration's deferred queries (ballot-free: exclusive scan of per-lane counts)
         const uint32_t mine = __popc(defer);
@@ -236,20 +290,25 @@ __global__ void __launch_bounds__(kThreads, 2) count_bucket_kernel(BucketView v,
             }
             const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
             uint32_t slot = wq_n + inc - mine;
-            const uint32_t rel0 = (uint32_t)(j0 - (uint64_t)blockIdx.x * kTileQ);
+            const uint32_t rel0 = (uint32_t)(j0 - (uint64_t)blockIdx.x * kTileQ);  // incl. the thread's offset
 #pragma unroll
             for (int k = 0; k < kQPT; k++)
-                if (defer & (1u << k)) wq[slot++] = rel0 + k;
+                if (defer & (1u << k)) {
+                    wq[3 * slot] = rel0 + k;
+                    wq[3 * slot + 1] = qa.w[k];
+                    wq[3 * slot + 2] = qb.w[k];
+                    slot++;
+                }
             wq_n += total;
             __syncwarp();  // queue visible to the warp; also orders the vector store above before the drain's stores
             while (wq_n >= 32) {
                 wq_n -= 32;
-                count_deferred<kOut64>(v, qs, qe, (uint64_t)blockIdx.x * kTileQ, wq[wq_n + lane], o32, o64);
+                count_deferred<kOut64>(v, (uint64_t)blockIdx.x * kTileQ, wq + 3 * (wq_n + lane), o32, o64);
             }
             __syncwarp();
         }
     }
-    if (lane < wq_n) count_deferred<kOut64>(v, qs, qe, (uint64_t)blockIdx.x * kTileQ, wq[lane], o32, o64);
+    if (lane < wq_n) count_deferred<kOut64>(v, (uint64_t)blockIdx.x * kTileQ, wq + 3 * lane, o32, o64);
 }
 
 // ---- count, bucket path, any alignment / ragged tail: one query per thread
@@ -360,7 +419,7 @@ __device__ __forceinline__ uint32_t rank_lb_starts(const FindView &f, uint32_t k
     if (f.has_buckets) {
         const uint32_t bk = bucket_of(f.bv, key);
         const Sector s = ld_sector_cached(f.bv.buckets + bk);
-        return lb_from_sector(f.bv, s, bk, key);
+        return lb_from_sector(f.bv, s, key);
     }
     return lower_bound_u32(f.S, 0, f.n, key);
 }
@@ -368,7 +427,7 @@ __device__ __forceinline__ uint32_t rank_ub_stops(const FindView &f, uint32_t ke
     if (f.has_buckets) {
         const uint32_t bk = bucket_of(f.bv, key);
         const Sector s = ld_sector_cached(f.bv.buckets + bk);
-        return ub_from_sector(f.bv, s, bk, key);
+        return ub_from_sector(f.bv, s, key);
     }
     return upper_bound_u32(f.E, 0, f.n, key);
 }
@@ -648,6 +707,8 @@ __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const u
 BucketView make_bucket_view(const DeviceIndex &ix) {
     BucketView v;
     v.buckets = ix.buckets;
+    v.pool = ix.pool;
+    v.margin = ix.margin;
     v.S = ix.starts;
     v.E = ix.stops_sorted;
     v.n = (uint32_t)ix.n;
@@ -710,7 +771,7 @@ void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d
         const uint64_t ntiles = aligned ? nq / kTileQ : 0;
         if (ntiles) {
             // persistent: 148 SMs x 2 resident CTAs (128 registers x 256 threads each)
-            const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, 148 * 2);
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, 148 * LAPPER_MIN_CTAS);
             if (out64)
                 count_bucket_kernel<true><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, ntiles, nullptr, d_out64);
             else

@@ -21,6 +21,9 @@ _ffi.check(lib.lapper_build_u32_dev(C.c_void_p(s.data_ptr()), C.c_void_p(e.data_
 out = torch.empty(nq, dtype=torch.int32, device=dev)
 for name, (qs, qe) in (("random", synth.queries_fixed_len(43, nq, synth.GRCH38, 150, device=dev)),
                        ("sorted", synth.queries_sorted_fixed_len(45, nq, synth.GRCH38, 150, device=dev))):
+    for _ in range(int(os.environ.get("WARM", 2))):
+        _ffi.check(lib.lapper_count_batch_u32_dev(h, C.c_void_p(qs.data_ptr()), C.c_void_p(qe.data_ptr()), nq,
+                                                  C.c_void_p(out.data_ptr()), sp))
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
