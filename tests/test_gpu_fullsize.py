@@ -1,0 +1,163 @@
+"""BASELINE.json's full sizes on the GPU (device-resident, through the `_dev` C-ABI entry points), checked
+through size-independent properties -- the oracle cannot enumerate 100 M queries in test time:
+
+  * count: sum(count) == number of CSR hits find produces for the same queries (the reference's own
+    cross-check idiom, find(..).count() == count(..), src/lib.rs:1028 ff.);
+  * find: offsets start at 0, are non-decreasing, end at the hit total; every query's slice is strictly
+    ascending (iterator order); every emitted position satisfies the overlap predicate (src/lib.rs:140-142);
+  * a random sample of queries is compared bit for bit with the oracle;
+  * cfg 4 (pathological long intervals): count is unaffected by max_len -- same checks on a sample.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+N_IV = 10_000_000
+NQ = 100_000_000
+
+
+def _vp(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _build(lib, s, e, dev):
+    import torch
+
+    from rust_lapper_b200 import _ffi
+
+    h = C.c_void_p(0)
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _ffi.check(lib.lapper_build_u32_dev(_vp(s), _vp(e), s.numel(), dev.index, 0, sp, C.byref(h)))
+    return h, sp
+
+
+def _count(lib, h, qs, qe, sp):
+    import torch
+
+    from rust_lapper_b200 import _ffi
+
+    out = torch.empty(qs.numel(), dtype=torch.int32, device=qs.device)
+    _ffi.check(lib.lapper_count_batch_u32_dev(h, _vp(qs), _vp(qe), qs.numel(), _vp(out), sp))
+    torch.cuda.synchronize()
+    return out
+
+
+def _find(lib, h, qs, qe, sp):
+    import torch
+
+    from rust_lapper_b200 import _ffi
+
+    nq = qs.numel()
+    off = torch.empty(nq + 1, dtype=torch.int64, device=qs.device)
+    total = C.c_uint64(0)
+    _ffi.check(lib.lapper_find_batch_offsets_u32_dev(h, _vp(qs), _vp(qe), nq, _vp(off), C.byref(total), sp))
+    idx = torch.empty(max(int(total.value), 1), dtype=torch.int32, device=qs.device)
+    _ffi.check(lib.lapper_find_batch_fill_u32_dev(h, _vp(qs), _vp(qe), nq, _vp(off), _vp(idx), sp))
+    torch.cuda.synchronize()
+    return off, idx[: int(total.value)], int(total.value)
+
+
+def _check_csr_properties(torch, view, qs, qe, off, idx, total):
+    nq = qs.numel()
+    assert int(off[0]) == 0 and int(off[-1]) == total
+    assert bool((off[1:] >= off[:-1]).all())
+    # strictly ascending inside every query slice: a descent may only happen at a slice boundary
+    if total > 1:
+        descents = torch.nonzero(idx[1:] <= idx[:-1]).flatten() + 1  # positions p with idx[p] <= idx[p-1]
+        if descents.numel():
+            is_boundary = torch.zeros(total + 1, dtype=torch.bool, device=idx.device)
+            is_boundary[off] = True
+            assert bool(is_boundary[descents].all()), "positions not ascending inside a query's slice"
+    # every emitted position overlaps its query: start_i < q_stop and stop_i > q_start
+    owner = torch.repeat_interleave(torch.arange(nq, device=idx.device), (off[1:] - off[:-1]))
+    to_i64 = lambda t: t.to(torch.int64) & 0xFFFFFFFF  # noqa: E731  (u32 stored as int32)
+    s = to_i64(view["starts"][idx.to(torch.int64)])
+    e = to_i64(view["stops"][idx.to(torch.int64)])
+    assert bool(((s < to_i64(qe)[owner]) & (e > to_i64(qs)[owner])).all())
+
+
+@pytest.mark.parametrize("cfg", ["cfg2_random", "cfg3_sorted"])
+def test_full_size_properties(oracle, cfg):
+    import torch
+
+    from rust_lapper_b200 import _ffi, synth
+
+    dev = torch.device("cuda", 0)
+    lib = _ffi.lib()
+    U = synth.GRCH38
+    if cfg == "cfg2_random":
+        s, e = synth.intervals_uniform(42, N_IV, U, 50, 5000, device=dev)
+        qs, qe = synth.queries_fixed_len(43, NQ, U, 150, device=dev)
+        hs, he = synth.intervals_uniform(42, N_IV, U, 50, 5000)
+    else:
+        s, e = synth.intervals_gene_exon(44, N_IV, U, device=dev)
+        qs, qe = synth.queries_sorted_fixed_len(45, NQ, U, 150, device=dev)
+        hs, he = synth.intervals_gene_exon(44, N_IV, U)
+    h, sp = _build(lib, s, e, dev)
+    try:
+        counts = _count(lib, h, qs, qe, sp)
+        off, idx, total = _find(lib, h, qs, qe, sp)
+        assert int(counts.to(torch.int64).sum()) == total  # find(..).count() == count(..), summed
+        assert bool(((off[1:] - off[:-1]) == (counts.to(torch.int64) & 0xFFFFFFFF)).all())
+        # the engine's own sorted arrays, straight from the handle (device view)
+        v = _ffi.DevView()
+        _ffi.check(lib.lapper_get_dev_view(h, C.byref(v)))
+        n = int(v.n)
+        assert n == N_IV
+        host_s, host_e = np.empty(n, np.uint32), np.empty(n, np.uint32)
+        _ffi.check(lib.lapper_get_intervals(h, C.c_void_p(host_s.ctypes.data), C.c_void_p(host_e.ctypes.data), None))
+        assert np.all(np.diff(host_s.astype(np.int64)) >= 0)  # sortedness of the build
+        view = {"starts": torch.from_numpy(host_s.view(np.int32)).to(dev), "stops": torch.from_numpy(host_e.view(np.int32)).to(dev)}
+        _check_csr_properties(torch, view, qs, qe, off, idx, total)
+        # a sample against the oracle, bit for bit
+        rng = np.random.default_rng(1)
+        pick = np.sort(rng.choice(NQ, 200_000, replace=False))
+        pick_t = torch.from_numpy(pick).to(dev)
+        sq, se = synth.to_numpy_u32(qs[pick_t]), synth.to_numpy_u32(qe[pick_t])
+        cpu = oracle.OracleLapper(starts=hs, stops=he)
+        assert np.array_equal(cpu.intervals_soa()[0], host_s) and np.array_equal(cpu.intervals_soa()[1], host_e)
+        want_counts = cpu.count_batch(sq, se, 8)
+        assert np.array_equal(counts[pick_t].cpu().numpy().view(np.uint32).astype(np.uint64), want_counts)
+        woff, widx = cpu.find_batch(sq, se, 8)
+        off_c = off.cpu().numpy()
+        idx_c = idx.cpu().numpy().view(np.uint32)
+        for k in rng.choice(pick.size, 2000, replace=False):
+            j = int(pick[k])
+            assert np.array_equal(idx_c[off_c[j]:off_c[j + 1]], widx[int(woff[k]):int(woff[k + 1])])
+    finally:
+        lib.lapper_free(h)
+
+
+def test_pathological_count_and_find_sample(oracle):
+    """cfg 4: 1 % of intervals span > 50 % of the universe (max_len ~ 0.9 U).  count at 100 M queries is
+    unaffected (BITS); find is checked on a sample (each query has ~70 k hits, so the batch is small)."""
+    import torch
+
+    from rust_lapper_b200 import _ffi, synth
+
+    dev = torch.device("cuda", 0)
+    lib = _ffi.lib()
+    U = synth.GRCH38
+    n = 2_000_000
+    s, e = synth.intervals_pathological(46, n, U, device=dev)
+    hs, he = synth.intervals_pathological(46, n, U)
+    qs, qe = synth.queries_fixed_len(47, NQ, U, 150, device=dev)
+    h, sp = _build(lib, s, e, dev)
+    try:
+        counts = _count(lib, h, qs, qe, sp)
+        cpu = oracle.OracleLapper(starts=hs, stops=he)
+        assert cpu.max_len > U // 2
+        m = 300_000
+        want = cpu.count_batch(synth.to_numpy_u32(qs[:m]), synth.to_numpy_u32(qe[:m]), 8)
+        assert np.array_equal(counts[:m].cpu().numpy().view(np.uint32).astype(np.uint64), want)
+        k = 2_000
+        off, idx, total = _find(lib, h, qs[:k].contiguous(), qe[:k].contiguous(), sp)
+        assert total == int(want[:k].sum())
+        woff, widx = cpu.find_batch(synth.to_numpy_u32(qs[:k]), synth.to_numpy_u32(qe[:k]), 8)
+        assert np.array_equal(off.cpu().numpy().astype(np.uint64), woff)
+        assert np.array_equal(idx.cpu().numpy().view(np.uint32), widx)
+    finally:
+        lib.lapper_free(h)
