@@ -601,11 +601,9 @@ __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t 
     }
 }
 
-// ---- emit.  One query per lane; a warp's 32 consecutive queries own one contiguous slice of the
-// CSR `indices` array, so each lane writes its hits into a per-warp shared-memory stage at
-// (offset - warp base) and the warp then copies the stage out with fully coalesced stores.  Slices
-// that do not fit the stage are written straight to global memory (warp-uniform choice).
-constexpr int kEmitStage = 1536;  // u32 slots per warp: 6 KB, 48 KB per CTA
+constexpr int kEmitCand = 64;                       // candidates a warp can sweep cooperatively
+constexpr int kEmitWarpWords = 1536;                 // u32 words of shared memory per warp (6 KB; 48 KB per CTA)
+constexpr int kEmitStage = kEmitWarpWords - 3 * kEmitCand;  // output slots staged per warp
 
 struct ClassCursor {
     uint32_t cur, end, g;
@@ -618,14 +616,14 @@ __device__ __forceinline__ void cursor_settle(const FindView &f, int c, ClassCur
     k.g = k.cur < k.end ? __ldg(f.cg + f.cls_off[c] + k.cur) : 0xFFFFFFFFu;
 }
 
-template <typename Out>
-__device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, uint32_t b, Out out, uint64_t room) {
+// per-lane emission (any query order): k-way merge of the class hit streams by global position
+__device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, uint32_t b, uint32_t *out, uint64_t room) {
     if (f.ncls == 1) {  // single class: its positions are the global positions
         uint32_t lo, hi;
         class_window(f, 0, a, b, lo, hi);
         for (uint32_t i = lo; i < hi && room; i++)
             if (__ldg(f.ce + i) > a) {
-                out.put(i);
+                *out++ = i;
                 room--;
             }
         return;
@@ -645,7 +643,7 @@ __device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, ui
         const uint32_t m01 = min(k[0].g, k[1].g), m23 = min(k[2].g, k[3].g);
         const uint32_t m = min(m01, m23);
         if (m == 0xFFFFFFFFu) break;
-        out.put(m);
+        *out++ = m;
         room--;
 #pragma unroll
         for (int c = 0; c < 4; c++)
@@ -656,22 +654,23 @@ __device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, ui
     }
 }
 
-struct OutGlobal {
-    uint32_t *p;
-    __device__ __forceinline__ void put(uint32_t v) { *p++ = v; }
-};
-struct OutShared {
-    uint32_t *p;
-    __device__ __forceinline__ void put(uint32_t v) { *p++ = v; }
-};
-
+// ---- emit.  One query per lane; a warp's 32 consecutive queries own one contiguous slice of the CSR
+// `indices` array, so hits are staged in a per-warp shared-memory slice at (offset - warp base) and
+// copied out with fully coalesced stores.
+// Fast path (start-sorted or otherwise clustered queries): the 32 queries share nearly all their
+// candidates, so the warp gathers the UNION of the class windows once -- at most kEmitCand
+// intervals --, ranks them by global position (their merged order), and every lane then sweeps that one
+// sorted list with broadcast shared-memory reads, appending the candidates that overlap its own query.
+// Slow path (union too large: random-order queries, very long intervals): each lane merges its own
+// class streams.  Either way the order is the reference iterator's (ascending position).
 __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const uint32_t *__restrict__ qs,
                                                              const uint32_t *__restrict__ qe, uint64_t nq,
                                                              const uint64_t *__restrict__ offsets,
                                                              uint32_t *__restrict__ indices) {
-    __shared__ uint32_t stage_all[kThreads / 32][kEmitStage];
+    __shared__ uint32_t smem_all[kThreads / 32][kEmitWarpWords];
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t *const stage = stage_all[threadIdx.x >> 5];
+    uint32_t *const stage = smem_all[threadIdx.x >> 5];       // kEmitStage output slots ...
+    uint32_t *const sorted = stage + kEmitStage;               // ... then kEmitCand x (start, stop, position)
     const uint64_t nwarps = (uint64_t)gridDim.x * (kThreads / 32);
     const uint64_t nchunks = div_up(nq, 32);
     for (uint64_t chunk = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); chunk < nchunks; chunk += nwarps) {
@@ -688,18 +687,72 @@ __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const u
         const uint64_t wend = __shfl_sync(0xFFFFFFFFu, o1, last_lane);
         const uint64_t wtotal = wend - wbase;
         if (wtotal == 0) continue;
-        uint32_t a = 0, b = 0;
-        if (live && o1 > o0) {
+        const bool mine = live && o1 > o0;
+        uint32_t a = 0xFFFFFFFFu, b = 0;
+        if (mine) {
             a = ld_stream_u32(qs + j);
             b = ld_stream_u32(qe + j);
         }
-        if (wtotal <= kEmitStage) {
-            if (live && o1 > o0) emit_one_query(f, a, b, OutShared{stage + (o0 - wbase)}, o1 - o0);
+        const bool staged = wtotal <= kEmitStage;
+        // ---- union of the class windows over the queries that have hits
+        const uint32_t amin = __reduce_min_sync(0xFFFFFFFFu, a), bmax = __reduce_max_sync(0xFFFFFFFFu, b);
+        uint32_t r = 0;
+        if (lane < 8 && (lane & 3u) < f.ncls) {
+            const int c = (int)(lane & 3u);
+            r = class_lb(f, c, (lane >> 2) ? bmax : (amin >= f.cls_maxlen[c] ? amin - f.cls_maxlen[c] : 0u));
+        }
+        uint32_t lo[4], cnt[4], T = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            lo[c] = __shfl_sync(0xFFFFFFFFu, r, c);
+            const uint32_t hi = __shfl_sync(0xFFFFFFFFu, r, c + 4);
+            cnt[c] = hi > lo[c] ? hi - lo[c] : 0u;
+            T += cnt[c];
+        }
+        if (staged && T <= kEmitCand) {
+            // raw candidates (class-major) into the head of the stage area, which is still unused
+            uint32_t *const raw = stage;
+            for (uint32_t i = lane; i < T; i += 32) {
+                uint32_t c = 0, base = 0;  // class of candidate i and the index of that class's first candidate
+                if (i >= cnt[0]) {
+                    c = 1, base = cnt[0];
+                    if (i >= base + cnt[1]) {
+                        c = 2, base += cnt[1];
+                        if (i >= base + cnt[2]) c = 3, base += cnt[2];
+                    }
+                }
+                const uint32_t p = f.cls_off[c] + lo[c] + (i - base);
+                raw[i] = __ldg(f.cg + p);
+                raw[kEmitCand + i] = __ldg(f.cs + p);
+                raw[2 * kEmitCand + i] = __ldg(f.ce + p);
+            }
+            __syncwarp();
+            // merged order = rank of the global position among all candidates (positions are distinct)
+            for (uint32_t i = lane; i < T; i += 32) {
+                const uint32_t g = raw[i];
+                uint32_t rank = 0;
+                for (uint32_t x = 0; x < T; x++) rank += (raw[x] < g);
+                sorted[3 * rank] = raw[kEmitCand + i];
+                sorted[3 * rank + 1] = raw[2 * kEmitCand + i];
+                sorted[3 * rank + 2] = g;
+            }
+            __syncwarp();
+            // every lane sweeps the sorted candidates for its own query (broadcast reads)
+            uint32_t cur = (uint32_t)(o0 - wbase);
+            for (uint32_t x = 0; x < T; x++) {
+                const uint32_t s = sorted[3 * x], e = sorted[3 * x + 1];
+                if (s < b && e > a) stage[cur++] = sorted[3 * x + 2];  // src/lib.rs:140-142
+            }
+            __syncwarp();
+            for (uint32_t i = lane; i < (uint32_t)wtotal; i += 32) indices[wbase + i] = stage[i];
+            __syncwarp();
+        } else if (staged) {
+            if (mine) emit_one_query(f, a, b, stage + (o0 - wbase), o1 - o0);
             __syncwarp();
             for (uint32_t i = lane; i < (uint32_t)wtotal; i += 32) indices[wbase + i] = stage[i];
             __syncwarp();
         } else {
-            if (live && o1 > o0) emit_one_query(f, a, b, OutGlobal{indices + o0}, o1 - o0);
+            if (mine) emit_one_query(f, a, b, indices + o0, o1 - o0);
         }
     }
 }
