@@ -12,6 +12,28 @@
 
 using namespace lap;
 
+namespace lap {
+cudaMemPool_t scratch_pool() {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    int dev = 0;
+    LAPPER_CUDA_CHECK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64) throw Error(LAPPER_ERR_INVALID_ARG, "device index out of range for the scratch pool");
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        LAPPER_CUDA_CHECK(cudaMemPoolCreate(&pools[dev], &props));
+        uint64_t keep = ~0ull;
+        LAPPER_CUDA_CHECK(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    return pools[dev];
+}
+}  // namespace lap
+
 namespace {
 
 thread_local std::string g_last_error;

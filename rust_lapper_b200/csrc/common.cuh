@@ -52,7 +52,11 @@ struct DeviceGuard {
     }
 };
 
-// Stream-ordered scratch buffer.
+// Stream-ordered scratch memory from a library-owned pool (one per device).  The release threshold is
+// "never": a batch call that needs 400 MB of scratch gets it back from the pool on the next call
+// instead of from the driver (which costs about a millisecond per call).
+cudaMemPool_t scratch_pool();  // api.cu
+
 template <typename T>
 struct Scratch {
     T *p = nullptr;
@@ -63,7 +67,7 @@ struct Scratch {
         release();
         s = stream;
         if (count == 0) count = 1;
-        LAPPER_CUDA_CHECK(cudaMallocAsync((void **)&p, count * sizeof(T), stream));
+        LAPPER_CUDA_CHECK(cudaMallocFromPoolAsync((void **)&p, count * sizeof(T), scratch_pool(), stream));
     }
     void release() {
         if (p) cudaFreeAsync(p, s);

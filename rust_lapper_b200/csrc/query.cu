@@ -150,246 +150,6 @@ __device__ __forceinline__ void store_count(uint32_t *o32, uint64_t *o64, uint64
         st_stream_u32(o32 + j, lb - ub);
 }
 
-// ---- count, bucket path, full tiles.  Persistent CTAs walk tiles of 2048 queries; each thread owns
-// eight consecutive queries: two 256-bit loads (starts, stops), eight independent sector gathers
-// (LDG.E.256), a second predicated round for the ~15 % of queries whose start falls in another
-// bucket than their stop, one 256-bit store.  Queries that meet an overflowing bucket are NOT
-// resolved in line (that would serialise a divergent search behind every warp): their index goes to
-// a per-warp shared-memory queue, and whenever a warp has 32 of them it resolves them one per lane.
-// No CTA barrier anywhere in the loop.
-constexpr int kWarps = kThreads / 32;
-constexpr int kWQCap = 32 + 32 * kQPT;  // leftovers below one drain + one full iteration of deferrals
-
-template <bool kOut64>
-__device__ __forceinline__ void count_deferred(const BucketView &v, uint64_t base, const uint32_t *entry,
-                                               uint32_t *__restrict__ o32, uint64_t *__restrict__ o64) {
-    uint32_t lb, ub;
-    bits_count_slow(v, entry[1], entry[2], lb, ub);
-    store_count<kOut64>(o32, o64, base + entry[0], lb, ub);
-}
-
-// at deferral time: pull the child sector an overflowing parent points at into L2, so that the
-// drain (which runs a few iterations later) finds it there
-__device__ __forceinline__ void prefetch_child(const BucketView &v, const Sector &par, uint32_t key) {
-    if (sector_overflow(par) && par.w[2] != kNoChild) {
-        const uint32_t low = key & ((1u << v.shift) - 1u);
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(v.pool + par.w[2] + (low >> (v.shift - par.w[3]))));
-    }
-}
-
-// load the kQPT starts and stops this thread owns in tile `tile`
-__device__ __forceinline__ void load_queries(const uint32_t *__restrict__ qs, const uint32_t *__restrict__ qe,
-                                             uint64_t j0, Sector &qa, Sector &qb) {
-    if (kQPT == 8) {
-        qa = ld_stream_v8(qs + j0);
-        qb = ld_stream_v8(qe + j0);
-    } else {
-        const uint64_t pol = l2_policy_evict_first();  // streams must not push the table out of L2
-        const uint4 ta = ld_v4_hint(qs + j0, pol), tb = ld_v4_hint(qe + j0, pol);
-        qa.w[0] = ta.x, qa.w[1] = ta.y, qa.w[2] = ta.z, qa.w[3] = ta.w;
-        qb.w[0] = tb.x, qb.w[1] = tb.y, qb.w[2] = tb.z, qb.w[3] = tb.w;
-    }
-}
-
-template <bool kOut64>
-__global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel(BucketView v, const uint32_t *__restrict__ qs,
-                                                                   const uint32_t *__restrict__ qe, uint64_t ntiles,
-                                                                   uint32_t *__restrict__ o32,
-                                                                   uint64_t *__restrict__ o64) {
-    __shared__ uint32_t wqueue[kWarps][kWQCap * 3];  // (relative query index, start, stop) per entry
-    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t *const wq = wqueue[warp];
-    uint32_t wq_n = 0;  // warp-uniform
-    const uint32_t width = 1u << v.shift, mask = width - 1u;
-    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const uint64_t j0 = tile * kTileQ + (uint64_t)threadIdx.x * kQPT;
-        if (tile + gridDim.x < ntiles) {  // next tile's queries -> L2 while this one is counted
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(qs + j0 + (uint64_t)gridDim.x * kTileQ));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(qe + j0 + (uint64_t)gridDim.x * kTileQ));
-        }
-        Sector qa, qb;
-        load_queries(qs, qe, j0, qa, qb);
-        uint32_t bb[kQPT];
-        Sector sec[kQPT];
-#pragma unroll
-        for (int k = 0; k < kQPT; k++) {
-            bb[k] = bucket_of(v, qb.w[k]);
-            sec[k] = ld_sector_cached(v.buckets + bb[k]);
-        }
-        uint32_t res[kQPT];
-        uint32_t defer = 0, second = 0;
-#pragma unroll
-        for (int k = 0; k < kQPT; k++) {
-            const uint32_t a = qa.w[k], b = qb.w[k];
-            // lower_bound(starts, b) = rs + 12 - #{lanes >= b - base}
-            int acc = (int)(sec[k].w[0] + kBucketLanes);
-            acc = sub_lanes_ge(sec[k], (b & mask) * 0x10001u, acc);
-            if (sector_overflow(sec[k])) {
-                defer |= 1u << k;
-                prefetch_child(v, sec[k], b);
-            }
-            // the same sector also answers the stop side when a lies in [base - margin, base + w)
-            const uint32_t a_rel = a - (bb[k] << v.shift) + v.margin;
-            if (a_rel < width + v.margin && (b >> v.shift) == bb[k]) {
-                int ub = sub_lanes_ge(sec[k], (width + a_rel + 1u) * 0x10001u, (int)sec[k].w[1]);
-                if (a == 0xFFFFFFFFu) ub = 0;  // src/lib.rs:614 wrap
-                res[k] = (uint32_t)(acc - ub);
-            } else {
-                res[k] = (uint32_t)acc;
-                second |= 1u << k;
-            }
-        }
-        if (second) {
-            // start far below the stop's bucket (long or inverted query): its own bucket's sector
-#pragma unroll
-            for (int k = 0; k < kQPT; k++)
-                if (second & (1u << k)) sec[k] = ld_sector_cached(v.buckets + bucket_of(v, qa.w[k]));
-#pragma unroll
-            for (int k = 0; k < kQPT; k++)
-                if (second & (1u << k)) {
-                    const uint32_t a = qa.w[k];
-                    int ub = sub_lanes_ge(sec[k], (width + (a & mask) + v.margin + 1u) * 0x10001u, (int)sec[k].w[1]);
-                    if (a == 0xFFFFFFFFu) ub = 0;
-                    res[k] -= (uint32_t)ub;
-                    if (sector_overflow(sec[k])) {
-                        defer |= 1u << k;
-                        prefetch_child(v, sec[k], a);
-                    }
-                }
-        }
-        if (kOut64) {
-#pragma unroll
-            for (int k = 0; k < kQPT; k += 4) {
-                // a negative difference only arises from an inverted query or interval; it must widen the
-                // way usize wraps, which needs lb and ub separately -> such queries take the deferred path
-                Sector o;
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    o.w[2 * q] = res[k + q];
-                    o.w[2 * q + 1] = 0;
-                    defer |= (uint32_t)((int32_t)res[k + q] < 0) << (k + q);
-                }
-                st_stream_v8(o64 + j0 + k, o);
-            }
-        } else if (kQPT == 8) {
-            Sector o;
-#pragma unroll
-            for (int k = 0; k < kQPT; k++) o.w[k] = res[k];
-            st_stream_v8(o32 + j0, o);
-        } else {
-            st_v4_hint(o32 + j0, make_uint4(res[0], res[1], res[2], res[3]), l2_policy_evict_first());
-        }
-        // ---- enqueue this iteration's deferred queries (ballot-free: exclusive scan of per-lane counts)
-        const uint32_t mine = __popc(defer);
-        if (__any_sync(0xFFFFFFFFu, mine != 0)) {
-            uint32_t inc = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-                if (lane >= (uint32_t)o) inc += y;
-            }
-            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-            uint32_t slot = wq_n + inc - mine;
-            const uint32_t rel0 = (uint32_t)(j0 - (uint64_t)blockIdx.x * kTileQ);  // incl. the thread's offset
-#pragma unroll
-            for (int k = 0; k < kQPT; k++)
-                if (defer & (1u << k)) {
-                    wq[3 * slot] = rel0 + k;
-                    wq[3 * slot + 1] = qa.w[k];
-                    wq[3 * slot + 2] = qb.w[k];
-                    slot++;
-                }
-            wq_n += total;
-            __syncwarp();  // queue visible to the warp; also orders the vector store above before the drain's stores
-            while (wq_n >= 32) {
-                wq_n -= 32;
-                count_deferred<kOut64>(v, (uint64_t)blockIdx.x * kTileQ, wq + 3 * (wq_n + lane), o32, o64);
-            }
-            __syncwarp();
-        }
-    }
-    if (lane < wq_n) count_deferred<kOut64>(v, (uint64_t)blockIdx.x * kTileQ, wq + 3 * lane, o32, o64);
-}
-
-// ---- count, bucket path, any alignment / ragged tail: one query per thread
-template <bool kOut64>
-__global__ void __launch_bounds__(kThreads) count_bucket_tail_kernel(BucketView v, const uint32_t *__restrict__ qs,
-                                                                     const uint32_t *__restrict__ qe, uint64_t nq,
-                                                                     uint32_t *__restrict__ o32,
-                                                                     uint64_t *__restrict__ o64) {
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t lb, ub;
-        bits_count_slow(v, ld_stream_u32(qs + j), ld_stream_u32(qe + j), lb, ub);
-        store_count<kOut64>(o32, o64, j, lb, ub);
-    }
-}
-
-// ---- count, direct path: bisect the sorted arrays under a sampled-key directory in shared memory
-// (every 2^dshift-th key; the top levels of both searches never leave the SM).
-constexpr uint32_t kDirSlots = 2048;
-
-struct PlainView {
-    const uint32_t *S;
-    const uint32_t *E;
-    uint32_t n;
-    uint32_t dshift;  // directory stride = 2^dshift
-    uint32_t nsamp;   // ceil(n / stride) <= kDirSlots
-};
-
-__device__ __forceinline__ uint32_t dir_count_lt(const uint32_t *dir, uint32_t key) {
-    // #directory keys < key; dir is padded with 0xFFFFFFFF up to kDirSlots (a power of two)
-    uint32_t pos = 0;
-#pragma unroll
-    for (uint32_t step = kDirSlots >> 1; step > 0; step >>= 1) pos += (dir[pos + step - 1] < key) ? step : 0u;
-    return pos + (dir[pos] < key ? 1u : 0u);
-}
-__device__ __forceinline__ uint32_t dir_count_le(const uint32_t *dir, uint32_t nsamp, uint32_t key) {
-    uint32_t lo = 0, hi = nsamp;  // padding equals 0xFFFFFFFF and must not count when key == 0xFFFFFFFF
-    while (lo < hi) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (dir[mid] <= key)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    return lo;
-}
-
-__device__ __forceinline__ uint32_t plain_lb(const PlainView &v, const uint32_t *dirS, uint32_t key) {
-    const uint32_t j = min(dir_count_lt(dirS, key), v.nsamp);
-    const uint32_t lo = j ? (j - 1) << v.dshift : 0u;
-    const uint32_t hi = min(j << v.dshift, v.n);
-    return lower_bound_u32(v.S, lo, hi, key);
-}
-__device__ __forceinline__ uint32_t plain_ub(const PlainView &v, const uint32_t *dirE, uint32_t key) {
-    const uint32_t j = dir_count_le(dirE, v.nsamp, key);
-    const uint32_t lo = j ? (j - 1) << v.dshift : 0u;
-    const uint32_t hi = min(j << v.dshift, v.n);
-    return upper_bound_u32(v.E, lo, hi, key);
-}
-
-template <bool kOut64>
-__global__ void __launch_bounds__(kThreads) count_plain_kernel(PlainView v, const uint32_t *__restrict__ qs,
-                                                               const uint32_t *__restrict__ qe, uint64_t nq,
-                                                               uint32_t *__restrict__ o32,
-                                                               uint64_t *__restrict__ o64) {
-    __shared__ uint32_t dirS[kDirSlots];
-    __shared__ uint32_t dirE[kDirSlots];
-    for (uint32_t i = threadIdx.x; i < kDirSlots; i += blockDim.x) {
-        const bool ok = i < v.nsamp;
-        dirS[i] = ok ? __ldg(v.S + ((uint64_t)i << v.dshift)) : 0xFFFFFFFFu;
-        dirE[i] = ok ? __ldg(v.E + ((uint64_t)i << v.dshift)) : 0xFFFFFFFFu;
-    }
-    __syncthreads();
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t a = ld_stream_u32(qs + j), b = ld_stream_u32(qe + j);
-        const uint32_t lb = v.n ? plain_lb(v, dirS, b) : 0u;
-        uint32_t ub = v.n ? plain_ub(v, dirE, a) : 0u;
-        if (a == 0xFFFFFFFFu) ub = 0;  // src/lib.rs:614 wrap
-        store_count<kOut64>(o32, o64, j, lb, ub);
-    }
-}
-
 // ------------------------------------------------------------------------------------- find
 // find(a, b) = ascending i with start_i < b and stop_i > a (src/lib.rs:704-717; the start offset
 // :632-635 and the early break :712-713 only prune).  The reference scans one window
@@ -477,8 +237,288 @@ __device__ __forceinline__ uint32_t find_count_one(const FindView &f, uint32_t a
     return find_count_scan(f, a, b);
 }
 
+
+// ---- count, bucket path, full tiles.  Persistent CTAs walk tiles of 2048 queries; each thread owns
+// eight consecutive queries: two 256-bit loads (starts, stops), eight independent sector gathers
+// (LDG.E.256), a second predicated round for the ~15 % of queries whose start falls in another
+// bucket than their stop, one 256-bit store.  Queries that meet an overflowing bucket are NOT
+// resolved in line (that would serialise a divergent search behind every warp): their index goes to
+// a per-warp shared-memory queue, and whenever a warp has 32 of them it resolves them one per lane.
+// No CTA barrier anywhere in the loop.
+constexpr int kWarps = kThreads / 32;
+constexpr int kWQCap = 32 + 32 * kQPT;  // leftovers below one drain + one full iteration of deferrals
+
 constexpr int kFindQPT = 4;
-constexpr int kFindTile = kThreads * kFindQPT;
+constexpr int kFindTile = 256 * kFindQPT;  // queries per tile of the offsets scan
+static_assert(kFindTile == kTileQ, "find's offsets tiles must coincide with the count kernel's tiles");
+
+template <bool kOut64, bool kFind>
+__device__ __forceinline__ void count_deferred(const BucketView &v, const FindView &f, uint64_t base,
+                                               const uint32_t *entry, uint32_t *__restrict__ o32,
+                                               uint64_t *__restrict__ o64, uint64_t *__restrict__ tile_sums) {
+    const uint64_t j = base + entry[0];
+    if (kFind) {
+        // find mode: the number of positions find() yields (BITS count when it is exact, the predicate otherwise)
+        const uint32_t c = find_count_one(f, entry[1], entry[2]);
+        o32[j] = c;
+        if (c) atomicAdd(reinterpret_cast<unsigned long long *>(tile_sums + j / kFindTile), (unsigned long long)c);
+    } else {
+        uint32_t lb, ub;
+        bits_count_slow(v, entry[1], entry[2], lb, ub);
+        store_count<kOut64>(o32, o64, j, lb, ub);
+    }
+}
+
+// at deferral time: pull the child sector an overflowing parent points at into L2, so that the
+// drain (which runs a few iterations later) finds it there
+__device__ __forceinline__ void prefetch_child(const BucketView &v, const Sector &par, uint32_t key) {
+    if (sector_overflow(par) && par.w[2] != kNoChild) {
+        const uint32_t low = key & ((1u << v.shift) - 1u);
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(v.pool + par.w[2] + (low >> (v.shift - par.w[3]))));
+    }
+}
+
+// load the kQPT starts and stops this thread owns in tile `tile`
+__device__ __forceinline__ void load_queries(const uint32_t *__restrict__ qs, const uint32_t *__restrict__ qe,
+                                             uint64_t j0, Sector &qa, Sector &qb) {
+    if (kQPT == 8) {
+        qa = ld_stream_v8(qs + j0);
+        qb = ld_stream_v8(qe + j0);
+    } else {
+        const uint64_t pol = l2_policy_evict_first();  // streams must not push the table out of L2
+        const uint4 ta = ld_v4_hint(qs + j0, pol), tb = ld_v4_hint(qe + j0, pol);
+        qa.w[0] = ta.x, qa.w[1] = ta.y, qa.w[2] = ta.z, qa.w[3] = ta.w;
+        qb.w[0] = tb.x, qb.w[1] = tb.y, qb.w[2] = tb.z, qb.w[3] = tb.w;
+    }
+}
+
+// kFind: "find mode" for the offsets pass of find_batch -- the same counts (u32), plus per-tile sums
+// accumulated into tile_sums (zeroed by the caller) and queries outside the validity of BITS for find
+// (start >= stop) sent to the deferred path, where they are counted by the overlap predicate.
+template <bool kOut64, bool kFind>
+__global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel(BucketView v, const FindView f,
+                                                                   const uint32_t *__restrict__ qs,
+                                                                   const uint32_t *__restrict__ qe, uint64_t ntiles,
+                                                                   uint32_t *__restrict__ o32,
+                                                                   uint64_t *__restrict__ o64,
+                                                                   uint64_t *__restrict__ tile_sums) {
+    __shared__ uint32_t wqueue[kWarps][kWQCap * 3];  // (relative query index, start, stop) per entry
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t *const wq = wqueue[warp];
+    uint32_t wq_n = 0;  // warp-uniform
+    const uint32_t width = 1u << v.shift, mask = width - 1u;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t j0 = tile * kTileQ + (uint64_t)threadIdx.x * kQPT;
+        if (tile + gridDim.x < ntiles) {  // next tile's queries -> L2 while this one is counted
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(qs + j0 + (uint64_t)gridDim.x * kTileQ));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(qe + j0 + (uint64_t)gridDim.x * kTileQ));
+        }
+        Sector qa, qb;
+        load_queries(qs, qe, j0, qa, qb);
+        uint32_t bb[kQPT];
+        Sector sec[kQPT];
+#pragma unroll
+        for (int k = 0; k < kQPT; k++) {
+            bb[k] = bucket_of(v, qb.w[k]);
+            sec[k] = ld_sector_cached(v.buckets + bb[k]);
+        }
+        uint32_t res[kQPT];
+        uint32_t defer = 0, second = 0;
+#pragma unroll
+        for (int k = 0; k < kQPT; k++) {
+            const uint32_t a = qa.w[k], b = qb.w[k];
+            // lower_bound(starts, b) = rs + 12 - #{lanes >= b - base}
+            int acc = (int)(sec[k].w[0] + kBucketLanes);
+            acc = sub_lanes_ge(sec[k], (b & mask) * 0x10001u, acc);
+            if (sector_overflow(sec[k])) {
+                defer |= 1u << k;
+                prefetch_child(v, sec[k], b);
+            }
+            // the same sector also answers the stop side when a lies in [base - margin, base + w)
+            const uint32_t a_rel = a - (bb[k] << v.shift) + v.margin;
+            if (a_rel < width + v.margin && (b >> v.shift) == bb[k]) {
+                int ub = sub_lanes_ge(sec[k], (width + a_rel + 1u) * 0x10001u, (int)sec[k].w[1]);
+                if (a == 0xFFFFFFFFu) ub = 0;  // src/lib.rs:614 wrap
+                res[k] = (uint32_t)(acc - ub);
+            } else {
+                res[k] = (uint32_t)acc;
+                second |= 1u << k;
+            }
+        }
+        if (kFind) {
+#pragma unroll
+            for (int k = 0; k < kQPT; k++) defer |= (uint32_t)(!(qa.w[k] < qb.w[k])) << k;
+        }
+        if (second) {
+            // start far below the stop's bucket (long or inverted query): its own bucket's sector
+#pragma unroll
+            for (int k = 0; k < kQPT; k++)
+                if (second & (1u << k)) sec[k] = ld_sector_cached(v.buckets + bucket_of(v, qa.w[k]));
+#pragma unroll
+            for (int k = 0; k < kQPT; k++)
+                if (second & (1u << k)) {
+                    const uint32_t a = qa.w[k];
+                    int ub = sub_lanes_ge(sec[k], (width + (a & mask) + v.margin + 1u) * 0x10001u, (int)sec[k].w[1]);
+                    if (a == 0xFFFFFFFFu) ub = 0;
+                    res[k] -= (uint32_t)ub;
+                    if (sector_overflow(sec[k])) {
+                        defer |= 1u << k;
+                        prefetch_child(v, sec[k], a);
+                    }
+                }
+        }
+        if (kOut64) {
+#pragma unroll
+            for (int k = 0; k < kQPT; k += 4) {
+                // a negative difference only arises from an inverted query or interval; it must widen the
+                // way usize wraps, which needs lb and ub separately -> such queries take the deferred path
+                Sector o;
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    o.w[2 * q] = res[k + q];
+                    o.w[2 * q + 1] = 0;
+                    defer |= (uint32_t)((int32_t)res[k + q] < 0) << (k + q);
+                }
+                st_stream_v8(o64 + j0 + k, o);
+            }
+        } else if (kQPT == 8) {
+            Sector o;
+#pragma unroll
+            for (int k = 0; k < kQPT; k++) o.w[k] = res[k];
+            st_stream_v8(o32 + j0, o);
+        } else {
+            st_v4_hint(o32 + j0, make_uint4(res[0], res[1], res[2], res[3]), l2_policy_evict_first());
+        }
+        if (kFind) {
+            // this warp's contribution to its tile's hit total (deferred queries add theirs when resolved)
+            uint64_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < kQPT; k++) sum += (defer & (1u << k)) ? 0u : res[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+            if (lane == 0 && sum) atomicAdd(reinterpret_cast<unsigned long long *>(tile_sums + tile), (unsigned long long)sum);
+        }
+        // ---- enqueue this iteration's deferred queries (ballot-free: exclusive scan of per-lane counts)
+        const uint32_t mine = __popc(defer);
+        if (__any_sync(0xFFFFFFFFu, mine != 0)) {
+            uint32_t inc = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
+            }
+            const uint32_t total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+            uint32_t slot = wq_n + inc - mine;
+            const uint32_t rel0 = (uint32_t)(j0 - (uint64_t)blockIdx.x * kTileQ);  // incl. the thread's offset
+#pragma unroll
+            for (int k = 0; k < kQPT; k++)
+                if (defer & (1u << k)) {
+                    wq[3 * slot] = rel0 + k;
+                    wq[3 * slot + 1] = qa.w[k];
+                    wq[3 * slot + 2] = qb.w[k];
+                    slot++;
+                }
+            wq_n += total;
+            __syncwarp();  // queue visible to the warp; also orders the vector store above before the drain's stores
+            while (wq_n >= 32) {
+                wq_n -= 32;
+                count_deferred<kOut64, kFind>(v, f, (uint64_t)blockIdx.x * kTileQ, wq + 3 * (wq_n + lane), o32, o64, tile_sums);
+            }
+            __syncwarp();
+        }
+    }
+    if (lane < wq_n) count_deferred<kOut64, kFind>(v, f, (uint64_t)blockIdx.x * kTileQ, wq + 3 * lane, o32, o64, tile_sums);
+}
+
+// ---- count, bucket path, any alignment / ragged tail: one query per thread
+template <bool kOut64, bool kFind>
+__global__ void __launch_bounds__(kThreads) count_bucket_tail_kernel(BucketView v, const FindView f,
+                                                                     const uint32_t *__restrict__ qs,
+                                                                     const uint32_t *__restrict__ qe, uint64_t first,
+                                                                     uint64_t nq, uint32_t *__restrict__ o32,
+                                                                     uint64_t *__restrict__ o64,
+                                                                     uint64_t *__restrict__ tile_sums) {
+    for (uint64_t j = first + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq;
+         j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = ld_stream_u32(qs + j), b = ld_stream_u32(qe + j);
+        if (kFind) {
+            const uint32_t c = find_count_one(f, a, b);
+            o32[j] = c;
+            if (c) atomicAdd(reinterpret_cast<unsigned long long *>(tile_sums + j / kFindTile), (unsigned long long)c);
+        } else {
+            uint32_t lb, ub;
+            bits_count_slow(v, a, b, lb, ub);
+            store_count<kOut64>(o32, o64, j, lb, ub);
+        }
+    }
+}
+
+// ---- count, direct path: bisect the sorted arrays under a sampled-key directory in shared memory
+// (every 2^dshift-th key; the top levels of both searches never leave the SM).
+constexpr uint32_t kDirSlots = 2048;
+
+struct PlainView {
+    const uint32_t *S;
+    const uint32_t *E;
+    uint32_t n;
+    uint32_t dshift;  // directory stride = 2^dshift
+    uint32_t nsamp;   // ceil(n / stride) <= kDirSlots
+};
+
+__device__ __forceinline__ uint32_t dir_count_lt(const uint32_t *dir, uint32_t key) {
+    // #directory keys < key; dir is padded with 0xFFFFFFFF up to kDirSlots (a power of two)
+    uint32_t pos = 0;
+#pragma unroll
+    for (uint32_t step = kDirSlots >> 1; step > 0; step >>= 1) pos += (dir[pos + step - 1] < key) ? step : 0u;
+    return pos + (dir[pos] < key ? 1u : 0u);
+}
+__device__ __forceinline__ uint32_t dir_count_le(const uint32_t *dir, uint32_t nsamp, uint32_t key) {
+    uint32_t lo = 0, hi = nsamp;  // padding equals 0xFFFFFFFF and must not count when key == 0xFFFFFFFF
+    while (lo < hi) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (dir[mid] <= key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t plain_lb(const PlainView &v, const uint32_t *dirS, uint32_t key) {
+    const uint32_t j = min(dir_count_lt(dirS, key), v.nsamp);
+    const uint32_t lo = j ? (j - 1) << v.dshift : 0u;
+    const uint32_t hi = min(j << v.dshift, v.n);
+    return lower_bound_u32(v.S, lo, hi, key);
+}
+__device__ __forceinline__ uint32_t plain_ub(const PlainView &v, const uint32_t *dirE, uint32_t key) {
+    const uint32_t j = dir_count_le(dirE, v.nsamp, key);
+    const uint32_t lo = j ? (j - 1) << v.dshift : 0u;
+    const uint32_t hi = min(j << v.dshift, v.n);
+    return upper_bound_u32(v.E, lo, hi, key);
+}
+
+template <bool kOut64>
+__global__ void __launch_bounds__(kThreads) count_plain_kernel(PlainView v, const uint32_t *__restrict__ qs,
+                                                               const uint32_t *__restrict__ qe, uint64_t nq,
+                                                               uint32_t *__restrict__ o32,
+                                                               uint64_t *__restrict__ o64) {
+    __shared__ uint32_t dirS[kDirSlots];
+    __shared__ uint32_t dirE[kDirSlots];
+    for (uint32_t i = threadIdx.x; i < kDirSlots; i += blockDim.x) {
+        const bool ok = i < v.nsamp;
+        dirS[i] = ok ? __ldg(v.S + ((uint64_t)i << v.dshift)) : 0xFFFFFFFFu;
+        dirE[i] = ok ? __ldg(v.E + ((uint64_t)i << v.dshift)) : 0xFFFFFFFFu;
+    }
+    __syncthreads();
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t a = ld_stream_u32(qs + j), b = ld_stream_u32(qe + j);
+        const uint32_t lb = v.n ? plain_lb(v, dirS, b) : 0u;
+        uint32_t ub = v.n ? plain_ub(v, dirE, a) : 0u;
+        if (a == 0xFFFFFFFFu) ub = 0;  // src/lib.rs:614 wrap
+        store_count<kOut64>(o32, o64, j, lb, ub);
+    }
+}
+
 
 __device__ __forceinline__ uint64_t block_reduce_sum_u64(uint64_t v, uint64_t *smem /* 8 */) {
 #pragma unroll
@@ -495,10 +535,8 @@ __device__ __forceinline__ uint64_t block_reduce_sum_u64(uint64_t v, uint64_t *s
     return r;  // valid in thread 0
 }
 
-// pass 1: per-query hit counts (thread t of a tile owns queries t*4..t*4+3) and per-tile sums.
-// kHaveCounts: `counts` already holds the BITS count of every query (the fast count kernel ran);
-// only queries outside its validity (a >= b) are recounted by the predicate.
-template <bool kHaveCounts>
+// pass 1 (general form; the fused form is count_bucket_kernel<.., kFind = true>): per-query hit counts
+// (thread t of a tile owns queries t*4..t*4+3) and per-tile sums
 __global__ void __launch_bounds__(kThreads) find_count_kernel(FindView f, const uint32_t *__restrict__ qs,
                                                               const uint32_t *__restrict__ qe, uint64_t nq,
                                                               uint32_t *__restrict__ counts,
@@ -510,18 +548,8 @@ __global__ void __launch_bounds__(kThreads) find_count_kernel(FindView f, const 
     for (int k = 0; k < kFindQPT; k++) {
         const uint64_t j = base + k;
         if (j < nq) {
-            const uint32_t a = ld_stream_u32(qs + j), b = ld_stream_u32(qe + j);
-            uint32_t c;
-            if (kHaveCounts) {
-                c = counts[j];
-                if (!(a < b)) {
-                    c = find_count_scan(f, a, b);
-                    counts[j] = c;
-                }
-            } else {
-                c = find_count_one(f, a, b);
-                counts[j] = c;
-            }
+            const uint32_t c = find_count_one(f, ld_stream_u32(qs + j), ld_stream_u32(qe + j));
+            counts[j] = c;
             local += c;
         }
     }
@@ -529,43 +557,42 @@ __global__ void __launch_bounds__(kThreads) find_count_kernel(FindView f, const 
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
 }
 
-// pass 2: exclusive scan of the tile sums (one block; ntiles ~ nq / 1024)
+// pass 2: exclusive scan of the tile sums (one block of 1024 threads, each owning a contiguous segment
+// of ceil(ntiles / 1024) sums; ntiles ~ nq / 1024, so the whole array is a few hundred KB in L2)
 __global__ void __launch_bounds__(1024) scan_tile_sums_kernel(uint64_t *__restrict__ tile_sums, uint64_t ntiles,
                                                               uint64_t *__restrict__ total_out) {
     __shared__ uint64_t warp_tot[32];
-    __shared__ uint64_t carry_s;
-    if (threadIdx.x == 0) carry_s = 0;
-    __syncthreads();
+    const uint64_t seg = div_up(ntiles, 1024);
+    const uint64_t lo = min((uint64_t)threadIdx.x * seg, ntiles), hi = min(lo + seg, ntiles);
+    uint64_t mine = 0;
+    for (uint64_t i = lo; i < hi; i++) mine += tile_sums[i];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (uint64_t base = 0; base < ntiles; base += 1024) {
-        const uint64_t i = base + threadIdx.x;
-        const uint64_t x = i < ntiles ? tile_sums[i] : 0;
-        uint64_t inc = x;
+    uint64_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const uint64_t t = warp_tot[lane];
+        uint64_t ti = t;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-            if (lane >= o) inc += y;
+            const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, ti, o);
+            if (lane >= o) ti += y;
         }
-        if (lane == 31) warp_tot[w] = inc;
-        __syncthreads();
-        if (w == 0) {
-            uint64_t t = warp_tot[lane], ti = t;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, ti, o);
-                if (lane >= o) ti += y;
-            }
-            warp_tot[lane] = ti - t;  // exclusive
-        }
-        __syncthreads();
-        const uint64_t carry = carry_s;
-        const uint64_t excl = carry + warp_tot[w] + inc - x;
-        if (i < ntiles) tile_sums[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 1023) carry_s = excl + x;
-        __syncthreads();
+        warp_tot[lane] = ti - t;  // exclusive
+        if (lane == 31) *total_out = ti;
     }
-    if (threadIdx.x == 0) *total_out = carry_s;
+    __syncthreads();
+    uint64_t run = warp_tot[w] + inc - mine;
+    for (uint64_t i = lo; i < hi; i++) {
+        const uint64_t x = tile_sums[i];
+        tile_sums[i] = run;
+        run += x;
+    }
 }
 
 // pass 3: offsets[j] = tile base + exclusive scan of the tile's counts
@@ -594,10 +621,17 @@ __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t 
 #pragma unroll
     for (int i = 0; i < kThreads / 32; i++) wbase += (i < w) ? warp_tot[i] : 0;
     uint64_t run = tile_base[blockIdx.x] + wbase + inc - local;
+    if (base + kFindQPT <= nq) {  // 32 contiguous bytes per thread: two 128-bit stores
+        const uint64_t r0 = run, r1 = r0 + c[0], r2 = r1 + c[1], r3 = r2 + c[2];
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(offsets + base);
+        dst[0] = make_ulonglong2(r0, r1);
+        dst[1] = make_ulonglong2(r2, r3);
+    } else {
 #pragma unroll
-    for (int k = 0; k < kFindQPT; k++) {
-        if (base + k < nq) offsets[base + k] = run;
-        run += c[k];
+        for (int k = 0; k < kFindQPT; k++) {
+            if (base + k < nq) offsets[base + k] = run;
+            run += c[k];
+        }
     }
 }
 
@@ -663,6 +697,8 @@ __device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, ui
 // sorted list with broadcast shared-memory reads, appending the candidates that overlap its own query.
 // Slow path (union too large: random-order queries, very long intervals): each lane merges its own
 // class streams.  Either way the order is the reference iterator's (ascending position).
+constexpr int kEmitQ = 2;  // queries per lane: one candidate union serves 64 consecutive queries
+
 __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const uint32_t *__restrict__ qs,
                                                              const uint32_t *__restrict__ qe, uint64_t nq,
                                                              const uint64_t *__restrict__ offsets,
@@ -672,30 +708,41 @@ __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const u
     uint32_t *const stage = smem_all[threadIdx.x >> 5];       // kEmitStage output slots ...
     uint32_t *const sorted = stage + kEmitStage;               // ... then kEmitCand x (start, stop, position)
     const uint64_t nwarps = (uint64_t)gridDim.x * (kThreads / 32);
-    const uint64_t nchunks = div_up(nq, 32);
+    const uint64_t nchunks = div_up(nq, 32 * kEmitQ);
     for (uint64_t chunk = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); chunk < nchunks; chunk += nwarps) {
-        const uint64_t j = chunk * 32 + lane;
-        const bool live = j < nq;
-        const uint64_t o0 = live ? offsets[j] : 0;
-        // offsets[j + 1] is the next lane's o0; the last live lane reads it
-        uint64_t o1 = __shfl_down_sync(0xFFFFFFFFu, o0, 1);
-        const bool last = live && (lane == 31 || j + 1 == nq);
-        if (last) o1 = offsets[j + 1];
-        if (!live) o1 = 0;
-        const uint64_t wbase = __shfl_sync(0xFFFFFFFFu, o0, 0);
-        const uint32_t last_lane = 31u - __clz(__ballot_sync(0xFFFFFFFFu, live));
-        const uint64_t wend = __shfl_sync(0xFFFFFFFFu, o1, last_lane);
+        // lane's q-th query is chunk*64 + q*32 + lane: consecutive lanes hold consecutive queries
+        uint64_t o0[kEmitQ], o1[kEmitQ];
+        uint32_t a[kEmitQ], b[kEmitQ];
+        bool mine[kEmitQ];
+        const uint64_t jbase = chunk * (32 * kEmitQ);
+        const uint64_t jend = min(jbase + 32 * kEmitQ, nq);  // one past the chunk's last query
+#pragma unroll
+        for (int q = 0; q < kEmitQ; q++) {
+            const uint64_t j = jbase + q * 32 + lane;
+            const bool live = j < nq;
+            o0[q] = live ? offsets[j] : 0;
+            // offsets[j + 1] is the next lane's o0, except for lane 31 / the last query
+            o1[q] = __shfl_down_sync(0xFFFFFFFFu, o0[q], 1);
+            if (live && (lane == 31 || j + 1 == nq)) o1[q] = offsets[j + 1];
+            if (!live) o0[q] = o1[q] = 0;
+            mine[q] = live && o1[q] > o0[q];
+            a[q] = 0xFFFFFFFFu, b[q] = 0;
+            if (mine[q]) {
+                a[q] = ld_stream_u32(qs + j);
+                b[q] = ld_stream_u32(qe + j);
+            }
+        }
+        const uint64_t wbase = __shfl_sync(0xFFFFFFFFu, o0[0], 0);
+        const uint64_t wend = offsets[jend];  // same address for the whole warp: one broadcast load
         const uint64_t wtotal = wend - wbase;
         if (wtotal == 0) continue;
-        const bool mine = live && o1 > o0;
-        uint32_t a = 0xFFFFFFFFu, b = 0;
-        if (mine) {
-            a = ld_stream_u32(qs + j);
-            b = ld_stream_u32(qe + j);
-        }
         const bool staged = wtotal <= kEmitStage;
         // ---- union of the class windows over the queries that have hits
-        const uint32_t amin = __reduce_min_sync(0xFFFFFFFFu, a), bmax = __reduce_max_sync(0xFFFFFFFFu, b);
+        uint32_t amin = a[0], bmax = b[0];
+#pragma unroll
+        for (int q = 1; q < kEmitQ; q++) amin = min(amin, a[q]), bmax = max(bmax, b[q]);
+        amin = __reduce_min_sync(0xFFFFFFFFu, amin);
+        bmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
         uint32_t r = 0;
         if (lane < 8 && (lane & 3u) < f.ncls) {
             const int c = (int)(lane & 3u);
@@ -737,22 +784,30 @@ __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const u
                 sorted[3 * rank + 2] = g;
             }
             __syncwarp();
-            // every lane sweeps the sorted candidates for its own query (broadcast reads)
-            uint32_t cur = (uint32_t)(o0 - wbase);
+            // every lane sweeps the sorted candidates for its own queries (broadcast reads)
+            uint32_t cur[kEmitQ];
+#pragma unroll
+            for (int q = 0; q < kEmitQ; q++) cur[q] = (uint32_t)(o0[q] - wbase);
             for (uint32_t x = 0; x < T; x++) {
-                const uint32_t s = sorted[3 * x], e = sorted[3 * x + 1];
-                if (s < b && e > a) stage[cur++] = sorted[3 * x + 2];  // src/lib.rs:140-142
+                const uint32_t s = sorted[3 * x], e = sorted[3 * x + 1], g = sorted[3 * x + 2];
+#pragma unroll
+                for (int q = 0; q < kEmitQ; q++)
+                    if (s < b[q] && e > a[q]) stage[cur[q]++] = g;  // src/lib.rs:140-142
             }
             __syncwarp();
             for (uint32_t i = lane; i < (uint32_t)wtotal; i += 32) indices[wbase + i] = stage[i];
             __syncwarp();
         } else if (staged) {
-            if (mine) emit_one_query(f, a, b, stage + (o0 - wbase), o1 - o0);
+#pragma unroll
+            for (int q = 0; q < kEmitQ; q++)
+                if (mine[q]) emit_one_query(f, a[q], b[q], stage + (o0[q] - wbase), o1[q] - o0[q]);
             __syncwarp();
             for (uint32_t i = lane; i < (uint32_t)wtotal; i += 32) indices[wbase + i] = stage[i];
             __syncwarp();
         } else {
-            if (mine) emit_one_query(f, a, b, indices + o0, o1 - o0);
+#pragma unroll
+            for (int q = 0; q < kEmitQ; q++)
+                if (mine[q]) emit_one_query(f, a[q], b[q], indices + o0[q], o1[q] - o0[q]);
         }
     }
 }
@@ -803,6 +858,44 @@ uint32_t capped_grid(uint64_t work_items, int per_block, int waves) {
 
 }  // namespace
 
+namespace {
+
+// count over the bucket table.  tile_sums != nullptr selects find mode (u32 counts + per-tile sums).
+void launch_count_buckets(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
+                          uint32_t *d_out32, uint64_t *d_out64, uint64_t *tile_sums, cudaStream_t stream) {
+    const BucketView v = make_bucket_view(ix);
+    const FindView f = make_find_view(ix);
+    const bool out64 = d_out64 != nullptr;
+    const void *out = out64 ? (const void *)d_out64 : (const void *)d_out32;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_qs) | reinterpret_cast<uintptr_t>(d_qe) |
+                           reinterpret_cast<uintptr_t>(out)) & 31u) == 0;
+    const uint64_t ntiles = aligned ? nq / kTileQ : 0;
+    if (ntiles) {
+        // persistent: 148 SMs x LAPPER_MIN_CTAS resident CTAs of 256 threads
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, 148 * LAPPER_MIN_CTAS);
+        if (tile_sums)
+            count_bucket_kernel<false, true><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, tile_sums);
+        else if (out64)
+            count_bucket_kernel<true, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, nullptr, d_out64, nullptr);
+        else
+            count_bucket_kernel<false, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, nullptr);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+    }
+    const uint64_t done = ntiles * kTileQ, rest = nq - done;
+    if (rest) {
+        const uint32_t grid = capped_grid(rest, kThreads, 16);
+        if (tile_sums)
+            count_bucket_tail_kernel<false, true><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, done, nq, d_out32, nullptr, tile_sums);
+        else if (out64)
+            count_bucket_tail_kernel<true, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, done, nq, nullptr, d_out64, nullptr);
+        else
+            count_bucket_tail_kernel<false, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, done, nq, d_out32, nullptr, nullptr);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+    }
+}
+
+}  // namespace
+
 void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, uint32_t *d_out32,
                   uint64_t *d_out64, cudaStream_t stream) {
     if (nq == 0) return;
@@ -817,30 +910,7 @@ void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d
     }
     const bool out64 = d_out64 != nullptr;
     if (ix.buckets) {
-        const BucketView v = make_bucket_view(ix);
-        const void *out = out64 ? (const void *)d_out64 : (const void *)d_out32;
-        const bool aligned = ((reinterpret_cast<uintptr_t>(d_qs) | reinterpret_cast<uintptr_t>(d_qe) |
-                               reinterpret_cast<uintptr_t>(out)) & 31u) == 0;
-        const uint64_t ntiles = aligned ? nq / kTileQ : 0;
-        if (ntiles) {
-            // persistent: 148 SMs x 2 resident CTAs (128 registers x 256 threads each)
-            const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, 148 * LAPPER_MIN_CTAS);
-            if (out64)
-                count_bucket_kernel<true><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, ntiles, nullptr, d_out64);
-            else
-                count_bucket_kernel<false><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, ntiles, d_out32, nullptr);
-            LAPPER_CUDA_CHECK(cudaGetLastError());
-        }
-        const uint64_t done = ntiles * kTileQ, rest = nq - done;
-        if (rest) {
-            const uint32_t grid = capped_grid(rest, kThreads, 16);
-            if (out64)
-                count_bucket_tail_kernel<true><<<grid, kThreads, 0, stream>>>(v, d_qs + done, d_qe + done, rest, nullptr,
-                                                                              d_out64 + done);
-            else
-                count_bucket_tail_kernel<false><<<grid, kThreads, 0, stream>>>(v, d_qs + done, d_qe + done, rest,
-                                                                               d_out32 + done, nullptr);
-        }
+        launch_count_buckets(ix, d_qs, d_qe, nq, d_out32, d_out64, nullptr, stream);
     } else {
         PlainView v;
         v.S = ix.starts;
@@ -875,12 +945,14 @@ uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const 
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
         return 0;
     }
-    if (!ix.has_inverted) {
-        // every interval has start <= stop: the BITS count IS the number of hits for non-empty queries
-        launch_count(ix, d_qs, d_qe, nq, counts.p, nullptr, stream);
-        find_count_kernel<true><<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
+    if (!ix.has_inverted && ix.buckets && nq < (1ull << 31)) {
+        // every interval has start <= stop: the BITS count IS the number of hits of a non-empty query, so
+        // the count kernel runs in find mode (it also accumulates the tile sums and recounts start >= stop
+        // queries by the predicate)
+        LAPPER_CUDA_CHECK(cudaMemsetAsync(tile_sums.p, 0, ntiles * sizeof(uint64_t), stream));
+        launch_count_buckets(ix, d_qs, d_qe, nq, counts.p, nullptr, tile_sums.p, stream);
     } else {
-        find_count_kernel<false><<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
+        find_count_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
     }
     LAPPER_CUDA_CHECK(cudaGetLastError());
     scan_tile_sums_kernel<<<1, 1024, 0, stream>>>(tile_sums.p, ntiles, d_offsets + nq);

@@ -45,6 +45,22 @@ for _ in range(reps):
 b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / reps
+# phase split
+torch.cuda.synchronize()
+a.record()
+for _ in range(reps):
+    t = C.c_uint64(0)
+    _ffi.check(lib.lapper_find_batch_offsets_u32_dev(h, vp(qs), vp(qe), nq, vp(off), C.byref(t), sp))
+b.record()
+torch.cuda.synchronize()
+ms_off = a.elapsed_time(b) / reps
+a.record()
+for _ in range(reps):
+    _ffi.check(lib.lapper_find_batch_fill_u32_dev(h, vp(qs), vp(qe), nq, vp(off), vp(idx), sp))
+b.record()
+torch.cuda.synchronize()
+ms_fill = a.elapsed_time(b) / reps
+print(f"  offsets phase {ms_off:.3f} ms, fill phase {ms_fill:.3f} ms")
 print(f"find {order}: {ms:.3f} ms per pass, {int(total.value)} hits ({int(total.value) / nq:.2f}/query), "
       f"{nq / ms / 1e6:.2f} Gq/s, {int(total.value) / ms / 1e6:.1f} Ghits/s, checksum {int(idx[: int(total.value)].to(torch.int64).sum())}")
 lib.lapper_free(h)
