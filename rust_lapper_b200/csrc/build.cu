@@ -1,22 +1,15 @@
 // build.cu -- index build: Lapper::new (/root/reference/src/lib.rs:196-236) on the device.
 //
-//   sort by (start, stop), stable   -> LSD radix sort of the 64-bit key (start << 32) | stop with
-//                                      the input position as payload (src/lib.rs:145-157, :201)
+//   sort by (start, stop), stable   -> hand-written LSD radix sort (8-bit digits) of the 64-bit key
+//                                      (start << 32) | stop with the input position as payload
+//                                      (src/lib.rs:145-157, :201); stable like Vec::sort
 //   starts / stops                  -> unzip of the sorted keys; stops sorted on their own (:203-216)
 //   max_len                         -> max(stop (-) start) reduction, checked_sub -> 0 (:218-227)
 //   + prefix_max, + the BITS bucket sectors described in index.cuh (new; the reference searches
 //     the sorted vectors directly).
-#include <cub/device/device_radix_sort.cuh>
-
 #include <algorithm>
 
 #include "index.cuh"
-
-#ifdef THRUST_CUB_WRAPPED_NAMESPACE
-namespace cubns = THRUST_CUB_WRAPPED_NAMESPACE::cub;  // private copy of CUB: no symbol clashes with torch's
-#else
-namespace cubns = cub;
-#endif
 
 namespace lap {
 
@@ -39,6 +32,106 @@ __global__ void unpack_keys_kernel(const uint64_t *__restrict__ keys, uint64_t n
     uint64_t k = keys[i];
     s[i] = (uint32_t)(k >> 32);
     e[i] = (uint32_t)k;
+}
+
+// ---- LSD radix sort, 8-bit digits.  One pass = histogram kernel -> exclusive scan of the
+// (digit-major, block-minor) histogram -> scatter kernel.  A block owns a tile of 4096 consecutive
+// items; inside the tile, warp w owns 512 consecutive items as 16 rows of 32, and items are ranked
+// within their digit in exactly that order (row by row, lane by lane) with __match_any_sync, so every
+// pass is stable and the whole sort keeps equal keys in input order.
+constexpr int kRsItems = 16;
+constexpr int kRsTile = kThreads * kRsItems;  // 4096
+constexpr int kRsWarps = kThreads / 32;
+
+template <typename K>
+__device__ __forceinline__ uint32_t rs_digit(K k, int shift) {
+    return (uint32_t)(k >> shift) & 255u;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(kThreads) rs_hist_kernel(const K *__restrict__ keys, uint64_t n, int shift,
+                                                           uint32_t *__restrict__ block_hist, uint32_t nblocks) {
+    __shared__ uint32_t h[256];
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint64_t base = (uint64_t)blockIdx.x * kRsTile;
+#pragma unroll
+    for (int i = 0; i < kRsItems; i++) {
+        const uint64_t idx = base + (uint64_t)i * kThreads + threadIdx.x;
+        if (idx < n) atomicAdd(&h[rs_digit(keys[idx], shift)], 1u);
+    }
+    __syncthreads();
+    block_hist[(uint64_t)threadIdx.x * nblocks + blockIdx.x] = h[threadIdx.x];
+}
+
+template <typename K, bool kHasVal>
+__global__ void __launch_bounds__(kThreads) rs_scatter_kernel(const K *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                                              K *__restrict__ kout, uint32_t *__restrict__ vout,
+                                                              uint64_t n, int shift,
+                                                              const uint32_t *__restrict__ block_off, uint32_t nblocks) {
+    __shared__ uint32_t wcount[kRsWarps][256];
+    __shared__ uint32_t gbase[256];
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kRsWarps * 256; i += kThreads) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    const uint64_t seg = (uint64_t)blockIdx.x * kRsTile + (uint64_t)w * (32 * kRsItems);
+    K k[kRsItems];
+    uint32_t v[kRsItems], rank[kRsItems];
+#pragma unroll
+    for (int r = 0; r < kRsItems; r++) {
+        const uint64_t idx = seg + (uint64_t)r * 32 + lane;
+        const bool valid = idx < n;
+        k[r] = valid ? kin[idx] : (K)0;
+        if (kHasVal) v[r] = valid ? vin[idx] : 0u;
+        const uint32_t d = rs_digit(k[r], shift);
+        // lanes holding the same digit in this row; out-of-range lanes only match themselves
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, valid ? d : 256u + lane);
+        rank[r] = wcount[w][d] + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+        if (valid && lane == (uint32_t)(__ffs(peers) - 1)) wcount[w][d] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // thread t = digit t: exclusive prefix of the warps' counts, and the block's global base for the digit
+        uint32_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < kRsWarps; i++) {
+            const uint32_t c = wcount[i][threadIdx.x];
+            wcount[i][threadIdx.x] = acc;
+            acc += c;
+        }
+        gbase[threadIdx.x] = block_off[(uint64_t)threadIdx.x * nblocks + blockIdx.x];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRsItems; r++) {
+        const uint64_t idx = seg + (uint64_t)r * 32 + lane;
+        if (idx < n) {
+            const uint32_t d = rs_digit(k[r], shift);
+            const uint32_t pos = gbase[d] + wcount[w][d] + rank[r];
+            kout[pos] = k[r];
+            if (kHasVal) vout[pos] = v[r];
+        }
+    }
+}
+
+// Sorts n keys (and their u32 payloads) by bits [0, nbits) of the key.  `keys`/`vals` hold the input and,
+// on return, the output (nbits is a multiple of 16, so the ping-pong ends where it started).
+template <typename K, bool kHasVal>
+void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, uint64_t n, int nbits, cudaStream_t stream) {
+    const uint32_t nblocks = (uint32_t)div_up(n, kRsTile);
+    Scratch<uint32_t> hist((uint64_t)256 * nblocks, stream);
+    K *kin = keys, *kout = keys_tmp;
+    uint32_t *vin = vals, *vout = vals_tmp;
+    for (int shift = 0; shift < nbits; shift += 8) {
+        rs_hist_kernel<K><<<nblocks, kThreads, 0, stream>>>(kin, n, shift, hist.p, nblocks);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        launch_exclusive_sum(hist.p, hist.p, (uint64_t)256 * nblocks, stream);
+        rs_scatter_kernel<K, kHasVal><<<nblocks, kThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, hist.p, nblocks);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        std::swap(kin, kout);
+        std::swap(vin, vout);
+    }
 }
 
 struct BuildStats {
@@ -448,23 +541,17 @@ void build_index_from_unsorted(DeviceIndex &ix, const uint32_t *d_starts, const 
         ix.stops_sorted = dev_alloc<uint32_t>(n, ix.bytes);
         ix.perm = dev_alloc<uint32_t>(n, ix.bytes);
         {
-            Scratch<uint64_t> keys_in(n, stream), keys_out(n, stream);
-            Scratch<uint32_t> pos_in(n, stream);
-            pack_keys_kernel<<<grid_for(n), kThreads, 0, stream>>>(d_starts, d_stops, n, keys_in.p, pos_in.p);
+            Scratch<uint64_t> keys(n, stream), keys_tmp(n, stream);
+            Scratch<uint32_t> pos_tmp(n, stream), stops_tmp(n, stream);
+            pack_keys_kernel<<<grid_for(n), kThreads, 0, stream>>>(d_starts, d_stops, n, keys.p, ix.perm);
             LAPPER_CUDA_CHECK(cudaGetLastError());
-            // LSD radix sort: stable, so equal (start, stop) keep input order like Vec::sort.
-            size_t tmp_pairs = 0, tmp_keys = 0;
-            LAPPER_CUDA_CHECK(cubns::DeviceRadixSort::SortPairs(nullptr, tmp_pairs, keys_in.p, keys_out.p, pos_in.p,
-                                                              ix.perm, n, 0, 64, stream));
-            LAPPER_CUDA_CHECK(cubns::DeviceRadixSort::SortKeys(nullptr, tmp_keys, d_stops, ix.stops_sorted, n, 0, 32,
-                                                             stream));
-            Scratch<uint8_t> tmp(std::max(tmp_pairs, tmp_keys), stream);
-            LAPPER_CUDA_CHECK(cubns::DeviceRadixSort::SortPairs(tmp.p, tmp_pairs, keys_in.p, keys_out.p, pos_in.p,
-                                                              ix.perm, n, 0, 64, stream));
-            unpack_keys_kernel<<<grid_for(n), kThreads, 0, stream>>>(keys_out.p, n, ix.starts, ix.stops_by_iv);
+            // (start, stop) order, stable: 8 passes over the 64-bit key, payload = input position
+            radix_sort<uint64_t, true>(keys.p, keys_tmp.p, ix.perm, pos_tmp.p, n, 64, stream);
+            unpack_keys_kernel<<<grid_for(n), kThreads, 0, stream>>>(keys.p, n, ix.starts, ix.stops_by_iv);
             LAPPER_CUDA_CHECK(cudaGetLastError());
-            LAPPER_CUDA_CHECK(cubns::DeviceRadixSort::SortKeys(tmp.p, tmp_keys, d_stops, ix.stops_sorted, n, 0, 32,
-                                                             stream));
+            // the reference's private `stops`: the stops sorted on their own (src/lib.rs:215)
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(ix.stops_sorted, d_stops, n * 4, cudaMemcpyDeviceToDevice, stream));
+            radix_sort<uint32_t, false>(ix.stops_sorted, stops_tmp.p, nullptr, nullptr, n, 32, stream);
         }
         finish_index_from_sorted(ix, flags, stream);
     } catch (...) {

@@ -120,6 +120,8 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
 // setops.cu --------------------------------------------------------------------------------------
 // order-preserving split of the sorted intervals into length classes (fills ix.cls_starts/stops/gidx)
 void launch_class_partition(DeviceIndex &ix, const uint8_t *class_of_bin /* host, 33 entries */, cudaStream_t stream);
+// exclusive prefix sum (u32, wrapping) of `in` into `out` (may alias)
+void launch_exclusive_sum(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream);
 // inclusive prefix max of `in` (n elements) into `out`
 void launch_prefix_max(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream);
 uint32_t compute_cov(const DeviceIndex &ix, cudaStream_t stream);

@@ -276,6 +276,10 @@ void launch_class_partition(DeviceIndex &ix, const uint8_t *class_of_bin, cudaSt
     }
 }
 
+void launch_exclusive_sum(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream) {
+    scan3<AddOp>(LoadArray{in}, n, StoreExclusiveSink{out}, nullptr, stream);
+}
+
 void launch_prefix_max(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream) {
     scan3<MaxOp>(LoadArray{in}, n, StoreSink{out}, nullptr, stream);
 }
