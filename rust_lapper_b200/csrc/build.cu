@@ -188,14 +188,8 @@ __global__ void fill_buckets_kernel(const uint32_t *__restrict__ S, const uint32
     if (B > nb) return;
     Sector sec;
     const uint32_t w = 1u << shift;
-    if (B == nb) {  // sentinel: every key is below it
-        sec.w[0] = n;
-        sec.w[1] = n;
-#pragma unroll
-        for (int j = 2; j < 8; j++) sec.w[j] = (0x8000u | w) * 0x10001u;
-        buckets[B] = sec;
-        return;
-    }
+    // B == nb is the sentinel (first bucket past the last key): no keys of its own, rs = re_hi = n fall out of
+    // the bisections below, but it does hold the stops of its margin like every other bucket
     const uint64_t base = B << shift, next = base + w;
     const uint64_t lo_m = base >= margin ? base - margin : 0;
     const uint32_t rs = lb64(S, 0, n, base), rs_next = lb64(S, rs, n, next);
@@ -242,7 +236,7 @@ __global__ void fill_children_kernel(const uint32_t *__restrict__ S, const uint3
                                      uint32_t shift, uint64_t nb, const Sector *__restrict__ buckets,
                                      Sector *__restrict__ pool) {
     const uint64_t B = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (B >= nb) return;
+    if (B > nb) return;
     const Sector par = buckets[B];
     if (par.w[7] != 0xFFFFFFFFu || par.w[2] == kNoChild) return;
     const uint32_t j = par.w[3], cshift = shift - j, cw = 1u << cshift;
@@ -518,7 +512,7 @@ void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stre
         ix.npool = npool;
         if (npool) {
             ix.pool = dev_alloc<Sector>(npool, ix.bytes);
-            fill_children_kernel<<<grid_for(ix.nbuckets), kThreads, 0, stream>>>(
+            fill_children_kernel<<<grid_for(ix.nbuckets + 1), kThreads, 0, stream>>>(
                 ix.starts, ix.stops_sorted, (uint32_t)n, shift, ix.nbuckets, ix.buckets, ix.pool);
             LAPPER_CUDA_CHECK(cudaGetLastError());
         }

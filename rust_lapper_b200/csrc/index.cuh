@@ -34,7 +34,8 @@ namespace lap {
 // points at 2^w[3] child sectors in `pool`, each a sector of the same format for a 2^(shift - w[3])
 // wide slice of the bucket (margin 0); w[4] = #starts < base + w and w[5] = #stops < base bound the
 // bucket's slices of the sorted arrays for the rare child that still overflows (many equal
-// coordinates).  Sector nb is a sentinel (rs = re_hi = n, no lanes) for coordinates beyond the last key.
+// coordinates).  Sector nb is a sentinel for coordinates beyond the last key: rs = re_hi = n, no keys of its
+// own, only the stops of its margin.
 constexpr uint32_t kBucketLanes = 12;
 constexpr uint32_t kMaxBucketShift = 13;
 constexpr uint32_t kLaneGuard = 0x80008000u;

@@ -192,3 +192,25 @@ def test_seek_cursor_protocol(oracle):
             a, b = int(qs[j]), int(qe[j])
             assert gpu.seek_idx(a, b, cg) == cpu.seek_idx(a, b, cc)
             assert cg == cc
+
+
+@pytest.mark.parametrize("shift", [0, 2, 5, 9, 13])
+def test_queries_around_bucket_boundaries_and_last_bucket(oracle, shift):
+    """Regression: a query whose stop lies in the first bucket past the last key (the sentinel) and whose
+    start lies within the stop margin below it must still see the stops of that margin.  Sweeps starts and
+    lengths around several bucket boundaries, including the last one, for forced bucket widths."""
+    w = 1 << shift
+    rng = np.random.default_rng(shift)
+    top = 50 * w + w // 3
+    s = rng.integers(0, top, 400).astype(np.uint32)
+    e = np.minimum(s + rng.integers(0, 3 * w + 2, 400), top).astype(np.uint32)
+    e[:40] = top  # many stops at the very last coordinate
+    gpu, cpu = _both(oracle, s, e, 2 | ((shift + 1) << 8))
+    assert gpu.bucket_shift == shift
+    qs, qe = [], []
+    for boundary in (w, 7 * w, 49 * w, 50 * w, 51 * w, 52 * w):
+        for a in range(max(boundary - w - 2, 0), boundary + w + 3, max(w // 16, 1)):
+            for ln in (0, 1, w // 8, w // 4, w // 4 + 1, w // 2, w, 2 * w + 1):
+                qs.append(a)
+                qe.append(a + ln)
+    _assert_same_queries(gpu, cpu, np.array(qs, np.uint32), np.array(qe, np.uint32))
