@@ -39,20 +39,6 @@ struct BucketView {
     uint32_t nb;  // index of the sentinel bucket
 };
 
-// Table phases (random-order queries over a table larger than L2 can hold).  The count is run as
-// `nphases` launches; launch p resolves only the queries whose sector lies in slice p of the table
-// ([split[p], split[p+1]) in bucket indices), so the slice being gathered from stays L2-resident and
-// the random gathers stop going to DRAM.  The queries are streamed once per phase, which costs far
-// less than the sector misses it removes.  A warp whose 128 queries are bucket-local (start-sorted
-// input) resolves all of them in the phase of its first bucket; `remaining` counts the queries phase 0
-// left for later phases, and later launches exit at once when it is zero -- sorted input pays nothing.
-struct PhaseCtl {
-    uint32_t phase, nphases;
-    uint32_t split[5];
-    uint32_t local_span;
-    unsigned int *remaining;
-};
-
 // bytes 1 and 3 of t0 and of t1 (the high byte of every 16-bit lane), each replaced by its sign bit
 // replicated: 0xFF where the lane's guard bit survived the subtraction, 0x00 where it did not
 __device__ __forceinline__ uint32_t guard_bytes(uint32_t t0, uint32_t t1) {
@@ -315,15 +301,12 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
                                                                    const uint32_t *__restrict__ qe, uint64_t ntiles,
                                                                    uint32_t *__restrict__ o32,
                                                                    uint64_t *__restrict__ o64,
-                                                                   uint64_t *__restrict__ tile_sums, const PhaseCtl ph) {
+                                                                   uint64_t *__restrict__ tile_sums) {
     __shared__ uint32_t wqueue[kWarps][kWQCap * 3];  // (relative query index, start, stop) per entry
-    if (ph.phase > 0 && *reinterpret_cast<volatile unsigned int *>(ph.remaining) == 0) return;  // nothing was left over
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t *const wq = wqueue[warp];
     uint32_t wq_n = 0;  // warp-uniform
-    uint32_t left_over = 0;  // queries this thread left to later phases
     const uint32_t width = 1u << v.shift, mask = width - 1u;
-    constexpr uint32_t kAll = (1u << kQPT) - 1u;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t j0 = tile * kTileQ + (uint64_t)threadIdx.x * kQPT;
         if (tile + gridDim.x < ntiles) {  // next tile's queries -> L2 while this one is counted
@@ -335,33 +318,14 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
         uint32_t bb[kQPT];
         Sector sec[kQPT];
 #pragma unroll
-        for (int k = 0; k < kQPT; k++) bb[k] = bucket_of(v, qb.w[k]);
-        uint32_t active = kAll;  // queries of this thread resolved by this launch
-        if (ph.nphases > 1) {
-            uint32_t mn = bb[0], mx = bb[0];
-#pragma unroll
-            for (int k = 1; k < kQPT; k++) mn = min(mn, bb[k]), mx = max(mx, bb[k]);
-            mn = __reduce_min_sync(0xFFFFFFFFu, mn);
-            mx = __reduce_max_sync(0xFFFFFFFFu, mx);
-            const bool local = mx - mn <= ph.local_span;  // warp-uniform
-            active = 0;
-#pragma unroll
-            for (int k = 0; k < kQPT; k++) {
-                const uint32_t key = local ? mn : bb[k];
-                const uint32_t p = (uint32_t)(key >= ph.split[1]) + (uint32_t)(key >= ph.split[2]) + (uint32_t)(key >= ph.split[3]);
-                active |= (uint32_t)(p == ph.phase) << k;
-            }
-            if (ph.phase == 0) left_over += kQPT - __popc(active);
+        for (int k = 0; k < kQPT; k++) {
+            bb[k] = bucket_of(v, qb.w[k]);
+            sec[k] = ld_sector_cached(v.buckets + bb[k]);
         }
-#pragma unroll
-        for (int k = 0; k < kQPT; k++)
-            if (active & (1u << k)) sec[k] = ld_sector_cached(v.buckets + bb[k]);
         uint32_t res[kQPT];
         uint32_t defer = 0, second = 0;
 #pragma unroll
         for (int k = 0; k < kQPT; k++) {
-            res[k] = 0;
-            if (!(active & (1u << k))) continue;
             const uint32_t a = qa.w[k], b = qb.w[k];
             // lower_bound(starts, b) = rs + 12 - #{lanes >= b - base}
             int acc = (int)(sec[k].w[0] + kBucketLanes);
@@ -384,7 +348,6 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
         if (kFind) {
 #pragma unroll
             for (int k = 0; k < kQPT; k++) defer |= (uint32_t)(!(qa.w[k] < qb.w[k])) << k;
-            defer &= active;
         }
         if (second) {
             // start far below the stop's bucket (long or inverted query): its own bucket's sector
@@ -423,14 +386,8 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
 #pragma unroll
             for (int k = 0; k < kQPT; k++) o.w[k] = res[k];
             st_stream_v8(o32 + j0, o);
-        } else if (ph.phase == 0 || active == kAll) {
-            // phase 0 writes every slot (zeros for the queries it leaves to later phases), so result sectors
-            // are written whole at least once
-            st_v4_hint(o32 + j0, make_uint4(res[0], res[1], res[2], res[3]), l2_policy_evict_first());
         } else {
-#pragma unroll
-            for (int k = 0; k < kQPT; k++)
-                if (active & (1u << k)) st_stream_u32(o32 + j0 + k, res[k]);
+            st_v4_hint(o32 + j0, make_uint4(res[0], res[1], res[2], res[3]), l2_policy_evict_first());
         }
         if (kFind) {
             // this warp's contribution to its tile's hit total (deferred queries add theirs when resolved)
@@ -471,10 +428,6 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
         }
     }
     if (lane < wq_n) count_deferred<kOut64, kFind>(v, f, (uint64_t)blockIdx.x * kTileQ, wq + 3 * lane, o32, o64, tile_sums);
-    if (ph.nphases > 1 && ph.phase == 0) {
-        left_over = __reduce_add_sync(0xFFFFFFFFu, left_over);
-        if (lane == 0 && left_over) atomicAdd(ph.remaining, left_over);
-    }
 }
 
 // ---- count, bucket path, any alignment / ragged tail: one query per thread
@@ -920,32 +873,13 @@ void launch_count_buckets(const DeviceIndex &ix, const uint32_t *d_qs, const uin
     if (ntiles) {
         // persistent: 148 SMs x LAPPER_MIN_CTAS resident CTAs of 256 threads
         const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, 148 * LAPPER_MIN_CTAS);
-        // table phases: slices of at most ~56 MB stay L2-resident on B200 (tools/mb_gather.cu); more than four
-        // phases would stream the queries too often to pay off
-        PhaseCtl ph = {};
-        ph.nphases = 1;
-        const uint64_t table_bytes = (ix.nbuckets + 1) * sizeof(Sector);
-        static const uint64_t slice_bytes = getenv("LAPPER_PHASE_SLICE_MB") ? strtoull(getenv("LAPPER_PHASE_SLICE_MB"), nullptr, 10) << 20 : 56ull << 20;
-        if (!out64 && slice_bytes && table_bytes > (64ull << 20) && div_up(table_bytes, slice_bytes) <= 4 && ntiles >= 1024)
-            ph.nphases = (uint32_t)div_up(table_bytes, slice_bytes);
-        // test hook: force a phase count on any input size (tests/test_gpu_phases.py)
-        static const uint32_t forced = getenv("LAPPER_FORCE_PHASES") ? (uint32_t)atoi(getenv("LAPPER_FORCE_PHASES")) : 0u;
-        if (forced >= 1 && forced <= 4 && !out64) ph.nphases = forced;
-        for (uint32_t p = 0; p <= 4; p++)
-            ph.split[p] = p >= ph.nphases ? 0xFFFFFFFFu : (uint32_t)((ix.nbuckets + 1) * p / ph.nphases);
-        ph.local_span = 4096;
-        Scratch<unsigned int> remaining(1, stream);
-        ph.remaining = remaining.p;
-        if (ph.nphases > 1) LAPPER_CUDA_CHECK(cudaMemsetAsync(remaining.p, 0, sizeof(unsigned int), stream));
-        for (ph.phase = 0; ph.phase < ph.nphases; ph.phase++) {
-            if (tile_sums)
-                count_bucket_kernel<false, true><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, tile_sums, ph);
-            else if (out64)
-                count_bucket_kernel<true, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, nullptr, d_out64, nullptr, ph);
-            else
-                count_bucket_kernel<false, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, nullptr, ph);
-            LAPPER_CUDA_CHECK(cudaGetLastError());
-        }
+        if (tile_sums)
+            count_bucket_kernel<false, true><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, tile_sums);
+        else if (out64)
+            count_bucket_kernel<true, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, nullptr, d_out64, nullptr);
+        else
+            count_bucket_kernel<false, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, nullptr);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
     }
     const uint64_t done = ntiles * kTileQ, rest = nq - done;
     if (rest) {

@@ -214,3 +214,26 @@ def test_queries_around_bucket_boundaries_and_last_bucket(oracle, shift):
                 qs.append(a)
                 qe.append(a + ln)
     _assert_same_queries(gpu, cpu, np.array(qs, np.uint32), np.array(qe, np.uint32))
+
+
+def test_query_shapes_on_dense_gene_exon_set(oracle):
+    """300 k gene/exon-like intervals in a 40 M universe (dense: bucket width 512, frequent overflow and child
+    sectors) against random, start-sorted, mixed, long and inverted queries -- count and find, bit for bit.
+    (This shape caught the sentinel-bucket margin bug.)"""
+    from rust_lapper_b200 import synth
+
+    U = 40_000_000
+    s, e = synth.intervals_gene_exon(44, 300_000, U)
+    gpu, cpu = _both(oracle, s, e, 2)
+    nq = 300_000 + 77
+    rq = synth.queries_fixed_len(43, nq, U, 150)
+    sq = synth.queries_sorted_fixed_len(45, nq, U, 150)
+    mixed = (np.concatenate([sq[0][:100_000], rq[0][:100_077], sq[0][200_000:300_000]]),
+             np.concatenate([sq[1][:100_000], rq[1][:100_077], sq[1][200_000:300_000]]))
+    long_q = (rq[0], np.minimum(rq[0].astype(np.int64) + 30_000, 0xFFFFFFFF).astype(np.uint32))
+    inverted = (rq[1], rq[0])
+    for name, (qs, qe) in (("random", rq), ("sorted", sq), ("mixed", mixed), ("long", long_q), ("inverted", inverted)):
+        assert np.array_equal(gpu.count_batch_c32(qs, qe), cpu.count_batch(qs, qe, 4).astype(np.uint32)), name
+        go, gi = gpu.find_batch(qs, qe)
+        co, ci = cpu.find_batch(qs, qe, 4)
+        assert np.array_equal(go, co) and np.array_equal(gi, ci), name
