@@ -473,6 +473,56 @@ def run_extras(args, lib, h, dev, stream, sp, n, nq, peak):
         "max_len": int(lib.lapper_max_len(h3)),
     }
     lib.lapper_free(h3)
+    del s3, e3, q3s, q3e, offsets, indices
+
+    # cfg 5 shape on one GPU: 50 M intervals (cfg-2 distribution): build, cov, merge_overlaps,
+    # union_and_intersect and random-order count against the larger (485 MB) table
+    n5 = args.big_intervals
+    if n5:
+        s5, e5 = synth.intervals_uniform(SEED_IV, n5, UNIVERSE, 50, 5000, device=dev)
+        torch.cuda.synchronize()
+
+        def wall(fn, reps=3):
+            best = None
+            for _ in range(reps):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                r = fn()
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            return best * 1e3, r
+
+        def build5():
+            hh = C.c_void_p(0)
+            _ffi.check(lib.lapper_build_u32_dev(_vp(s5), _vp(e5), n5, dev.index, 0, sp, C.byref(hh)))
+            return hh
+
+        handles = []
+        ms_build, h5 = wall(lambda: handles.append(build5()) or handles[-1])
+        for hh in handles[:-1]:
+            lib.lapper_free(hh)
+        cov = C.c_uint32(0)
+        ms_cov, _ = wall(lambda: _ffi.check(lib.lapper_cov(h5, C.byref(cov))))
+        q5s, q5e = synth.queries_fixed_len(SEED_Q, nq, UNIVERSE, QLEN, device=dev)
+        c5 = torch.empty(nq, dtype=torch.int32, device=dev)
+        ms_cnt = timed(lambda: _ffi.check(lib.lapper_count_batch_u32_dev(h5, _vp(q5s), _vp(q5e), nq, _vp(c5), sp)), 5)
+        s5b, e5b = synth.intervals_uniform(SEED_IV + 100, n5 // 5, UNIVERSE, 50, 5000, device=dev)
+        h5b = C.c_void_p(0)
+        _ffi.check(lib.lapper_build_u32_dev(_vp(s5b), _vp(e5b), n5 // 5, dev.index, 0, sp, C.byref(h5b)))
+        u, i = C.c_uint32(0), C.c_uint32(0)
+        ms_ui, _ = wall(lambda: _ffi.check(lib.lapper_union_and_intersect(h5, h5b, C.byref(u), C.byref(i))))
+        ms_merge, _ = wall(lambda: _ffi.check(lib.lapper_merge_overlaps(h5)), reps=1)
+        out["cfg5_50M_intervals_one_gpu"] = {
+            "intervals": n5, "build_ms": ms_build, "build_intervals_per_s": n5 / (ms_build * 1e-3),
+            "cov_ms": ms_cov, "cov": int(cov.value), "cov_GBps": n5 * 8 / (ms_cov * 1e-3) / 1e9,
+            "merge_overlaps_ms": ms_merge, "merged_runs": int(lib.lapper_len(h5)),
+            "union_and_intersect_ms_vs_10M_set": ms_ui, "union": int(u.value), "intersect": int(i.value),
+            "count_random_100M_ms": ms_cnt, "count_random_queries_per_s": nq / (ms_cnt * 1e-3),
+            "note": "wall-clock per call through the C ABI (includes allocations and the D2H of the scalar results)",
+        }
+        lib.lapper_free(h5)
+        lib.lapper_free(h5b)
     return out
 
 
@@ -485,6 +535,7 @@ def main():
     ap.add_argument("--intervals", type=int, default=N_INTERVALS)
     ap.add_argument("--queries", type=int, default=NQ_PER_GPU, help="queries per GPU per step")
     ap.add_argument("--find-queries", type=int, default=100_000_000)
+    ap.add_argument("--big-intervals", type=int, default=50_000_000, help="cfg-5 extras leg (0 = skip)")
     ap.add_argument("--no-extras", action="store_true", help="skip the sorted-query count and cfg-3 find legs (N = 1 only)")
     ap.add_argument("--extras", action="store_true", help=argparse.SUPPRESS)  # kept for old command lines; extras are on by default
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
