@@ -131,6 +131,13 @@ int lapper_find_batch_fill_u32_dev(const lapper_t *l, const uint32_t *d_q_start,
  * reference's `&mut usize` protocol: *cursor is updated exactly as the reference updates it. */
 int lapper_seek_cursor(const lapper_t *l, uint32_t start, uint64_t *cursor);
 
+/* ---- Lapper::insert (src/lib.rs:260-273): O(n) like the reference ("very inefficient", :238-239): the sorted
+ *      arrays are rebuilt on the device with the new interval at the reference's insert positions
+ *      (bsearch_seq_ref: BEFORE any equal (start, stop)), max_len is updated, cov and overlaps_merged are
+ *      cleared.  perm of the new interval is *input_position_out = the number of intervals ever given to
+ *      this handle before it (so a caller appends its val to its own list). */
+int lapper_insert_u32(lapper_t *l, uint32_t start, uint32_t stop, uint64_t *input_position_out);
+
 /* ---- Lapper::merge_overlaps (src/lib.rs:361-416): prefix-max scan, run heads, compaction; rebuilds
  *      starts / stops / max_len; sets overlaps_merged iff the lapper is non-empty.
  *      LAPPER_ERR_PRECONDITION if some interval has stop < start. */

@@ -113,6 +113,14 @@ class Lapper {
         return out;
     }
 
+    // src/lib.rs:260-273 (O(n), like the reference)
+    void insert(const Interval<T> &elem) {
+        uint64_t pos = 0;
+        check(lapper_insert_u32(h_, elem.start, elem.stop, &pos));
+        if (input_.size() <= pos) input_.resize(pos + 1, elem);
+        input_[pos] = elem;
+        refresh();
+    }
     void merge_overlaps() {
         check(lapper_merge_overlaps(h_));
         refresh();

@@ -157,6 +157,31 @@ __global__ void seek_cursor_kernel(const uint32_t *__restrict__ S, uint32_t n, u
     *cursor_out = c;
 }
 
+// positions the reference's insert() picks (src/lib.rs:261-263): lower_bound of the interval among the sorted
+// intervals by (start, stop), and of its stop among the sorted stops
+__global__ void insert_positions_kernel(const uint32_t *__restrict__ S, const uint32_t *__restrict__ Eiv,
+                                        const uint32_t *__restrict__ E, uint32_t n, uint32_t start, uint32_t stop,
+                                        uint32_t *__restrict__ out) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {  // first interval that is not < (start, stop)
+        const uint32_t mid = lo + ((hi - lo) >> 1);
+        const uint32_t s = S[mid], e = Eiv[mid];
+        if (s < start || (s == start && e < stop))
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    out[0] = lo;
+    out[1] = lower_bound_u32(E, 0, n, stop);
+}
+
+// dst[0..pos) = src[0..pos), dst[pos] = value, dst[pos+1..n+1) = src[pos..n)
+void insert_into(uint32_t *dst, const uint32_t *src, uint64_t n, uint64_t pos, uint32_t value, cudaStream_t stream) {
+    if (pos) LAPPER_CUDA_CHECK(cudaMemcpyAsync(dst, src, pos * 4, cudaMemcpyDeviceToDevice, stream));
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(dst + pos, &value, 4, cudaMemcpyHostToDevice, stream));
+    if (n > pos) LAPPER_CUDA_CHECK(cudaMemcpyAsync(dst + pos + 1, src + pos, (n - pos) * 4, cudaMemcpyDeviceToDevice, stream));
+}
+
 void replace_index_with_sorted(lapper_t *l, uint32_t *s, uint32_t *e, uint32_t *perm, uint64_t m,
                                cudaStream_t stream) {
     uint32_t *e_sorted = nullptr;
@@ -208,6 +233,7 @@ int lapper_build_u32_dev(const uint32_t *d_starts, const uint32_t *d_stops, uint
         l->device = device;
         l->build_flags = flags;
         build_index_from_unsorted(l->ix, d_starts, d_stops, n, flags, (cudaStream_t)stream);
+        l->next_input_id = n;
         LAPPER_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
         *out = l.release();
     });
@@ -231,6 +257,7 @@ int lapper_build_u32_ex(const uint32_t *starts, const uint32_t *stops, uint64_t 
         l->device = device;
         l->build_flags = flags;
         build_index_from_unsorted(l->ix, d_s.p, d_e.p, n, flags, st.s);
+        l->next_input_id = n;
         d_s.release();
         d_e.release();
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
@@ -257,6 +284,7 @@ int lapper_from_sorted_dev(const uint32_t *d_starts, const uint32_t *d_stops_by_
         l->device = device;
         l->build_flags = flags;
         l->overlaps_merged = overlaps_merged != 0;
+        l->next_input_id = n;
         DeviceIndex &ix = l->ix;
         ix.n = n;
         try {
@@ -470,6 +498,51 @@ int lapper_seek_cursor(const lapper_t *l, uint32_t start, uint64_t *cursor) {
         LAPPER_CUDA_CHECK(cudaMemcpyAsync(cursor, d_c.p, 8, cudaMemcpyDeviceToHost, st.s));
         d_c.release();
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+    });
+}
+
+int lapper_insert_u32(lapper_t *l, uint32_t start, uint32_t stop, uint64_t *input_position_out) {
+    return guarded([&] {
+        check_handle(l);
+        DeviceGuard dg(l->device);
+        StreamOwner st;
+        DeviceIndex &ix = l->ix;
+        const uint64_t n = ix.n;
+        LAPPER_REQUIRE(n + 1 < 0xFFFFFFF0ull, "lapper_insert: too many intervals");
+        uint32_t pos[2] = {0, 0};
+        if (n) {
+            Scratch<uint32_t> d_pos(2, st.s);
+            insert_positions_kernel<<<1, 1, 0, st.s>>>(ix.starts, ix.stops_by_iv, ix.stops_sorted, (uint32_t)n, start, stop, d_pos.p);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(pos, d_pos.p, 8, cudaMemcpyDeviceToHost, st.s));
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+        }
+        const uint64_t id = l->next_input_id;
+        uint32_t *arr[4] = {nullptr, nullptr, nullptr, nullptr};
+        try {
+            for (auto &a : arr) LAPPER_CUDA_CHECK(cudaMalloc((void **)&a, (n + 1) * 4));
+            insert_into(arr[0], ix.starts, n, pos[0], start, st.s);
+            insert_into(arr[1], ix.stops_by_iv, n, pos[0], stop, st.s);
+            insert_into(arr[2], ix.stops_sorted, n, pos[1], stop, st.s);
+            insert_into(arr[3], ix.perm, n, pos[0], (uint32_t)id, st.s);
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));  // the host-side scalars above are read by the copies
+        } catch (...) {
+            for (auto a : arr) cudaFree(a);
+            throw;
+        }
+        free_index(ix);
+        ix.n = n + 1;
+        ix.starts = arr[0];
+        ix.stops_by_iv = arr[1];
+        ix.stops_sorted = arr[2];
+        ix.perm = arr[3];
+        ix.bytes = 16 * (n + 1);
+        finish_index_from_sorted(ix, l->build_flags, st.s);  // max_len (src/lib.rs:264-267) falls out of the rebuild
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+        l->next_input_id = id + 1;
+        l->cov_is_some = false;       // src/lib.rs:271
+        l->overlaps_merged = false;   // src/lib.rs:272
+        if (input_position_out) *input_position_out = id;
     });
 }
 

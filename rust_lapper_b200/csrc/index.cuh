@@ -89,6 +89,7 @@ struct lapper {
     bool cov_is_some = false;
     uint32_t cov = 0;
     uint32_t build_flags = 0;
+    uint64_t next_input_id = 0;  // input position handed to the next inserted interval
 };
 
 struct lapper_result {

@@ -205,6 +205,16 @@ class Lapper:
         s, e, _ = self._sorted()
         return [(int(s[i]), int(e[i])) for i in self.seek_idx(start, stop, cursor)]
 
+    def insert(self, start: int, stop: int, val: Any = None) -> None:
+        """src/lib.rs:260-273: sorted insert (before equal intervals); clears cov and overlaps_merged."""
+        pos = C.c_uint64(0)
+        _ffi.check(self._lib.lapper_insert_u32(self._h, start, stop, C.byref(pos)))
+        if self._vals is not None:
+            while len(self._vals) < int(pos.value):
+                self._vals.append(None)
+            self._vals.append(val)
+        self._cache = None
+
     # ---------------------------------------------------------------- set operations
     def merge_overlaps(self) -> None:  # src/lib.rs:361-416
         _ffi.check(self._lib.lapper_merge_overlaps(self._h))

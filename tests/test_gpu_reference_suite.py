@@ -35,3 +35,48 @@ def test_stable_ties_keep_input_order(make):
     s, e, p = lap.intervals_soa()
     assert list(zip(s.tolist(), e.tolist())) == sorted(ivs)
     assert p.tolist() == [1, 4, 3, 0, 2, 5]
+
+
+@pytest.mark.parametrize(
+    "data",
+    [rs.nonoverlapping(), rs.overlapping(), rs.badlapper(), rs.single()],
+    ids=["nonoverlapping", "overlapping", "badlapper", "single"],
+)
+def test_insert_equality(make, data):  # src/lib.rs:907-948, :976-1019
+    new_lapper = make(data)
+    insert_lapper = make([])
+    for s, e in data:
+        insert_lapper.insert(s, e)
+    assert new_lapper.starts.tolist() == insert_lapper.starts.tolist()
+    assert new_lapper.stops.tolist() == insert_lapper.stops.tolist()
+    assert new_lapper.intervals == insert_lapper.intervals
+    assert new_lapper.max_len == insert_lapper.max_len
+
+
+def test_insert_equality_half_and_half(make):  # src/lib.rs:952-974
+    data = [(x, x + 15) for x in range(100)]
+    new_lapper = make(data)
+    insert_lapper = make(data[:50])
+    for s, e in reversed(data[50:]):
+        insert_lapper.insert(s, e)
+    assert new_lapper.starts.tolist() == insert_lapper.starts.tolist()
+    assert new_lapper.stops.tolist() == insert_lapper.stops.tolist()
+    assert new_lapper.intervals == insert_lapper.intervals
+    assert new_lapper.max_len == insert_lapper.max_len
+
+
+def test_insert_doctest_and_side_effects(make, oracle):  # src/lib.rs:243-259, :271-272
+    lapper = make([(0, 5), (6, 10)])
+    lapper.merge_overlaps()
+    lapper.set_cov()
+    lapper.insert(0, 20)
+    assert len(lapper.intervals) == 3
+    assert lapper.find(1, 3) == [(0, 5), (0, 20)]
+    assert not lapper.overlaps_merged
+    assert lapper.cov() == 20
+    # a duplicate goes BEFORE the equal intervals already there (bsearch_seq_ref), like the oracle
+    cpu = oracle.OracleLapper([(5, 9), (5, 9), (1, 3)])
+    gpu = make([(5, 9), (5, 9), (1, 3)])
+    cpu.insert(5, 9, 3)
+    gpu.insert(5, 9)
+    assert gpu.intervals_soa()[2].tolist() == cpu.intervals_soa()[2].tolist() == [2, 3, 0, 1]
