@@ -148,7 +148,12 @@ int lapper_set_cov(lapper_t *l, uint32_t *cov_out);
 /* ---- Lapper::union_and_intersect / intersect / union (src/lib.rs:512-559) */
 int lapper_union_and_intersect(const lapper_t *a, const lapper_t *b, uint32_t *union_out, uint32_t *intersect_out);
 
-/* frees buffers the library malloc'ed for the caller (lapper_group_find_batch_u32) */
+/* ---- Lapper::depth() + IterDepth (src/lib.rs:576-598, :720-784): maximal runs of equal coverage depth inside
+ *      the merged intervals, in order: (starts[r], stops[r], depth[r]) for r < *n_out.  The three arrays are
+ *      malloc'ed by the library (lapper_host_free).  The reference panics on an empty lapper
+ *      (src/lib.rs:744): LAPPER_ERR_INVALID_ARG here.  LAPPER_ERR_PRECONDITION if some stop < start. */
+int lapper_depth(const lapper_t *l, uint64_t *n_out, uint32_t **starts_out, uint32_t **stops_out, uint32_t **depth_out);
+/* frees buffers the library malloc'ed for the caller (lapper_depth, lapper_group_find_batch_u32) */
 void lapper_host_free(void *p);
 
 /* ---- multi-GPU, single process: the index is replicated (peer copies over NVLink), queries are

@@ -140,6 +140,18 @@ class Lapper {
         check(lapper_union_and_intersect(h_, other.h_, &u, &i));
         return {u, i};
     }
+    // depth() / IterDepth (src/lib.rs:576-598, :720-784): runs of equal coverage depth, val = the depth
+    std::vector<Interval<uint32_t>> depth() const {
+        uint64_t n = 0;
+        uint32_t *s = nullptr, *e = nullptr, *d = nullptr;
+        check(lapper_depth(h_, &n, &s, &e, &d));
+        std::vector<Interval<uint32_t>> out;
+        for (uint64_t i = 0; i < n; i++) out.push_back(Interval<uint32_t>{s[i], e[i], d[i]});
+        lapper_host_free(s);
+        lapper_host_free(e);
+        lapper_host_free(d);
+        return out;
+    }
     uint32_t intersect(const Lapper &o) const { return union_and_intersect(o).second; }
     uint32_t union_(const Lapper &o) const { return union_and_intersect(o).first; }
 

@@ -83,6 +83,7 @@ SIGNATURES = {
     "lapper_cov": (_int, [_vp, C.POINTER(_u32)]),
     "lapper_set_cov": (_int, [_vp, C.POINTER(_u32)]),
     "lapper_union_and_intersect": (_int, [_vp, _vp, C.POINTER(_u32), C.POINTER(_u32)]),
+    "lapper_depth": (_int, [_vp, C.POINTER(_u64), _pvp, _pvp, _pvp]),
     "lapper_host_free": (None, [_vp]),
     "lapper_replicate": (_int, [_vp, C.POINTER(_int), _int, _pvp]),
     "lapper_group_free": (None, [_vp]),

@@ -610,6 +610,40 @@ int lapper_union_and_intersect(const lapper_t *a, const lapper_t *b, uint32_t *u
     });
 }
 
+int lapper_depth(const lapper_t *l, uint64_t *n_out, uint32_t **starts_out, uint32_t **stops_out, uint32_t **depth_out) {
+    return guarded([&] {
+        check_handle(l);
+        LAPPER_REQUIRE(n_out && starts_out && stops_out && depth_out, "lapper_depth: null pointer");
+        *n_out = 0;
+        *starts_out = *stops_out = *depth_out = nullptr;
+        LAPPER_REQUIRE(l->ix.n > 0, "depth() on an empty lapper: the reference panics here (src/lib.rs:744)");
+        need_valid_intervals(l, "depth");
+        DeviceGuard dg(l->device);
+        StreamOwner st;
+        uint32_t *d[3] = {nullptr, nullptr, nullptr};
+        const uint64_t nr = compute_depth(l->ix, &d[0], &d[1], &d[2], st.s);
+        uint32_t *h[3] = {nullptr, nullptr, nullptr};
+        try {
+            for (int i = 0; i < 3; i++) {
+                h[i] = (uint32_t *)malloc(std::max<uint64_t>(nr, 1) * 4);
+                if (!h[i]) throw std::bad_alloc();
+                if (nr) LAPPER_CUDA_CHECK(cudaMemcpy(h[i], d[i], nr * 4, cudaMemcpyDeviceToHost));
+            }
+        } catch (...) {
+            for (int i = 0; i < 3; i++) {
+                free(h[i]);
+                cudaFree(d[i]);
+            }
+            throw;
+        }
+        for (int i = 0; i < 3; i++) cudaFree(d[i]);
+        *n_out = nr;
+        *starts_out = h[0];
+        *stops_out = h[1];
+        *depth_out = h[2];
+    });
+}
+
 void lapper_host_free(void *p) { free(p); }
 
 int lapper_host_alloc_pinned(uint64_t bytes, void **out) {

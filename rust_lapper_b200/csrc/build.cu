@@ -445,6 +445,10 @@ void build_find_classes(DeviceIndex &ix, cudaStream_t stream) {
 
 }  // namespace
 
+void launch_sort_u32(uint32_t *keys, uint32_t *tmp, uint64_t n, cudaStream_t stream) {
+    if (n > 1) radix_sort<uint32_t, false>(keys, tmp, nullptr, nullptr, n, 32, stream);
+}
+
 void free_index(DeviceIndex &ix) {
     cudaFree(ix.cls_starts);
     cudaFree(ix.cls_stops);

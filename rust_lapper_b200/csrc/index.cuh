@@ -109,6 +109,8 @@ void build_index_from_unsorted(DeviceIndex &ix, const uint32_t *d_starts, const 
 // Arrays already sorted (import / after merge_overlaps).  Takes ownership of the four arrays.
 void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stream);
 void free_index(DeviceIndex &ix);
+// in-place ascending sort of n u32 keys (hand-written LSD radix sort); tmp holds n keys
+void launch_sort_u32(uint32_t *keys, uint32_t *tmp, uint64_t n, cudaStream_t stream);
 
 // query.cu ---------------------------------------------------------------------------------------
 void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, uint32_t *d_out32,
@@ -130,6 +132,10 @@ uint32_t compute_cov(const DeviceIndex &ix, cudaStream_t stream);
 // merged (start, stop, head perm) arrays; returns m.  Outputs are cudaMalloc'ed (m may be 0).
 uint64_t compute_merged(const DeviceIndex &ix, uint32_t **m_starts, uint32_t **m_stops, uint32_t **m_perm,
                         cudaStream_t stream);
+// depth(): maximal runs of equal coverage depth (src/lib.rs:576-598, :735-784).  Device arrays (cudaMalloc),
+// returns the number of runs.
+uint64_t compute_depth(const DeviceIndex &ix, uint32_t **d_starts, uint32_t **d_stops, uint32_t **d_depth,
+                       cudaStream_t stream);
 // measure of (union of a) intersected with (union of b), wrapping u32
 uint32_t compute_intersect_measure(const DeviceIndex &a, const DeviceIndex &b, cudaStream_t stream);
 

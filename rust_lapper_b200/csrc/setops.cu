@@ -8,6 +8,8 @@
 //   cov     = sum over runs of (P_last - start_head)       (src/lib.rs:327-350; u32, wrapping)
 //   A n B   = sum over merged runs a of F_B(a.stop) - F_B(a.start), F_B(x) = |union(B) n [0, x)|
 //             (what src/lib.rs:517-543 computes by enumerating pairs, in either branch)
+#include <algorithm>
+
 #include "index.cuh"
 
 namespace lap {
@@ -197,6 +199,70 @@ struct MergeSink {
     }
 };
 
+// ---- depth(): functors of the two compactions (see compute_depth)
+struct UniqueFlag {  // first occurrence of each coordinate in the sorted event list
+    const uint32_t *X;
+    __device__ __forceinline__ uint32_t operator()(uint64_t i) const { return (i == 0 || X[i] != X[i - 1]) ? 1u : 0u; }
+};
+struct UniqueSink {
+    const uint32_t *X;
+    uint32_t *U;
+    __device__ __forceinline__ void operator()(uint64_t i, uint32_t flag, uint32_t inclusive) const {
+        if (flag) U[inclusive - 1] = X[i];
+    }
+};
+// emit points among the unique coordinates: depth changes, and zero-length merged runs (depth 0 before and
+// at the coordinate, with an interval starting there) other than the very first run
+struct EmitPointFlag {
+    const uint32_t *D;
+    const uint32_t *has_start;
+    __device__ __forceinline__ bool zero_run(uint64_t t) const { return t > 0 && D[t] == 0 && D[t - 1] == 0 && has_start[t]; }
+    __device__ __forceinline__ uint32_t operator()(uint64_t t) const {
+        return (t == 0 || D[t] != D[t - 1] || zero_run(t)) ? 1u : 0u;
+    }
+};
+struct EmitPointSink {
+    const uint32_t *U;
+    EmitPointFlag f;
+    uint32_t *eu, *ed, *ez;
+    __device__ __forceinline__ void operator()(uint64_t t, uint32_t flag, uint32_t inclusive) const {
+        if (flag) {
+            eu[inclusive - 1] = U[t];
+            ed[inclusive - 1] = f.D[t];
+            ez[inclusive - 1] = f.zero_run(t) ? 1u : 0u;
+        }
+    }
+};
+struct RunFlag {  // emit points that produce a run: positive depth, or a zero-length merged run
+    const uint32_t *ed, *ez;
+    __device__ __forceinline__ uint32_t operator()(uint64_t q) const { return (ed[q] > 0 || ez[q]) ? 1u : 0u; }
+};
+struct RunSink {
+    const uint32_t *eu, *ed, *ez;
+    uint32_t *os, *oe, *od;
+    __device__ __forceinline__ void operator()(uint64_t q, uint32_t flag, uint32_t inclusive) const {
+        if (flag) {
+            const uint32_t r = inclusive - 1;
+            os[r] = eu[q];
+            // a positive-depth run ends at the next emit point, which is always a depth change
+            oe[r] = ez[q] ? eu[q] : eu[q + 1];
+            od[r] = ed[q];
+        }
+    }
+};
+
+// depth at every unique coordinate u: #{start <= u} - #{stop <= u}, and whether an interval starts at u
+__global__ void __launch_bounds__(kThreads) depth_eval_kernel(const uint32_t *__restrict__ S, const uint32_t *__restrict__ E,
+                                                              uint32_t n, const uint32_t *__restrict__ U, uint64_t m,
+                                                              uint32_t *__restrict__ D, uint32_t *__restrict__ has_start) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t u = U[t];
+        const uint32_t ub_s = upper_bound_u32(S, 0, n, u);
+        D[t] = ub_s - upper_bound_u32(E, 0, n, u);
+        has_start[t] = lower_bound_u32(S, 0, n, u) < ub_s ? 1u : 0u;
+    }
+}
+
 template <typename Op, typename In, typename Sink>
 void scan3(In in, uint64_t n, Sink sink, uint32_t *d_total, cudaStream_t stream) {
     if (n == 0) {
@@ -326,6 +392,57 @@ uint64_t compute_merged(const DeviceIndex &ix, uint32_t **m_starts, uint32_t **m
     *m_perm = out.perm;
     out.s = out.e = out.perm = nullptr;
     return m;
+}
+
+// Closed form of IterDepth (src/lib.rs:735-784), verified against the literal loop in
+// tests/test_oracle_golden.py::test_depth_closed_form: over the sorted unique event coordinates u_t with
+// depth D_t = #{start <= u_t} - #{stop <= u_t}, a run starts wherever D changes to a positive value and
+// ends at the next change; a zero-length merged run (an isolated coordinate where only zero-length
+// intervals sit) is reported as (u, u, 0) unless it is the first run of the set.
+uint64_t compute_depth(const DeviceIndex &ix, uint32_t **d_starts, uint32_t **d_stops, uint32_t **d_depth,
+                       cudaStream_t stream) {
+    *d_starts = *d_stops = *d_depth = nullptr;
+    const uint64_t n = ix.n, n2 = 2 * n;
+    Scratch<uint32_t> X(n2, stream), tmp(n2, stream), U(n2, stream), D(n2, stream), HS(n2, stream);
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(X.p, ix.starts, n * 4, cudaMemcpyDeviceToDevice, stream));
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(X.p + n, ix.stops_sorted, n * 4, cudaMemcpyDeviceToDevice, stream));
+    launch_sort_u32(X.p, tmp.p, n2, stream);
+    Scratch<uint32_t> d_count(1, stream);
+    uint32_t m = 0, ne = 0, nr = 0;
+    scan3<AddOp>(UniqueFlag{X.p}, n2, UniqueSink{X.p, U.p}, d_count.p, stream);
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&m, d_count.p, 4, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    depth_eval_kernel<<<reduce_grid(m), kThreads, 0, stream>>>(ix.starts, ix.stops_sorted, (uint32_t)n, U.p, m, D.p, HS.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    Scratch<uint32_t> eu((uint64_t)m + 1, stream), ed((uint64_t)m + 1, stream), ez((uint64_t)m + 1, stream);
+    const EmitPointFlag epf{D.p, HS.p};
+    scan3<AddOp>(epf, m, EmitPointSink{U.p, epf, eu.p, ed.p, ez.p}, d_count.p, stream);
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&ne, d_count.p, 4, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    // count the runs first, then size the outputs
+    const RunFlag rf{ed.p, ez.p};
+    {
+        const uint64_t ntiles = div_up(ne, kTile);
+        Scratch<uint32_t> agg(ntiles, stream);
+        tile_reduce_kernel<AddOp, RunFlag><<<(uint32_t)ntiles, kThreads, 0, stream>>>(rf, ne, agg.p);
+        tile_scan_kernel<AddOp><<<1, kThreads, 0, stream>>>(agg.p, ntiles, d_count.p);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(&nr, d_count.p, 4, cudaMemcpyDeviceToHost, stream));
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+        DevArrays out;
+        LAPPER_CUDA_CHECK(cudaMalloc((void **)&out.s, std::max<uint64_t>(nr, 1) * 4));
+        LAPPER_CUDA_CHECK(cudaMalloc((void **)&out.e, std::max<uint64_t>(nr, 1) * 4));
+        LAPPER_CUDA_CHECK(cudaMalloc((void **)&out.perm, std::max<uint64_t>(nr, 1) * 4));
+        tile_apply_kernel<AddOp, RunFlag, RunSink><<<(uint32_t)ntiles, kThreads, 0, stream>>>(
+            rf, ne, agg.p, RunSink{eu.p, ed.p, ez.p, out.s, out.e, out.perm});
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+        *d_starts = out.s;
+        *d_stops = out.e;
+        *d_depth = out.perm;
+        out.s = out.e = out.perm = nullptr;
+    }
+    return nr;
 }
 
 uint32_t compute_intersect_measure(const DeviceIndex &a, const DeviceIndex &b, cudaStream_t stream) {

@@ -242,6 +242,23 @@ class Lapper:
         return self.union_and_intersect(other)[0]
 
 
+    def depth(self) -> List[Tuple[int, int, int]]:
+        """src/lib.rs:576-598 + IterDepth: (start, stop, depth) runs inside the merged intervals, in order."""
+        n = C.c_uint64(0)
+        ps, pe, pd = C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)
+        rc = self._lib.lapper_depth(self._h, C.byref(n), C.byref(ps), C.byref(pe), C.byref(pd))
+        if rc == _ffi.ERR_INVALID_ARG and len(self) == 0:
+            raise IndexError("depth() on an empty lapper panics in the reference (src/lib.rs:744)")
+        _ffi.check(rc)
+        try:
+            k = int(n.value)
+            cols = [np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(k,)).tolist() if k else [] for p in (ps, pe, pd)]
+        finally:
+            for p in (ps, pe, pd):
+                self._lib.lapper_host_free(p)
+        return list(zip(*cols)) if k else []
+
+
 class LapperGroup:
     """One replica of the index per GPU of this process; queries sharded contiguously
     (device g owns [g*nq/G, (g+1)*nq/G)), results identical to the single-GPU call."""

@@ -142,6 +142,28 @@ int main() {
         ex.merge_overlaps();
         CHECK(ex.union_and_intersect(other) == std::make_pair(88u, 27u));
     }
+    {  // test_depth_sanity / test_depth_hard  :1279-1313
+        Lapper<uint32_t> l1({{0, 10, 0}, {5, 10, 0}});
+        auto d = l1.depth();
+        CHECK(d.size() == 2 && d[0] == (Interval<uint32_t>{0, 5, 1}) && d[0].val == 1 && d[1] == (Interval<uint32_t>{5, 10, 2}) && d[1].val == 2);
+        Lapper<uint32_t> l2({{1, 10, 0}, {2, 5, 0}, {3, 8, 0}, {3, 8, 0}, {3, 8, 0}, {5, 8, 0}, {9, 11, 0}});
+        const uint32_t want[6][3] = {{1, 2, 1}, {2, 3, 2}, {3, 8, 5}, {8, 9, 1}, {9, 10, 2}, {10, 11, 1}};
+        auto d2 = l2.depth();
+        CHECK(d2.size() == 6);
+        for (size_t i = 0; i < 6 && i < d2.size(); i++)
+            CHECK(d2[i].start == want[i][0] && d2[i].stop == want[i][1] && d2[i].val == want[i][2]);
+    }
+    {  // insert doctest :243-259 and insert_equality_overlapping :929-948
+        Lapper<uint32_t> lapper({{0, 5, 1}, {6, 10, 2}});
+        lapper.insert(Iv{0, 20, 5});
+        CHECK(lapper.len() == 3);
+        CHECK(same(lapper.find(1, 3), {{0, 5, 1}, {0, 20, 5}}));
+        CHECK(lapper.find(1, 3)[1]->val == 5);
+        Lapper<uint32_t> a(overlapping()), b(std::vector<Iv>{});
+        for (const Iv &iv : overlapping()) b.insert(iv);
+        CHECK(a.intervals.size() == b.intervals.size() && a.max_len() == b.max_len());
+        for (size_t i = 0; i < a.intervals.size() && i < b.intervals.size(); i++) CHECK(a.intervals[i] == b.intervals[i]);
+    }
     std::printf(failures ? "%d FAILED\n" : "all reference tests passed (C++ facade)\n", failures);
     return failures ? 1 : 0;
 }

@@ -80,3 +80,24 @@ def test_insert_doctest_and_side_effects(make, oracle):  # src/lib.rs:243-259, :
     cpu.insert(5, 9, 3)
     gpu.insert(5, 9)
     assert gpu.intervals_soa()[2].tolist() == cpu.intervals_soa()[2].tolist() == [2, 3, 0, 1]
+
+
+def test_depth_reference_vectors(make):  # src/lib.rs:1279-1337 and the doctest :565-575
+    rs.check_depth(make)
+
+
+def test_depth_matches_oracle_on_random_sets(make, oracle):
+    import numpy as np
+
+    rng = np.random.default_rng(77)
+    for _ in range(25):
+        n = int(rng.integers(1, 60))
+        U = int(rng.choice([15, 60, 400]))
+        s = rng.integers(0, U, n)
+        ln = rng.integers(0, int(rng.choice([1, 3, 9, 50])), n)
+        if rng.random() < 0.5:
+            ln[rng.random(n) < 0.4] = 0
+        ivs = list(zip(s.tolist(), (s + ln).tolist()))
+        assert make(ivs).depth() == oracle.OracleLapper(ivs).depth()
+    with pytest.raises(IndexError):
+        make([]).depth()

@@ -169,3 +169,36 @@ def test_threads_agree(oracle):
     o4, i4 = lap.find_batch(qs, qe, 4)
     assert np.array_equal(o1, o4) and np.array_equal(i1, i4)
     assert lap.find_count_sum(qs, qe, 3) == int(o1[-1])
+
+
+def depth_closed_form(s, e):
+    """Closed form of IterDepth (src/lib.rs:735-784) that the GPU implements (csrc/setops.cu compute_depth)."""
+    S, E = np.sort(np.asarray(s, np.int64)), np.sort(np.asarray(e, np.int64))
+    U = np.unique(np.concatenate([S, E]))
+    D = np.searchsorted(S, U, "right") - np.searchsorted(E, U, "right")
+    has_start = np.searchsorted(S, U, "left") < np.searchsorted(S, U, "right")
+    prev = np.concatenate([[-1], D[:-1]])
+    change = prev != D
+    zero = (D == 0) & (prev == 0) & has_start
+    zero[0] = False
+    ep = np.nonzero(change | zero)[0]
+    out = []
+    for q, t in enumerate(ep):
+        if zero[t]:
+            out.append((int(U[t]), int(U[t]), 0))
+        elif D[t] > 0:
+            out.append((int(U[t]), int(U[ep[q + 1]]), int(D[t])))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_depth_closed_form(oracle, seed):
+    rng = np.random.default_rng(400 + seed)
+    for _ in range(300):
+        n = int(rng.integers(1, 25))
+        U = int(rng.choice([12, 40, 200]))
+        s = rng.integers(0, U, n)
+        ln = rng.integers(0, int(rng.choice([1, 2, 6, 30])), n)
+        if rng.random() < 0.5:
+            ln[rng.random(n) < 0.4] = 0  # zero-length intervals: the IterDepth quirks live here
+        assert oracle.OracleLapper(starts=s, stops=s + ln).depth() == depth_closed_form(s, s + ln)
