@@ -475,6 +475,65 @@ def run_extras(args, lib, h, dev, stream, sp, n, nq, peak):
     lib.lapper_free(h3)
     del s3, e3, q3s, q3e, offsets, indices
 
+    # cfg 4: pathological set (1 % of the intervals span > 50 % of the universe; max_len ~ 0.9 U).  count is
+    # unaffected (BITS); find returns ~1 % of all intervals per query, so the batch is small and output-bound.
+    s4, e4 = synth.intervals_pathological(46, n, UNIVERSE, device=dev)
+    h4 = C.c_void_p(0)
+    _ffi.check(lib.lapper_build_u32_dev(_vp(s4), _vp(e4), n, dev.index, 0, sp, C.byref(h4)))
+    q4s, q4e = synth.queries_fixed_len(47, nq, UNIVERSE, QLEN, device=dev)
+    c4 = torch.empty(nq, dtype=torch.int32, device=dev)
+    ms = timed(lambda: _ffi.check(lib.lapper_count_batch_u32_dev(h4, _vp(q4s), _vp(q4e), nq, _vp(c4), sp)), 5)
+    nq4 = 10_000
+    off4 = torch.empty(nq4 + 1, dtype=torch.int64, device=dev)
+    t4 = C.c_uint64(0)
+    _ffi.check(lib.lapper_find_batch_offsets_u32_dev(h4, _vp(q4s), _vp(q4e), nq4, _vp(off4), C.byref(t4), sp))
+    idx4 = torch.empty(max(int(t4.value), 1), dtype=torch.int32, device=dev)
+
+    def find4():
+        t = C.c_uint64(0)
+        _ffi.check(lib.lapper_find_batch_offsets_u32_dev(h4, _vp(q4s), _vp(q4e), nq4, _vp(off4), C.byref(t), sp))
+        _ffi.check(lib.lapper_find_batch_fill_u32_dev(h4, _vp(q4s), _vp(q4e), nq4, _vp(off4), _vp(idx4), sp))
+
+    ms_f = timed(find4, 3)
+    out["cfg4_pathological_long_intervals"] = {
+        "max_len": int(lib.lapper_max_len(h4)),
+        "count_random_100M_ms": ms, "count_queries_per_s": nq / (ms * 1e-3),
+        "find_queries": nq4, "find_hits": int(t4.value), "find_ms": ms_f,
+        "find_hits_per_s": int(t4.value) / (ms_f * 1e-3), "find_output_GBps": int(t4.value) * 4 / (ms_f * 1e-3) / 1e9,
+        "note": "the reference scans ~n/2 intervals per find() here (src/lib.rs:36-47); length classes keep the scan to the long class",
+    }
+    lib.lapper_free(h4)
+    del s4, e4, q4s, q4e, c4, off4, idx4
+
+    # cfg 1a: README interval_bakeoff shape (README.md:51-61): 50,000 intervals, universe 100,000, len 500..80,000,
+    # plus one universe-spanning interval; A-vs-A: find and count over the set's own intervals
+    (sa, ea), _ = synth.bakeoff_sets(1, 2, 50_000, 100_000)
+    ta = torch.from_numpy(sa.view("int32")).to(dev)
+    tb = torch.from_numpy(ea.view("int32")).to(dev)
+    h1 = C.c_void_p(0)
+    _ffi.check(lib.lapper_build_u32_dev(_vp(ta), _vp(tb), ta.numel(), dev.index, 0, sp, C.byref(h1)))
+    n1 = ta.numel()
+    off1 = torch.empty(n1 + 1, dtype=torch.int64, device=dev)
+    t1 = C.c_uint64(0)
+    _ffi.check(lib.lapper_find_batch_offsets_u32_dev(h1, _vp(ta), _vp(tb), n1, _vp(off1), C.byref(t1), sp))
+    idx1 = torch.empty(max(int(t1.value), 1), dtype=torch.int32, device=dev)
+    c1 = torch.empty(n1, dtype=torch.int32, device=dev)
+
+    def find1():
+        t = C.c_uint64(0)
+        _ffi.check(lib.lapper_find_batch_offsets_u32_dev(h1, _vp(ta), _vp(tb), n1, _vp(off1), C.byref(t), sp))
+        _ffi.check(lib.lapper_find_batch_fill_u32_dev(h1, _vp(ta), _vp(tb), n1, _vp(off1), _vp(idx1), sp))
+
+    ms_f1 = timed(find1, 3)
+    ms_c1 = timed(lambda: _ffi.check(lib.lapper_count_batch_u32_dev(h1, _vp(ta), _vp(tb), n1, _vp(c1), sp)), 10)
+    out["cfg1a_readme_bakeoff_A_vs_A"] = {
+        "intervals": n1, "hits": int(t1.value), "find_ms": ms_f1, "find_hits_per_s": int(t1.value) / (ms_f1 * 1e-3),
+        "count_ms": ms_c1, "count_equals_find_total": int(c1.to(torch.int64).sum().item()) == int(t1.value),
+        "published_reference": "README.md:73-76: find 4.78125 s (1,469,068,763 hits, unseeded data), count 15.625 ms (timer floor), unstated CPU",
+    }
+    lib.lapper_free(h1)
+    del idx1, off1
+
     # cfg 5 shape on one GPU: 50 M intervals (cfg-2 distribution): build, cov, merge_overlaps,
     # union_and_intersect and random-order count against the larger (485 MB) table
     n5 = args.big_intervals

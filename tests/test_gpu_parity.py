@@ -237,3 +237,36 @@ def test_query_shapes_on_dense_gene_exon_set(oracle):
         go, gi = gpu.find_batch(qs, qe)
         co, ci = cpu.find_batch(qs, qe, 4)
         assert np.array_equal(go, co) and np.array_equal(gi, ci), name
+
+
+def test_concurrent_const_calls_from_host_threads(oracle):
+    """One handle shared by several host threads (the reference's shared `&Lapper`, src/lib.rs:7): concurrent
+    count_batch / find_batch / cov calls must each return the oracle's answer."""
+    import threading
+
+    rng = np.random.default_rng(9)
+    s, e, _, _ = rs.random_case(rng, 200_000, 50_000_000, 3000, 1, 1)
+    gpu, cpu = _both(oracle, s, e)
+    want_cov = cpu.cov()
+    jobs = []
+    for t in range(8):
+        _, _, qs, qe = rs.random_case(np.random.default_rng(100 + t), 1, 50_000_000, 3000, 40_000 + 1000 * t, 400)
+        jobs.append((qs, qe, cpu.count_batch(qs, qe), cpu.find_batch(qs, qe)))
+    errors = []
+
+    def worker(qs, qe, want_c, want_f):
+        try:
+            for _ in range(3):
+                assert np.array_equal(gpu.count_batch(qs, qe), want_c)
+                off, idx = gpu.find_batch(qs, qe)
+                assert np.array_equal(off, want_f[0]) and np.array_equal(idx, want_f[1])
+                assert gpu.cov() == want_cov
+        except Exception as ex:  # noqa: BLE001
+            errors.append(repr(ex))
+
+    threads = [threading.Thread(target=worker, args=j) for j in jobs]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
