@@ -266,6 +266,17 @@ __global__ void fill_children_kernel(const uint32_t *__restrict__ S, const uint3
     }
 }
 
+// max stop of every 32 consecutive sorted intervals (one warp per block), then of every 32 such blocks
+__global__ void __launch_bounds__(kThreads) block_max_kernel(const uint32_t *__restrict__ in, uint64_t n,
+                                                             uint32_t *__restrict__ out, uint64_t nblocks) {
+    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    if (warp >= nblocks) return;
+    const uint64_t i = warp * 32 + lane;
+    const uint32_t v = __reduce_max_sync(0xFFFFFFFFu, i < n ? in[i] : 0u);
+    if (lane == 0) out[warp] = v;
+}
+
 struct LenHist {
     unsigned long long count[33];
     uint32_t maxlen[33];
@@ -454,6 +465,8 @@ void free_index(DeviceIndex &ix) {
     cudaFree(ix.cls_stops);
     cudaFree(ix.cls_gidx);
     cudaFree(ix.cls_dir);
+    cudaFree(ix.blkmax32);
+    cudaFree(ix.blkmax1024);
     cudaFree(ix.starts);
     cudaFree(ix.stops_by_iv);
     cudaFree(ix.stops_sorted);
@@ -496,6 +509,14 @@ void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stre
     ix.max_coord = std::max(last_start, last_stop);
 
     build_find_classes(ix, stream);
+    {
+        const uint64_t nb32 = div_up(n, 32), nb1024 = div_up(nb32, 32);
+        ix.blkmax32 = dev_alloc<uint32_t>(nb32, ix.bytes);
+        ix.blkmax1024 = dev_alloc<uint32_t>(nb1024, ix.bytes);
+        block_max_kernel<<<(uint32_t)div_up(nb32 * 32, kThreads), kThreads, 0, stream>>>(ix.stops_by_iv, n, ix.blkmax32, nb32);
+        block_max_kernel<<<(uint32_t)div_up(nb1024 * 32, kThreads), kThreads, 0, stream>>>(ix.blkmax32, nb32, ix.blkmax1024, nb1024);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+    }
 
     uint32_t shift = 0;
     if (choose_shift(n, ix.max_coord, flags, shift)) {

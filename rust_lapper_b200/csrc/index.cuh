@@ -74,6 +74,12 @@ struct DeviceIndex {
     uint32_t *cls_stops = nullptr;
     uint32_t *cls_gidx = nullptr;
     uint4 *cls_dir = nullptr;  // cls_nb + 1 entries
+
+    // ---- find, heavy queries: max(stops_by_iv) over blocks of 32 and of 1024 consecutive sorted intervals.
+    // A warp that scans one query's window skips every block whose max stop is <= the query start (the
+    // `max_ends` idea of the reference's devlog.md:2-5).
+    uint32_t *blkmax32 = nullptr;    // ceil(n / 32)
+    uint32_t *blkmax1024 = nullptr;  // ceil(n / 1024)
     uint32_t cls_shift = 0;
     uint64_t cls_nb = 0;
 };

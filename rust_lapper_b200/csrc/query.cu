@@ -173,6 +173,8 @@ struct FindView {
     const uint32_t *cs, *ce, *cg;
     const uint4 *dir;
     uint32_t cls_shift, cls_nb;
+    // heavy queries
+    const uint32_t *pmax, *blkmax32, *blkmax1024;
 };
 
 __device__ __forceinline__ uint32_t rank_lb_starts(const FindView &f, uint32_t key) {
@@ -698,11 +700,14 @@ __device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, ui
 // Slow path (union too large: random-order queries, very long intervals): each lane merges its own
 // class streams.  Either way the order is the reference iterator's (ascending position).
 constexpr int kEmitQ = 2;  // queries per lane: one candidate union serves 64 consecutive queries
+constexpr uint32_t kHeavyHits = 256;  // a query with at least this many hits gets a warp of its own (find_heavy_kernel)
 
 __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const uint32_t *__restrict__ qs,
                                                              const uint32_t *__restrict__ qe, uint64_t nq,
                                                              const uint64_t *__restrict__ offsets,
-                                                             uint32_t *__restrict__ indices) {
+                                                             uint32_t *__restrict__ indices,
+                                                             uint32_t *__restrict__ heavy_list,
+                                                             unsigned int *__restrict__ heavy_count) {
     __shared__ uint32_t smem_all[kThreads / 32][kEmitWarpWords];
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t *const stage = smem_all[threadIdx.x >> 5];       // kEmitStage output slots ...
@@ -726,6 +731,11 @@ __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const u
             if (live && (lane == 31 || j + 1 == nq)) o1[q] = offsets[j + 1];
             if (!live) o0[q] = o1[q] = 0;
             mine[q] = live && o1[q] > o0[q];
+            if (mine[q] && o1[q] - o0[q] >= kHeavyHits) {
+                // too many hits for one lane: hand the query to find_heavy_kernel (a warp per query)
+                heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)j;
+                mine[q] = false;
+            }
             a[q] = 0xFFFFFFFFu, b[q] = 0;
             if (mine[q]) {
                 a[q] = ld_stream_u32(qs + j);
@@ -812,6 +822,72 @@ __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const u
     }
 }
 
+// ---- heavy queries: one warp per query scans the window [lo, hi) of the single sorted vector -- the
+// reference's own scan (src/lib.rs:704-717) -- 32 intervals per step, skipping every block of 32 / 1024
+// intervals whose max stop is <= the query start, and ballot-compacts the hits into coalesced stores.
+// Positions come out ascending by construction: no merge.  Warps fetch queries from an atomic counter.
+__global__ void __launch_bounds__(kThreads) find_heavy_kernel(FindView f, const uint32_t *__restrict__ qs,
+                                                              const uint32_t *__restrict__ qe,
+                                                              const uint64_t *__restrict__ offsets,
+                                                              uint32_t *__restrict__ indices,
+                                                              const uint32_t *__restrict__ heavy_list,
+                                                              const unsigned int *__restrict__ heavy_count,
+                                                              unsigned int *__restrict__ next) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt = (1u << lane) - 1u;
+    const unsigned int total = *heavy_count;
+    for (;;) {
+        unsigned int item = 0;
+        if (lane == 0) item = atomicAdd(next, 1u);
+        item = __shfl_sync(0xFFFFFFFFu, item, 0);
+        if (item >= total) return;
+        const uint64_t j = heavy_list[item];
+        const uint32_t a = __ldg(qs + j), b = __ldg(qe + j);
+        const uint64_t o0 = offsets[j], room = offsets[j + 1] - o0;
+        // window: starts in [a - max_len, b), tightened by the running max of stops (nothing before the
+        // first position whose prefix max exceeds a can end after a)
+        uint32_t r = 0;
+        if (lane == 0) r = rank_lb_starts(f, b);
+        if (lane == 1) r = rank_lb_starts(f, a >= f.max_len ? a - f.max_len : 0u);
+        if (lane == 2) r = upper_bound_u32(f.pmax, 0, f.n, a);
+        const uint32_t hi = __shfl_sync(0xFFFFFFFFu, r, 0);
+        const uint32_t lo = max(__shfl_sync(0xFFFFFFFFu, r, 1), __shfl_sync(0xFFFFFFFFu, r, 2));
+        uint32_t *out = indices + o0;
+        uint64_t written = 0;
+        for (uint32_t b2 = lo >> 10; ((uint64_t)b2 << 10) < hi && written < room; b2++) {
+            if (__ldg(f.blkmax1024 + b2) <= a) continue;  // warp-uniform
+            const uint32_t b1 = b2 * 32 + lane;            // this lane's block of 32 intervals
+            const uint64_t base1 = (uint64_t)b1 << 5;
+            const bool live = base1 < hi && base1 + 32 > lo && __ldg(f.blkmax32 + b1) > a;
+            uint32_t m = __ballot_sync(0xFFFFFFFFu, live);
+            while (m) {
+                // up to four surviving blocks per step: their loads are independent, so the latency of the
+                // scattered 128-byte reads overlaps
+                uint64_t idx[4];
+                bool hit[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool have = m != 0;
+                    const uint32_t l1 = have ? __ffs(m) - 1 : 0u;
+                    m &= m - 1;  // 0 stays 0
+                    idx[u] = (((uint64_t)b2 * 32 + l1) << 5) + lane;
+                    hit[u] = have && idx[u] >= lo && idx[u] < hi;  // start < b holds for every i < hi
+                }
+                uint32_t e[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) e[u] = hit[u] ? __ldg(f.Eiv + idx[u]) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool h = hit[u] && e[u] > a;
+                    const uint32_t hm = __ballot_sync(0xFFFFFFFFu, h);
+                    if (h && written + __popc(hm & lt) < room) out[written + __popc(hm & lt)] = (uint32_t)idx[u];
+                    written += __popc(hm);
+                }
+            }
+        }
+    }
+}
+
 BucketView make_bucket_view(const DeviceIndex &ix) {
     BucketView v;
     v.buckets = ix.buckets;
@@ -847,6 +923,9 @@ FindView make_find_view(const DeviceIndex &ix) {
     f.dir = ix.cls_dir;
     f.cls_shift = ix.cls_shift;
     f.cls_nb = (uint32_t)ix.cls_nb;
+    f.pmax = ix.prefix_max;
+    f.blkmax32 = ix.blkmax32;
+    f.blkmax1024 = ix.blkmax1024;
     return f;
 }
 
@@ -968,10 +1047,24 @@ uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const 
 void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
                       const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream) {
     if (nq == 0 || ix.n == 0) return;
+    LAPPER_REQUIRE(nq < (1ull << 32), "find_batch: at most 2^32 - 1 queries per call");
     const FindView f = make_find_view(ix);
+    // heavy queries (>= kHeavyHits hits): at most total / kHeavyHits of them; the total is offsets[nq]
+    uint64_t total = 0;
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const uint64_t cap = std::min<uint64_t>(total / kHeavyHits + 1, nq);
+    Scratch<uint32_t> heavy(cap, stream);
+    Scratch<unsigned int> counters(2, stream);
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned int), stream));
     const uint32_t grid = capped_grid(nq, kThreads, 4 * 8);
-    find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices);
+    find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p);
     LAPPER_CUDA_CHECK(cudaGetLastError());
+    if (total >= kHeavyHits) {
+        // persistent warps; exits at once when the list is empty
+        find_heavy_kernel<<<148 * 8, kThreads, 0, stream>>>(f, d_qs, d_qe, d_offsets, d_indices, heavy.p, counters.p, counters.p + 1);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+    }
 }
 
 }  // namespace lap
