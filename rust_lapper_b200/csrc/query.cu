@@ -332,13 +332,12 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
             // lower_bound(starts, b) = rs + 12 - #{lanes >= b - base}
             int acc = (int)(sec[k].w[0] + kBucketLanes);
             acc = sub_lanes_ge(sec[k], (b & mask) * 0x10001u, acc);
-            if (sector_overflow(sec[k])) {
-                defer |= 1u << k;
-                prefetch_child(v, sec[k], b);
-            }
-            // the same sector also answers the stop side when a lies in [base - margin, base + w)
+            defer |= (uint32_t)sector_overflow(sec[k]) << k;
+            // The same sector also answers the stop side when a lies in [base - margin, base + w).  (A stop
+            // beyond the last key is clamped to the sentinel bucket; both formulas stay right for it: the
+            // sentinel has rs = re_hi = n, no starts, and only margin stops, all of which are >= any low(b).)
             const uint32_t a_rel = a - (bb[k] << v.shift) + v.margin;
-            if (a_rel < width + v.margin && (b >> v.shift) == bb[k]) {
+            if (a_rel < width + v.margin) {
                 int ub = sub_lanes_ge(sec[k], (width + a_rel + 1u) * 0x10001u, (int)sec[k].w[1]);
                 if (a == 0xFFFFFFFFu) ub = 0;  // src/lib.rs:614 wrap
                 res[k] = (uint32_t)(acc - ub);
@@ -363,10 +362,7 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
                     int ub = sub_lanes_ge(sec[k], (width + (a & mask) + v.margin + 1u) * 0x10001u, (int)sec[k].w[1]);
                     if (a == 0xFFFFFFFFu) ub = 0;
                     res[k] -= (uint32_t)ub;
-                    if (sector_overflow(sec[k])) {
-                        defer |= 1u << k;
-                        prefetch_child(v, sec[k], a);
-                    }
+                    defer |= (uint32_t)sector_overflow(sec[k]) << k;
                 }
         }
         if (kOut64) {
@@ -415,6 +411,7 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
 #pragma unroll
             for (int k = 0; k < kQPT; k++)
                 if (defer & (1u << k)) {
+                    prefetch_child(v, sec[k], (second & (1u << k)) ? qa.w[k] : qb.w[k]);  // sec[k] is the sector that overflowed (or a harmless one)
                     wq[3 * slot] = rel0 + k;
                     wq[3 * slot + 1] = qa.w[k];
                     wq[3 * slot + 2] = qb.w[k];
