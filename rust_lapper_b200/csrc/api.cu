@@ -245,6 +245,7 @@ int lapper_build_u32_ex(const uint32_t *starts, const uint32_t *stops, uint64_t 
         LAPPER_REQUIRE(out, "null output handle");
         *out = nullptr;
         LAPPER_REQUIRE(n == 0 || (starts && stops), "lapper_build: null interval arrays");
+        LAPPER_REQUIRE(n < 0xFFFFFFF0ull, "lapper_build: n must be < 2^32 - 16 (positions are u32)");
         require_device(device);
         DeviceGuard dg(device);
         StreamOwner st;
