@@ -445,7 +445,28 @@ def run_extras(args, lib, h, dev, stream, sp, n, nq, peak):
     ms = timed(lambda: _ffi.check(lib.lapper_count_batch_u32_dev(h, _vp(qs), _vp(qe), nq, _vp(counts), sp)), 10)
     gbs = (nq * 12 + n * 8) / (ms * 1e-3) / 1e9
     out["count_sorted_queries"] = {"queries_per_s": nq / (ms * 1e-3), "ms": ms, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
-    del qs, qe, counts
+    del qs, qe
+
+    # variant C: random-order queries INCLUDING an on-device sort by start, the count
+    # on the sorted order, and the un-permute of the results.  The sort here is torch.sort (a library call) used
+    # only to quantify this alternative -- the engine itself never pre-sorts, because this is slower than
+    # counting the random order directly.
+    rq_s, rq_e = synth.queries_fixed_len(SEED_Q, nq, UNIVERSE, QLEN, device=dev)
+    out_c = torch.empty(nq, dtype=torch.int32, device=dev)
+
+    def variant_c():
+        key = rq_s.to(torch.int64) & 0xFFFFFFFF
+        _, order = torch.sort(key)
+        ss, se = rq_s[order].contiguous(), rq_e[order].contiguous()
+        _ffi.check(lib.lapper_count_batch_u32_dev(h, _vp(ss), _vp(se), nq, _vp(counts), sp))
+        out_c[order] = counts
+
+    ms_c = timed(variant_c, 3)
+    out["count_random_incl_device_sort"] = {
+        "queries_per_s": nq / (ms_c * 1e-3), "ms": ms_c,
+        "note": "torch.sort + gather + count on sorted order + scatter back; direct random-order count is the headline `value`",
+    }
+    del rq_s, rq_e, out_c, counts
 
     # cfg 3: find with CSR output, gene/exon-like intervals x start-sorted 150-bp queries
     nq3 = min(nq, args.find_queries)
