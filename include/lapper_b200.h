@@ -46,6 +46,9 @@ extern "C" {
 #define LAPPER_BUILD_DEFAULT 0u
 #define LAPPER_BUILD_NO_BUCKETS 1u    /* search the sorted arrays directly (sampled keys in smem) */
 #define LAPPER_BUILD_FORCE_BUCKETS 2u /* build the bucket-rank table even for tiny sets */
+#define LAPPER_BUILD_NO_DENSE 4u      /* no packed (12-bit lane) table in front of the sector table */
+#define LAPPER_BUILD_FORCE_DENSE 8u   /* build the packed table whenever the sector table exists */
+#define LAPPER_BUILD_DENSE_WIDTH(w) (((uint32_t)(w)) << 16) /* force the packed table with bucket width w, 2 <= w <= 1820 */
 #define LAPPER_BUILD_SHIFT(k) ((((uint32_t)(k)) + 1u) << 8) /* force bucket width 2^k, 0 <= k <= 13 */
 
 typedef struct lapper lapper_t;               /* Lapper<u32, T>              src/lib.rs:102-123 */
@@ -74,6 +77,9 @@ int lapper_has_inverted(const lapper_t *l); /* 1 if some interval has stop < sta
 int lapper_device(const lapper_t *l);
 uint32_t lapper_bucket_shift(const lapper_t *l);  /* 0xFFFFFFFF when no bucket table is in use */
 uint64_t lapper_index_bytes(const lapper_t *l);   /* device bytes held by the handle */
+/* the packed (12-bit lane) table in front of the sector table: bucket width (0 = not built), number of
+ * sectors and how many of them overflowed (their queries fall back to the sector table); pointers may be NULL */
+int lapper_packed_table_info(const lapper_t *l, uint32_t *width_out, uint64_t *sectors_out, uint64_t *overflowed_out);
 /* `intervals` in sorted order as SoA + perm; any pointer may be NULL.  After merge_overlaps perm is
  * the input position of each run's first interval (whose val the reference keeps, src/lib.rs:385-389). */
 int lapper_get_intervals(const lapper_t *l, uint32_t *starts_out, uint32_t *stops_out, uint32_t *perm_out);

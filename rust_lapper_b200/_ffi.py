@@ -18,10 +18,16 @@ ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_PRECONDITION, ERR_NO_DEVICE = 1, 2, 3, 4
 BUILD_DEFAULT = 0
 BUILD_NO_BUCKETS = 1
 BUILD_FORCE_BUCKETS = 2
+BUILD_NO_DENSE = 4
+BUILD_FORCE_DENSE = 8
 
 
 def build_shift(k: int) -> int:
     return (k + 1) << 8
+
+
+def build_dense_width(w: int) -> int:
+    return w << 16
 
 
 class LapperError(RuntimeError):
@@ -60,6 +66,7 @@ SIGNATURES = {
     "lapper_device": (_int, [_vp]),
     "lapper_bucket_shift": (_u32, [_vp]),
     "lapper_index_bytes": (_u64, [_vp]),
+    "lapper_packed_table_info": (_int, [_vp, C.POINTER(_u32), C.POINTER(_u64), C.POINTER(_u64)]),
     "lapper_get_intervals": (_int, [_vp, _vp, _vp, _vp]),
     "lapper_get_starts": (_int, [_vp, _vp]),
     "lapper_get_stops": (_int, [_vp, _vp]),

@@ -328,6 +328,16 @@ uint64_t lapper_index_bytes(const lapper_t *l) {
     return l ? l->ix.bytes : 0;
 }
 
+int lapper_packed_table_info(const lapper_t *l, uint32_t *width_out, uint64_t *sectors_out, uint64_t *overflowed_out) {
+    return guarded([&] {
+        check_handle(l);
+        const bool built = l->ix.dense != nullptr;
+        if (width_out) *width_out = built ? l->ix.dense_w : 0u;
+        if (sectors_out) *sectors_out = built ? l->ix.dense_nb + 1 : 0u;
+        if (overflowed_out) *overflowed_out = built ? l->ix.dense_overflow : 0u;
+    });
+}
+
 int lapper_get_intervals(const lapper_t *l, uint32_t *starts_out, uint32_t *stops_out, uint32_t *perm_out) {
     return guarded([&] {
         check_handle(l);

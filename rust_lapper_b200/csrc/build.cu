@@ -8,6 +8,7 @@
 //   + prefix_max, + the BITS bucket sectors described in index.cuh (new; the reference searches
 //     the sorted vectors directly).
 #include <algorithm>
+#include <cstdlib>
 
 #include "index.cuh"
 
@@ -266,6 +267,17 @@ __global__ void fill_children_kernel(const uint32_t *__restrict__ S, const uint3
     }
 }
 
+// Packed sectors (packed_sector.cuh): one thread per bucket of width w (any width), one 32-byte store.
+__global__ void fill_dense_kernel(const uint32_t *__restrict__ S, const uint32_t *__restrict__ E, uint32_t n,
+                                  PackedParams p, Sector *__restrict__ dense,
+                                  unsigned long long *__restrict__ overflow_count) {
+    const uint64_t B = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (B > p.nb) return;  // B == nb: the sentinel
+    Sector sec;
+    if (!packed_fill(S, E, n, p, B, sec.w)) atomicAdd(overflow_count, 1ull);
+    dense[B] = sec;
+}
+
 // max stop of every 32 consecutive sorted intervals (one warp per block), then of every 32 such blocks
 __global__ void __launch_bounds__(kThreads) block_max_kernel(const uint32_t *__restrict__ in, uint64_t n,
                                                              uint32_t *__restrict__ out, uint64_t nblocks) {
@@ -361,6 +373,39 @@ bool choose_shift(uint64_t n, uint32_t max_coord, uint32_t flags, uint32_t &shif
     }
     shift_out = k;
     return true;
+}
+
+// Width of the packed table's buckets: about 4.5 starts (and 5.1 stops incl. the margin's) per 18-lane
+// sector, i.e. 7.1 bytes per interval -- 71 MB at the cfg-2 shape with 2.3 % of the sectors overflowing.
+// Measured there (profiles/r1_exp_packed_table_fill.log): 4.0 -> 0.688 ms, 4.5 -> 0.672, 5.0 -> 0.725,
+// 5.5 -> 0.788 (a smaller table stays in L2 better, but every overflowing sector sends its queries through
+// the deferred path).  Only built where it pays: the sector table is too large to stay L2-resident and the
+// packed one is not.
+bool choose_dense_width(uint64_t n, uint32_t max_coord, uint32_t flags, uint64_t sector_table_bytes, uint32_t &w_out) {
+    if (flags & LAPPER_BUILD_NO_DENSE) return false;
+    const uint32_t forced = (flags >> 16) & 0xFFFu;
+    if (forced) {
+        LAPPER_REQUIRE(forced >= 2 && forced <= kDenseMaxWidth, "LAPPER_BUILD_DENSE_WIDTH: width must be in [2, 1820]");
+        // a forced width never makes the table larger than 2^26 sectors (2 GB); widen it instead
+        uint32_t w = forced;
+        while (w < kDenseMaxWidth && (uint64_t)max_coord / w + 2 > (1ull << 26)) w = std::min(2 * w, kDenseMaxWidth);
+        w_out = w;
+        return true;
+    }
+    const bool force = (flags & LAPPER_BUILD_FORCE_DENSE) != 0;
+    double per_sector = 4.25;
+    if (const char *env = std::getenv("LAPPER_DENSE_STARTS_PER_SECTOR")) per_sector = std::max(0.5, atof(env));  // experiments
+    const double span = (double)max_coord + 1.0;
+    double w = per_sector * span / (double)std::max<uint64_t>(n, 1);
+    if (w > (double)kDenseMaxWidth) w = (double)kDenseMaxWidth;
+    if (w < (double)kDenseMinWidth) {
+        if (!force) return false;
+        w = (double)kDenseMinWidth;
+    }
+    w_out = (uint32_t)w;
+    if (force) return true;
+    const uint64_t bytes = ((uint64_t)max_coord / w_out + 2) * sizeof(Sector);
+    return sector_table_bytes > (40ull << 20) && bytes <= (128ull << 20) && bytes * 5 <= sector_table_bytes * 4;
 }
 
 // Choose up to kMaxClasses contiguous groups of length bins minimising the expected number of
@@ -474,6 +519,7 @@ void free_index(DeviceIndex &ix) {
     cudaFree(ix.prefix_max);
     cudaFree(ix.buckets);
     cudaFree(ix.pool);
+    cudaFree(ix.dense);
     ix = DeviceIndex();
 }
 
@@ -487,6 +533,9 @@ void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stre
     ix.npool = 0;
     ix.margin = 0;
     ix.ncls = 0;
+    ix.dense_nb = 0;
+    ix.dense_w = ix.dense_m = ix.dense_magic = 0;
+    ix.dense_overflow = 0;
     if (n == 0) return;
 
     Scratch<BuildStats> d_stats(1, stream);
@@ -542,6 +591,25 @@ void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stre
             LAPPER_CUDA_CHECK(cudaGetLastError());
         }
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+
+        uint32_t dw = 0;
+        if (choose_dense_width(n, ix.max_coord, flags, (ix.nbuckets + 1 + ix.npool) * sizeof(Sector), dw)) {
+            const PackedParams pp = packed_params(dw, ix.max_coord);
+            ix.dense_w = pp.w;
+            ix.dense_m = pp.m;
+            ix.dense_magic = pp.magic;
+            ix.dense_nb = pp.nb;
+            ix.dense = dev_alloc<Sector>(ix.dense_nb + 1, ix.bytes);
+            Scratch<unsigned long long> d_over(1, stream);
+            LAPPER_CUDA_CHECK(cudaMemsetAsync(d_over.p, 0, 8, stream));
+            fill_dense_kernel<<<grid_for(ix.dense_nb + 1), kThreads, 0, stream>>>(
+                ix.starts, ix.stops_sorted, (uint32_t)n, pp, ix.dense, d_over.p);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+            unsigned long long nover = 0;
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(&nover, d_over.p, 8, cudaMemcpyDeviceToHost, stream));
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+            ix.dense_overflow = nover;
+        }
     }
 }
 

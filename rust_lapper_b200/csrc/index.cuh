@@ -13,6 +13,7 @@
 #include <mutex>
 
 #include "common.cuh"
+#include "packed_sector.cuh"
 
 namespace lap {
 
@@ -41,6 +42,8 @@ constexpr uint32_t kMaxBucketShift = 13;
 constexpr uint32_t kLaneGuard = 0x80008000u;
 constexpr uint32_t kNoChild = 0xFFFFFFFFu;
 
+// The packed ("dense") table in front of this one: packed_sector.cuh.
+
 struct DeviceIndex {
     uint64_t n = 0;
     uint32_t *starts = nullptr;
@@ -53,6 +56,11 @@ struct DeviceIndex {
     Sector *pool = nullptr;  // child sectors of overflowing buckets
     uint64_t npool = 0;
     uint32_t margin = 0;     // stops this far below a bucket are also in its lanes
+    Sector *dense = nullptr;  // packed sectors, dense_nb + 1 of them (the last one is the sentinel)
+    uint64_t dense_nb = 0;
+    uint32_t dense_w = 0, dense_m = 0;
+    uint32_t dense_magic = 0;  // ceil(2^32 / dense_w)
+    uint64_t dense_overflow = 0;  // sectors that did not fit (their queries fall back)
     uint32_t shift = 0xFFFFFFFFu;
     uint32_t max_len = 0;
     uint32_t max_coord = 0;

@@ -37,6 +37,10 @@ struct BucketView {
     uint32_t shift;
     uint32_t margin;
     uint32_t nb;  // index of the sentinel bucket
+    // packed table in front of the sector table (index.cuh); dense == nullptr when there is none
+    const Sector *dense;
+    PackedParams pk;
+    uint32_t local_span;  // a warp whose threads each see their queries within this span stays on the sector-table path
 };
 
 // bytes 1 and 3 of t0 and of t1 (the high byte of every 16-bit lane), each replaced by its sign bit
@@ -319,13 +323,37 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
         load_queries(qs, qe, j0, qa, qb);
         uint32_t bb[kQPT];
         Sector sec[kQPT];
+        uint32_t res[kQPT];
+        uint32_t defer = 0, second = 0;
+        // ---- packed-table path: taken by a warp whose 128 queries are spread out (no sector would be shared
+        // between lanes) and mostly short enough for one packed sector each
+        bool dense_tile = false;
+        if (v.dense != nullptr) {
+            // spread-out test on the thread's own kQPT consecutive queries: start-sorted batches have them within a
+            // few sectors of each other (those warps share sectors between lanes and stay on the sector-table path)
+            if (__any_sync(0xFFFFFFFFu, qb.w[kQPT - 1] - qb.w[0] + v.local_span >= 2u * v.local_span)) {
+                uint32_t xs[kQPT], te[kQPT], bad = 0;
+#pragma unroll
+                for (int k = 0; k < kQPT; k++) bad |= (uint32_t)(!packed_locate(v.pk, qa.w[k], qb.w[k], bb[k], xs[k], te[k])) << k;
+                dense_tile = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(bad)) <= 8u * kQPT;  // <= a quarter fall back
+                if (dense_tile) {
+#pragma unroll
+                    for (int k = 0; k < kQPT; k++) sec[k] = ld_sector_stream(v.dense + bb[k]);
+#pragma unroll
+                    for (int k = 0; k < kQPT; k++) {
+                        res[k] = packed_count(sec[k].w, xs[k], te[k]);
+                        bad |= (sec[k].w[7] >> 31) << k;
+                    }
+                    defer = bad;
+                }
+            }
+        }
+        if (!dense_tile) {
 #pragma unroll
         for (int k = 0; k < kQPT; k++) {
             bb[k] = bucket_of(v, qb.w[k]);
             sec[k] = ld_sector_cached(v.buckets + bb[k]);
         }
-        uint32_t res[kQPT];
-        uint32_t defer = 0, second = 0;
 #pragma unroll
         for (int k = 0; k < kQPT; k++) {
             const uint32_t a = qa.w[k], b = qb.w[k];
@@ -336,8 +364,9 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
             // The same sector also answers the stop side when a lies in [base - margin, base + w).  (A stop
             // beyond the last key is clamped to the sentinel bucket; both formulas stay right for it: the
             // sentinel has rs = re_hi = n, no starts, and only margin stops, all of which are >= any low(b).)
+            // (a <= b keeps an inverted query whose start is within the margin of 2^32 from wrapping a_rel into range)
             const uint32_t a_rel = a - (bb[k] << v.shift) + v.margin;
-            if (a_rel < width + v.margin) {
+            if (a_rel < width + v.margin && a <= b) {
                 int ub = sub_lanes_ge(sec[k], (width + a_rel + 1u) * 0x10001u, (int)sec[k].w[1]);
                 if (a == 0xFFFFFFFFu) ub = 0;  // src/lib.rs:614 wrap
                 res[k] = (uint32_t)(acc - ub);
@@ -345,6 +374,7 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
                 res[k] = (uint32_t)acc;
                 second |= 1u << k;
             }
+        }
         }
         if (kFind) {
 #pragma unroll
@@ -411,7 +441,10 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
 #pragma unroll
             for (int k = 0; k < kQPT; k++)
                 if (defer & (1u << k)) {
-                    prefetch_child(v, sec[k], (second & (1u << k)) ? qa.w[k] : qb.w[k]);  // sec[k] is the sector that overflowed (or a harmless one)
+                    if (dense_tile)  // the fallback starts from the sector table: pull b's sector into L2
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(v.buckets + bucket_of(v, qb.w[k])));
+                    else
+                        prefetch_child(v, sec[k], (second & (1u << k)) ? qa.w[k] : qb.w[k]);  // sec[k] is the sector that overflowed (or a harmless one)
                     wq[3 * slot] = rel0 + k;
                     wq[3 * slot + 1] = qa.w[k];
                     wq[3 * slot + 2] = qb.w[k];
@@ -895,6 +928,12 @@ BucketView make_bucket_view(const DeviceIndex &ix) {
     v.n = (uint32_t)ix.n;
     v.shift = ix.shift;
     v.nb = (uint32_t)ix.nbuckets;
+    v.dense = ix.dense;
+    v.pk.w = ix.dense_w;
+    v.pk.m = ix.dense_m;
+    v.pk.magic = ix.dense_magic;
+    v.pk.nb = (uint32_t)ix.dense_nb;
+    v.local_span = 4u << ix.shift;  // shift <= 13
     return v;
 }
 

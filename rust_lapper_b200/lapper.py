@@ -109,6 +109,13 @@ class Lapper:
         k = int(self._lib.lapper_bucket_shift(self._h))
         return None if k == 0xFFFFFFFF else k
 
+    @property
+    def packed_table(self) -> Optional[Tuple[int, int, int]]:
+        """(bucket width, sectors, overflowed sectors) of the packed table, None when it was not built."""
+        w, ns, no = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        _ffi.check(self._lib.lapper_packed_table_info(self._h, C.byref(w), C.byref(ns), C.byref(no)))
+        return (int(w.value), int(ns.value), int(no.value)) if w.value else None
+
     def _sorted(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         if self._cache is None:
             n = len(self)

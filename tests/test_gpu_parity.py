@@ -58,6 +58,56 @@ def test_inverted_intervals_and_queries(oracle, flags):
     _assert_same_queries(gpu, cpu, qs, qe)
 
 
+# ---- the packed table in front of the sector table (csrc/packed_sector.cuh).  It is only consulted by full,
+# aligned tiles of 1024 queries whose warps see spread-out queries, so these cases use >= 1024 random queries.
+PACKED_FLAGS = {"auto_width": 2 | 8, "w2": 2 | (2 << 16), "w7": 2 | (7 << 16), "w100": 2 | (100 << 16),
+                "w257": 2 | (257 << 16), "w1550": 2 | (1550 << 16), "w1820": 2 | (1820 << 16),
+                "w1000_shift3": (1000 << 16) | ((3 + 1) << 8)}
+
+
+@pytest.mark.parametrize("flags", list(PACKED_FLAGS))
+def test_packed_table_random(oracle, flags):
+    rng = np.random.default_rng(100 + list(PACKED_FLAGS).index(flags))
+    for universe, n, max_len, qlen in [(3_000_000, 20_000, 700, 150), (60_000, 20_000, 10, 3), (4 * 10**9, 50_000, 5000, 150),
+                                       (3_000_000, 3_000, 400_000, 30), (5_000_000, 30_000, 0, 2500)]:
+        s, e, qs, qe = rs.random_case(rng, n, min(universe, 0xFFFFFFFF - 1), max_len, 6 * 1024 + 77, qlen)
+        gpu, cpu = _both(oracle, s, e, PACKED_FLAGS[flags])
+        assert gpu.packed_table is not None
+        _assert_same_queries(gpu, cpu, qs, qe)
+        # mixed batch: a quarter of the queries long / inverted / at the extremes -> per-query fallback inside packed tiles
+        k = qs.size // 4
+        qs2, qe2 = qs.copy(), qe.copy()
+        idx = rng.permutation(qs.size)[:k]
+        qe2[idx[: k // 3]] = np.minimum(qs2[idx[: k // 3]].astype(np.uint64) + universe // 3, 0xFFFFFFFF).astype(np.uint32)
+        qs2[idx[k // 3: 2 * k // 3]], qe2[idx[k // 3: 2 * k // 3]] = qe2[idx[k // 3: 2 * k // 3]], qs2[idx[k // 3: 2 * k // 3]].copy()
+        qs2[idx[2 * k // 3:]] = 0xFFFFFFFF
+        _assert_same_queries(gpu, cpu, qs2, qe2)
+
+
+def test_packed_table_is_built_and_used_where_it_pays(oracle):
+    """Auto mode: the packed table exists only next to a sector table too large for L2 (none at this size),
+    and forcing it changes nothing about the answers, on sorted (sector-table path) or random queries."""
+    from rust_lapper_b200 import Lapper, synth
+
+    U = synth.GRCH38 // 20
+    s, e = synth.intervals_uniform(42, 500_000, U, 50, 5000)
+    qs, qe = synth.queries_fixed_len(43, 1_000_000, U, 150)
+    auto = Lapper(starts=s, stops=e)
+    assert auto.packed_table is None
+    forced = Lapper(starts=s, stops=e, flags=8)
+    w, nsect, nover = forced.packed_table
+    assert 16 <= w <= 1820 and nsect == (int(max(s.max(), e.max())) // w) + 2 and nover < nsect // 8
+    want = auto.count_batch(qs, qe)
+    assert np.array_equal(forced.count_batch(qs, qe), want)
+    order = np.argsort(qs, kind="stable")
+    assert np.array_equal(forced.count_batch(qs[order], qe[order]), want[order])
+    cpu = oracle.OracleLapper(starts=s, stops=e)
+    assert np.array_equal(want[:200_000], cpu.count_batch(qs[:200_000], qe[:200_000]))
+    go, gi = forced.find_batch(qs[:300_000], qe[:300_000])
+    co, ci = cpu.find_batch(qs[:300_000], qe[:300_000])
+    assert np.array_equal(go, co) and np.array_equal(gi, ci)
+
+
 def test_extreme_coordinates(oracle):
     X = 0xFFFFFFFF
     s = np.array([0, 0, X - 5, X, X - 1, 7, X], dtype=np.uint32)
@@ -65,9 +115,11 @@ def test_extreme_coordinates(oracle):
     vals = [0, 1, 5, 7, X - 6, X - 5, X - 1, X]
     qs, qe = np.meshgrid(vals, vals)
     qs, qe = qs.ravel().astype(np.uint32), qe.ravel().astype(np.uint32)
-    for flags in (0, 1, 2, 2 | ((13 + 1) << 8)):
+    for flags in (0, 1, 2, 2 | ((13 + 1) << 8), 2 | 8, 2 | (1820 << 16), 2 | (3 << 16)):
         gpu, cpu = _both(oracle, s, e, flags)
         _assert_same_queries(gpu, cpu, qs, qe)
+        # the same 64 queries tiled to full 1024-query tiles (the packed path only sees full tiles)
+        _assert_same_queries(gpu, cpu, np.tile(qs, 40), np.tile(qe, 40))
 
 
 def test_empty_and_ragged(oracle):

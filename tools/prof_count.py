@@ -17,7 +17,12 @@ lib = _ffi.lib()
 s, e = synth.intervals_uniform(42, n, synth.GRCH38, 50, 5000, device=dev)
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 h = C.c_void_p(0)
-_ffi.check(lib.lapper_build_u32_dev(C.c_void_p(s.data_ptr()), C.c_void_p(e.data_ptr()), n, 0, 0, sp, C.byref(h)))
+flags = int(os.environ.get("FLAGS", 0))  # e.g. 4 = LAPPER_BUILD_NO_DENSE
+_ffi.check(lib.lapper_build_u32_dev(C.c_void_p(s.data_ptr()), C.c_void_p(e.data_ptr()), n, 0, flags, sp, C.byref(h)))
+w, ns, no = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+_ffi.check(lib.lapper_packed_table_info(h, C.byref(w), C.byref(ns), C.byref(no)))
+print(f"flags {flags}: sector-table shift {lib.lapper_bucket_shift(h)}, packed table width {w.value}, "
+      f"{ns.value} sectors ({ns.value * 32 / 1e6:.1f} MB), {no.value} overflowed ({100.0 * no.value / max(ns.value, 1):.2f} %)")
 out = torch.empty(nq, dtype=torch.int32, device=dev)
 for name, (qs, qe) in (("random", synth.queries_fixed_len(43, nq, synth.GRCH38, 150, device=dev)),
                        ("sorted", synth.queries_sorted_fixed_len(45, nq, synth.GRCH38, 150, device=dev))):
