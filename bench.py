@@ -324,9 +324,9 @@ def run_ours(args):
         "algorithmic_bytes_per_launch": algo_bytes,
         "launch_ms_avg": kernel_ms,
         "launch_ms_isolated_median": statistics.median(per_launch),
-        "note": "random-order queries: one 32-byte sector of a 97 MB table per query; L2 keeps about a quarter of it, so the "
-                "kernel moves ~6 GB of real DRAM traffic per launch (see traffic) and is DRAM-bound on that, not on the "
-                "1.28 GB of algorithmic bytes; DESIGN.md section 4",
+        "note": "random-order queries: one 32-byte sector of the 75 MB packed table per query (csrc/packed_sector.cuh); "
+                "about 64 % of those gathers hit L2, the rest cost 64 B of DRAM each (see traffic); L2, L1 and DRAM "
+                "throughput are all at 65-71 % of their peaks in the ncu capture; DESIGN.md section 4",
     }
 
     # ---- end to end: host pointers (pinned), H2D + kernel + D2H inside the timed region
