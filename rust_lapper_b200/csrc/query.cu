@@ -668,8 +668,15 @@ __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t 
 }
 
 constexpr int kEmitCand = 64;                       // candidates a warp can sweep cooperatively
-constexpr int kEmitWarpWords = 1536;                 // u32 words of shared memory per warp (6 KB; 48 KB per CTA)
-constexpr int kEmitStage = kEmitWarpWords - 3 * kEmitCand;  // output slots staged per warp
+constexpr uint32_t kEmitRawMax = 512;                // class-window slots a warp filters down to those candidates
+#ifndef LAPPER_EMIT_WORDS
+#define LAPPER_EMIT_WORDS 1536
+#endif
+#ifndef LAPPER_EMIT_MIN_CTAS
+#define LAPPER_EMIT_MIN_CTAS 4
+#endif
+constexpr int kEmitWarpWords = LAPPER_EMIT_WORDS;    // u32 words of shared memory per warp (6 KB; 48 KB per CTA)
+constexpr int kEmitStage = kEmitWarpWords - 4 * kEmitCand;  // output slots staged per warp
 
 struct ClassCursor {
     uint32_t cur, end, g;
@@ -729,19 +736,25 @@ __device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, ui
 // sorted list with broadcast shared-memory reads, appending the candidates that overlap its own query.
 // Slow path (union too large: random-order queries, very long intervals): each lane merges its own
 // class streams.  Either way the order is the reference iterator's (ascending position).
+#ifdef LAPPER_EMIT_STATS
+__device__ unsigned long long g_emit_stats[8];  // chunks, fast, staged-slow, unstaged, sum T raw, sum T kept, sum wtotal, empty
+#define EMIT_STAT(i, v) do { if (lane == 0) atomicAdd(&g_emit_stats[i], (unsigned long long)(v)); } while (0)
+#else
+#define EMIT_STAT(i, v) do { } while (0)
+#endif
 constexpr int kEmitQ = 2;  // queries per lane: one candidate union serves 64 consecutive queries
 constexpr uint32_t kHeavyHits = 256;  // a query with at least this many hits gets a warp of its own (find_heavy_kernel)
 
-__global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const uint32_t *__restrict__ qs,
+__global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kernel(FindView f, const uint32_t *__restrict__ qs,
                                                              const uint32_t *__restrict__ qe, uint64_t nq,
                                                              const uint64_t *__restrict__ offsets,
                                                              uint32_t *__restrict__ indices,
                                                              uint32_t *__restrict__ heavy_list,
                                                              unsigned int *__restrict__ heavy_count) {
-    __shared__ uint32_t smem_all[kThreads / 32][kEmitWarpWords];
+    __shared__ __align__(16) uint32_t smem_all[kThreads / 32][kEmitWarpWords];
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t *const stage = smem_all[threadIdx.x >> 5];       // kEmitStage output slots ...
-    uint32_t *const sorted = stage + kEmitStage;               // ... then kEmitCand x (start, stop, position)
+    uint4 *const sorted = reinterpret_cast<uint4 *>(stage + kEmitStage);  // ... then kEmitCand x (start, stop, position, -)
     const uint64_t nwarps = (uint64_t)gridDim.x * (kThreads / 32);
     const uint64_t nchunks = div_up(nq, 32 * kEmitQ);
     for (uint64_t chunk = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); chunk < nchunks; chunk += nwarps) {
@@ -775,79 +788,148 @@ __global__ void __launch_bounds__(kThreads) find_fill_kernel(FindView f, const u
         const uint64_t wbase = __shfl_sync(0xFFFFFFFFu, o0[0], 0);
         const uint64_t wend = offsets[jend];  // same address for the whole warp: one broadcast load
         const uint64_t wtotal = wend - wbase;
-        if (wtotal == 0) continue;
-        const bool staged = wtotal <= kEmitStage;
+        EMIT_STAT(0, 1);
+        if (wtotal == 0) { EMIT_STAT(7, 1); continue; }
+        EMIT_STAT(6, wtotal);
+        // The stage mirrors the 16-byte alignment of the warp's slice of `indices` (pad words in front), so the
+        // copy-out below moves whole 128-bit groups.
+        uint32_t *const wdst = indices + wbase;
+        const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(wdst) >> 2) & 3u;
+        const bool staged = wtotal + pad <= kEmitStage;
         // ---- union of the class windows over the queries that have hits
         uint32_t amin = a[0], bmax = b[0];
 #pragma unroll
         for (int q = 1; q < kEmitQ; q++) amin = min(amin, a[q]), bmax = max(bmax, b[q]);
         amin = __reduce_min_sync(0xFFFFFFFFu, amin);
         bmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
+        // eight class bounds (4 classes x {window start, window end}), four lanes each: the directory gives a
+        // rank range of at most 16 class starts, which the four lanes probe with independent loads (one memory
+        // round trip instead of a serial walk)
         uint32_t r = 0;
-        if (lane < 8 && (lane & 3u) < f.ncls) {
-            const int c = (int)(lane & 3u);
-            r = class_lb(f, c, (lane >> 2) ? bmax : (amin >= f.cls_maxlen[c] ? amin - f.cls_maxlen[c] : 0u));
+        {
+            const int c = (int)((lane >> 2) & 3u);
+            const uint32_t sub = lane & 3u;
+            const bool on = c < (int)f.ncls;
+            const uint32_t key = (lane >> 4) ? bmax : (amin >= f.cls_maxlen[c] ? amin - f.cls_maxlen[c] : 0u);
+            const uint32_t *cs = f.cs + f.cls_off[c];
+            uint32_t r0 = 0, hi = 0, cnt = 0;
+            if (on) {
+                const uint32_t B = min(key >> f.cls_shift, f.cls_nb);
+                r0 = dir_get(__ldg(f.dir + B), c);
+                hi = B < f.cls_nb ? dir_get(__ldg(f.dir + B + 1), c) : r0;
+                if (hi - r0 <= 16u) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (uint32_t t = 0; t < 4; t++) {
+                        const uint32_t i = r0 + sub * 4 + t;
+                        v[t] = i < hi ? __ldg(cs + i) : 0xFFFFFFFFu;
+                    }
+#pragma unroll
+                    for (uint32_t t = 0; t < 4; t++) cnt += (r0 + sub * 4 + t < hi) && (v[t] < key);
+                }
+            }
+            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1);
+            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
+            r = r0 + cnt;
+            if (on && hi - r0 > 16u) r = lower_bound_u32(cs, r0, hi, key);
         }
         uint32_t lo[4], cnt[4], T = 0;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            lo[c] = __shfl_sync(0xFFFFFFFFu, r, c);
-            const uint32_t hi = __shfl_sync(0xFFFFFFFFu, r, c + 4);
+            lo[c] = __shfl_sync(0xFFFFFFFFu, r, 4 * c);
+            const uint32_t hi = __shfl_sync(0xFFFFFFFFu, r, 16 + 4 * c);
             cnt[c] = hi > lo[c] ? hi - lo[c] : 0u;
             T += cnt[c];
         }
-        if (staged && T <= kEmitCand) {
-            // raw candidates (class-major) into the head of the stage area, which is still unused
-            uint32_t *const raw = stage;
-            for (uint32_t i = lane; i < T; i += 32) {
-                uint32_t c = 0, base = 0;  // class of candidate i and the index of that class's first candidate
-                if (i >= cnt[0]) {
-                    c = 1, base = cnt[0];
-                    if (i >= base + cnt[1]) {
-                        c = 2, base += cnt[1];
-                        if (i >= base + cnt[2]) c = 3, base += cnt[2];
+        // raw candidates (class-major) into the head of the stage area, which is still unused -- but only those
+        // that can overlap some query of the chunk at all: a class window reaches maxlen_c below the smallest query
+        // start, and most of the intervals starting down there end before it (stop <= amin)
+        uint32_t *const raw = stage;
+        uint32_t Tk = 0;  // candidates kept (warp-uniform)
+        bool fits = staged && T <= kEmitRawMax;
+        if (fits) {
+            for (uint32_t i0 = 0; i0 < T; i0 += 32) {
+                const uint32_t i = i0 + lane;
+                uint32_t g = 0, cs = 0, ce = 0;
+                if (i < T) {
+                    uint32_t c = 0, base = 0;  // class of candidate i and the index of that class's first candidate
+                    if (i >= cnt[0]) {
+                        c = 1, base = cnt[0];
+                        if (i >= base + cnt[1]) {
+                            c = 2, base += cnt[1];
+                            if (i >= base + cnt[2]) c = 3, base += cnt[2];
+                        }
                     }
+                    const uint32_t p = f.cls_off[c] + lo[c] + (i - base);
+                    ce = __ldg(f.ce + p);  // three independent loads
+                    g = __ldg(f.cg + p);
+                    cs = __ldg(f.cs + p);
                 }
-                const uint32_t p = f.cls_off[c] + lo[c] + (i - base);
-                raw[i] = __ldg(f.cg + p);
-                raw[kEmitCand + i] = __ldg(f.cs + p);
-                raw[2 * kEmitCand + i] = __ldg(f.ce + p);
+                const bool keep = i < T && ce > amin;
+                const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                const uint32_t pos = Tk + __popc(km & ((1u << lane) - 1u));
+                if (keep && pos < (uint32_t)kEmitCand) {
+                    raw[pos] = g;
+                    raw[kEmitCand + pos] = cs;
+                    raw[2 * kEmitCand + pos] = ce;
+                }
+                Tk += __popc(km);
             }
+            fits = Tk <= (uint32_t)kEmitCand;
+        }
+        EMIT_STAT(4, T);
+        if (fits) {
+            EMIT_STAT(1, 1);
+            EMIT_STAT(5, Tk);
+            T = Tk;
             __syncwarp();
             // merged order = rank of the global position among all candidates (positions are distinct)
             for (uint32_t i = lane; i < T; i += 32) {
                 const uint32_t g = raw[i];
                 uint32_t rank = 0;
                 for (uint32_t x = 0; x < T; x++) rank += (raw[x] < g);
-                sorted[3 * rank] = raw[kEmitCand + i];
-                sorted[3 * rank + 1] = raw[2 * kEmitCand + i];
-                sorted[3 * rank + 2] = g;
+                sorted[rank] = make_uint4(raw[kEmitCand + i], raw[2 * kEmitCand + i], g, 0u);
             }
             __syncwarp();
             // every lane sweeps the sorted candidates for its own queries (broadcast reads)
-            uint32_t cur[kEmitQ];
+            uint32_t *wp[kEmitQ];
 #pragma unroll
-            for (int q = 0; q < kEmitQ; q++) cur[q] = (uint32_t)(o0[q] - wbase);
+            for (int q = 0; q < kEmitQ; q++) wp[q] = stage + pad + (uint32_t)(o0[q] - wbase);
             for (uint32_t x = 0; x < T; x++) {
-                const uint32_t s = sorted[3 * x], e = sorted[3 * x + 1], g = sorted[3 * x + 2];
+                const uint4 c = sorted[x];  // one broadcast LDS.128: (start, stop, position)
 #pragma unroll
                 for (int q = 0; q < kEmitQ; q++)
-                    if (s < b[q] && e > a[q]) stage[cur[q]++] = g;  // src/lib.rs:140-142
+                    if (c.x < b[q] && c.y > a[q]) *wp[q]++ = c.z;  // src/lib.rs:140-142
             }
             __syncwarp();
-            for (uint32_t i = lane; i < (uint32_t)wtotal; i += 32) indices[wbase + i] = stage[i];
-            __syncwarp();
         } else if (staged) {
+            EMIT_STAT(2, 1);
 #pragma unroll
             for (int q = 0; q < kEmitQ; q++)
-                if (mine[q]) emit_one_query(f, a[q], b[q], stage + (o0[q] - wbase), o1[q] - o0[q]);
-            __syncwarp();
-            for (uint32_t i = lane; i < (uint32_t)wtotal; i += 32) indices[wbase + i] = stage[i];
+                if (mine[q]) emit_one_query(f, a[q], b[q], stage + pad + (o0[q] - wbase), o1[q] - o0[q]);
             __syncwarp();
         } else {
+            EMIT_STAT(3, 1);
 #pragma unroll
             for (int q = 0; q < kEmitQ; q++)
                 if (mine[q]) emit_one_query(f, a[q], b[q], indices + o0[q], o1[q] - o0[q]);
+        }
+        if (staged) {
+            // copy-out: stage word pad + i -> wdst[i]; whole 128-bit groups except at the two ragged ends
+            const uint32_t W = pad + (uint32_t)wtotal;
+            uint32_t *const dst0 = wdst - pad;  // 16-byte aligned; words below pad are never touched
+            for (uint32_t g4 = lane * 4; g4 < W; g4 += 128) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(stage + g4);
+                if (g4 >= pad && g4 + 4 <= W) {
+                    st_stream_v4(dst0 + g4, v);
+                } else {
+                    if (g4 + 0 >= pad && g4 + 0 < W) dst0[g4 + 0] = v.x;
+                    if (g4 + 1 >= pad && g4 + 1 < W) dst0[g4 + 1] = v.y;
+                    if (g4 + 2 >= pad && g4 + 2 < W) dst0[g4 + 2] = v.z;
+                    if (g4 + 3 >= pad && g4 + 3 < W) dst0[g4 + 3] = v.w;
+                }
+            }
+            __syncwarp();
         }
     }
 }
@@ -1043,6 +1125,17 @@ void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d
     LAPPER_CUDA_CHECK(cudaGetLastError());
 }
 
+#ifdef LAPPER_EMIT_STATS
+extern "C" void lapper_debug_emit_stats(unsigned long long *out, int reset) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_emit_stats, sizeof(g_emit_stats));
+    if (reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyToSymbol(g_emit_stats, z, sizeof(z));
+    }
+}
+#endif
+
 uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
                              uint64_t *d_offsets, cudaStream_t stream) {
     if (nq == 0) {
@@ -1093,7 +1186,7 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
     Scratch<uint32_t> heavy(cap, stream);
     Scratch<unsigned int> counters(2, stream);
     LAPPER_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned int), stream));
-    const uint32_t grid = capped_grid(nq, kThreads, 4 * 8);
+    const uint32_t grid = capped_grid(nq, kThreads, LAPPER_EMIT_MIN_CTAS * 8);
     find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p);
     LAPPER_CUDA_CHECK(cudaGetLastError());
     if (total >= kHeavyHits) {

@@ -63,4 +63,14 @@ ms_fill = a.elapsed_time(b) / reps
 print(f"  offsets phase {ms_off:.3f} ms, fill phase {ms_fill:.3f} ms")
 print(f"find {order}: {ms:.3f} ms per pass, {int(total.value)} hits ({int(total.value) / nq:.2f}/query), "
       f"{nq / ms / 1e6:.2f} Gq/s, {int(total.value) / ms / 1e6:.1f} Ghits/s, checksum {int(idx[: int(total.value)].to(torch.int64).sum())}")
+if os.environ.get("EMIT_STATS"):
+    import ctypes
+    raw = ctypes.CDLL(_ffi.LIB_PATH)
+    st = (ctypes.c_ulonglong * 8)()
+    raw.lapper_debug_emit_stats(st, 1)
+    _ffi.check(lib.lapper_find_batch_fill_u32_dev(h, vp(qs), vp(qe), nq, vp(off), vp(idx), sp))
+    raw.lapper_debug_emit_stats(st, 0)
+    ch = max(st[0] - st[7], 1)
+    print(f"  emit stats: chunks {st[0]} (empty {st[7]}), fast {st[1]} ({100.0 * st[1] / ch:.2f} %), staged-slow {st[2]} ({100.0 * st[2] / ch:.2f} %), "
+          f"unstaged {st[3]} ({100.0 * st[3] / ch:.2f} %), T raw/chunk {st[4] / ch:.1f}, T kept/fast chunk {st[5] / max(st[1], 1):.1f}, hits/chunk {st[6] / ch:.0f}")
 lib.lapper_free(h)
