@@ -750,19 +750,25 @@ __global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kern
                                                              const uint64_t *__restrict__ offsets,
                                                              uint32_t *__restrict__ indices,
                                                              uint32_t *__restrict__ heavy_list,
-                                                             unsigned int *__restrict__ heavy_count) {
+                                                             unsigned int *__restrict__ heavy_count,
+                                                             const uint32_t *__restrict__ tile_list,
+                                                             const unsigned int *__restrict__ tile_count) {
     __shared__ __align__(16) uint32_t smem_all[kThreads / 32][kEmitWarpWords];
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t *const stage = smem_all[threadIdx.x >> 5];       // kEmitStage output slots ...
     uint4 *const sorted = reinterpret_cast<uint4 *>(stage + kEmitStage);  // ... then kEmitCand x (start, stop, position, -)
     const uint64_t nwarps = (uint64_t)gridDim.x * (kThreads / 32);
-    const uint64_t nchunks = div_up(nq, 32 * kEmitQ);
-    for (uint64_t chunk = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); chunk < nchunks; chunk += nwarps) {
+    // with a tile list (the tiles find_fill_tile_kernel left over) the chunks are the 16 chunks of each listed tile
+    constexpr uint32_t kChunksPerTile = kFindTile / (32 * kEmitQ);
+    const uint64_t nchunks = tile_list ? (uint64_t)*tile_count * kChunksPerTile : div_up(nq, 32 * kEmitQ);
+    for (uint64_t ci = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); ci < nchunks; ci += nwarps) {
+        const uint64_t chunk = tile_list ? (uint64_t)tile_list[ci / kChunksPerTile] * kChunksPerTile + ci % kChunksPerTile : ci;
         // lane's q-th query is chunk*64 + q*32 + lane: consecutive lanes hold consecutive queries
         uint64_t o0[kEmitQ], o1[kEmitQ];
         uint32_t a[kEmitQ], b[kEmitQ];
         bool mine[kEmitQ];
         const uint64_t jbase = chunk * (32 * kEmitQ);
+        if (jbase >= nq) continue;
         const uint64_t jend = min(jbase + 32 * kEmitQ, nq);  // one past the chunk's last query
 #pragma unroll
         for (int q = 0; q < kEmitQ; q++) {
@@ -930,6 +936,362 @@ __global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kern
                 }
             }
             __syncwarp();
+        }
+    }
+}
+
+// ---- emit, tile form.  A CTA owns a tile of 1024 consecutive queries (the tile of the offsets scan): the tile's
+// offsets are loaded once (coalesced, as 32-bit tile-relative values in shared memory), the candidates of the WHOLE
+// tile -- the class windows, filtered to intervals that end after the tile's smallest query start -- are gathered
+// once by all threads, merged into position order (each class list is already ordered, so an element's rank is its
+// own index plus one binary search per other class) and kept in shared memory.  Each warp then takes 64-query
+// groups: it filters the tile list down to its own candidates with a ballot (no global loads, already in order),
+// every lane sweeps that list for its two queries, and the group's slice of `indices` leaves through the staged
+// 128-bit copy-out.  The serial chain of global-memory round trips (offsets -> queries -> directory -> class starts
+// -> candidates) is paid once per 1024 queries instead of once per 64, and small CTAs (4 warps) keep seven tiles in
+// flight per SM so one tile's chain hides behind the other tiles' sweeps.  Tiles whose candidate set does not fit
+// (queries without locality, very long class windows) are appended to `fallback_tiles` and left to find_fill_kernel.
+#ifndef LAPPER_TILE_THREADS
+#define LAPPER_TILE_THREADS 128
+#endif
+#ifndef LAPPER_TILE_CAND
+#define LAPPER_TILE_CAND 384
+#endif
+#ifndef LAPPER_TILE_CTAS
+#define LAPPER_TILE_CTAS 7
+#endif
+constexpr int kTT = LAPPER_TILE_THREADS;   // threads per CTA
+constexpr int kTW = kTT / 32;              // warps per CTA
+constexpr int kTQPT = kFindTile / kTT;     // queries per thread in the tile prologue
+constexpr int kTCand = LAPPER_TILE_CAND;   // filtered candidates per tile
+constexpr uint32_t kTRawMax = 4096;        // class-window slots a tile is willing to filter
+#ifndef LAPPER_TILE_STAGE
+#define LAPPER_TILE_STAGE 1024
+#endif
+constexpr int kTStage = LAPPER_TILE_STAGE;  // staged output words per warp
+constexpr int kTWarpWords = kTStage + 4 * kEmitCand;  // + the warp's own candidate list (64 x uint4)
+constexpr int kTRelWords = kFindTile + 4;
+constexpr int kTCtlWords = 32;
+constexpr int kTSmemWords = 4 * kTCand + kTW * kTWarpWords + kTRelWords + kTCtlWords;
+static_assert(3 * kTCand <= kTW * kTWarpWords, "the raw candidate list aliases the warps' areas");
+static_assert(kTQPT == 4 || kTQPT == 8, "tile prologue: 4 or 8 queries per thread");
+
+__device__ __forceinline__ uint32_t smem_lower_bound(const uint32_t *a, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(FindView f, const uint32_t *__restrict__ qs,
+                                                                    const uint32_t *__restrict__ qe, uint64_t nq,
+                                                                    const uint64_t *__restrict__ offsets,
+                                                                    uint32_t *__restrict__ indices,
+                                                                    uint32_t *__restrict__ heavy_list,
+                                                                    unsigned int *__restrict__ heavy_count,
+                                                                    uint32_t *__restrict__ fallback_tiles,
+                                                                    unsigned int *__restrict__ fallback_count) {
+    extern __shared__ __align__(16) uint32_t tsm[];
+    uint4 *const cand = reinterpret_cast<uint4 *>(tsm);      // kTCand x (start, stop, position, -)
+    uint32_t *const warp_area = tsm + 4 * kTCand;            // per warp: stage, then its candidate list
+    uint32_t *const rel = warp_area + kTW * kTWarpWords;     // tile-relative offsets [0, nqt]
+    // ctl: [0..3] class lo, [4..7] class window size, [8..11] kept per class, [12] amin, [13] bmax, [16..] warp counts
+    uint32_t *const ctl = rel + kTRelWords;
+    uint32_t *const rawg = warp_area, *const raws = warp_area + kTCand, *const rawe = warp_area + 2 * kTCand;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t *const stage = warp_area + warp * kTWarpWords;
+    uint4 *const wlist = reinterpret_cast<uint4 *>(stage + kTStage);
+    const uint64_t ntiles = div_up(nq, kFindTile);
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t q0 = tile * kFindTile;
+        const uint32_t nqt = (uint32_t)min((uint64_t)kFindTile, nq - q0);
+        const uint32_t jt = threadIdx.x * kTQPT;
+        {   // the next tile's offsets and queries on their way into L2 while this tile is emitted
+            const uint64_t qn = q0 + (uint64_t)gridDim.x * kFindTile + jt;
+            if (qn + kTQPT <= nq) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(offsets + qn));
+                if ((threadIdx.x & 3u) == 0) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qs + qn));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(qe + qn));
+                }
+            }
+        }
+        __syncthreads();  // the previous tile's groups are done with the shared arrays
+        if (threadIdx.x < 16) ctl[threadIdx.x] = threadIdx.x == 12 ? 0xFFFFFFFFu : 0u;
+        // ---- 1. the tile's offsets (thread t: queries t*kTQPT .. and the offset after them), heavy queries,
+        //         smallest start / largest stop over the queries this kernel emits
+        const uint64_t tile_o0 = offsets[q0];
+        uint32_t r[kTQPT + 1], qa[kTQPT], qb[kTQPT];
+        if (nqt == (uint32_t)kFindTile) {
+            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(offsets + q0 + jt);
+#pragma unroll
+            for (int k = 0; k < kTQPT / 2; k++) {
+                const ulonglong2 u = src[k];
+                r[2 * k] = (uint32_t)(u.x - tile_o0), r[2 * k + 1] = (uint32_t)(u.y - tile_o0);
+            }
+            r[kTQPT] = (uint32_t)(offsets[q0 + jt + kTQPT] - tile_o0);
+#pragma unroll
+            for (int k = 0; k < kTQPT / 4; k++) {
+                const uint4 va = ld_stream_v4(qs + q0 + jt + 4 * k), vb = ld_stream_v4(qe + q0 + jt + 4 * k);
+                qa[4 * k] = va.x, qa[4 * k + 1] = va.y, qa[4 * k + 2] = va.z, qa[4 * k + 3] = va.w;
+                qb[4 * k] = vb.x, qb[4 * k + 1] = vb.y, qb[4 * k + 2] = vb.z, qb[4 * k + 3] = vb.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k <= kTQPT; k++) r[k] = (uint32_t)(offsets[q0 + min(jt + k, nqt)] - tile_o0);
+#pragma unroll
+            for (int k = 0; k < kTQPT; k++) {
+                const bool live = jt + k < nqt;
+                qa[k] = live ? ld_stream_u32(qs + q0 + jt + k) : 0xFFFFFFFFu;
+                qb[k] = live ? ld_stream_u32(qe + q0 + jt + k) : 0u;
+            }
+        }
+        uint32_t hmask = 0, amin = 0xFFFFFFFFu, bmax = 0;
+#pragma unroll
+        for (int k = 0; k < kTQPT; k++) {
+            const uint32_t hits = r[k + 1] - r[k];
+            if (hits >= kHeavyHits)
+                hmask |= 1u << k;
+            else if (hits)
+                amin = min(amin, qa[k]), bmax = max(bmax, qb[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kTQPT / 4; k++)
+            *reinterpret_cast<uint4 *>(rel + jt + 4 * k) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        if (threadIdx.x == kTT - 1) rel[kFindTile] = r[kTQPT];
+        amin = __reduce_min_sync(0xFFFFFFFFu, amin);
+        bmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
+        __syncthreads();  // ctl initialised
+        if (lane == 0) {
+            atomicMin(&ctl[12], amin);
+            atomicMax(&ctl[13], bmax);
+        }
+        __syncthreads();
+        if (rel[nqt] == 0) continue;
+        amin = ctl[12], bmax = ctl[13];
+        // ---- 2. class windows of the tile (warp 0; four lanes per bound, as in find_fill_kernel)
+        if (warp == 0) {
+            const int c = (int)((lane >> 2) & 3u);
+            const uint32_t sub = lane & 3u;
+            const bool on = c < (int)f.ncls && amin != 0xFFFFFFFFu;
+            const uint32_t key = (lane >> 4) ? bmax : (amin >= f.cls_maxlen[c] ? amin - f.cls_maxlen[c] : 0u);
+            const uint32_t *cs = f.cs + f.cls_off[c];
+            uint32_t r0 = 0, hi = 0, cnt = 0;
+            if (on) {
+                const uint32_t B = min(key >> f.cls_shift, f.cls_nb);
+                r0 = dir_get(__ldg(f.dir + B), c);
+                hi = B < f.cls_nb ? dir_get(__ldg(f.dir + B + 1), c) : r0;
+                if (hi - r0 <= 16u) {
+                    uint32_t v[4];
+#pragma unroll
+                    for (uint32_t t = 0; t < 4; t++) {
+                        const uint32_t i = r0 + sub * 4 + t;
+                        v[t] = i < hi ? __ldg(cs + i) : 0xFFFFFFFFu;
+                    }
+#pragma unroll
+                    for (uint32_t t = 0; t < 4; t++) cnt += (r0 + sub * 4 + t < hi) && (v[t] < key);
+                }
+            }
+            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1);
+            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
+            uint32_t rk = r0 + cnt;
+            if (on && hi - r0 > 16u) rk = lower_bound_u32(cs, r0, hi, key);
+            const uint32_t rhi = __shfl_down_sync(0xFFFFFFFFu, rk, 16);
+            if (lane < 16 && sub == 0) {
+                ctl[c] = rk;
+                ctl[4 + c] = (on && rhi > rk) ? rhi - rk : 0u;
+            }
+        }
+        __syncthreads();
+        // ---- 3. the windows' intervals that end after amin, compacted in class-major order by all threads
+        const uint32_t n0 = ctl[4], n1 = ctl[5], n2 = ctl[6], n3 = ctl[7];
+        const uint32_t R = n0 + n1 + n2 + n3;
+        bool nice = n0 <= kTRawMax && n1 <= kTRawMax && n2 <= kTRawMax && n3 <= kTRawMax && R <= kTRawMax;
+        uint32_t K = 0;  // kept so far (uniform)
+        for (uint32_t i0 = 0; nice && i0 < R; i0 += kTT) {
+            const uint32_t i = i0 + threadIdx.x;
+            uint32_t g = 0, cs = 0, ce = 0, c = 0;
+            if (i < R) {
+                uint32_t k = i;
+                if (k >= n0) {
+                    c = 1, k -= n0;
+                    if (k >= n1) {
+                        c = 2, k -= n1;
+                        if (k >= n2) c = 3, k -= n2;
+                    }
+                }
+                const uint32_t p = f.cls_off[c] + ctl[c] + k;
+                ce = __ldg(f.ce + p);
+                g = __ldg(f.cg + p);
+                cs = __ldg(f.cs + p);
+            }
+            const bool keep = i < R && ce > amin;
+            const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+            if (lane == 0) ctl[16 + warp] = __popc(km);
+            if (keep) atomicAdd(&ctl[8 + c], 1u);
+            __syncthreads();
+            uint32_t before = 0, all = 0;
+#pragma unroll
+            for (int w = 0; w < kTW; w++) {
+                const uint32_t x = ctl[16 + w];
+                before += w < (int)warp ? x : 0u;
+                all += x;
+            }
+            const uint32_t pos = K + before + __popc(km & ((1u << lane) - 1u));
+            if (keep && pos < (uint32_t)kTCand) rawg[pos] = g, raws[pos] = cs, rawe[pos] = ce;
+            K += all;
+            nice = K <= (uint32_t)kTCand;
+            __syncthreads();
+        }
+        if (!nice) {
+            if (threadIdx.x == 0) fallback_tiles[atomicAdd(fallback_count, 1u)] = (uint32_t)tile;
+            if (warp == 0) EMIT_STAT(2, 1);
+            continue;
+        }
+        if (warp == 0) {
+            EMIT_STAT(0, 1);
+            EMIT_STAT(1, K);
+            EMIT_STAT(3, R);
+        }
+#pragma unroll
+        for (int k = 0; k < kTQPT; k++)
+            if (hmask & (1u << k)) heavy_list[atomicAdd(heavy_count, 1u)] = (uint32_t)(q0 + jt + k);
+        // ---- 4. merge the class sublists by position (sublist c = [s_c, s_c + k_c) of the raw list)
+        {
+            const uint32_t k0 = ctl[8], k1 = ctl[9], k2 = ctl[10], k3 = ctl[11];
+            for (uint32_t i = threadIdx.x; i < K; i += kTT) {
+                uint32_t c = 0, k = i;
+                if (k >= k0) {
+                    c = 1, k -= k0;
+                    if (k >= k1) {
+                        c = 2, k -= k1;
+                        if (k >= k2) c = 3, k -= k2;
+                    }
+                }
+                const uint32_t g = rawg[i];
+                uint32_t rank = k;
+                if (c != 0) rank += smem_lower_bound(rawg, k0, g);
+                if (c != 1) rank += smem_lower_bound(rawg + k0, k1, g);
+                if (c != 2) rank += smem_lower_bound(rawg + k0 + k1, k2, g);
+                if (c != 3) rank += smem_lower_bound(rawg + k0 + k1 + k2, k3, g);
+                cand[rank] = make_uint4(raws[i], rawe[i], g, 0u);
+            }
+        }
+        __syncthreads();  // cand complete; the raw list (aliasing the warps' areas) is dead
+        // ---- 5. 64-query groups
+        for (uint32_t gq = warp * 64; gq < nqt; gq += kTW * 64) {
+            const uint32_t gq_end = min(gq + 64u, nqt);
+            const uint32_t gbase = rel[gq];
+            if (rel[gq_end] == gbase) continue;
+            uint32_t ro0[kEmitQ], ro1[kEmitQ], a[kEmitQ], b[kEmitQ];
+            bool mine[kEmitQ];
+#pragma unroll
+            for (int q = 0; q < kEmitQ; q++) {
+                const uint32_t jl = min(gq + q * 32 + lane, nqt);  // beyond the tile: rel[nqt] twice = no hits
+                ro0[q] = rel[jl];
+                ro1[q] = rel[min(jl + 1, nqt)];
+                const uint32_t hits = ro1[q] - ro0[q];
+                mine[q] = hits != 0 && hits < kHeavyHits;
+                a[q] = 0xFFFFFFFFu, b[q] = 0;
+                if (mine[q]) {
+                    a[q] = __ldg(qs + q0 + jl);
+                    b[q] = __ldg(qe + q0 + jl);
+                }
+            }
+            uint32_t gamin = min(a[0], a[1]), gbmax = max(b[0], b[1]);
+            gamin = __reduce_min_sync(0xFFFFFFFFu, gamin);
+            gbmax = __reduce_max_sync(0xFFFFFFFFu, gbmax);
+            // the group's candidates: tile candidates that start before its largest stop and end after its smallest
+            // start, in order (the tile list is ordered by position, i.e. by start: stop at the first round past gbmax)
+            uint32_t T = 0;
+            for (uint32_t x0 = 0; x0 < K; x0 += 32) {
+                const uint32_t x = x0 + lane;
+                uint4 c = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
+                if (x < K) c = cand[x];
+                const bool keep = c.x < gbmax && c.y > gamin;
+                const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                const uint32_t pos = T + __popc(km & ((1u << lane) - 1u));
+                if (keep && pos < (uint32_t)kEmitCand) wlist[pos] = c;
+                T += __popc(km);
+                if (__all_sync(0xFFFFFFFFu, c.x >= gbmax)) break;
+            }
+            const bool fits = T <= (uint32_t)kEmitCand;
+            __syncwarp();
+            // The group's slice of `indices` goes through the warp's stage in one pass when it fits (nearly always),
+            // else in passes over consecutive sub-ranges of its queries; a query that does not fit on its own is
+            // heavy (find_heavy_kernel writes it), so every pass makes progress.
+            for (uint32_t sub_lo = gq; sub_lo < gq_end;) {
+                const uint32_t sbase = rel[sub_lo];
+                uint32_t *const wdst = indices + tile_o0 + sbase;
+                const uint32_t pad = (uint32_t)(reinterpret_cast<uintptr_t>(wdst) >> 2) & 3u;
+                uint32_t sub_hi = gq_end;
+                if (rel[gq_end] - sbase + pad > (uint32_t)kTStage) {
+                    // largest sub_hi with rel[sub_hi] - sbase + pad <= kTStage (rel is non-decreasing)
+                    sub_hi = sub_lo;
+#pragma unroll
+                    for (int q = 0; q < kEmitQ; q++) {
+                        const uint32_t idx = sub_lo + 1 + q * 32 + lane;
+                        const bool ok = idx <= gq_end && rel[min(idx, nqt)] - sbase + pad <= (uint32_t)kTStage;
+                        sub_hi += __popc(__ballot_sync(0xFFFFFFFFu, ok));
+                    }
+                    EMIT_STAT(7, 1);
+                    if (sub_hi == sub_lo) {
+                        sub_lo++;
+                        continue;
+                    }
+                }
+                const uint32_t wtotal = rel[sub_hi] - sbase;
+                if (wtotal) {
+                    uint32_t sa[kEmitQ], sb[kEmitQ];
+                    bool act[kEmitQ];
+#pragma unroll
+                    for (int q = 0; q < kEmitQ; q++) {
+                        const uint32_t jl = gq + q * 32 + lane;
+                        act[q] = mine[q] && jl >= sub_lo && jl < sub_hi;
+                        sa[q] = act[q] ? a[q] : 0xFFFFFFFFu;
+                        sb[q] = act[q] ? b[q] : 0u;
+                    }
+                    if (fits) {
+                        EMIT_STAT(4, 1);
+                        EMIT_STAT(5, T);
+                        uint32_t *wp[kEmitQ];
+#pragma unroll
+                        for (int q = 0; q < kEmitQ; q++) wp[q] = stage + pad + (ro0[q] - sbase);
+                        for (uint32_t x = 0; x < T; x++) {
+                            const uint4 c = wlist[x];  // one broadcast LDS.128: (start, stop, position)
+#pragma unroll
+                            for (int q = 0; q < kEmitQ; q++)
+                                if (c.x < sb[q] && c.y > sa[q]) *wp[q]++ = c.z;  // src/lib.rs:140-142
+                        }
+                    } else {
+                        EMIT_STAT(6, 1);
+#pragma unroll
+                        for (int q = 0; q < kEmitQ; q++)
+                            if (act[q]) emit_one_query(f, a[q], b[q], stage + pad + (ro0[q] - sbase), ro1[q] - ro0[q]);
+                    }
+                    __syncwarp();
+                    const uint32_t W = pad + wtotal;
+                    uint32_t *const dst0 = wdst - pad;
+                    for (uint32_t g4 = lane * 4; g4 < W; g4 += 128) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(stage + g4);
+                        if (g4 >= pad && g4 + 4 <= W) {
+                            st_stream_v4(dst0 + g4, v);
+                        } else {
+                            if (g4 + 0 >= pad && g4 + 0 < W) dst0[g4 + 0] = v.x;
+                            if (g4 + 1 >= pad && g4 + 1 < W) dst0[g4 + 1] = v.y;
+                            if (g4 + 2 >= pad && g4 + 2 < W) dst0[g4 + 2] = v.z;
+                            if (g4 + 3 >= pad && g4 + 3 < W) dst0[g4 + 3] = v.w;
+                        }
+                    }
+                    __syncwarp();
+                }
+                sub_lo = sub_hi;
+            }
         }
     }
 }
@@ -1173,6 +1535,15 @@ uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const 
     return total;
 }
 
+// LAPPER_FIND_NO_TILE=1 (experiments / tests): per-warp emit kernel only
+static bool find_tile_disabled() {
+    static const bool off = [] {
+        const char *e = std::getenv("LAPPER_FIND_NO_TILE");
+        return e && atoi(e) != 0;
+    }();
+    return off;
+}
+
 void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
                       const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream) {
     if (nq == 0 || ix.n == 0) return;
@@ -1183,11 +1554,31 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
     LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
     LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
     const uint64_t cap = std::min<uint64_t>(total / kHeavyHits + 1, nq);
+    const uint64_t ntiles = div_up(nq, kFindTile);
     Scratch<uint32_t> heavy(cap, stream);
-    Scratch<unsigned int> counters(2, stream);
-    LAPPER_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, 2 * sizeof(unsigned int), stream));
+    Scratch<uint32_t> fallback(ntiles, stream);
+    Scratch<unsigned int> counters(3, stream);  // heavy queries, next heavy query, fallback tiles
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, 3 * sizeof(unsigned int), stream));
     const uint32_t grid = capped_grid(nq, kThreads, LAPPER_EMIT_MIN_CTAS * 8);
-    find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p);
+    const bool tiled = ((reinterpret_cast<uintptr_t>(d_offsets) | reinterpret_cast<uintptr_t>(d_qs) |
+                         reinterpret_cast<uintptr_t>(d_qe)) & 15u) == 0 && !find_tile_disabled();
+    if (tiled) {
+        // tile form first; the tiles it cannot take (no locality) are left to the per-warp kernel
+        static const bool smem_ok = [] {
+            return cudaFuncSetAttribute(find_fill_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        kTSmemWords * (int)sizeof(uint32_t)) == cudaSuccess;
+        }();
+        LAPPER_REQUIRE(smem_ok, "find_fill_tile_kernel: cannot reserve shared memory");
+        const uint32_t tgrid = (uint32_t)std::min<uint64_t>(ntiles, 148 * LAPPER_TILE_CTAS);
+        find_fill_tile_kernel<<<tgrid, kTT, kTSmemWords * sizeof(uint32_t), stream>>>(
+            f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p,
+                                                        fallback.p, counters.p + 2);
+    } else {
+        find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, nullptr,
+                                                        nullptr);
+    }
     LAPPER_CUDA_CHECK(cudaGetLastError());
     if (total >= kHeavyHits) {
         // persistent warps; exits at once when the list is empty

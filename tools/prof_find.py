@@ -70,7 +70,7 @@ if os.environ.get("EMIT_STATS"):
     raw.lapper_debug_emit_stats(st, 1)
     _ffi.check(lib.lapper_find_batch_fill_u32_dev(h, vp(qs), vp(qe), nq, vp(off), vp(idx), sp))
     raw.lapper_debug_emit_stats(st, 0)
-    ch = max(st[0] - st[7], 1)
-    print(f"  emit stats: chunks {st[0]} (empty {st[7]}), fast {st[1]} ({100.0 * st[1] / ch:.2f} %), staged-slow {st[2]} ({100.0 * st[2] / ch:.2f} %), "
-          f"unstaged {st[3]} ({100.0 * st[3] / ch:.2f} %), T raw/chunk {st[4] / ch:.1f}, T kept/fast chunk {st[5] / max(st[1], 1):.1f}, hits/chunk {st[6] / ch:.0f}")
+    print("  emit stats (tile kernel): nice tiles %d, fallback tiles %d, K/tile %.1f, raw/tile %.1f, fast groups %d (T %.1f), "
+          "staged-slow groups %d, unstaged groups %d" % (st[0], st[2], st[1] / max(st[0], 1), st[3] / max(st[0], 1), st[4],
+                                                         st[5] / max(st[4], 1), st[6], st[7]))
 lib.lapper_free(h)
