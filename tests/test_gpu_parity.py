@@ -108,6 +108,36 @@ def test_packed_table_is_built_and_used_where_it_pays(oracle):
     assert np.array_equal(go, co) and np.array_equal(gi, ci)
 
 
+@pytest.mark.parametrize("depth", [12, 40, 150, 260, 600])
+@pytest.mark.parametrize("order", ["sorted", "random"])
+def test_find_tile_emit_dense_groups(oracle, depth, order):
+    """The tile-form emit kernel (find_fill_tile_kernel) away from its comfortable case: groups of 64 queries whose
+    hits exceed the warp's stage (sub-range passes), more than 64 candidates per group (per-lane merge into the stage),
+    queries around the heavy threshold of 256 hits (handed to find_heavy_kernel), several length classes, ragged last
+    tile; and the same queries in random order (tiles without locality fall back to the per-warp kernel)."""
+    rng = np.random.default_rng(depth)
+    U = 400_000
+    n = 12_000
+    mean_len = depth * U // n
+    ln = np.concatenate([rng.integers(1, 2 * mean_len, n - n // 8), rng.integers(20 * mean_len, 40 * mean_len, n // 8) // 16])
+    s = rng.integers(0, U, n)
+    e = np.minimum(s + ln, 0xFFFFFFFF)
+    s, e = s.astype(np.uint32), e.astype(np.uint32)
+    nq = 7 * 1024 + 333
+    qs = rng.integers(0, U + 1000, nq)
+    if order == "sorted":
+        qs = np.sort(qs)
+    qe = qs + rng.integers(0, 300, nq)
+    qs, qe = qs.astype(np.uint32), qe.astype(np.uint32)
+    gpu, cpu = _both(oracle, s, e)
+    go, gi = gpu.find_batch(qs, qe)
+    co, ci = cpu.find_batch(qs, qe)
+    assert np.array_equal(go, co)
+    assert np.array_equal(gi, ci)
+    hits = np.diff(co)
+    assert hits.max() > 2 * depth // 3  # the shape is what the name says
+
+
 def test_extreme_coordinates(oracle):
     X = 0xFFFFFFFF
     s = np.array([0, 0, X - 5, X, X - 1, 7, X], dtype=np.uint32)
