@@ -420,10 +420,20 @@ __global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel
         if (kFind) {
             // this warp's contribution to its tile's hit total (deferred queries add theirs when resolved)
             uint64_t sum = 0;
+            uint32_t big = 0;
 #pragma unroll
-            for (int k = 0; k < kQPT; k++) sum += (defer & (1u << k)) ? 0u : res[k];
+            for (int k = 0; k < kQPT; k++) {
+                const uint32_t c = (defer & (1u << k)) ? 0u : res[k];
+                sum += c;
+                big |= c;
+            }
+            if (!__any_sync(0xFFFFFFFFu, big >> 24)) {
+                // 128 counts below 2^24 each: the warp's total fits 32 bits, one REDUX instead of ten shuffles
+                sum = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)sum);
+            } else {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+            }
             if (lane == 0 && sum) atomicAdd(reinterpret_cast<unsigned long long *>(tile_sums + tile), (unsigned long long)sum);
         }
         // ---- enqueue this iteration's deferred queries (ballot-free: exclusive scan of per-lane counts)
@@ -589,49 +599,39 @@ __global__ void __launch_bounds__(kThreads) find_count_kernel(FindView f, const 
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
 }
 
-// pass 2: exclusive scan of the tile sums (one block of 1024 threads, each owning a contiguous segment
-// of ceil(ntiles / 1024) sums; ntiles ~ nq / 1024, so the whole array is a few hundred KB in L2)
-__global__ void __launch_bounds__(1024) scan_tile_sums_kernel(uint64_t *__restrict__ tile_sums, uint64_t ntiles,
-                                                              uint64_t *__restrict__ total_out) {
-    __shared__ uint64_t warp_tot[32];
-    const uint64_t seg = div_up(ntiles, 1024);
-    const uint64_t lo = min((uint64_t)threadIdx.x * seg, ntiles), hi = min(lo + seg, ntiles);
-    uint64_t mine = 0;
-    for (uint64_t i = lo; i < hi; i++) mine += tile_sums[i];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint64_t inc = mine;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += y;
-    }
-    if (lane == 31) warp_tot[w] = inc;
-    __syncthreads();
-    if (w == 0) {
-        const uint64_t t = warp_tot[lane];
-        uint64_t ti = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, ti, o);
-            if (lane >= o) ti += y;
-        }
-        warp_tot[lane] = ti - t;  // exclusive
-        if (lane == 31) *total_out = ti;
-    }
-    __syncthreads();
-    uint64_t run = warp_tot[w] + inc - mine;
-    for (uint64_t i = lo; i < hi; i++) {
-        const uint64_t x = tile_sums[i];
-        tile_sums[i] = run;
-        run += x;
-    }
+// pass 2: sums of 256 consecutive tile sums ("super-tiles").  The tile bases are not materialised: a CTA of pass 3
+// adds up the super-tile sums before its super-tile (a few hundred values) and the tile sums before it inside the
+// super-tile (at most 255) -- all of it L2-resident -- instead of waiting for a serial scan of ~100 k sums.
+constexpr int kSuperTiles = 256;
+__global__ void __launch_bounds__(kSuperTiles) super_sums_kernel(const uint64_t *__restrict__ tile_sums, uint64_t ntiles,
+                                                                 uint64_t *__restrict__ super_sums) {
+    __shared__ uint64_t red[8];
+    const uint64_t t = (uint64_t)blockIdx.x * kSuperTiles + threadIdx.x;
+    const uint64_t s = block_reduce_sum_u64(t < ntiles ? tile_sums[t] : 0ull, red);
+    if (threadIdx.x == 0) super_sums[blockIdx.x] = s;
 }
 
-// pass 3: offsets[j] = tile base + exclusive scan of the tile's counts
+// pass 3: offsets[j] = tile base + exclusive scan of the tile's counts; the last tile also writes offsets[nq]
 __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t *__restrict__ counts,
-                                                                 const uint64_t *__restrict__ tile_base, uint64_t nq,
+                                                                 const uint64_t *__restrict__ tile_sums,
+                                                                 const uint64_t *__restrict__ super_sums, uint64_t nq,
                                                                  uint64_t *__restrict__ offsets) {
     __shared__ uint64_t warp_tot[kThreads / 32];
+    __shared__ uint64_t red[8];
+    __shared__ uint64_t tile_base_s;
+    static_assert(kThreads == kSuperTiles, "one thread per tile of the super-tile");
+    {
+        const uint64_t sb = blockIdx.x / kSuperTiles;
+        uint64_t part = 0;
+        for (uint64_t i = threadIdx.x; i < sb; i += kThreads) part += super_sums[i];
+        const uint64_t t = sb * kSuperTiles + threadIdx.x;
+        if (t < blockIdx.x) part += tile_sums[t];
+        const uint64_t tb = block_reduce_sum_u64(part, red);
+        if (threadIdx.x == 0) {
+            tile_base_s = tb;
+            if (blockIdx.x == gridDim.x - 1) offsets[nq] = tb + tile_sums[blockIdx.x];
+        }
+    }
     const uint64_t base = (uint64_t)blockIdx.x * kFindTile + (uint64_t)threadIdx.x * kFindQPT;
     uint32_t c[kFindQPT];
     uint64_t local = 0;
@@ -652,7 +652,7 @@ __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t 
     uint64_t wbase = 0;
 #pragma unroll
     for (int i = 0; i < kThreads / 32; i++) wbase += (i < w) ? warp_tot[i] : 0;
-    uint64_t run = tile_base[blockIdx.x] + wbase + inc - local;
+    uint64_t run = tile_base_s + wbase + inc - local;
     if (base + kFindQPT <= nq) {  // 32 contiguous bytes per thread: two 128-bit stores
         const uint64_t r0 = run, r1 = r0 + c[0], r2 = r1 + c[1], r3 = r2 + c[2];
         ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(offsets + base);
@@ -1525,9 +1525,11 @@ uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const 
         find_count_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
     }
     LAPPER_CUDA_CHECK(cudaGetLastError());
-    scan_tile_sums_kernel<<<1, 1024, 0, stream>>>(tile_sums.p, ntiles, d_offsets + nq);
+    const uint64_t nsuper = div_up(ntiles, kSuperTiles);
+    Scratch<uint64_t> super_sums(nsuper, stream);
+    super_sums_kernel<<<(uint32_t)nsuper, kSuperTiles, 0, stream>>>(tile_sums.p, ntiles, super_sums.p);
     LAPPER_CUDA_CHECK(cudaGetLastError());
-    write_offsets_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(counts.p, tile_sums.p, nq, d_offsets);
+    write_offsets_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(counts.p, tile_sums.p, super_sums.p, nq, d_offsets);
     LAPPER_CUDA_CHECK(cudaGetLastError());
     uint64_t total = 0;
     LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
