@@ -428,7 +428,7 @@ def run_extras(args, lib, h, dev, stream, sp, n, nq, peak):
     out = {}
 
     def timed(fn, steps):
-        for _ in range(2):
+        for _ in range(3):
             fn()
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -485,7 +485,7 @@ def run_extras(args, lib, h, dev, stream, sp, n, nq, peak):
         _ffi.check(lib.lapper_find_batch_offsets_u32_dev(h3, _vp(q3s), _vp(q3e), nq3, _vp(offsets), C.byref(t), sp))
         _ffi.check(lib.lapper_find_batch_fill_u32_dev(h3, _vp(q3s), _vp(q3e), nq3, _vp(offsets), _vp(indices), sp))
 
-    ms = timed(find_step, 3)
+    ms = timed(find_step, 5)
     fbytes = nq3 * 16 + hits * 4 + n * 8
     gbs = fbytes / (ms * 1e-3) / 1e9
     out["find_cfg3_sorted_queries"] = {

@@ -1247,6 +1247,8 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                 }
                 const uint32_t wtotal = rel[sub_hi] - sbase;
                 if (wtotal) {
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous slice has left the stage
+                    __syncwarp();
                     uint32_t sa[kEmitQ], sb[kEmitQ];
                     bool act[kEmitQ];
 #pragma unroll
@@ -1274,25 +1276,34 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                         for (int q = 0; q < kEmitQ; q++)
                             if (act[q]) emit_one_query(f, a[q], b[q], stage + pad + (ro0[q] - sbase), ro1[q] - ro0[q]);
                     }
+                    // copy-out: the whole 16-byte groups of the slice leave as ONE bulk copy shared -> global issued by
+                    // lane 0 (cp.async.bulk, the TMA path: no LDS/STG instructions, no LSU wavefronts); the ragged
+                    // words at the two ends are stored by lanes 0..7.  The stage is reused only after the copy has
+                    // finished reading it (wait at the top of the next pass).
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this lane's STS -> visible to the async proxy
                     __syncwarp();
                     const uint32_t W = pad + wtotal;
-                    uint32_t *const dst0 = wdst - pad;
-                    for (uint32_t g4 = lane * 4; g4 < W; g4 += 128) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(stage + g4);
-                        if (g4 >= pad && g4 + 4 <= W) {
-                            st_stream_v4(dst0 + g4, v);
-                        } else {
-                            if (g4 + 0 >= pad && g4 + 0 < W) dst0[g4 + 0] = v.x;
-                            if (g4 + 1 >= pad && g4 + 1 < W) dst0[g4 + 1] = v.y;
-                            if (g4 + 2 >= pad && g4 + 2 < W) dst0[g4 + 2] = v.z;
-                            if (g4 + 3 >= pad && g4 + 3 < W) dst0[g4 + 3] = v.w;
-                        }
+                    uint32_t *const dst0 = wdst - pad;  // 16-byte aligned; words below pad are never touched
+                    const uint32_t hb = pad ? 4u : 0u, tb = W & ~3u;
+                    const bool body = tb > hb;
+                    if (lane < 8) {
+                        const uint32_t idx = (body && lane >= 4) ? tb + lane - 4 : lane;
+                        const bool edge = body ? (lane < 4 ? (pad != 0 && idx >= pad) : idx < W) : (idx >= pad && idx < W);
+                        if (edge) dst0[idx] = stage[idx];
                     }
-                    __syncwarp();
+                    if (lane == 0 && body) {
+                        const uint32_t src = (uint32_t)__cvta_generic_to_shared(stage + hb);
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst0 + hb), "r"(src),
+                                     "r"((tb - hb) * 4u)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
                 }
                 sub_lo = sub_hi;
             }
         }
+        // the warp's last slice must have left its stage before the next tile's candidate lists overwrite it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
 }
 
@@ -1566,11 +1577,17 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
                          reinterpret_cast<uintptr_t>(d_qe)) & 15u) == 0 && !find_tile_disabled();
     if (tiled) {
         // tile form first; the tiles it cannot take (no locality) are left to the per-warp kernel
-        static const bool smem_ok = [] {
-            return cudaFuncSetAttribute(find_fill_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kTSmemWords * (int)sizeof(uint32_t)) == cudaSuccess;
-        }();
-        LAPPER_REQUIRE(smem_ok, "find_fill_tile_kernel: cannot reserve shared memory");
+        // once per device: all of the SM's L1/shared array as shared memory, so that LAPPER_TILE_CTAS tiles are resident
+        static std::atomic<bool> prepared[64];
+        int dev = 0;
+        LAPPER_CUDA_CHECK(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !prepared[dev].load(std::memory_order_acquire)) {
+            LAPPER_CUDA_CHECK(cudaFuncSetAttribute(find_fill_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   kTSmemWords * (int)sizeof(uint32_t)));
+            LAPPER_CUDA_CHECK(cudaFuncSetAttribute(find_fill_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                   cudaSharedmemCarveoutMaxShared));
+            prepared[dev].store(true, std::memory_order_release);
+        }
         const uint32_t tgrid = (uint32_t)std::min<uint64_t>(ntiles, 148 * LAPPER_TILE_CTAS);
         find_fill_tile_kernel<<<tgrid, kTT, kTSmemWords * sizeof(uint32_t), stream>>>(
             f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2);
