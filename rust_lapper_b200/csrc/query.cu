@@ -960,6 +960,11 @@ __global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kern
 #ifndef LAPPER_TILE_CTAS
 #define LAPPER_TILE_CTAS 7
 #endif
+#ifdef LAPPER_NO_TILE_GUARD  // test-of-the-test builds only
+#define TILE_GUARD(x) true
+#else
+#define TILE_GUARD(x) (x)
+#endif
 constexpr int kTT = LAPPER_TILE_THREADS;   // threads per CTA
 constexpr int kTW = kTT / 32;              // warps per CTA
 constexpr int kTQPT = kFindTile / kTT;     // queries per thread in the tile prologue
@@ -1000,7 +1005,8 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
     uint4 *const cand = reinterpret_cast<uint4 *>(tsm);      // kTCand x (start, stop, position, -)
     uint32_t *const warp_area = tsm + 4 * kTCand;            // per warp: stage, then its candidate list
     uint32_t *const rel = warp_area + kTW * kTWarpWords;     // tile-relative offsets [0, nqt]
-    // ctl: [0..3] class lo, [4..7] class window size, [8..11] kept per class, [12] amin, [13] bmax, [16..] warp counts
+    // ctl: [0..3] class lo, [4..7] class window size, [8..11] kept per class, [12] amin, [13] bmax, [14] tile hits >> 32,
+    // [16..] warp counts
     uint32_t *const ctl = rel + kTRelWords;
     uint32_t *const rawg = warp_area, *const raws = warp_area + kTCand, *const rawe = warp_area + 2 * kTCand;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
@@ -1022,7 +1028,7 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
             }
         }
         __syncthreads();  // the previous tile's groups are done with the shared arrays
-        if (threadIdx.x < 16) ctl[threadIdx.x] = threadIdx.x == 12 ? 0xFFFFFFFFu : 0u;
+        if (threadIdx.x < 14) ctl[threadIdx.x] = threadIdx.x == 12 ? 0xFFFFFFFFu : 0u;  // [14] is written below
         // ---- 1. the tile's offsets (thread t: queries t*kTQPT .. and the offset after them), heavy queries,
         //         smallest start / largest stop over the queries this kernel emits
         const uint64_t tile_o0 = offsets[q0];
@@ -1063,7 +1069,11 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
 #pragma unroll
         for (int k = 0; k < kTQPT / 4; k++)
             *reinterpret_cast<uint4 *>(rel + jt + 4 * k) = make_uint4(r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
-        if (threadIdx.x == kTT - 1) rel[kFindTile] = r[kTQPT];
+        if (threadIdx.x == kTT - 1) {
+            rel[kFindTile] = r[kTQPT];
+            // tile-relative offsets are 32-bit: a tile with 2^32 or more hits is left to find_fill_kernel (64-bit offsets)
+            ctl[14] = (uint32_t)((offsets[q0 + nqt] - tile_o0) >> 32);
+        }
         amin = __reduce_min_sync(0xFFFFFFFFu, amin);
         bmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
         __syncthreads();  // ctl initialised
@@ -1072,7 +1082,7 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
             atomicMax(&ctl[13], bmax);
         }
         __syncthreads();
-        if (rel[nqt] == 0) continue;
+        if (rel[nqt] == 0 && ctl[14] == 0) continue;
         amin = ctl[12], bmax = ctl[13];
         // ---- 2. class windows of the tile (warp 0; four lanes per bound, as in find_fill_kernel)
         if (warp == 0) {
@@ -1111,7 +1121,7 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
         // ---- 3. the windows' intervals that end after amin, compacted in class-major order by all threads
         const uint32_t n0 = ctl[4], n1 = ctl[5], n2 = ctl[6], n3 = ctl[7];
         const uint32_t R = n0 + n1 + n2 + n3;
-        bool nice = n0 <= kTRawMax && n1 <= kTRawMax && n2 <= kTRawMax && n3 <= kTRawMax && R <= kTRawMax;
+        bool nice = n0 <= kTRawMax && n1 <= kTRawMax && n2 <= kTRawMax && n3 <= kTRawMax && R <= kTRawMax && TILE_GUARD(ctl[14] == 0);
         uint32_t K = 0;  // kept so far (uniform)
         for (uint32_t i0 = 0; nice && i0 < R; i0 += kTT) {
             const uint32_t i = i0 + threadIdx.x;

@@ -161,3 +161,50 @@ def test_pathological_count_and_find_sample(oracle):
         assert np.array_equal(idx.cpu().numpy().view(np.uint32), widx)
     finally:
         lib.lapper_free(h)
+
+
+def test_tile_with_more_than_2_pow_32_hits():
+    """One 1024-query tile whose hits exceed 2^32 (4.4 M identical intervals x 1000 queries inside them), followed in the
+    same tile by light queries on a distant cluster: the tile emit kernel's 32-bit tile-relative offsets cannot
+    address that, so the tile must go to the 64-bit path; every slice is checked on the device."""
+    import torch
+
+    from rust_lapper_b200 import _ffi
+
+    dev = torch.device("cuda", 0)
+    lib = _ffi.lib()
+    n_big, n_small = 4_400_000, 64
+    s = torch.cat([torch.full((n_big,), 1000, dtype=torch.int32, device=dev),
+                   torch.arange(n_small, dtype=torch.int32, device=dev) * 10 + 1_000_000])
+    e = torch.cat([torch.full((n_big,), 2000, dtype=torch.int32, device=dev),
+                   torch.arange(n_small, dtype=torch.int32, device=dev) * 10 + 1_000_040])
+    nq_big, nq = 1000, 3000
+    qs = torch.cat([torch.full((nq_big,), 1500, dtype=torch.int32, device=dev),
+                    (torch.arange(nq - nq_big, dtype=torch.int32, device=dev) % 600) + 1_000_000])
+    qe = qs + 7
+    h, sp = _build(lib, s, e, dev)
+    try:
+        off, idx, total = _find(lib, h, qs, qe, sp)
+        counts = _count(lib, h, qs, qe, sp)
+        assert total > 2**32
+        hits = off[1:] - off[:-1]
+        assert bool((hits == (counts.to(torch.int64) & 0xFFFFFFFF)).all())
+        assert bool((hits[:nq_big] == n_big).all())
+        # heavy slices: positions 0 .. n_big-1 in order (the identical intervals sort first)
+        big = idx[: nq_big * n_big].view(nq_big, n_big)
+        assert bool((big == torch.arange(n_big, dtype=torch.int32, device=dev)).all())
+        del big
+        # light slices: ascending positions inside the small cluster, each overlapping its query
+        lo = int(off[nq_big])
+        light = idx[lo:].to(torch.int64)
+        owner = torch.repeat_interleave(torch.arange(nq_big, nq, device=dev), hits[nq_big:])
+        assert bool((light >= n_big).all())
+        ls = (light - n_big) * 10 + 1_000_000
+        assert bool(((ls < qe[owner].to(torch.int64)) & (ls + 40 > qs[owner].to(torch.int64))).all())
+        # and the counts are what the geometry says: starts 10 apart, 40 long, query 7 long
+        q = qs[nq_big:].to(torch.int64) - 1_000_000
+        k = torch.arange(n_small, device=dev, dtype=torch.int64)[None, :] * 10
+        want = ((k < (q[:, None] + 7)) & (k + 40 > q[:, None])).sum(1)
+        assert bool((want == hits[nq_big:]).all())
+    finally:
+        lib.lapper_free(h)
