@@ -1321,6 +1321,79 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
 // reference's own scan (src/lib.rs:704-717) -- 32 intervals per step, skipping every block of 32 / 1024
 // intervals whose max stop is <= the query start, and ballot-compacts the hits into coalesced stores.
 // Positions come out ascending by construction: no merge.  Warps fetch queries from an atomic counter.
+// Heavy query, sparse case: the hits are a small fraction of the single sorted vector's window (cfg 4: 1 % of
+// the intervals are long and spread over the whole vector, so nearly every block of it has to be looked at for
+// about one hit).  The length classes hold exactly those intervals contiguously: the warp scans the class windows
+// instead -- a block of 32 entries per class and round -- and merges the class hit streams by position on the fly.
+// G = the smallest last-loaded position over the classes that continue beyond their block: everything at or below
+// G is complete in registers, so those entries are consumed, and an emitted entry's place in the output is its rank
+// among the emitted entries of all classes (own class: ballot prefix; other classes: a 6-shuffle lower bound in
+// their sorted block, then a popcount of their emit mask).  The class that defines G consumes its whole block, so
+// every round makes progress.
+__device__ __forceinline__ void heavy_merge_classes(const FindView &f, uint32_t a, uint32_t b, uint32_t *__restrict__ out,
+                                                    uint64_t room, uint32_t lane, uint32_t wlo, uint32_t whi) {
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t p[4], end[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        p[c] = __shfl_sync(0xFFFFFFFFu, wlo, c);
+        end[c] = __shfl_sync(0xFFFFFFFFu, whi, c);
+        if (c >= (int)f.ncls) p[c] = end[c] = 0;
+    }
+    uint64_t written = 0;
+    for (;;) {
+        uint32_t g[4], em[4];
+        bool hit[4], valid[4];
+        uint32_t G = 0xFFFFFFFFu;
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            g[c] = 0xFFFFFFFFu, hit[c] = false, valid[c] = false, em[c] = 0;
+            if (p[c] < end[c]) {  // warp-uniform
+                any = true;
+                const uint32_t i = p[c] + lane;
+                valid[c] = i < end[c];
+                if (valid[c]) {
+                    g[c] = __ldg(f.cg + f.cls_off[c] + i);
+                    hit[c] = __ldg(f.ce + f.cls_off[c] + i) > a;  // start < b holds inside the class window
+                }
+                if (p[c] + 32 < end[c]) G = min(G, __shfl_sync(0xFFFFFFFFu, g[c], 31));
+            }
+        }
+        if (!any) break;
+        uint32_t total = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (p[c] < end[c]) {
+                const bool take = valid[c] && g[c] <= G;
+                em[c] = __ballot_sync(0xFFFFFFFFu, take && hit[c]);
+                p[c] += __popc(__ballot_sync(0xFFFFFFFFu, take));
+                total += __popc(em[c]);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            if (em[c] == 0) continue;  // warp-uniform
+            uint32_t r = __popc(em[c] & lt);
+#pragma unroll
+            for (int c2 = 0; c2 < 4; c2++) {
+                if (c2 == c || em[c2] == 0) continue;  // warp-uniform
+                // #entries of class c2's block with position < g[c]: lower bound over the 32 lanes (ascending, padded
+                // with 0xFFFFFFFF)
+                uint32_t pos = 0;
+#pragma unroll
+                for (uint32_t step = 16; step >= 1; step >>= 1)
+                    if (__shfl_sync(0xFFFFFFFFu, g[c2], pos + step - 1) < g[c]) pos += step;
+                if (__shfl_sync(0xFFFFFFFFu, g[c2], pos) < g[c]) pos++;
+                r += __popc(em[c2] & (pos >= 32 ? 0xFFFFFFFFu : (1u << pos) - 1u));
+            }
+            if ((em[c] >> lane) & 1u)
+                if (written + r < room) out[written + r] = g[c];
+        }
+        written += total;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) find_heavy_kernel(FindView f, const uint32_t *__restrict__ qs,
                                                               const uint32_t *__restrict__ qe,
                                                               const uint64_t *__restrict__ offsets,
@@ -1348,6 +1421,17 @@ __global__ void __launch_bounds__(kThreads) find_heavy_kernel(FindView f, const 
         const uint32_t hi = __shfl_sync(0xFFFFFFFFu, r, 0);
         const uint32_t lo = max(__shfl_sync(0xFFFFFFFFu, r, 1), __shfl_sync(0xFFFFFFFFu, r, 2));
         uint32_t *out = indices + o0;
+        // class windows (lane c: class c); scanning them and merging pays when they are much shorter than [lo, hi)
+        uint32_t wlo = 0, whi = 0;
+        if (lane < f.ncls) class_window(f, (int)lane, a, b, wlo, whi);
+        uint32_t wsum = whi - wlo;
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) wsum += __shfl_xor_sync(0xFFFFFFFFu, wsum, o);
+        wsum = __shfl_sync(0xFFFFFFFFu, wsum, 0);
+        if (f.ncls > 0 && (uint64_t)wsum * 8 < (uint64_t)(hi > lo ? hi - lo : 0u)) {
+            heavy_merge_classes(f, a, b, out, room, lane, wlo, whi);
+            continue;
+        }
         uint64_t written = 0;
         for (uint32_t b2 = lo >> 10; ((uint64_t)b2 << 10) < hi && written < room; b2++) {
             if (__ldg(f.blkmax1024 + b2) <= a) continue;  // warp-uniform

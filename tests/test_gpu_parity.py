@@ -138,6 +138,44 @@ def test_find_tile_emit_dense_groups(oracle, depth, order):
     assert hits.max() > 2 * depth // 3  # the shape is what the name says
 
 
+@pytest.mark.parametrize("shape", ["one_long_class", "three_long_classes", "long_and_dense_short"])
+def test_heavy_queries_sparse_windows(oracle, shape):
+    """Heavy queries (>= 256 hits) whose hits are a small fraction of the sorted vector's window: find_heavy_kernel
+    scans the length-class windows and merges their hit streams by position (heavy_merge_classes) -- one, several
+    and unevenly sized classes, duplicates and ties included."""
+    rng = np.random.default_rng({"one_long_class": 1, "three_long_classes": 2, "long_and_dense_short": 3}[shape])
+    U = 50_000_000
+    n = 300_000
+    s = rng.integers(0, U, n)
+    ln = rng.integers(10, 200, n)
+    if shape == "one_long_class":
+        k = n // 100
+        ln[:k] = rng.integers(U // 2, 9 * U // 10, k)
+    elif shape == "three_long_classes":
+        k = n // 150
+        ln[:k] = rng.integers(U // 2, 9 * U // 10, k)
+        ln[k:2 * k] = rng.integers(U // 40, U // 20, k)
+        ln[2 * k:3 * k] = rng.integers(U // 400, U // 200, k)
+        s[3 * k:3 * k + 500] = s[0]  # ties on start across classes
+    else:
+        k = n // 200
+        ln[:k] = rng.integers(U // 3, U // 2, k)
+        s[k:k + 40_000] = rng.integers(U // 2, U // 2 + 3000, 40_000)  # a dense cluster of short intervals
+    e = np.minimum(s + ln, 0xFFFFFFFF)
+    s, e = s.astype(np.uint32), e.astype(np.uint32)
+    nq = 1024 + 40
+    qs = rng.integers(U // 4, 3 * U // 4, nq)
+    qs[:16] = U // 2 + rng.integers(0, 3000, 16)  # into the dense cluster
+    qe = qs + rng.integers(1, 400, nq)
+    qs, qe = qs.astype(np.uint32), qe.astype(np.uint32)
+    gpu, cpu = _both(oracle, s, e)
+    go, gi = gpu.find_batch(qs, qe)
+    co, ci = cpu.find_batch(qs, qe)
+    assert np.array_equal(go, co)
+    assert np.array_equal(gi, ci)
+    assert np.diff(co).max() >= 256
+
+
 def test_extreme_coordinates(oracle):
     X = 0xFFFFFFFF
     s = np.array([0, 0, X - 5, X, X - 1, 7, X], dtype=np.uint32)
