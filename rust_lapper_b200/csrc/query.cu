@@ -689,8 +689,95 @@ __device__ __forceinline__ void cursor_settle(const FindView &f, int c, ClassCur
     k.g = k.cur < k.end ? __ldg(f.cg + f.cls_off[c] + k.cur) : 0xFFFFFFFFu;
 }
 
+// lower bounds of key[c] among the starts of class c, all classes at once: the directory loads of every class are
+// issued together, then the (at most 16-entry) rank ranges are probed four independent loads at a time -- a lane
+// that owns a query on its own pays a few memory round trips instead of one per probed entry
+__device__ __forceinline__ void class_lb_all(const FindView &f, const uint32_t key[4], uint32_t r[4]) {
+    uint32_t r0[4], hi[4];
+    {
+        uint4 d0[4], d1[4];
+        uint32_t B[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            B[c] = min(key[c] >> f.cls_shift, f.cls_nb);
+            d0[c] = __ldg(f.dir + B[c]);
+            d1[c] = __ldg(f.dir + min(B[c] + 1, f.cls_nb));
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            r0[c] = dir_get(d0[c], c);
+            hi[c] = B[c] < f.cls_nb ? dir_get(d1[c], c) : r0[c];
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        r[c] = r0[c];
+        if (c >= (int)f.ncls) continue;
+        const uint32_t *cs = f.cs + f.cls_off[c];
+        if (hi[c] - r0[c] > 16u) {
+            r[c] = lower_bound_u32(cs, r0[c], hi[c], key[c]);
+            continue;
+        }
+        uint32_t x = r0[c];
+        while (x < hi[c]) {
+            uint32_t v[4];
+#pragma unroll
+            for (uint32_t t = 0; t < 4; t++) v[t] = x + t < hi[c] ? __ldg(cs + x + t) : 0xFFFFFFFFu;
+            uint32_t cnt = 0;
+#pragma unroll
+            for (uint32_t t = 0; t < 4; t++) cnt += (x + t < hi[c]) && (v[t] < key[c]);
+            x += cnt;
+            if (cnt < 4) break;
+        }
+        r[c] = x;
+    }
+}
+
+// per-lane emission, few hits (the common case of a query that owns its lane: random-order batches): the class
+// windows are scanned four independent loads at a time, the hits of each class appended (ascending within the
+// class), and the <= 32 positions then merged by an insertion sort in place
+constexpr uint32_t kEmitSmall = 32;
+__device__ __forceinline__ void emit_one_query_small(const FindView &f, uint32_t a, uint32_t b, uint32_t *out, uint32_t room) {
+    uint32_t key_lo[4], key_hi[4], lo[4], hi[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        key_lo[c] = a >= f.cls_maxlen[c] ? a - f.cls_maxlen[c] : 0u;
+        key_hi[c] = b;
+    }
+    class_lb_all(f, key_hi, hi);
+    class_lb_all(f, key_lo, lo);
+    uint32_t k = 0, first_run = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        if (c >= (int)f.ncls) continue;
+        const uint32_t *ce = f.ce + f.cls_off[c], *cg = f.cg + f.cls_off[c];
+        for (uint32_t i = lo[c]; i < hi[c]; i += 4) {
+            uint32_t e[4];
+#pragma unroll
+            for (uint32_t t = 0; t < 4; t++) e[t] = i + t < hi[c] ? __ldg(ce + i + t) : 0u;
+#pragma unroll
+            for (uint32_t t = 0; t < 4; t++)
+                if (i + t < hi[c] && e[t] > a && k < room) out[k++] = __ldg(cg + i + t);
+        }
+        if (c == 0) first_run = k;
+    }
+    for (uint32_t j = first_run; j < k; j++) {  // runs are ascending: only elements of later runs ever move
+        const uint32_t v = out[j];
+        uint32_t q = j;
+        while (q > 0 && out[q - 1] > v) {
+            out[q] = out[q - 1];
+            q--;
+        }
+        out[q] = v;
+    }
+}
+
 // per-lane emission (any query order): k-way merge of the class hit streams by global position
 __device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, uint32_t b, uint32_t *out, uint64_t room) {
+    if (f.ncls > 1 && room <= kEmitSmall) {
+        emit_one_query_small(f, a, b, out, (uint32_t)room);
+        return;
+    }
     if (f.ncls == 1) {  // single class: its positions are the global positions
         uint32_t lo, hi;
         class_window(f, 0, a, b, lo, hi);
