@@ -1569,7 +1569,7 @@ BucketView make_bucket_view(const DeviceIndex &ix) {
     v.pk.m = ix.dense_m;
     v.pk.magic = ix.dense_magic;
     v.pk.nb = (uint32_t)ix.dense_nb;
-    v.local_span = 4u << ix.shift;  // shift <= 13
+    v.local_span = ix.shift <= kMaxBucketShift ? 4u << ix.shift : 0u;  // (no sector table: no packed table either)
     return v;
 }
 
