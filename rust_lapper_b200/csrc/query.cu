@@ -599,39 +599,74 @@ __global__ void __launch_bounds__(kThreads) find_count_kernel(FindView f, const 
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = s;
 }
 
-// pass 2: sums of 256 consecutive tile sums ("super-tiles").  The tile bases are not materialised: a CTA of pass 3
-// adds up the super-tile sums before its super-tile (a few hundred values) and the tile sums before it inside the
-// super-tile (at most 255) -- all of it L2-resident -- instead of waiting for a serial scan of ~100 k sums.
+// pass 2: tile bases in two levels instead of one serial scan of ~100 k sums: (a) every block of 256 consecutive
+// tiles ("super-tile") turns its tile sums into exclusive prefixes within the super-tile and emits its total;
+// (b) one block scans the few hundred super-tile totals.  A tile's base is then super_base[tile / 256] + tile_sums[tile].
 constexpr int kSuperTiles = 256;
-__global__ void __launch_bounds__(kSuperTiles) super_sums_kernel(const uint64_t *__restrict__ tile_sums, uint64_t ntiles,
+__global__ void __launch_bounds__(kSuperTiles) super_sums_kernel(uint64_t *__restrict__ tile_sums, uint64_t ntiles,
                                                                  uint64_t *__restrict__ super_sums) {
-    __shared__ uint64_t red[8];
+    __shared__ uint64_t warp_tot[kSuperTiles / 32];
     const uint64_t t = (uint64_t)blockIdx.x * kSuperTiles + threadIdx.x;
-    const uint64_t s = block_reduce_sum_u64(t < ntiles ? tile_sums[t] : 0ull, red);
-    if (threadIdx.x == 0) super_sums[blockIdx.x] = s;
+    const uint64_t mine = t < ntiles ? tile_sums[t] : 0ull;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    uint64_t wbase = 0, all = 0;
+#pragma unroll
+    for (int i = 0; i < kSuperTiles / 32; i++) {
+        wbase += (i < w) ? warp_tot[i] : 0;
+        all += warp_tot[i];
+    }
+    if (t < ntiles) tile_sums[t] = wbase + inc - mine;  // exclusive within the super-tile
+    if (threadIdx.x == 0) super_sums[blockIdx.x] = all;
 }
 
-// pass 3: offsets[j] = tile base + exclusive scan of the tile's counts; the last tile also writes offsets[nq]
+// exclusive scan of the super-tile totals in place (one block; nsuper is a few hundred) + the grand total
+__global__ void __launch_bounds__(1024) scan_super_sums_kernel(uint64_t *__restrict__ super_sums, uint64_t nsuper,
+                                                               uint64_t *__restrict__ total_out) {
+    __shared__ uint64_t warp_tot[32];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (uint64_t i0 = 0; i0 < nsuper; i0 += 1024) {
+        const uint64_t i = i0 + threadIdx.x;
+        const uint64_t mine = i < nsuper ? super_sums[i] : 0ull;
+        uint64_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        uint64_t wbase = 0, all = 0;
+        for (int k = 0; k < 32; k++) {
+            wbase += (k < w) ? warp_tot[k] : 0;
+            all += warp_tot[k];
+        }
+        const uint64_t carry = carry_s;
+        if (i < nsuper) super_sums[i] = carry + wbase + inc - mine;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + all;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+// pass 3: offsets[j] = tile base + exclusive scan of the tile's counts
 __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t *__restrict__ counts,
                                                                  const uint64_t *__restrict__ tile_sums,
                                                                  const uint64_t *__restrict__ super_sums, uint64_t nq,
                                                                  uint64_t *__restrict__ offsets) {
     __shared__ uint64_t warp_tot[kThreads / 32];
-    __shared__ uint64_t red[8];
-    __shared__ uint64_t tile_base_s;
-    static_assert(kThreads == kSuperTiles, "one thread per tile of the super-tile");
-    {
-        const uint64_t sb = blockIdx.x / kSuperTiles;
-        uint64_t part = 0;
-        for (uint64_t i = threadIdx.x; i < sb; i += kThreads) part += super_sums[i];
-        const uint64_t t = sb * kSuperTiles + threadIdx.x;
-        if (t < blockIdx.x) part += tile_sums[t];
-        const uint64_t tb = block_reduce_sum_u64(part, red);
-        if (threadIdx.x == 0) {
-            tile_base_s = tb;
-            if (blockIdx.x == gridDim.x - 1) offsets[nq] = tb + tile_sums[blockIdx.x];
-        }
-    }
+    const uint64_t tile_base = super_sums[blockIdx.x / kSuperTiles] + tile_sums[blockIdx.x];
     const uint64_t base = (uint64_t)blockIdx.x * kFindTile + (uint64_t)threadIdx.x * kFindQPT;
     uint32_t c[kFindQPT];
     uint64_t local = 0;
@@ -652,7 +687,7 @@ __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t 
     uint64_t wbase = 0;
 #pragma unroll
     for (int i = 0; i < kThreads / 32; i++) wbase += (i < w) ? warp_tot[i] : 0;
-    uint64_t run = tile_base_s + wbase + inc - local;
+    uint64_t run = tile_base + wbase + inc - local;
     if (base + kFindQPT <= nq) {  // 32 contiguous bytes per thread: two 128-bit stores
         const uint64_t r0 = run, r1 = r0 + c[0], r2 = r1 + c[1], r3 = r2 + c[2];
         ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(offsets + base);
@@ -1720,6 +1755,8 @@ uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const 
     const uint64_t nsuper = div_up(ntiles, kSuperTiles);
     Scratch<uint64_t> super_sums(nsuper, stream);
     super_sums_kernel<<<(uint32_t)nsuper, kSuperTiles, 0, stream>>>(tile_sums.p, ntiles, super_sums.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    scan_super_sums_kernel<<<1, 1024, 0, stream>>>(super_sums.p, nsuper, d_offsets + nq);
     LAPPER_CUDA_CHECK(cudaGetLastError());
     write_offsets_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(counts.p, tile_sums.p, super_sums.p, nq, d_offsets);
     LAPPER_CUDA_CHECK(cudaGetLastError());
