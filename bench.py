@@ -37,6 +37,13 @@ UNIT = "queries/s"
 WORKLOAD = "cfg2: BITS count, 10M intervals (len 50-5000) in 3.1 Gbp universe x 100M random-order 150-bp queries per GPU"
 
 
+def packed_info(lib, h):
+    """bucket width / sectors / overflowed sectors of the packed count table (None when it was not built)"""
+    w, ns, no = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+    lib.lapper_packed_table_info(h, C.byref(w), C.byref(ns), C.byref(no))
+    return {"bucket_width": int(w.value), "sectors": int(ns.value), "overflowed": int(no.value)} if w.value else None
+
+
 def env_int(name, default):
     try:
         return int(os.environ.get(name, default))
@@ -324,9 +331,11 @@ def run_ours(args):
         "algorithmic_bytes_per_launch": algo_bytes,
         "launch_ms_avg": kernel_ms,
         "launch_ms_isolated_median": statistics.median(per_launch),
-        "note": "random-order queries: one 32-byte sector of the 75 MB packed table per query (csrc/packed_sector.cuh); "
-                "about 64 % of those gathers hit L2, the rest cost 64 B of DRAM each (see traffic); L2, L1 and DRAM "
-                "throughput are all at 65-71 % of their peaks in the ncu capture; DESIGN.md section 4",
+        "note": ("random-order queries: one 32-byte sector of the 75 MB packed table per query (csrc/packed_sector.cuh); "
+                 "about 64 % of those gathers hit L2, the rest cost 64 B of DRAM each (see traffic); L2, L1 and DRAM "
+                 "throughput are all at 65-71 % of their peaks in the ncu capture; DESIGN.md section 4")
+        if (n == N_INTERVALS and nq == NQ_PER_GPU) else
+        "non-default size: a sector table far beyond L2 is bound by the random 64-byte DRAM access rate; DESIGN.md section 4",
     }
 
     # ---- end to end: host pointers (pinned), H2D + kernel + D2H inside the timed region
@@ -392,9 +401,12 @@ def run_ours(args):
             "dtype": "u32",
             "data": "synthetic",
             "config": {
-                "workload": WORKLOAD,
+                "workload": WORKLOAD if (n == N_INTERVALS and nq == NQ_PER_GPU) else (
+                    f"cfg5-style: BITS count, {n} intervals (len 50-5000) in 3.1 Gbp universe x {nq} random-order 150-bp "
+                    f"queries per GPU ({world * nq} in all)"),
                 "intervals": n,
                 "queries_per_gpu": nq,
+                "packed_table": packed_info(lib, h),
                 "query_order": "random (as given; no pre-sort)",
                 "bucket_shift": None if shift == 0xFFFFFFFF else shift,
                 "index_bytes": int(lib.lapper_index_bytes(h)),
