@@ -375,14 +375,24 @@ bool choose_shift(uint64_t n, uint32_t max_coord, uint32_t flags, uint32_t &shif
     return true;
 }
 
-// Width of the packed table's buckets: about 4.5 starts (and 5.1 stops incl. the margin's) per 18-lane
-// sector, i.e. 7.1 bytes per interval -- 71 MB at the cfg-2 shape with 2.3 % of the sectors overflowing.
-// Measured there (profiles/r1_exp_packed_table_fill.log): 4.0 -> 0.688 ms, 4.5 -> 0.672, 5.0 -> 0.725,
-// 5.5 -> 0.788 (a smaller table stays in L2 better, but every overflowing sector sends its queries through
-// the deferred path).  Only built where it pays: the sector table is too large to stay L2-resident and the
-// packed one is not.
-bool choose_dense_width(uint64_t n, uint32_t max_coord, uint32_t flags, uint64_t sector_table_bytes, uint32_t &w_out) {
+// Shape of the packed table: bucket width w and stop margin m.
+//   * fill: about 4.25 starts (and 4.8 stops incl. the margin's) per 18-lane sector, i.e. 7.5 bytes per interval --
+//     75 MB at the cfg-2 shape with 1.6 % of the sectors overflowing.  Measured there
+//     (profiles/r1_exp_packed_table_fill*.log): 4.0 -> 0.688 ms, 4.25 -> 0.665, 4.5 -> 0.672, 5.0 -> 0.725, 5.5 -> 0.788
+//     (a smaller table stays in L2 better, but every overflowing sector sends its queries through the deferred path).
+//   * margin: w / 8, but at least kDenseMinMargin coordinates (capped at 3/4 w): a query whose start lies further
+//     below its stop's bucket needs a second sector, and on dense sets the buckets are narrower than a read-sized
+//     query (50 M intervals: w = 263).  The extra margin stops are paid for by a narrower bucket at the same fill.
+//   * where: next to a sector table too large to stay in L2 -- either the packed one does (<= 128 MB and clearly
+//     smaller), or neither does and the packed table saves second DRAM accesses (its margin covers longer queries
+//     than the sector table's w / 4).
+constexpr uint32_t kDenseMinMargin = 160;
+bool choose_dense_shape(uint64_t n, uint32_t max_coord, uint32_t flags, uint64_t sector_table_bytes, uint32_t sector_margin,
+                        uint32_t &w_out, uint32_t &m_out) {
     if (flags & LAPPER_BUILD_NO_DENSE) return false;
+    uint32_t min_margin = kDenseMinMargin;
+    if (const char *env = std::getenv("LAPPER_DENSE_MIN_MARGIN")) min_margin = (uint32_t)atoi(env);  // experiments
+    const auto margin_for = [&](uint32_t w) { return std::min(std::max(w / 8, std::min(min_margin, (3 * w) / 4)), 2047u - w); };
     const uint32_t forced = (flags >> 16) & 0xFFFu;
     if (forced) {
         LAPPER_REQUIRE(forced >= 2 && forced <= kDenseMaxWidth, "LAPPER_BUILD_DENSE_WIDTH: width must be in [2, 1820]");
@@ -390,22 +400,34 @@ bool choose_dense_width(uint64_t n, uint32_t max_coord, uint32_t flags, uint64_t
         uint32_t w = forced;
         while (w < kDenseMaxWidth && (uint64_t)max_coord / w + 2 > (1ull << 26)) w = std::min(2 * w, kDenseMaxWidth);
         w_out = w;
+        m_out = w / 8;
         return true;
     }
     const bool force = (flags & LAPPER_BUILD_FORCE_DENSE) != 0;
     double per_sector = 4.25;
     if (const char *env = std::getenv("LAPPER_DENSE_STARTS_PER_SECTOR")) per_sector = std::max(0.5, atof(env));  // experiments
     const double span = (double)max_coord + 1.0;
-    double w = per_sector * span / (double)std::max<uint64_t>(n, 1);
+    const double density = (double)std::max<uint64_t>(n, 1) / span;  // intervals per coordinate
+    const double entries = per_sector * 2.125;                      // lanes in use per sector at margin w / 8
+    double w = per_sector / density;
+    for (int it = 0; it < 4; it++) {  // narrower buckets where the minimum margin adds stops
+        w = std::min(w, (double)kDenseMaxWidth);
+        const double m = (double)margin_for((uint32_t)std::max(w, 2.0));
+        if (density * (2.0 * w + m) <= entries * 1.001) break;
+        w = (entries / density - m) / 2.0;
+    }
     if (w > (double)kDenseMaxWidth) w = (double)kDenseMaxWidth;
     if (w < (double)kDenseMinWidth) {
         if (!force) return false;
         w = (double)kDenseMinWidth;
     }
     w_out = (uint32_t)w;
+    m_out = margin_for(w_out);
     if (force) return true;
     const uint64_t bytes = ((uint64_t)max_coord / w_out + 2) * sizeof(Sector);
-    return sector_table_bytes > (40ull << 20) && bytes <= (128ull << 20) && bytes * 5 <= sector_table_bytes * 4;
+    if (sector_table_bytes <= (40ull << 20)) return false;  // the sector table is L2-resident: nothing to gain
+    if (bytes <= (128ull << 20) && bytes * 5 <= sector_table_bytes * 4) return true;
+    return sector_table_bytes > (192ull << 20) && m_out > sector_margin && bytes <= 2 * sector_table_bytes;
 }
 
 // Choose up to kMaxClasses contiguous groups of length bins minimising the expected number of
@@ -592,9 +614,9 @@ void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stre
         }
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
 
-        uint32_t dw = 0;
-        if (choose_dense_width(n, ix.max_coord, flags, (ix.nbuckets + 1 + ix.npool) * sizeof(Sector), dw)) {
-            const PackedParams pp = packed_params(dw, ix.max_coord);
+        uint32_t dw = 0, dm = 0;
+        if (choose_dense_shape(n, ix.max_coord, flags, (ix.nbuckets + 1 + ix.npool) * sizeof(Sector), ix.margin, dw, dm)) {
+            const PackedParams pp = packed_params(dw, ix.max_coord, dm);
             ix.dense_w = pp.w;
             ix.dense_m = pp.m;
             ix.dense_magic = pp.magic;

@@ -12,7 +12,8 @@
 // the margin below the bucket of the query stop, bucket not overflowing); everything else falls back to
 // the sector table.
 //
-// Bucket B = floor(x / w) covers [base, base + w), base = B * w, margin m = w / 8:
+// Bucket B = floor(x / w) covers [base, base + w), base = B * w, stop margin m (build.cu::choose_dense_shape: w / 8, but
+// at least ~160 coordinates where the buckets are narrow, so that a read-sized query needs one sector):
 //   w[0]      h = #starts < base  -  #sorted stops < base - m  +  L          (wrapping u32)
 //   w[1..7]   a 224-bit little-endian number: lane i (12 bits: guard bit 11 set, 11 value bits) at bit 12 i,
 //             i < 18; bits 216..223 are flags.  Lanes [0, L) are the S region, lanes [L, 18) the E region,
@@ -40,7 +41,7 @@
 namespace lap {
 
 constexpr uint32_t kDenseLanes = 18;
-constexpr uint32_t kDenseMaxWidth = 1820;  // w + w / 8 <= 2047
+constexpr uint32_t kDenseMaxWidth = 1820;  // w + w / 8 <= 2047 (margins are clamped to 2047 - w)
 constexpr uint32_t kDenseMinWidth = 16;
 constexpr uint32_t kDenseOverflow = 0x80000000u;
 
@@ -51,10 +52,14 @@ struct PackedParams {
     uint32_t nb;     // index of the sentinel sector = floor(max_coord / w) + 1
 };
 
-LAPPER_HD PackedParams packed_params(uint32_t w, uint32_t max_coord) {
+LAPPER_HD uint32_t pk_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+LAPPER_HD uint32_t pk_max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+
+// m: stop margin, clamped so that w + m <= 2047 (lane values have 11 bits)
+LAPPER_HD PackedParams packed_params(uint32_t w, uint32_t max_coord, uint32_t m) {
     PackedParams p;
     p.w = w;
-    p.m = w / 8;
+    p.m = pk_min(m, 2047u - w);
     p.magic = (uint32_t)(((1ull << 32) + w - 1) / w);
     p.nb = max_coord / w + 1;
     return p;
@@ -74,8 +79,6 @@ LAPPER_HD uint32_t pk_popc(uint32_t x) {
     return (uint32_t)__builtin_popcount(x);
 #endif
 }
-LAPPER_HD uint32_t pk_min(uint32_t a, uint32_t b) { return a < b ? a : b; }
-LAPPER_HD uint32_t pk_max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
 // #elements of the sorted array a[lo, hi) that are < key (key may exceed 32 bits)
 LAPPER_HD uint32_t pk_lower_bound(const uint32_t *a, uint32_t lo, uint32_t hi, uint64_t key) {

@@ -45,8 +45,10 @@ int main() {
         std::sort(S.begin(), S.end());
         std::sort(E.begin(), E.end());
         const uint32_t max_coord = std::max(S.back(), E.back());
-        const PackedParams p = packed_params(w, max_coord);
-        if (p.m != w / 8 || (uint64_t)p.magic * w < (1ull << 32) || (uint64_t)(p.magic - 1) * w >= (1ull << 32)) {
+        // margins: the default w / 8, none, most of the bucket, more than fits (clamped to 2047 - w)
+        const uint32_t margins[] = {w / 8, 0, (3 * w) / 4, 160, 5000};
+        const PackedParams p = packed_params(w, max_coord, margins[(round / 3) % 5]);
+        if (p.w + p.m > 2047 || (uint64_t)p.magic * w < (1ull << 32) || (uint64_t)(p.magic - 1) * w >= (1ull << 32)) {
             printf("bad params for w=%u\n", w);
             return 1;
         }
@@ -57,14 +59,14 @@ int main() {
             const int kind = j % 8;
             const uint32_t anchor = (kind < 5) ? S[rng() % n] : (uint32_t)(rng() % ((uint64_t)max_coord + 2000));
             const uint32_t qlen = (kind == 0) ? 0 : (kind == 1 ? 1 : (uint32_t)(rng() % (2 * w + 3)));
-            const uint32_t back = (uint32_t)(rng() % (w + 2));
+            const uint32_t back = (uint32_t)(rng() % (w + p.m + 2));
             a = anchor >= back ? anchor - back : 0;
             b = (uint32_t)std::min<uint64_t>((uint64_t)a + qlen, 0xFFFFFFFFull);
             if (kind == 7) std::swap(a, b);                       // inverted query
             if (j == 17) a = 0xFFFFFFFFu, b = 0xFFFFFFFFu;        // the start + 1 wrap
             if (j == 18) a = 0, b = 0;
             if (j == 19) a = 0xFFFFFFFEu, b = 0xFFFFFFFFu;
-            if (j >= 20 && j < 40) a = 0xFFFFFFFFu - (uint32_t)(rng() % (w / 8 + 3)), b = (uint32_t)(rng() % (w + 1));  // a - base + m wraps
+            if (j >= 20 && j < 40) a = 0xFFFFFFFFu - (uint32_t)(rng() % (p.m + 3)), b = (uint32_t)(rng() % (w + 1));  // a - base + m wraps
             uint32_t B, xs, te;
             const bool ok = packed_locate(p, a, b, B, xs, te);
             checked++;

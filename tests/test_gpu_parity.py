@@ -69,7 +69,8 @@ PACKED_FLAGS = {"auto_width": 2 | 8, "w2": 2 | (2 << 16), "w7": 2 | (7 << 16), "
 def test_packed_table_random(oracle, flags):
     rng = np.random.default_rng(100 + list(PACKED_FLAGS).index(flags))
     for universe, n, max_len, qlen in [(3_000_000, 20_000, 700, 150), (60_000, 20_000, 10, 3), (4 * 10**9, 50_000, 5000, 150),
-                                       (3_000_000, 3_000, 400_000, 30), (5_000_000, 30_000, 0, 2500)]:
+                                       (3_000_000, 3_000, 400_000, 30), (5_000_000, 30_000, 0, 2500),
+                                       (1_200_000, 20_000, 3000, 150)]:  # last: buckets narrower than the queries (minimum margin)
         s, e, qs, qe = rs.random_case(rng, n, min(universe, 0xFFFFFFFF - 1), max_len, 6 * 1024 + 77, qlen)
         gpu, cpu = _both(oracle, s, e, PACKED_FLAGS[flags])
         assert gpu.packed_table is not None
