@@ -1605,6 +1605,9 @@ BucketView make_bucket_view(const DeviceIndex &ix) {
     v.pk.magic = ix.dense_magic;
     v.pk.nb = (uint32_t)ix.dense_nb;
     v.local_span = ix.shift <= kMaxBucketShift ? 4u << ix.shift : 0u;  // (no sector table: no packed table either)
+    // dense sets: the packed table's margin covers longer queries than the sector table's and fewer of its sectors
+    // overflow, so it serves start-sorted batches better too -- every warp takes the packed path
+    if (ix.dense && ix.dense_m > ix.margin) v.local_span = 0;
     return v;
 }
 
