@@ -177,6 +177,24 @@ def test_heavy_queries_sparse_windows(oracle, shape):
     assert np.diff(co).max() >= 256
 
 
+@pytest.mark.parametrize("length", [0, 1, 37, 1000])
+def test_find_tile_emit_single_length_class(oracle, length):
+    """All intervals of one length (one length class; length 0 and 1 are never / barely found): start-sorted queries
+    through the tile emit kernel, ragged last tile, unaligned `indices` slices."""
+    rng = np.random.default_rng(1000 + length)
+    U = 300_000
+    s = rng.integers(0, U, 40_000)
+    e = s + length
+    nq = 5 * 1024 + 17
+    qs = np.sort(rng.integers(0, U, nq))
+    qe = qs + rng.integers(0, 120, nq)
+    gpu, cpu = _both(oracle, s.astype(np.uint32), e.astype(np.uint32))
+    go, gi = gpu.find_batch(qs.astype(np.uint32), qe.astype(np.uint32))
+    co, ci = cpu.find_batch(qs.astype(np.uint32), qe.astype(np.uint32))
+    assert np.array_equal(go, co)
+    assert np.array_equal(gi, ci)
+
+
 def test_extreme_coordinates(oracle):
     X = 0xFFFFFFFF
     s = np.array([0, 0, X - 5, X, X - 1, 7, X], dtype=np.uint32)
