@@ -58,6 +58,8 @@ typedef struct lapper_group lapper_group_t;   /* one replica per GPU, queries sh
 int lapper_version(void);
 const char *lapper_last_error(void);
 int lapper_device_count(int *count_out);
+/* number of kernels the count / find entry points have launched in this process so far (measurement aid) */
+uint64_t lapper_query_kernel_launches(void);
 
 /* ---- Lapper::new (src/lib.rs:196-236): stable sort by (start, stop), sorted starts, sorted stops,
  *      max_len.  Built on `device` by a radix sort + reductions.  n may be 0. */

@@ -329,6 +329,8 @@ uint64_t lapper_index_bytes(const lapper_t *l) {
     return l ? l->ix.bytes : 0;
 }
 
+uint64_t lapper_query_kernel_launches(void) { return lap::g_query_launches.load(); }
+
 int lapper_packed_table_info(const lapper_t *l, uint32_t *width_out, uint64_t *sectors_out, uint64_t *overflowed_out) {
     return guarded([&] {
         check_handle(l);

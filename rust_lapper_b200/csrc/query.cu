@@ -11,10 +11,15 @@
 // sets) the kernels bisect the sorted arrays under a sampled-key directory held in shared memory.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "index.cuh"
 
 namespace lap {
+
+// kernels launched by the query path in this process (lapper_query_kernel_launches(): what bench.py reports as
+// `gpu_launches`, counted rather than derived)
+std::atomic<uint64_t> g_query_launches{0};
 
 namespace {
 
@@ -301,13 +306,29 @@ __device__ __forceinline__ void load_queries(const uint32_t *__restrict__ qs, co
 // kFind: "find mode" for the offsets pass of find_batch -- the same counts (u32), plus per-tile sums
 // accumulated into tile_sums (zeroed by the caller) and queries outside the validity of BITS for find
 // (start >= stop) sent to the deferred path, where they are counted by the overlap predicate.
-template <bool kOut64, bool kFind>
-__global__ void __launch_bounds__(kThreads, LAPPER_MIN_CTAS) count_bucket_kernel(BucketView v, const FindView f,
+// Two builds of the kernel differ only in registers per thread: 3 CTAs/SM (80 registers: the packed path keeps four
+// gathers and their thresholds in flight -- best for order-less batches: 0.663 vs 0.785 ms at cfg 2) and 4 CTAs/SM
+// (64 registers: the issue-bound sector-table path of start-sorted batches gains from 32 warps/SM: 0.335 vs 0.371 ms).
+// For large batches both are launched back to back and every CTA of both takes the same decision from the same 32
+// sampled query groups (`batch_looks_sorted`), so exactly one of them does the work and the other exits at once:
+// no host round trip, no extra pass over the queries.
+constexpr int kRunAlways = 0, kRunIfSorted = 1, kRunIfNotSorted = 2;
+__device__ __forceinline__ bool batch_looks_sorted(const BucketView &v, const uint32_t *__restrict__ qe, uint64_t ntiles) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t j = (ntiles * lane / 32) * kTileQ + 4 * lane;  // one group of four consecutive queries per lane
+    const uint32_t d = __ldg(qe + j + 3) - __ldg(qe + j);
+    const bool local = d + v.local_span < 2u * v.local_span;
+    return __popc(__ballot_sync(0xFFFFFFFFu, local)) >= 28;
+}
+
+template <bool kOut64, bool kFind, int kCtas>
+__global__ void __launch_bounds__(kThreads, kCtas) count_bucket_kernel(BucketView v, const FindView f,
                                                                    const uint32_t *__restrict__ qs,
                                                                    const uint32_t *__restrict__ qe, uint64_t ntiles,
                                                                    uint32_t *__restrict__ o32,
                                                                    uint64_t *__restrict__ o64,
-                                                                   uint64_t *__restrict__ tile_sums) {
+                                                                   uint64_t *__restrict__ tile_sums, int run_mode) {
+    if (run_mode != kRunAlways && batch_looks_sorted(v, qe, ntiles) != (run_mode == kRunIfSorted)) return;
     __shared__ uint32_t wqueue[kWarps][kWQCap * 3];  // (relative query index, start, stop) per entry
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t *const wq = wqueue[warp];
@@ -1649,6 +1670,15 @@ uint32_t capped_grid(uint64_t work_items, int per_block, int waves) {
 
 namespace {
 
+// LAPPER_COUNT_NO_DUAL=1 (experiments / tests): one build of the count kernel only
+static bool count_dual_disabled() {
+    static const bool off = [] {
+        const char *e = std::getenv("LAPPER_COUNT_NO_DUAL");
+        return e && atoi(e) != 0;
+    }();
+    return off;
+}
+
 // count over the bucket table.  tile_sums != nullptr selects find mode (u32 counts + per-tile sums).
 void launch_count_buckets(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
                           uint32_t *d_out32, uint64_t *d_out64, uint64_t *tile_sums, cudaStream_t stream) {
@@ -1660,25 +1690,36 @@ void launch_count_buckets(const DeviceIndex &ix, const uint32_t *d_qs, const uin
                            reinterpret_cast<uintptr_t>(out)) & 31u) == 0;
     const uint64_t ntiles = aligned ? nq / kTileQ : 0;
     if (ntiles) {
-        // persistent: 148 SMs x LAPPER_MIN_CTAS resident CTAs of 256 threads
-        const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, 148 * LAPPER_MIN_CTAS);
-        if (tile_sums)
-            count_bucket_kernel<false, true><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, tile_sums);
-        else if (out64)
-            count_bucket_kernel<true, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, nullptr, d_out64, nullptr);
-        else
-            count_bucket_kernel<false, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, nullptr);
-        LAPPER_CUDA_CHECK(cudaGetLastError());
+        // persistent grids: 148 SMs x resident CTAs of 256 threads.  Large batches over an index that has both paths:
+        // the 4-CTA build for start-sorted batches and the 3-CTA build for the rest, selected on the device.
+        const bool dual = ntiles >= 4096 && v.dense != nullptr && v.local_span != 0 && !count_dual_disabled();
+        const auto launch = [&](auto ctas, int mode) {
+            constexpr int kCtas = decltype(ctas)::value;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, 148 * kCtas);
+            if (tile_sums)
+                g_query_launches++, count_bucket_kernel<false, true, kCtas><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, tile_sums, mode);
+            else if (out64)
+                g_query_launches++, count_bucket_kernel<true, false, kCtas><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, nullptr, d_out64, nullptr, mode);
+            else
+                g_query_launches++, count_bucket_kernel<false, false, kCtas><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, nullptr, mode);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+        };
+        if (dual) {
+            launch(std::integral_constant<int, 4>{}, kRunIfSorted);
+            launch(std::integral_constant<int, LAPPER_MIN_CTAS>{}, kRunIfNotSorted);
+        } else {
+            launch(std::integral_constant<int, LAPPER_MIN_CTAS>{}, kRunAlways);
+        }
     }
     const uint64_t done = ntiles * kTileQ, rest = nq - done;
     if (rest) {
         const uint32_t grid = capped_grid(rest, kThreads, 16);
         if (tile_sums)
-            count_bucket_tail_kernel<false, true><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, done, nq, d_out32, nullptr, tile_sums);
+            g_query_launches++, count_bucket_tail_kernel<false, true><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, done, nq, d_out32, nullptr, tile_sums);
         else if (out64)
-            count_bucket_tail_kernel<true, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, done, nq, nullptr, d_out64, nullptr);
+            g_query_launches++, count_bucket_tail_kernel<true, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, done, nq, nullptr, d_out64, nullptr);
         else
-            count_bucket_tail_kernel<false, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, done, nq, d_out32, nullptr, nullptr);
+            g_query_launches++, count_bucket_tail_kernel<false, false><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, done, nq, d_out32, nullptr, nullptr);
         LAPPER_CUDA_CHECK(cudaGetLastError());
     }
 }
@@ -1710,9 +1751,9 @@ void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d
         v.nsamp = (uint32_t)div_up(ix.n, 1ull << v.dshift);
         const uint32_t grid = capped_grid(nq, kThreads, 8);
         if (out64)
-            count_plain_kernel<true><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, nullptr, d_out64);
+            g_query_launches++, count_plain_kernel<true><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, nullptr, d_out64);
         else
-            count_plain_kernel<false><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, d_out32, nullptr);
+            g_query_launches++, count_plain_kernel<false><<<grid, kThreads, 0, stream>>>(v, d_qs, d_qe, nq, d_out32, nullptr);
     }
     LAPPER_CUDA_CHECK(cudaGetLastError());
 }
@@ -1752,16 +1793,16 @@ uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const 
         LAPPER_CUDA_CHECK(cudaMemsetAsync(tile_sums.p, 0, ntiles * sizeof(uint64_t), stream));
         launch_count_buckets(ix, d_qs, d_qe, nq, counts.p, nullptr, tile_sums.p, stream);
     } else {
-        find_count_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
+        g_query_launches++, find_count_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
     }
     LAPPER_CUDA_CHECK(cudaGetLastError());
     const uint64_t nsuper = div_up(ntiles, kSuperTiles);
     Scratch<uint64_t> super_sums(nsuper, stream);
-    super_sums_kernel<<<(uint32_t)nsuper, kSuperTiles, 0, stream>>>(tile_sums.p, ntiles, super_sums.p);
+    g_query_launches++, super_sums_kernel<<<(uint32_t)nsuper, kSuperTiles, 0, stream>>>(tile_sums.p, ntiles, super_sums.p);
     LAPPER_CUDA_CHECK(cudaGetLastError());
-    scan_super_sums_kernel<<<1, 1024, 0, stream>>>(super_sums.p, nsuper, d_offsets + nq);
+    g_query_launches++, scan_super_sums_kernel<<<1, 1024, 0, stream>>>(super_sums.p, nsuper, d_offsets + nq);
     LAPPER_CUDA_CHECK(cudaGetLastError());
-    write_offsets_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(counts.p, tile_sums.p, super_sums.p, nq, d_offsets);
+    g_query_launches++, write_offsets_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(counts.p, tile_sums.p, super_sums.p, nq, d_offsets);
     LAPPER_CUDA_CHECK(cudaGetLastError());
     uint64_t total = 0;
     LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
@@ -1810,19 +1851,19 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
             prepared[dev].store(true, std::memory_order_release);
         }
         const uint32_t tgrid = (uint32_t)std::min<uint64_t>(ntiles, 148 * LAPPER_TILE_CTAS);
-        find_fill_tile_kernel<<<tgrid, kTT, kTSmemWords * sizeof(uint32_t), stream>>>(
+        g_query_launches++, find_fill_tile_kernel<<<tgrid, kTT, kTSmemWords * sizeof(uint32_t), stream>>>(
             f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2);
         LAPPER_CUDA_CHECK(cudaGetLastError());
-        find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p,
+        g_query_launches++, find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p,
                                                         fallback.p, counters.p + 2);
     } else {
-        find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, nullptr,
+        g_query_launches++, find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, nullptr,
                                                         nullptr);
     }
     LAPPER_CUDA_CHECK(cudaGetLastError());
     if (total >= kHeavyHits) {
         // persistent warps; exits at once when the list is empty
-        find_heavy_kernel<<<148 * 8, kThreads, 0, stream>>>(f, d_qs, d_qe, d_offsets, d_indices, heavy.p, counters.p, counters.p + 1);
+        g_query_launches++, find_heavy_kernel<<<148 * 8, kThreads, 0, stream>>>(f, d_qs, d_qe, d_offsets, d_indices, heavy.p, counters.p, counters.p + 1);
         LAPPER_CUDA_CHECK(cudaGetLastError());
     }
 }
