@@ -793,15 +793,8 @@ __device__ __forceinline__ void class_lb_all(const FindView &f, const uint32_t k
 // windows are scanned four independent loads at a time, the hits of each class appended (ascending within the
 // class), and the <= 32 positions then merged by an insertion sort in place
 constexpr uint32_t kEmitSmall = 32;
-__device__ __forceinline__ void emit_one_query_small(const FindView &f, uint32_t a, uint32_t b, uint32_t *out, uint32_t room) {
-    uint32_t key_lo[4], key_hi[4], lo[4], hi[4];
-#pragma unroll
-    for (int c = 0; c < 4; c++) {
-        key_lo[c] = a >= f.cls_maxlen[c] ? a - f.cls_maxlen[c] : 0u;
-        key_hi[c] = b;
-    }
-    class_lb_all(f, key_hi, hi);
-    class_lb_all(f, key_lo, lo);
+__device__ __forceinline__ void emit_one_query_small(const FindView &f, uint32_t a, const uint32_t lo[4], const uint32_t hi[4],
+                                                     uint32_t *out, uint32_t room) {
     uint32_t k = 0, first_run = 0;
 #pragma unroll
     for (int c = 0; c < 4; c++) {
@@ -828,16 +821,47 @@ __device__ __forceinline__ void emit_one_query_small(const FindView &f, uint32_t
     }
 }
 
-// per-lane emission (any query order): k-way merge of the class hit streams by global position
-__device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, uint32_t b, uint32_t *out, uint64_t room) {
+// A lane must not walk long class windows on its own (cfg 4: a query near the end of the universe has few hits,
+// but its window in the long class is every long interval that starts before it -- 100 k dependent loads): such a
+// query goes on the heavy list whatever its hit count, and find_heavy_kernel gives it a warp.
+constexpr uint32_t kLaneWindowMax = 1024;
+struct HeavyList {
+    uint32_t *list;
+    unsigned int *count;      // entries in the list (queries with >= kHeavyHits hits + admitted long-window queries)
+    unsigned int *admitted;   // long-window queries admitted so far
+    uint32_t max_admitted;    // the list has room for total / kHeavyHits + 1 + max_admitted entries
+};
+
+// per-lane emission (any query order) of query j: merge of the class hit streams by global position
+__device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, uint32_t b, uint32_t *out, uint64_t room,
+                                               const HeavyList &heavy, uint64_t j) {
+    uint32_t lo[4], hi[4];
+    {
+        uint32_t key_lo[4], key_hi[4];
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            key_lo[c] = a >= f.cls_maxlen[c] ? a - f.cls_maxlen[c] : 0u;
+            key_hi[c] = b;
+        }
+        class_lb_all(f, key_hi, hi);
+        class_lb_all(f, key_lo, lo);
+    }
+    uint32_t wsum = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        if (c >= (int)f.ncls || lo[c] > hi[c]) lo[c] = hi[c];
+        wsum += hi[c] - lo[c];
+    }
+    if (wsum > kLaneWindowMax && atomicAdd(heavy.admitted, 1u) < heavy.max_admitted) {
+        heavy.list[atomicAdd(heavy.count, 1u)] = (uint32_t)j;
+        return;  // (no room on the list: walk the windows here after all)
+    }
     if (f.ncls > 1 && room <= kEmitSmall) {
-        emit_one_query_small(f, a, b, out, (uint32_t)room);
+        emit_one_query_small(f, a, lo, hi, out, (uint32_t)room);
         return;
     }
     if (f.ncls == 1) {  // single class: its positions are the global positions
-        uint32_t lo, hi;
-        class_window(f, 0, a, b, lo, hi);
-        for (uint32_t i = lo; i < hi && room; i++)
+        for (uint32_t i = lo[0]; i < hi[0] && room; i++)
             if (__ldg(f.ce + i) > a) {
                 *out++ = i;
                 room--;
@@ -847,12 +871,9 @@ __device__ __forceinline__ void emit_one_query(const FindView &f, uint32_t a, ui
     ClassCursor k[4];
 #pragma unroll
     for (int c = 0; c < 4; c++) {
-        k[c].cur = k[c].end = 0;
+        k[c].cur = lo[c], k[c].end = hi[c];
         k[c].g = 0xFFFFFFFFu;
-        if (c < (int)f.ncls) {
-            class_window(f, c, a, b, k[c].cur, k[c].end);
-            cursor_settle(f, c, k[c], a);
-        }
+        if (c < (int)f.ncls) cursor_settle(f, c, k[c], a);
     }
     while (room) {
         // smallest global position among the class heads
@@ -895,7 +916,9 @@ __global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kern
                                                              uint32_t *__restrict__ heavy_list,
                                                              unsigned int *__restrict__ heavy_count,
                                                              const uint32_t *__restrict__ tile_list,
-                                                             const unsigned int *__restrict__ tile_count) {
+                                                             const unsigned int *__restrict__ tile_count,
+                                                             unsigned int *__restrict__ heavy_admitted, uint32_t heavy_max_admitted) {
+    const HeavyList heavy = {heavy_list, heavy_count, heavy_admitted, heavy_max_admitted};
     __shared__ __align__(16) uint32_t smem_all[kThreads / 32][kEmitWarpWords];
     const uint32_t lane = threadIdx.x & 31u;
     uint32_t *const stage = smem_all[threadIdx.x >> 5];       // kEmitStage output slots ...
@@ -1055,13 +1078,13 @@ __global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kern
             EMIT_STAT(2, 1);
 #pragma unroll
             for (int q = 0; q < kEmitQ; q++)
-                if (mine[q]) emit_one_query(f, a[q], b[q], stage + pad + (o0[q] - wbase), o1[q] - o0[q]);
+                if (mine[q]) emit_one_query(f, a[q], b[q], stage + pad + (o0[q] - wbase), o1[q] - o0[q], heavy, jbase + q * 32 + lane);
             __syncwarp();
         } else {
             EMIT_STAT(3, 1);
 #pragma unroll
             for (int q = 0; q < kEmitQ; q++)
-                if (mine[q]) emit_one_query(f, a[q], b[q], indices + o0[q], o1[q] - o0[q]);
+                if (mine[q]) emit_one_query(f, a[q], b[q], indices + o0[q], o1[q] - o0[q], heavy, jbase + q * 32 + lane);
         }
         if (staged) {
             // copy-out: stage word pad + i -> wdst[i]; whole 128-bit groups except at the two ragged ends
@@ -1143,7 +1166,9 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                                                                     uint32_t *__restrict__ heavy_list,
                                                                     unsigned int *__restrict__ heavy_count,
                                                                     uint32_t *__restrict__ fallback_tiles,
-                                                                    unsigned int *__restrict__ fallback_count) {
+                                                                    unsigned int *__restrict__ fallback_count,
+                                                                    unsigned int *__restrict__ heavy_admitted, uint32_t heavy_max_admitted) {
+    const HeavyList heavy = {heavy_list, heavy_count, heavy_admitted, heavy_max_admitted};
     extern __shared__ __align__(16) uint32_t tsm[];
     uint4 *const cand = reinterpret_cast<uint4 *>(tsm);      // kTCand x (start, stop, position, -)
     uint32_t *const warp_area = tsm + 4 * kTCand;            // per warp: stage, then its candidate list
@@ -1427,7 +1452,9 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                         EMIT_STAT(6, 1);
 #pragma unroll
                         for (int q = 0; q < kEmitQ; q++)
-                            if (act[q]) emit_one_query(f, a[q], b[q], stage + pad + (ro0[q] - sbase), ro1[q] - ro0[q]);
+                            if (act[q])
+                                emit_one_query(f, a[q], b[q], stage + pad + (ro0[q] - sbase), ro1[q] - ro0[q], heavy,
+                                               q0 + gq + q * 32 + lane);
                     }
                     // copy-out: the whole 16-byte groups of the slice leave as ONE bulk copy shared -> global issued by
                     // lane 0 (cp.async.bulk, the TMA path: no LDS/STG instructions, no LSU wavefronts); the ragged
@@ -1485,6 +1512,36 @@ __device__ __forceinline__ void heavy_merge_classes(const FindView &f, uint32_t 
     }
     uint64_t written = 0;
     for (;;) {
+        {   // one class left (the usual end game: the short classes' windows are short): nothing to merge with --
+            // stream it, four blocks of 32 per step with independent loads
+            int alive = 0, last = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+                if (p[c] < end[c]) alive++, last = c;
+            if (alive == 1) {
+                const uint32_t *ce = f.ce + f.cls_off[last], *cg = f.cg + f.cls_off[last];
+                for (uint32_t i0 = p[last]; i0 < end[last]; i0 += 128) {
+                    uint32_t e[4], gg[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t i = i0 + 32 * u + lane;
+                        ok[u] = i < end[last];
+                        e[u] = ok[u] ? __ldg(ce + i) : 0u;
+                        gg[u] = ok[u] ? __ldg(cg + i) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const bool h = ok[u] && e[u] > a;
+                        const uint32_t hm = __ballot_sync(0xFFFFFFFFu, h);
+                        const uint64_t at = written + __popc(hm & lt);
+                        if (h && at < room) out[at] = gg[u];
+                        written += __popc(hm);
+                    }
+                }
+                return;
+            }
+        }
         uint32_t g[4], em[4];
         bool hit[4], valid[4];
         uint32_t G = 0xFFFFFFFFu;
@@ -1828,12 +1885,15 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
     uint64_t total = 0;
     LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
     LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
-    const uint64_t cap = std::min<uint64_t>(total / kHeavyHits + 1, nq);
+    // the heavy list: queries with >= kHeavyHits hits (at most total / kHeavyHits) + light queries with long class
+    // windows, admitted up to a sixteenth of the batch
+    const uint32_t max_admitted = (uint32_t)std::min<uint64_t>(nq, nq / 16 + 1024);
+    const uint64_t cap = std::min<uint64_t>(total / kHeavyHits + 1, nq) + max_admitted;
     const uint64_t ntiles = div_up(nq, kFindTile);
     Scratch<uint32_t> heavy(cap, stream);
     Scratch<uint32_t> fallback(ntiles, stream);
-    Scratch<unsigned int> counters(3, stream);  // heavy queries, next heavy query, fallback tiles
-    LAPPER_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, 3 * sizeof(unsigned int), stream));
+    Scratch<unsigned int> counters(4, stream);  // heavy queries, next heavy query, fallback tiles, admitted long-window queries
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned int), stream));
     const uint32_t grid = capped_grid(nq, kThreads, LAPPER_EMIT_MIN_CTAS * 8);
     const bool tiled = ((reinterpret_cast<uintptr_t>(d_offsets) | reinterpret_cast<uintptr_t>(d_qs) |
                          reinterpret_cast<uintptr_t>(d_qe)) & 15u) == 0 && !find_tile_disabled();
@@ -1852,17 +1912,17 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
         }
         const uint32_t tgrid = (uint32_t)std::min<uint64_t>(ntiles, 148 * LAPPER_TILE_CTAS);
         g_query_launches++, find_fill_tile_kernel<<<tgrid, kTT, kTSmemWords * sizeof(uint32_t), stream>>>(
-            f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2);
+            f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2, counters.p + 3, max_admitted);
         LAPPER_CUDA_CHECK(cudaGetLastError());
         g_query_launches++, find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p,
-                                                        fallback.p, counters.p + 2);
+                                                        fallback.p, counters.p + 2, counters.p + 3, max_admitted);
     } else {
         g_query_launches++, find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, nullptr,
-                                                        nullptr);
+                                                        nullptr, counters.p + 3, max_admitted);
     }
     LAPPER_CUDA_CHECK(cudaGetLastError());
-    if (total >= kHeavyHits) {
-        // persistent warps; exits at once when the list is empty
+    {
+        // persistent warps; exits at once when the list is empty (it may also hold light queries with long windows)
         g_query_launches++, find_heavy_kernel<<<148 * 8, kThreads, 0, stream>>>(f, d_qs, d_qe, d_offsets, d_indices, heavy.p, counters.p, counters.p + 1);
         LAPPER_CUDA_CHECK(cudaGetLastError());
     }
