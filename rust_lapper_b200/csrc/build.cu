@@ -476,6 +476,29 @@ void choose_classes(const LenHist &h, uint64_t span, uint8_t class_of_bin[33], u
         }
         j = i;
     }
+    // Adjacent classes that are both scan-heavy (more than ~1000 expected window slots per query) become one: no
+    // lane ever walks such a window -- their queries get a warp in find_heavy_kernel, which streams ONE class at
+    // 128 entries per step but pays a position merge per 32 entries when several are active (cfg 4: the long
+    // intervals fall into two length bins; as two classes the merge was 80 % of that kernel's instructions).
+    {
+        const double kScanHeavy = 1024.0;
+        auto slots = [&](int c) {
+            return (double)cls_n[c] * ((double)cls_maxlen[c] + kQueryLen) / (double)std::max<uint64_t>(span, 1);
+        };
+        for (int c = 0; c + 1 < (int)ncls;) {
+            if (slots(c) > kScanHeavy && slots(c + 1) > kScanHeavy) {
+                cls_n[c] += cls_n[c + 1];
+                cls_maxlen[c] = std::max(cls_maxlen[c], cls_maxlen[c + 1]);
+                for (int k = c + 1; k + 1 < (int)ncls; k++) cls_n[k] = cls_n[k + 1], cls_maxlen[k] = cls_maxlen[k + 1];
+                cls_n[ncls - 1] = 0, cls_maxlen[ncls - 1] = 0;
+                for (int b = 0; b < 33; b++)
+                    if (class_of_bin[b] > c) class_of_bin[b]--;
+                ncls--;
+            } else {
+                c++;
+            }
+        }
+    }
     // empty bins between / beyond the groups: attach to the next class above so every bin maps somewhere valid
     int last = 0;
     for (int b = 0; b < 33; b++) {
@@ -504,6 +527,7 @@ void build_find_classes(DeviceIndex &ix, cudaStream_t stream) {
         ix.cls_off[c] = off;
         off += ix.cls_n[c];
     }
+
     ix.cls_starts = dev_alloc<uint32_t>(n, ix.bytes);
     ix.cls_stops = dev_alloc<uint32_t>(n, ix.bytes);
     ix.cls_gidx = dev_alloc<uint32_t>(n, ix.bytes);

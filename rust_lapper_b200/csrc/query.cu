@@ -1512,34 +1512,51 @@ __device__ __forceinline__ void heavy_merge_classes(const FindView &f, uint32_t 
     }
     uint64_t written = 0;
     for (;;) {
-        {   // one class left (the usual end game: the short classes' windows are short): nothing to merge with --
-            // stream it, four blocks of 32 per step with independent loads
-            int alive = 0, last = 0;
+        {   // Streaming step.  The class whose next entry has the smallest position can be emitted on its own as far
+            // as its positions stay below every other class's next position -- no merge needed for that stretch.
+            // (cfg 4: the hits of the short classes sit at the END of the merged order, next to the query, so the
+            // long class streams alone almost to its end although the short classes are still pending.)
+            uint32_t head[4];
+            int alive = 0;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                head[c] = 0xFFFFFFFFu;
+                if (p[c] < end[c]) {
+                    alive++;
+                    head[c] = __ldg(f.cg + f.cls_off[c] + p[c]);  // same address in every lane
+                }
+            }
+            if (alive == 0) break;
+            int cs = 0;
+#pragma unroll
+            for (int c = 1; c < 4; c++)
+                if (head[c] < head[cs]) cs = c;
+            uint32_t limit = 0xFFFFFFFFu;
 #pragma unroll
             for (int c = 0; c < 4; c++)
-                if (p[c] < end[c]) alive++, last = c;
-            if (alive == 1) {
-                const uint32_t *ce = f.ce + f.cls_off[last], *cg = f.cg + f.cls_off[last];
-                for (uint32_t i0 = p[last]; i0 < end[last]; i0 += 128) {
-                    uint32_t e[4], gg[4];
-                    bool ok[4];
+                if (c != cs) limit = min(limit, head[c]);
+            const uint32_t *ce = f.ce + f.cls_off[cs], *cg = f.cg + f.cls_off[cs];
+            const uint32_t step = min(end[cs] - p[cs], 128u);
+            if (alive == 1 || __ldg(cg + p[cs] + step - 1) < limit) {
+                uint32_t e[4], gg[4];
+                bool ok[4];
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const uint32_t i = i0 + 32 * u + lane;
-                        ok[u] = i < end[last];
-                        e[u] = ok[u] ? __ldg(ce + i) : 0u;
-                        gg[u] = ok[u] ? __ldg(cg + i) : 0u;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const bool h = ok[u] && e[u] > a;
-                        const uint32_t hm = __ballot_sync(0xFFFFFFFFu, h);
-                        const uint64_t at = written + __popc(hm & lt);
-                        if (h && at < room) out[at] = gg[u];
-                        written += __popc(hm);
-                    }
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t k = 32 * u + lane;
+                    ok[u] = k < step;
+                    e[u] = ok[u] ? __ldg(ce + p[cs] + k) : 0u;
+                    gg[u] = ok[u] ? __ldg(cg + p[cs] + k) : 0u;
                 }
-                return;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool h = ok[u] && e[u] > a;
+                    const uint32_t hm = __ballot_sync(0xFFFFFFFFu, h);
+                    const uint64_t at = written + __popc(hm & lt);
+                    if (h && at < room) out[at] = gg[u];
+                    written += __popc(hm);
+                }
+                p[cs] += step;
+                continue;
             }
         }
         uint32_t g[4], em[4];
