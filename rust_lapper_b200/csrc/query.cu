@@ -1650,6 +1650,28 @@ __global__ void __launch_bounds__(kThreads) find_heavy_kernel(FindView f, const 
             continue;
         }
         uint64_t written = 0;
+        if (room * 2 >= (uint64_t)(hi > lo ? hi - lo : 0u)) {
+            // dense window (README bakeoff shape: every second interval of the window is a hit): no block can be
+            // skipped, so stream it, 128 intervals per step with independent loads
+            for (uint32_t i0 = lo; i0 < hi; i0 += 128) {
+                uint32_t e[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + 32 * u + lane;
+                    e[u] = i < hi ? __ldg(f.Eiv + i) : 0u;  // stops are > a >= 0 for a hit; 0 never is
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const uint32_t i = i0 + 32 * u + lane;
+                    const bool h = i < hi && e[u] > a;
+                    const uint32_t hm = __ballot_sync(0xFFFFFFFFu, h);
+                    const uint64_t at = written + __popc(hm & lt);
+                    if (h && at < room) out[at] = i;
+                    written += __popc(hm);
+                }
+            }
+            continue;
+        }
         for (uint32_t b2 = lo >> 10; ((uint64_t)b2 << 10) < hi && written < room; b2++) {
             if (__ldg(f.blkmax1024 + b2) <= a) continue;  // warp-uniform
             const uint32_t b1 = b2 * 32 + lane;            // this lane's block of 32 intervals
