@@ -14,7 +14,10 @@ nq = int(os.environ.get("NQ", 100_000_000))
 reps = int(os.environ.get("REPS", 3))
 dev = torch.device("cuda", 0)
 lib = _ffi.lib()
-s, e = synth.intervals_uniform(42, n, synth.GRCH38, 50, 5000, device=dev)
+if os.environ.get("INTERVALS", "uniform") == "gene_exon":  # the cfg-3 interval set
+    s, e = synth.intervals_gene_exon(44, n, synth.GRCH38, device=dev)
+else:
+    s, e = synth.intervals_uniform(42, n, synth.GRCH38, 50, 5000, device=dev)
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 h = C.c_void_p(0)
 flags = int(os.environ.get("FLAGS", 0))  # e.g. 4 = LAPPER_BUILD_NO_DENSE
