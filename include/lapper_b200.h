@@ -153,6 +153,11 @@ int lapper_merge_overlaps(lapper_t *l);
 /* ---- Lapper::cov / set_cov (src/lib.rs:310-350) */
 int lapper_cov(const lapper_t *l, uint32_t *cov_out);
 int lapper_set_cov(lapper_t *l, uint32_t *cov_out);
+/* the cached fields `cov: Option<I>` and `overlaps_merged` (src/lib.rs:119-122) as they are, and their restoration
+ * when a serialised Lapper (the reference's `with_serde` feature, src/lib.rs:85-86, :1387-1409) is loaded back;
+ * any output pointer may be NULL */
+int lapper_get_cached_state(const lapper_t *l, int *cov_is_some_out, uint32_t *cov_out, int *overlaps_merged_out);
+int lapper_restore_cached_state(lapper_t *l, int cov_is_some, uint32_t cov, int overlaps_merged);
 /* ---- Lapper::union_and_intersect / intersect / union (src/lib.rs:512-559) */
 int lapper_union_and_intersect(const lapper_t *a, const lapper_t *b, uint32_t *union_out, uint32_t *intersect_out);
 

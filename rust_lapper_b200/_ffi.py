@@ -86,6 +86,8 @@ SIGNATURES = {
     "lapper_find_batch_offsets_u32_dev": (_int, [_vp, _vp, _vp, _u64, _vp, C.POINTER(_u64), _vp]),
     "lapper_find_batch_fill_u32_dev": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "lapper_seek_cursor": (_int, [_vp, _u32, C.POINTER(_u64)]),
+    "lapper_get_cached_state": (_int, [_vp, C.POINTER(_int), C.POINTER(_u32), C.POINTER(_int)]),
+    "lapper_restore_cached_state": (_int, [_vp, _int, _u32, _int]),
     "lapper_insert_u32": (_int, [_vp, _u32, _u32, C.POINTER(_u64)]),
     "lapper_merge_overlaps": (_int, [_vp]),
     "lapper_cov": (_int, [_vp, C.POINTER(_u32)]),

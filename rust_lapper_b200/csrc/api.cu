@@ -594,6 +594,25 @@ int lapper_cov(const lapper_t *l, uint32_t *cov_out) {
     });
 }
 
+/* the cached fields of src/lib.rs:119-122 (`cov: Option<I>`, `overlaps_merged`), for (de)serialisation */
+int lapper_get_cached_state(const lapper_t *l, int *cov_is_some_out, uint32_t *cov_out, int *overlaps_merged_out) {
+    return guarded([&] {
+        check_handle(l);
+        if (cov_is_some_out) *cov_is_some_out = l->cov_is_some ? 1 : 0;
+        if (cov_out) *cov_out = l->cov_is_some ? l->cov : 0u;
+        if (overlaps_merged_out) *overlaps_merged_out = l->overlaps_merged ? 1 : 0;
+    });
+}
+
+int lapper_restore_cached_state(lapper_t *l, int cov_is_some, uint32_t cov, int overlaps_merged) {
+    return guarded([&] {
+        check_handle(l);
+        l->cov_is_some = cov_is_some != 0;
+        l->cov = cov_is_some ? cov : 0u;
+        l->overlaps_merged = overlaps_merged != 0;
+    });
+}
+
 int lapper_set_cov(lapper_t *l, uint32_t *cov_out) {
     return guarded([&] {
         check_handle(l);
