@@ -60,6 +60,9 @@ const char *lapper_last_error(void);
 int lapper_device_count(int *count_out);
 /* number of kernels the count / find entry points have launched in this process so far (measurement aid) */
 uint64_t lapper_query_kernel_launches(void);
+/* builds with -DLAPPER_DEBUG_CHECKS carry bounds checks in the query kernels (compute-sanitizer is not available on
+ * every GPU pool): the number of violated checks on the current device so far; -1 in normal builds */
+long long lapper_debug_violations(void);
 
 /* ---- Lapper::new (src/lib.rs:196-236): stable sort by (start, stop), sorted starts, sorted stops,
  *      max_len.  Built on `device` by a radix sort + reductions.  n may be 0. */

@@ -331,6 +331,10 @@ uint64_t lapper_index_bytes(const lapper_t *l) {
 
 uint64_t lapper_query_kernel_launches(void) { return lap::g_query_launches.load(); }
 
+/* -DLAPPER_DEBUG_CHECKS builds: number of bounds checks the query kernels have seen violated on the current device
+ * (synchronises it); -1 in normal builds */
+long long lapper_debug_violations(void) { return lap::debug_violations(); }
+
 int lapper_packed_table_info(const lapper_t *l, uint32_t *width_out, uint64_t *sectors_out, uint64_t *overflowed_out) {
     return guarded([&] {
         check_handle(l);

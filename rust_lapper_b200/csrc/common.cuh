@@ -86,6 +86,21 @@ struct Scratch {
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
 
+// compute-sanitizer is not available on the GPU pool, so the kernels carry their own bounds checks: a build with
+// -DLAPPER_DEBUG_CHECKS counts violated conditions in a device counter (lapper_debug_violations(), api.cu) instead of
+// trusting the output comparison alone; the GPU test suite is run against that build (tests/conftest.py reports it).
+#ifdef LAPPER_DEBUG_CHECKS
+// (the counter lives in query.cu, the only file whose kernels carry checks: no relocatable device code needed)
+#define LAPPER_CHECK(cond)                                   \
+    do {                                                     \
+        if (!(cond)) atomicAdd(&::lap::g_debug_violations, 1ull); \
+    } while (0)
+#else
+#define LAPPER_CHECK(cond) \
+    do {                   \
+    } while (0)
+#endif
+
 struct __align__(32) Sector {
     uint32_t w[8];
 };

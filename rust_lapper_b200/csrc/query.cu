@@ -20,6 +20,9 @@ namespace lap {
 // kernels launched by the query path in this process (lapper_query_kernel_launches(): what bench.py reports as
 // `gpu_launches`, counted rather than derived)
 std::atomic<uint64_t> g_query_launches{0};
+#ifdef LAPPER_DEBUG_CHECKS
+__device__ unsigned long long g_debug_violations = 0;
+#endif
 
 namespace {
 
@@ -359,7 +362,10 @@ __global__ void __launch_bounds__(kThreads, kCtas) count_bucket_kernel(BucketVie
                 dense_tile = __reduce_add_sync(0xFFFFFFFFu, (uint32_t)__popc(bad)) <= 8u * kQPT;  // <= a quarter fall back
                 if (dense_tile) {
 #pragma unroll
-                    for (int k = 0; k < kQPT; k++) sec[k] = ld_sector_stream(v.dense + bb[k]);
+                    for (int k = 0; k < kQPT; k++) {
+                        LAPPER_CHECK(bb[k] <= v.pk.nb);
+                        sec[k] = ld_sector_stream(v.dense + bb[k]);
+                    }
 #pragma unroll
                     for (int k = 0; k < kQPT; k++) {
                         res[k] = packed_count(sec[k].w, xs[k], te[k]);
@@ -476,6 +482,7 @@ __global__ void __launch_bounds__(kThreads, kCtas) count_bucket_kernel(BucketVie
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(v.buckets + bucket_of(v, qb.w[k])));
                     else
                         prefetch_child(v, sec[k], (second & (1u << k)) ? qa.w[k] : qb.w[k]);  // sec[k] is the sector that overflowed (or a harmless one)
+                    LAPPER_CHECK(slot < (uint32_t)kWQCap);
                     wq[3 * slot] = rel0 + k;
                     wq[3 * slot + 1] = qa.w[k];
                     wq[3 * slot + 2] = qb.w[k];
@@ -806,7 +813,10 @@ __device__ __forceinline__ void emit_one_query_small(const FindView &f, uint32_t
             for (uint32_t t = 0; t < 4; t++) e[t] = i + t < hi[c] ? __ldg(ce + i + t) : 0u;
 #pragma unroll
             for (uint32_t t = 0; t < 4; t++)
-                if (i + t < hi[c] && e[t] > a && k < room) out[k++] = __ldg(cg + i + t);
+                if (i + t < hi[c] && e[t] > a) {
+                    LAPPER_CHECK(k < room);
+                    if (k < room) out[k++] = __ldg(cg + i + t);
+                }
         }
         if (c == 0) first_run = k;
     }
@@ -1071,7 +1081,10 @@ __global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kern
                 const uint4 c = sorted[x];  // one broadcast LDS.128: (start, stop, position)
 #pragma unroll
                 for (int q = 0; q < kEmitQ; q++)
-                    if (c.x < b[q] && c.y > a[q]) *wp[q]++ = c.z;  // src/lib.rs:140-142
+                    if (c.x < b[q] && c.y > a[q]) {  // src/lib.rs:140-142
+                        LAPPER_CHECK(wp[q] >= stage + pad && wp[q] < stage + pad + wtotal);
+                        *wp[q]++ = c.z;
+                    }
             }
             __syncwarp();
         } else if (staged) {
@@ -1321,6 +1334,7 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                 all += x;
             }
             const uint32_t pos = K + before + __popc(km & ((1u << lane) - 1u));
+            LAPPER_CHECK(!keep || pos < (uint32_t)kTCand || K + all > (uint32_t)kTCand);
             if (keep && pos < (uint32_t)kTCand) rawg[pos] = g, raws[pos] = cs, rawe[pos] = ce;
             K += all;
             nice = K <= (uint32_t)kTCand;
@@ -1357,6 +1371,7 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                 if (c != 1) rank += smem_lower_bound(rawg + k0, k1, g);
                 if (c != 2) rank += smem_lower_bound(rawg + k0 + k1, k2, g);
                 if (c != 3) rank += smem_lower_bound(rawg + k0 + k1 + k2, k3, g);
+                LAPPER_CHECK(rank < K);
                 cand[rank] = make_uint4(raws[i], rawe[i], g, 0u);
             }
         }
@@ -1446,7 +1461,10 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                             const uint4 c = wlist[x];  // one broadcast LDS.128: (start, stop, position)
 #pragma unroll
                             for (int q = 0; q < kEmitQ; q++)
-                                if (c.x < sb[q] && c.y > sa[q]) *wp[q]++ = c.z;  // src/lib.rs:140-142
+                                if (c.x < sb[q] && c.y > sa[q]) {  // src/lib.rs:140-142
+                                    LAPPER_CHECK(wp[q] >= stage + pad && wp[q] < stage + pad + wtotal);
+                                    *wp[q]++ = c.z;
+                                }
                         }
                     } else {
                         EMIT_STAT(6, 1);
@@ -1552,6 +1570,7 @@ __device__ __forceinline__ void heavy_merge_classes(const FindView &f, uint32_t 
                     const bool h = ok[u] && e[u] > a;
                     const uint32_t hm = __ballot_sync(0xFFFFFFFFu, h);
                     const uint64_t at = written + __popc(hm & lt);
+                    LAPPER_CHECK(!h || at < room);
                     if (h && at < room) out[at] = gg[u];
                     written += __popc(hm);
                 }
@@ -1604,8 +1623,10 @@ __device__ __forceinline__ void heavy_merge_classes(const FindView &f, uint32_t 
                 if (__shfl_sync(0xFFFFFFFFu, g[c2], pos) < g[c]) pos++;
                 r += __popc(em[c2] & (pos >= 32 ? 0xFFFFFFFFu : (1u << pos) - 1u));
             }
-            if ((em[c] >> lane) & 1u)
+            if ((em[c] >> lane) & 1u) {
+                LAPPER_CHECK(written + r < room);
                 if (written + r < room) out[written + r] = g[c];
+            }
         }
         written += total;
     }
@@ -1864,6 +1885,17 @@ extern "C" void lapper_debug_emit_stats(unsigned long long *out, int reset) {
     }
 }
 #endif
+
+long long debug_violations() {
+#ifdef LAPPER_DEBUG_CHECKS
+    unsigned long long v = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&v, g_debug_violations, sizeof(v));
+    return (long long)v;
+#else
+    return -1;
+#endif
+}
 
 uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
                              uint64_t *d_offsets, cudaStream_t stream) {
