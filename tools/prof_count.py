@@ -27,8 +27,9 @@ _ffi.check(lib.lapper_packed_table_info(h, C.byref(w), C.byref(ns), C.byref(no))
 print(f"flags {flags}: sector-table shift {lib.lapper_bucket_shift(h)}, packed table width {w.value}, "
       f"{ns.value} sectors ({ns.value * 32 / 1e6:.1f} MB), {no.value} overflowed ({100.0 * no.value / max(ns.value, 1):.2f} %)")
 out = torch.empty(nq, dtype=torch.int32, device=dev)
-for name, (qs, qe) in (("random", synth.queries_fixed_len(43, nq, synth.GRCH38, 150, device=dev)),
-                       ("sorted", synth.queries_sorted_fixed_len(45, nq, synth.GRCH38, 150, device=dev))):
+qlen = int(os.environ.get("QLEN", 150))
+for name, (qs, qe) in (("random", synth.queries_fixed_len(43, nq, synth.GRCH38, qlen, device=dev)),
+                       ("sorted", synth.queries_sorted_fixed_len(45, nq, synth.GRCH38, qlen, device=dev))):
     for _ in range(int(os.environ.get("WARM", 2))):
         _ffi.check(lib.lapper_count_batch_u32_dev(h, C.c_void_p(qs.data_ptr()), C.c_void_p(qe.data_ptr()), nq,
                                                   C.c_void_p(out.data_ptr()), sp))
