@@ -1554,27 +1554,37 @@ __device__ __forceinline__ void heavy_merge_classes(const FindView &f, uint32_t 
             for (int c = 0; c < 4; c++)
                 if (c != cs) limit = min(limit, head[c]);
             const uint32_t *ce = f.ce + f.cls_off[cs], *cg = f.cg + f.cls_off[cs];
-            const uint32_t step = min(end[cs] - p[cs], 128u);
-            if (alive == 1 || __ldg(cg + p[cs] + step - 1) < limit) {
-                uint32_t e[4], gg[4];
-                bool ok[4];
+            // worth streaming if at least the next 32 entries of the class lie below the limit
+            const uint32_t probe = min(end[cs] - p[cs], 32u);
+            if (alive == 1 || __ldg(cg + p[cs] + probe - 1) < limit) {
+                // 128 entries per step, loaded speculatively: those below the limit (a prefix: positions ascend) are
+                // consumed, and the stream goes on without looking at the other classes until one is not
+                for (;;) {
+                    const uint32_t step = min(end[cs] - p[cs], 128u);
+                    uint32_t e[4], gg[4];
+                    bool ok[4];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const uint32_t k = 32 * u + lane;
-                    ok[u] = k < step;
-                    e[u] = ok[u] ? __ldg(ce + p[cs] + k) : 0u;
-                    gg[u] = ok[u] ? __ldg(cg + p[cs] + k) : 0u;
-                }
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t k = 32 * u + lane;
+                        ok[u] = k < step;
+                        e[u] = ok[u] ? __ldg(ce + p[cs] + k) : 0u;
+                        gg[u] = ok[u] ? __ldg(cg + p[cs] + k) : 0xFFFFFFFFu;
+                    }
+                    uint32_t consumed = 0;
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const bool h = ok[u] && e[u] > a;
-                    const uint32_t hm = __ballot_sync(0xFFFFFFFFu, h);
-                    const uint64_t at = written + __popc(hm & lt);
-                    LAPPER_CHECK(!h || at < room);
-                    if (h && at < room) out[at] = gg[u];
-                    written += __popc(hm);
+                    for (int u = 0; u < 4; u++) {
+                        ok[u] = ok[u] && gg[u] < limit;
+                        consumed += __popc(__ballot_sync(0xFFFFFFFFu, ok[u]));
+                        const bool h = ok[u] && e[u] > a;
+                        const uint32_t hm = __ballot_sync(0xFFFFFFFFu, h);
+                        const uint64_t at = written + __popc(hm & lt);
+                        LAPPER_CHECK(!h || at < room);
+                        if (h && at < room) out[at] = gg[u];
+                        written += __popc(hm);
+                    }
+                    p[cs] += consumed;
+                    if (consumed < step || p[cs] >= end[cs]) break;
                 }
-                p[cs] += step;
                 continue;
             }
         }
