@@ -1224,7 +1224,9 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
             r[kTQPT] = (uint32_t)(offsets[q0 + jt + kTQPT] - tile_o0);
 #pragma unroll
             for (int k = 0; k < kTQPT / 4; k++) {
-                const uint4 va = ld_stream_v4(qs + q0 + jt + 4 * k), vb = ld_stream_v4(qe + q0 + jt + 4 * k);
+                // (normal caching, not evict-first: the groups read their queries again a few microseconds later, from L2)
+                const uint4 va = __ldg(reinterpret_cast<const uint4 *>(qs + q0 + jt + 4 * k));
+                const uint4 vb = __ldg(reinterpret_cast<const uint4 *>(qe + q0 + jt + 4 * k));
                 qa[4 * k] = va.x, qa[4 * k + 1] = va.y, qa[4 * k + 2] = va.z, qa[4 * k + 3] = va.w;
                 qb[4 * k] = vb.x, qb[4 * k + 1] = vb.y, qb[4 * k + 2] = vb.z, qb[4 * k + 3] = vb.w;
             }
