@@ -730,7 +730,10 @@ __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t 
     }
 }
 
-constexpr int kEmitCand = 64;                       // candidates a warp can sweep cooperatively
+#ifndef LAPPER_EMIT_CAND
+#define LAPPER_EMIT_CAND 64
+#endif
+constexpr int kEmitCand = LAPPER_EMIT_CAND;         // candidates a warp can sweep cooperatively
 constexpr uint32_t kEmitRawMax = 512;                // class-window slots a warp filters down to those candidates
 #ifndef LAPPER_EMIT_WORDS
 #define LAPPER_EMIT_WORDS 1536
