@@ -41,6 +41,7 @@ extern "C" {
 #define LAPPER_ERR_OOM 3
 #define LAPPER_ERR_PRECONDITION 4 /* input violates start <= stop where the closed form needs it */
 #define LAPPER_ERR_NO_DEVICE 5
+#define LAPPER_ERR_CAPACITY 6 /* a caller-allocated output buffer is too small; the size needed has been reported */
 
 /* lapper_build_u32_ex flags */
 #define LAPPER_BUILD_DEFAULT 0u
@@ -131,12 +132,30 @@ int lapper_result_copy(const lapper_result_t *r, uint64_t *offsets_out, uint32_t
 int lapper_result_dev(const lapper_result_t *r, const uint64_t **d_offsets, const uint32_t **d_indices);
 void lapper_result_free(lapper_result_t *r);
 
+/* host queries -> host CSR in ONE call, pipelined in chunks (queries in, count + emit, offsets and positions out, all
+ * overlapped; pinned buffers give full PCIe speed in both directions at once).  offsets_out has nq + 1 entries and is
+ * always written in full, *total_out = offsets_out[nq].  indices_out has room for indices_capacity positions:
+ *   - indices_out == NULL: size query (offsets and total only), returns LAPPER_OK;
+ *   - total <= indices_capacity: positions written, LAPPER_OK;
+ *   - otherwise LAPPER_ERR_CAPACITY with *total_out set (call again with a larger buffer; the positions that were
+ *     written are a prefix of the result). */
+int lapper_find_batch_u32_host(const lapper_t *l, const uint32_t *q_start, const uint32_t *q_stop, uint64_t nq,
+                               uint64_t *offsets_out, uint32_t *indices_out, uint64_t indices_capacity,
+                               uint64_t *total_out);
+
 /* two-phase, caller-allocated device buffers: phase 1 writes d_offsets[nq+1] and returns the total
- * (synchronises `stream`); phase 2 fills d_indices[total]. */
+ * (synchronises `stream`); phase 2 fills d_indices[total].  No alignment is required of any buffer (16-byte aligned
+ * d_offsets and 32-byte aligned query arrays -- what cudaMalloc and every tensor allocator give -- take the vectorised
+ * kernels; anything else takes scalar ones with the same results). */
 int lapper_find_batch_offsets_u32_dev(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop,
                                       uint64_t nq, uint64_t *d_offsets, uint64_t *total_out, void *stream);
 int lapper_find_batch_fill_u32_dev(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop,
                                    uint64_t nq, const uint64_t *d_offsets, uint32_t *d_indices, void *stream);
+/* same, for a caller that passes phase 1's total back (== d_offsets[nq]): nothing is read back from the device, so
+ * the call only enqueues and does not synchronise */
+int lapper_find_batch_fill_total_u32_dev(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop,
+                                         uint64_t nq, const uint64_t *d_offsets, uint64_t total, uint32_t *d_indices,
+                                         void *stream);
 
 /* Lapper::seek's cursor update (src/lib.rs:658-671) for one query, so a host shim can keep the
  * reference's `&mut usize` protocol: *cursor is updated exactly as the reference updates it. */
@@ -150,8 +169,12 @@ int lapper_seek_cursor(const lapper_t *l, uint32_t start, uint64_t *cursor);
 int lapper_insert_u32(lapper_t *l, uint32_t start, uint32_t stop, uint64_t *input_position_out);
 
 /* ---- Lapper::merge_overlaps (src/lib.rs:361-416): prefix-max scan, run heads, compaction; rebuilds
- *      starts / stops / max_len; sets overlaps_merged iff the lapper is non-empty.
- *      LAPPER_ERR_PRECONDITION if some interval has stop < start. */
+ *      starts / stops / max_len; sets overlaps_merged iff the lapper is non-empty.  The query tables of the merged set
+ *      are built on its first count / find.
+ *      DEVIATION: LAPPER_ERR_PRECONDITION if some interval has stop < start.  The reference's loop (comparisons and
+ *      checked_sub only) is well defined for such sets; the prefix-max closed form used here is not, so the call is
+ *      refused rather than answered differently.  (cov, union_and_intersect and depth refuse the same sets because
+ *      the reference itself overflows on them.) */
 int lapper_merge_overlaps(lapper_t *l);
 /* ---- Lapper::cov / set_cov (src/lib.rs:310-350) */
 int lapper_cov(const lapper_t *l, uint32_t *cov_out);

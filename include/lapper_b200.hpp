@@ -80,11 +80,13 @@ class Lapper {
 
     // batch entry points
     std::vector<uint64_t> count_batch(const std::vector<uint32_t> &qs, const std::vector<uint32_t> &qe) const {
+        if (qs.size() != qe.size()) throw Error(LAPPER_ERR_INVALID_ARG, "count_batch: q_start and q_stop differ in length");
         std::vector<uint64_t> out(qs.size());
         check(lapper_count_batch_u32(h_, qs.data(), qe.data(), qs.size(), out.data()));
         return out;
     }
     Csr find_batch(const std::vector<uint32_t> &qs, const std::vector<uint32_t> &qe) const {
+        if (qs.size() != qe.size()) throw Error(LAPPER_ERR_INVALID_ARG, "find_batch: q_start and q_stop differ in length");
         lapper_result_t *r = nullptr;
         check(lapper_find_batch_u32(h_, qs.data(), qe.data(), qs.size(), &r));
         Csr c;

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LAPPER_B200_LIB") or os.path.join(_HERE, "liblapper_b200.so")
 
 OK = 0
-ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_PRECONDITION, ERR_NO_DEVICE = 1, 2, 3, 4, 5
+ERR_INVALID_ARG, ERR_CUDA, ERR_OOM, ERR_PRECONDITION, ERR_NO_DEVICE, ERR_CAPACITY = 1, 2, 3, 4, 5, 6
 
 BUILD_DEFAULT = 0
 BUILD_NO_BUCKETS = 1
@@ -86,6 +86,8 @@ SIGNATURES = {
     "lapper_result_free": (None, [_vp]),
     "lapper_find_batch_offsets_u32_dev": (_int, [_vp, _vp, _vp, _u64, _vp, C.POINTER(_u64), _vp]),
     "lapper_find_batch_fill_u32_dev": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp]),
+    "lapper_find_batch_fill_total_u32_dev": (_int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp]),
+    "lapper_find_batch_u32_host": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64)]),
     "lapper_seek_cursor": (_int, [_vp, _u32, C.POINTER(_u64)]),
     "lapper_get_cached_state": (_int, [_vp, C.POINTER(_int), C.POINTER(_u32), C.POINTER(_int)]),
     "lapper_restore_cached_state": (_int, [_vp, _int, _u32, _int]),

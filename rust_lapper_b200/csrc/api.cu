@@ -6,6 +6,7 @@
 #include <cstring>
 #include <memory>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "index.cuh"
@@ -31,6 +32,21 @@ cudaMemPool_t scratch_pool() {
         LAPPER_CUDA_CHECK(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
     }
     return pools[dev];
+}
+
+uint32_t sm_count() {
+    static std::atomic<uint32_t> cached[64];
+    int dev = 0;
+    LAPPER_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) throw Error(LAPPER_ERR_INVALID_ARG, "device index out of range");
+    uint32_t v = cached[dev].load(std::memory_order_relaxed);
+    if (!v) {
+        int n = 0;
+        LAPPER_CUDA_CHECK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+        v = (uint32_t)std::max(n, 1);
+        cached[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
 }
 }  // namespace lap
 
@@ -81,12 +97,41 @@ struct StreamOwner {
 
 void check_handle(const lapper_t *l) { LAPPER_REQUIRE(l != nullptr, "null lapper handle"); }
 
+// count / find need the query tables; after merge_overlaps / insert they are built here, on first use.  Concurrent
+// const calls on one handle are allowed (include/lapper_b200.h), hence the lock.
+void ensure_tables(const lapper_t *cl, cudaStream_t stream) {
+    if (cl->tables_flag.load(std::memory_order_acquire)) return;
+    lapper_t *l = const_cast<lapper_t *>(cl);
+    std::lock_guard<std::mutex> lock(l->tables_mu);
+    if (!l->ix.tables_ready) build_query_tables(l->ix, l->build_flags, stream);  // synchronises `stream` at its end
+    l->tables_flag.store(true, std::memory_order_release);
+}
+
 void need_valid_intervals(const lapper_t *l, const char *what) {
     if (l->ix.has_inverted)
         throw Error(LAPPER_ERR_PRECONDITION,
-                    std::string(what) + ": the set holds an interval with stop < start; the reference's result is "
-                                        "an artefact of arithmetic overflow there and is not reproduced");
+                    std::string(what) + ": the set holds an interval with stop < start; the closed form used here "
+                                        "(prefix max of stops, SURVEY Appendix A.5-A.7) needs start <= stop for every "
+                                        "interval -- documented deviation, see include/lapper_b200.h");
 }
+
+// A DeviceIndex under construction: its arrays go back to the pool unless it is committed into a handle.
+struct IndexBuilder {
+    DeviceIndex ix;
+    cudaStream_t stream;
+    bool committed = false;
+    explicit IndexBuilder(cudaStream_t s) : stream(s) {}
+    ~IndexBuilder() {
+        if (!committed) free_index(ix, stream);
+    }
+    // replaces l's index (the old arrays are returned to the pool in stream order)
+    void commit(lapper_t *l) {
+        free_index(l->ix, stream);
+        l->ix = ix;
+        l->tables_flag.store(ix.tables_ready, std::memory_order_release);
+        committed = true;
+    }
+};
 
 // chunked host <-> device pipeline for count: three slots, each its own stream, so the H2D of chunk
 // i+1, the kernel of chunk i and the D2H of chunk i-1 overlap (PCIe is full duplex).
@@ -100,6 +145,7 @@ void count_host(const lapper_t *l, const uint32_t *qs, const uint32_t *qe, uint6
     // 8 M queries per chunk: measured best of 2^20 .. 2^25 (20.0 / 18.0 / 17.1 / 16.8 / 17.0 / 18.0 ms per 100 M queries)
     const uint64_t chunk = std::min<uint64_t>(nq, 1ull << 23);
     StreamOwner st[kSlots];
+    ensure_tables(l, st[0].s);
     Scratch<uint32_t> d_qs[kSlots], d_qe[kSlots];
     Scratch<OutT> d_out[kSlots];
     const int used = (int)std::min<uint64_t>(kSlots, div_up(nq, chunk));
@@ -129,23 +175,94 @@ void count_host(const lapper_t *l, const uint32_t *qs, const uint32_t *qe, uint6
     }
 }
 
+void free_result_arrays(lapper_result_t *r, cudaStream_t stream) {
+    pool_free(r->d_offsets, stream);
+    pool_free(r->d_indices, stream);
+    r->d_offsets = nullptr;
+    r->d_indices = nullptr;
+}
+
 lapper_result_t *find_on_device(const lapper_t *l, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
                                 cudaStream_t stream) {
+    ensure_tables(l, stream);
     std::unique_ptr<lapper_result_t> r(new lapper_result_t());
     r->device = l->device;
     r->nq = nq;
     try {
-        LAPPER_CUDA_CHECK(cudaMalloc((void **)&r->d_offsets, (nq + 1) * sizeof(uint64_t)));
+        uint64_t bytes = 0;
+        r->d_offsets = pool_alloc<uint64_t>(nq + 1, bytes, stream);
         r->total = launch_find_offsets(l->ix, d_qs, d_qe, nq, r->d_offsets, stream);
-        LAPPER_CUDA_CHECK(cudaMalloc((void **)&r->d_indices, std::max<uint64_t>(r->total, 1) * sizeof(uint32_t)));
-        launch_find_fill(l->ix, d_qs, d_qe, nq, r->d_offsets, r->d_indices, stream);
+        r->d_indices = pool_alloc<uint32_t>(r->total, bytes, stream);
+        launch_find_fill(l->ix, d_qs, d_qe, nq, r->d_offsets, r->d_indices, stream, r->total);
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
     } catch (...) {
-        cudaFree(r->d_offsets);
-        cudaFree(r->d_indices);
+        free_result_arrays(r.get(), stream);
         throw;
     }
     return r.release();
+}
+
+// find_batch from host queries straight into host CSR buffers, as a chunk pipeline: while chunk k is counted and
+// emitted, chunk k+1's queries are on their way in and chunk k-1's offsets and positions on their way out (three
+// slots, one stream each; PCIe is full duplex and the output side -- 8 B of offsets per query + 4 B per hit -- is what
+// bounds the call).  A chunk's offsets are computed chunk-local (the emit kernel addresses the chunk's own position
+// buffer with them) and rebased by the hits of the chunks before it on their way out.
+// Returns the total; positions are written only while they fit `capacity`.
+uint64_t find_host(const lapper_t *l, const uint32_t *qs, const uint32_t *qe, uint64_t nq, uint64_t *offsets_out,
+                   uint32_t *indices_out, uint64_t capacity, uint64_t offsets_base) {
+    check_handle(l);
+    DeviceGuard dg(l->device);
+    constexpr int kSlots = 3;
+    constexpr uint64_t kChunk = 1ull << 22;  // 4 M queries: 32 MB in, ~ 32 MB + 4 B/hit out per chunk
+    StreamOwner st[kSlots];
+    ensure_tables(l, st[0].s);
+    if (nq == 0) {
+        offsets_out[0] = offsets_base;
+        return 0;
+    }
+    const uint64_t chunk = std::min(nq, kChunk);
+    const uint64_t nchunks = div_up(nq, chunk);
+    Scratch<uint32_t> d_qs[kSlots], d_qe[kSlots], d_idx[kSlots];
+    Scratch<uint64_t> d_off[kSlots], d_goff[kSlots];
+    const int used = (int)std::min<uint64_t>(kSlots, nchunks);
+    for (int s = 0; s < used; s++) {
+        d_qs[s].alloc(chunk, st[s].s);
+        d_qe[s].alloc(chunk, st[s].s);
+        d_off[s].alloc(chunk + 1, st[s].s);
+        d_goff[s].alloc(chunk + 1, st[s].s);
+    }
+    const auto upload = [&](uint64_t k) {
+        const int s = (int)(k % kSlots);
+        const uint64_t lo = k * chunk, m = std::min(chunk, nq - lo);
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(d_qs[s].p, qs + lo, m * 4, cudaMemcpyHostToDevice, st[s].s));
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(d_qe[s].p, qe + lo, m * 4, cudaMemcpyHostToDevice, st[s].s));
+    };
+    upload(0);
+    uint64_t base = 0;  // hits of the chunks before this one
+    for (uint64_t k = 0; k < nchunks; k++) {
+        const int s = (int)(k % kSlots);
+        const uint64_t lo = k * chunk, m = std::min(chunk, nq - lo);
+        if (k + 1 < nchunks) upload(k + 1);  // (its slot's previous chunk drains in stream order first)
+        const uint64_t t = launch_find_offsets(l->ix, d_qs[s].p, d_qe[s].p, m, d_off[s].p, st[s].s);  // synchronises st[s]
+        const bool last = k + 1 == nchunks;
+        launch_rebase_offsets(d_off[s].p, d_goff[s].p, m + (last ? 1 : 0), offsets_base + base, st[s].s);
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(offsets_out + lo, d_goff[s].p, (m + (last ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, st[s].s));
+        if (indices_out && base + t <= capacity && t) {
+            d_idx[s].alloc(t, st[s].s);  // (the previous chunk's buffer of this slot goes back to the pool in stream order)
+            launch_find_fill(l->ix, d_qs[s].p, d_qe[s].p, m, d_off[s].p, d_idx[s].p, st[s].s, t);
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(indices_out + base, d_idx[s].p, t * 4, cudaMemcpyDeviceToHost, st[s].s));
+        }
+        base += t;
+    }
+    for (int s = 0; s < used; s++) {
+        d_qs[s].release();
+        d_qe[s].release();
+        d_off[s].release();
+        d_goff[s].release();
+        d_idx[s].release();
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st[s].s));
+    }
+    return base;
 }
 
 __global__ void seek_cursor_kernel(const uint32_t *__restrict__ S, uint32_t n, uint32_t max_len, uint32_t start,
@@ -177,25 +294,31 @@ __global__ void insert_positions_kernel(const uint32_t *__restrict__ S, const ui
 }
 
 // dst[0..pos) = src[0..pos), dst[pos] = value, dst[pos+1..n+1) = src[pos..n)
+__global__ void insert_into_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, uint64_t n, uint64_t pos,
+                                   uint32_t value) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = i < pos ? src[i] : i == pos ? value : src[i - 1];
+}
 void insert_into(uint32_t *dst, const uint32_t *src, uint64_t n, uint64_t pos, uint32_t value, cudaStream_t stream) {
-    if (pos) LAPPER_CUDA_CHECK(cudaMemcpyAsync(dst, src, pos * 4, cudaMemcpyDeviceToDevice, stream));
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(dst + pos, &value, 4, cudaMemcpyHostToDevice, stream));
-    if (n > pos) LAPPER_CUDA_CHECK(cudaMemcpyAsync(dst + pos + 1, src + pos, (n - pos) * 4, cudaMemcpyDeviceToDevice, stream));
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(div_up(n + 1, 256), (uint64_t)sm_count() * 8);
+    insert_into_kernel<<<grid, 256, 0, stream>>>(dst, src, n, pos, value);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
 }
 
-void replace_index_with_sorted(lapper_t *l, uint32_t *s, uint32_t *e, uint32_t *perm, uint64_t m,
-                               cudaStream_t stream) {
-    uint32_t *e_sorted = nullptr;
-    LAPPER_CUDA_CHECK(cudaMalloc((void **)&e_sorted, std::max<uint64_t>(m, 1) * 4));
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(e_sorted, e, m * 4, cudaMemcpyDeviceToDevice, stream));
-    free_index(l->ix);
-    l->ix.n = m;
-    l->ix.starts = s;
-    l->ix.stops_by_iv = e;
-    l->ix.stops_sorted = e_sorted;
-    l->ix.perm = perm;
-    l->ix.bytes = 4 * 4 * std::max<uint64_t>(m, 1);
-    finish_index_from_sorted(l->ix, l->build_flags, stream);
+// copy between devices (or within one); pool memory on either side
+void copy_dev_to_dev(void *dst, int dst_dev, const void *src, int src_dev, uint64_t bytes, cudaStream_t stream) {
+    if (bytes == 0) return;
+    if (dst_dev == src_dev)
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream));
+    else
+        LAPPER_CUDA_CHECK(cudaMemcpyPeerAsync(dst, dst_dev, src, src_dev, bytes, stream));
+}
+
+int device_of_pointer(const void *p, int fallback) {
+    cudaPointerAttributes a;
+    if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) return a.device;
+    cudaGetLastError();
+    return fallback;
 }
 
 }  // namespace
@@ -204,9 +327,43 @@ struct lapper_group {
     std::vector<lapper_t *> replicas;
 };
 
+namespace {
+
+// runs fn(g) for every replica concurrently (one host thread per GPU: each call blocks on its own device) and
+// rethrows the first failure
+template <typename F>
+void for_each_replica(const lapper_group_t *grp, F &&fn) {
+    const size_t G = grp->replicas.size();
+    std::vector<int> rc(G, LAPPER_OK);
+    std::vector<std::string> msg(G);
+    const auto body = [&](size_t g) {
+        try {
+            fn(g);
+        } catch (const Error &e) {
+            rc[g] = e.code, msg[g] = e.what();
+        } catch (const std::exception &e) {
+            rc[g] = LAPPER_ERR_CUDA, msg[g] = e.what();
+        } catch (...) {
+            rc[g] = LAPPER_ERR_CUDA, msg[g] = "unknown error";
+        }
+    };
+    if (G == 1) {
+        body(0);
+    } else {
+        std::vector<std::thread> th;
+        th.reserve(G);
+        for (size_t g = 0; g < G; g++) th.emplace_back(body, g);
+        for (auto &t : th) t.join();
+    }
+    for (size_t g = 0; g < G; g++)
+        if (rc[g] != LAPPER_OK) throw Error(rc[g], msg[g]);
+}
+
+}  // namespace
+
 extern "C" {
 
-int lapper_version(void) { return 100; }
+int lapper_version(void) { return 200; }
 
 const char *lapper_last_error(void) { return g_last_error.c_str(); }
 
@@ -234,6 +391,7 @@ int lapper_build_u32_dev(const uint32_t *d_starts, const uint32_t *d_stops, uint
         l->device = device;
         l->build_flags = flags;
         build_index_from_unsorted(l->ix, d_starts, d_stops, n, flags, (cudaStream_t)stream);
+        l->tables_flag.store(l->ix.tables_ready);
         l->next_input_id = n;
         LAPPER_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
         *out = l.release();
@@ -259,6 +417,7 @@ int lapper_build_u32_ex(const uint32_t *starts, const uint32_t *stops, uint64_t 
         l->device = device;
         l->build_flags = flags;
         build_index_from_unsorted(l->ix, d_s.p, d_e.p, n, flags, st.s);
+        l->tables_flag.store(l->ix.tables_ready);
         l->next_input_id = n;
         d_s.release();
         d_e.release();
@@ -286,25 +445,24 @@ int lapper_from_sorted_dev(const uint32_t *d_starts, const uint32_t *d_stops_by_
         l->device = device;
         l->build_flags = flags;
         l->overlaps_merged = overlaps_merged != 0;
-        l->next_input_id = n;
-        DeviceIndex &ix = l->ix;
-        ix.n = n;
-        try {
-            if (n) {
-                const uint32_t *src[4] = {d_starts, d_stops_by_iv, d_stops_sorted, d_perm};
-                uint32_t **dst[4] = {&ix.starts, &ix.stops_by_iv, &ix.stops_sorted, &ix.perm};
-                for (int i = 0; i < 4; i++) {
-                    LAPPER_CUDA_CHECK(cudaMalloc((void **)dst[i], n * 4));
-                    ix.bytes += n * 4;
-                    LAPPER_CUDA_CHECK(cudaMemcpyAsync(*dst[i], src[i], n * 4, cudaMemcpyDefault, s));
-                }
+        IndexBuilder b(s);
+        b.ix.n = n;
+        if (n) {
+            const uint32_t *src[4] = {d_starts, d_stops_by_iv, d_stops_sorted, d_perm};
+            uint32_t **dst[4] = {&b.ix.starts, &b.ix.stops_by_iv, &b.ix.stops_sorted, &b.ix.perm};
+            for (int i = 0; i < 4; i++) {
+                *dst[i] = pool_alloc<uint32_t>(n, b.ix.bytes, s);
+                // a peer copy over NVLink when the source lives on another GPU
+                copy_dev_to_dev(*dst[i], device, src[i], device_of_pointer(src[i], device), n * 4, s);
             }
-            finish_index_from_sorted(ix, flags, s);
-            LAPPER_CUDA_CHECK(cudaStreamSynchronize(s));
-        } catch (...) {
-            free_index(ix);
-            throw;
         }
+        finish_index_core(b.ix, s);
+        build_query_tables(b.ix, flags, s);
+        // the next inserted interval must not reuse an input position perm already refers to (after merge_overlaps
+        // perm holds original positions, which may exceed n)
+        l->next_input_id = n ? std::max<uint64_t>(n, (uint64_t)b.ix.stats.max_perm + 1) : 0;
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(s));
+        b.commit(l.get());
         *out = l.release();
     });
 }
@@ -314,7 +472,9 @@ void lapper_free(lapper_t *l) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(l->device);
-    free_index(l->ix);
+    // like cudaFree: work that still uses the index finishes first; the arrays then go back to the library pool
+    cudaDeviceSynchronize();
+    free_index(l->ix, nullptr);
     if (prev >= 0) cudaSetDevice(prev);
     delete l;
 }
@@ -324,10 +484,19 @@ uint32_t lapper_max_len(const lapper_t *l) { return l ? l->ix.max_len : 0; }
 int lapper_overlaps_merged(const lapper_t *l) { return l && l->overlaps_merged; }
 int lapper_has_inverted(const lapper_t *l) { return l && l->ix.has_inverted; }
 int lapper_device(const lapper_t *l) { return l ? l->device : -1; }
-uint32_t lapper_bucket_shift(const lapper_t *l) { return l ? l->ix.shift : 0xFFFFFFFFu; }
-uint64_t lapper_index_bytes(const lapper_t *l) {
-    return l ? l->ix.bytes : 0;
+
+/* (the three accessors below describe the query tables: after merge_overlaps / insert they build them if need be) */
+static bool tables_for_accessor(const lapper_t *l) {
+    if (!l) return false;
+    if (l->tables_flag.load(std::memory_order_acquire)) return true;
+    return guarded([&] {
+               DeviceGuard dg(l->device);
+               StreamOwner st;
+               ensure_tables(l, st.s);
+           }) == LAPPER_OK;
 }
+uint32_t lapper_bucket_shift(const lapper_t *l) { return tables_for_accessor(l) ? l->ix.shift : 0xFFFFFFFFu; }
+uint64_t lapper_index_bytes(const lapper_t *l) { return tables_for_accessor(l) ? l->ix.bytes : 0; }
 
 uint64_t lapper_query_kernel_launches(void) { return lap::g_query_launches.load(); }
 
@@ -338,6 +507,11 @@ long long lapper_debug_violations(void) { return lap::debug_violations(); }
 int lapper_packed_table_info(const lapper_t *l, uint32_t *width_out, uint64_t *sectors_out, uint64_t *overflowed_out) {
     return guarded([&] {
         check_handle(l);
+        {
+            DeviceGuard dg(l->device);
+            StreamOwner st;
+            ensure_tables(l, st.s);
+        }
         const bool built = l->ix.dense != nullptr;
         if (width_out) *width_out = built ? l->ix.dense_w : 0u;
         if (sectors_out) *sectors_out = built ? l->ix.dense_nb + 1 : 0u;
@@ -398,6 +572,7 @@ int lapper_count_batch_u32_dev(const lapper_t *l, const uint32_t *d_q_start, con
         check_handle(l);
         LAPPER_REQUIRE(nq == 0 || (d_q_start && d_q_stop && d_counts_out), "count_batch: null pointer");
         DeviceGuard dg(l->device);
+        ensure_tables(l, (cudaStream_t)stream);
         launch_count(l->ix, d_q_start, d_q_stop, nq, d_counts_out, nullptr, (cudaStream_t)stream);
     });
 }
@@ -408,6 +583,7 @@ int lapper_count_batch_u32_dev64(const lapper_t *l, const uint32_t *d_q_start, c
         check_handle(l);
         LAPPER_REQUIRE(nq == 0 || (d_q_start && d_q_stop && d_counts_out), "count_batch: null pointer");
         DeviceGuard dg(l->device);
+        ensure_tables(l, (cudaStream_t)stream);
         launch_count(l->ix, d_q_start, d_q_stop, nq, nullptr, d_counts_out, (cudaStream_t)stream);
     });
 }
@@ -445,6 +621,22 @@ int lapper_find_batch_u32(const lapper_t *l, const uint32_t *q_start, const uint
     });
 }
 
+int lapper_find_batch_u32_host(const lapper_t *l, const uint32_t *q_start, const uint32_t *q_stop, uint64_t nq,
+                               uint64_t *offsets_out, uint32_t *indices_out, uint64_t indices_capacity,
+                               uint64_t *total_out) {
+    return guarded([&] {
+        check_handle(l);
+        LAPPER_REQUIRE(offsets_out && total_out, "find_batch_host: null output");
+        LAPPER_REQUIRE(nq == 0 || (q_start && q_stop), "find_batch_host: null pointer");
+        *total_out = 0;
+        const uint64_t total = find_host(l, q_start, q_stop, nq, offsets_out, indices_out, indices_capacity, 0);
+        *total_out = total;
+        if (indices_out && total > indices_capacity)
+            throw Error(LAPPER_ERR_CAPACITY, "find_batch_host: " + std::to_string(total) + " positions do not fit the buffer of " +
+                                                 std::to_string(indices_capacity) + " (offsets and *total_out are complete)");
+    });
+}
+
 uint64_t lapper_result_nq(const lapper_result_t *r) { return r ? r->nq : 0; }
 uint64_t lapper_result_total(const lapper_result_t *r) { return r ? r->total : 0; }
 
@@ -472,8 +664,8 @@ void lapper_result_free(lapper_result_t *r) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(r->device);
-    cudaFree(r->d_offsets);
-    cudaFree(r->d_indices);
+    cudaDeviceSynchronize();  // like cudaFree: readers of the result finish first
+    free_result_arrays(r, nullptr);
     if (prev >= 0) cudaSetDevice(prev);
     delete r;
 }
@@ -484,6 +676,7 @@ int lapper_find_batch_offsets_u32_dev(const lapper_t *l, const uint32_t *d_q_sta
         check_handle(l);
         LAPPER_REQUIRE(d_offsets && (nq == 0 || (d_q_start && d_q_stop)), "find_batch_offsets: null pointer");
         DeviceGuard dg(l->device);
+        ensure_tables(l, (cudaStream_t)stream);
         const uint64_t t = launch_find_offsets(l->ix, d_q_start, d_q_stop, nq, d_offsets, (cudaStream_t)stream);
         if (total_out) *total_out = t;
     });
@@ -495,7 +688,20 @@ int lapper_find_batch_fill_u32_dev(const lapper_t *l, const uint32_t *d_q_start,
         check_handle(l);
         LAPPER_REQUIRE(nq == 0 || (d_q_start && d_q_stop && d_offsets), "find_batch_fill: null pointer");
         DeviceGuard dg(l->device);
+        ensure_tables(l, (cudaStream_t)stream);
         launch_find_fill(l->ix, d_q_start, d_q_stop, nq, d_offsets, d_indices, (cudaStream_t)stream);
+    });
+}
+
+int lapper_find_batch_fill_total_u32_dev(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop,
+                                         uint64_t nq, const uint64_t *d_offsets, uint64_t total, uint32_t *d_indices,
+                                         void *stream) {
+    return guarded([&] {
+        check_handle(l);
+        LAPPER_REQUIRE(nq == 0 || (d_q_start && d_q_stop && d_offsets), "find_batch_fill: null pointer");
+        DeviceGuard dg(l->device);
+        ensure_tables(l, (cudaStream_t)stream);
+        launch_find_fill(l->ix, d_q_start, d_q_stop, nq, d_offsets, d_indices, (cudaStream_t)stream, total);
     });
 }
 
@@ -524,7 +730,7 @@ int lapper_insert_u32(lapper_t *l, uint32_t start, uint32_t stop, uint64_t *inpu
         check_handle(l);
         DeviceGuard dg(l->device);
         StreamOwner st;
-        DeviceIndex &ix = l->ix;
+        const DeviceIndex &ix = l->ix;
         const uint64_t n = ix.n;
         LAPPER_REQUIRE(n + 1 < 0xFFFFFFF0ull, "lapper_insert: too many intervals");
         uint32_t pos[2] = {0, 0};
@@ -536,26 +742,19 @@ int lapper_insert_u32(lapper_t *l, uint32_t start, uint32_t stop, uint64_t *inpu
             LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
         }
         const uint64_t id = l->next_input_id;
-        uint32_t *arr[4] = {nullptr, nullptr, nullptr, nullptr};
-        try {
-            for (auto &a : arr) LAPPER_CUDA_CHECK(cudaMalloc((void **)&a, (n + 1) * 4));
-            insert_into(arr[0], ix.starts, n, pos[0], start, st.s);
-            insert_into(arr[1], ix.stops_by_iv, n, pos[0], stop, st.s);
-            insert_into(arr[2], ix.stops_sorted, n, pos[1], stop, st.s);
-            insert_into(arr[3], ix.perm, n, pos[0], (uint32_t)id, st.s);
-            LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));  // the host-side scalars above are read by the copies
-        } catch (...) {
-            for (auto a : arr) cudaFree(a);
-            throw;
-        }
-        free_index(ix);
-        ix.n = n + 1;
-        ix.starts = arr[0];
-        ix.stops_by_iv = arr[1];
-        ix.stops_sorted = arr[2];
-        ix.perm = arr[3];
-        ix.bytes = 16 * (n + 1);
-        finish_index_from_sorted(ix, l->build_flags, st.s);  // max_len (src/lib.rs:264-267) falls out of the rebuild
+        // the new index is complete before it replaces the old one: a failure leaves the handle as it was
+        IndexBuilder b(st.s);
+        b.ix.n = n + 1;
+        b.ix.starts = pool_alloc<uint32_t>(n + 1, b.ix.bytes, st.s);
+        b.ix.stops_by_iv = pool_alloc<uint32_t>(n + 1, b.ix.bytes, st.s);
+        b.ix.stops_sorted = pool_alloc<uint32_t>(n + 1, b.ix.bytes, st.s);
+        b.ix.perm = pool_alloc<uint32_t>(n + 1, b.ix.bytes, st.s);
+        insert_into(b.ix.starts, ix.starts, n, pos[0], start, st.s);
+        insert_into(b.ix.stops_by_iv, ix.stops_by_iv, n, pos[0], stop, st.s);
+        insert_into(b.ix.stops_sorted, ix.stops_sorted, n, pos[1], stop, st.s);
+        insert_into(b.ix.perm, ix.perm, n, pos[0], (uint32_t)id, st.s);
+        finish_index_core(b.ix, st.s);  // max_len (src/lib.rs:264-267) falls out of it; the query tables follow on first use
+        b.commit(l);
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
         l->next_input_id = id + 1;
         l->cov_is_some = false;       // src/lib.rs:271
@@ -571,13 +770,16 @@ int lapper_merge_overlaps(lapper_t *l) {
         need_valid_intervals(l, "merge_overlaps");
         DeviceGuard dg(l->device);
         StreamOwner st;
-        uint32_t *s = nullptr, *e = nullptr, *p = nullptr;
-        const uint64_t m = compute_merged(l->ix, &s, &e, &p, st.s);
-        try {
-            replace_index_with_sorted(l, s, e, p, m, st.s);
-        } catch (...) {
-            throw;
-        }
+        IndexBuilder b(st.s);
+        const uint64_t m = compute_merged(l->ix, &b.ix.starts, &b.ix.stops_by_iv, &b.ix.perm, st.s);
+        b.ix.n = m;
+        b.ix.bytes = 3 * 4 * std::max<uint64_t>(m, 1);
+        // runs are disjoint and ascending: their stops are already the sorted `stops` (src/lib.rs:396-406 sorts
+        // them again, a no-op)
+        b.ix.stops_sorted = pool_alloc<uint32_t>(m, b.ix.bytes, st.s);
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(b.ix.stops_sorted, b.ix.stops_by_iv, m * 4, cudaMemcpyDeviceToDevice, st.s));
+        finish_index_core(b.ix, st.s);  // max_len of the runs (src/lib.rs:408-415); the query tables follow on first use
+        b.commit(l);
         l->overlaps_merged = true;  // src/lib.rs:382; the cached cov is left alone like the reference
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
     });
@@ -664,16 +866,17 @@ int lapper_depth(const lapper_t *l, uint64_t *n_out, uint32_t **starts_out, uint
             for (int i = 0; i < 3; i++) {
                 h[i] = (uint32_t *)malloc(std::max<uint64_t>(nr, 1) * 4);
                 if (!h[i]) throw std::bad_alloc();
-                if (nr) LAPPER_CUDA_CHECK(cudaMemcpy(h[i], d[i], nr * 4, cudaMemcpyDeviceToHost));
+                if (nr) LAPPER_CUDA_CHECK(cudaMemcpyAsync(h[i], d[i], nr * 4, cudaMemcpyDeviceToHost, st.s));
             }
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
         } catch (...) {
             for (int i = 0; i < 3; i++) {
                 free(h[i]);
-                cudaFree(d[i]);
+                pool_free(d[i], st.s);
             }
             throw;
         }
-        for (int i = 0; i < 3; i++) cudaFree(d[i]);
+        for (int i = 0; i < 3; i++) pool_free(d[i], st.s);
         *n_out = nr;
         *starts_out = h[0];
         *stops_out = h[1];
@@ -708,13 +911,14 @@ int lapper_replicate(const lapper_t *l, const int *devices, int g, lapper_group_
                 DeviceGuard dg(devices[i]);
                 StreamOwner st;
                 lapper_t *rep = nullptr;
-                // cudaMemcpyDefault with unified addressing: a peer copy over NVLink when the source
-                // lives on another GPU
+                // peer copies (NVLink) of the four sorted arrays when the source lives on another GPU; the derived
+                // arrays are rebuilt locally
                 int rc = lapper_from_sorted_dev(l->ix.starts, l->ix.stops_by_iv, l->ix.stops_sorted, l->ix.perm, l->ix.n,
                                                 l->overlaps_merged, devices[i], l->build_flags, st.s, &rep);
                 if (rc != LAPPER_OK) throw Error(rc, g_last_error);
                 rep->cov_is_some = l->cov_is_some;
                 rep->cov = l->cov;
+                rep->next_input_id = l->next_input_id;
                 grp->replicas.push_back(rep);
             }
         } catch (...) {
@@ -745,36 +949,12 @@ int lapper_group_count_batch_u32(const lapper_group_t *grp, const uint32_t *q_st
         if (nq == 0) return;
         LAPPER_REQUIRE(q_start && q_stop && counts_out, "group_count_batch: null pointer");
         const uint64_t G = grp->replicas.size();
-        struct Shard {
-            std::unique_ptr<StreamOwner> st;
-            Scratch<uint32_t> qs, qe;
-            Scratch<uint64_t> out;
-        };
-        std::vector<Shard> sh(G);
-        // enqueue every shard asynchronously (device g owns [g*nq/G, (g+1)*nq/G)), then wait for all
-        for (uint64_t g = 0; g < G; g++) {
-            const uint64_t lo = nq * g / G, hi = nq * (g + 1) / G, m = hi - lo;
-            if (m == 0) continue;
-            const lapper_t *rep = grp->replicas[g];
-            DeviceGuard dg(rep->device);
-            sh[g].st.reset(new StreamOwner());
-            cudaStream_t s = sh[g].st->s;
-            sh[g].qs.alloc(m, s);
-            sh[g].qe.alloc(m, s);
-            sh[g].out.alloc(m, s);
-            LAPPER_CUDA_CHECK(cudaMemcpyAsync(sh[g].qs.p, q_start + lo, m * 4, cudaMemcpyHostToDevice, s));
-            LAPPER_CUDA_CHECK(cudaMemcpyAsync(sh[g].qe.p, q_stop + lo, m * 4, cudaMemcpyHostToDevice, s));
-            launch_count(rep->ix, sh[g].qs.p, sh[g].qe.p, m, nullptr, sh[g].out.p, s);
-            LAPPER_CUDA_CHECK(cudaMemcpyAsync(counts_out + lo, sh[g].out.p, m * 8, cudaMemcpyDeviceToHost, s));
-        }
-        for (uint64_t g = 0; g < G; g++) {
-            if (!sh[g].st) continue;
-            DeviceGuard dg(grp->replicas[g]->device);
-            sh[g].qs.release();
-            sh[g].qe.release();
-            sh[g].out.release();
-            LAPPER_CUDA_CHECK(cudaStreamSynchronize(sh[g].st->s));
-        }
+        // device g owns [g*nq/G, (g+1)*nq/G); every replica runs its own chunked H2D / kernel / D2H pipeline,
+        // all of them at once
+        for_each_replica(grp, [&](size_t g) {
+            const uint64_t lo = nq * g / G, hi = nq * (g + 1) / G;
+            count_host<uint64_t>(grp->replicas[g], q_start + lo, q_stop + lo, hi - lo, counts_out + lo);
+        });
     });
 }
 
@@ -783,40 +963,46 @@ int lapper_group_find_batch_u32(const lapper_group_t *grp, const uint32_t *q_sta
     return guarded([&] {
         LAPPER_REQUIRE(grp && !grp->replicas.empty(), "null group");
         LAPPER_REQUIRE(offsets_out && indices_out && total_out, "group_find_batch: null pointer");
+        LAPPER_REQUIRE(nq == 0 || (q_start && q_stop), "group_find_batch: null pointer");
         *indices_out = nullptr;
         *total_out = 0;
         const uint64_t G = grp->replicas.size();
         std::vector<lapper_result_t *> res(G, nullptr);
-        auto cleanup = [&] {
+        uint32_t *idx = nullptr;
+        const auto cleanup = [&] {
             for (auto *r : res) lapper_result_free(r);
         };
         try {
-            for (uint64_t g = 0; g < G; g++) {
+            // phase 1, all replicas at once: queries in, offsets + positions on the device
+            for_each_replica(grp, [&](size_t g) {
                 const uint64_t lo = nq * g / G, hi = nq * (g + 1) / G;
                 int rc = lapper_find_batch_u32(grp->replicas[g], q_start + lo, q_stop + lo, hi - lo, &res[g]);
                 if (rc != LAPPER_OK) throw Error(rc, g_last_error);
-            }
-            // rebase each shard's CSR by the totals of the shards before it
-            uint64_t total = 0;
-            for (auto *r : res) total += r->total;
-            uint32_t *idx = (uint32_t *)malloc(std::max<uint64_t>(total, 1) * 4);
+            });
+            // phase 2: each shard's CSR rebased (on its device) by the totals of the shards before it, all copies at once
+            std::vector<uint64_t> base(G + 1, 0);
+            for (uint64_t g = 0; g < G; g++) base[g + 1] = base[g] + res[g]->total;
+            const uint64_t total = base[G];
+            idx = (uint32_t *)malloc(std::max<uint64_t>(total, 1) * 4);
             if (!idx) throw std::bad_alloc();
-            uint64_t base = 0;
-            for (uint64_t g = 0; g < G; g++) {
-                const uint64_t lo = nq * g / G, m = res[g]->nq;
-                int rc = lapper_result_copy(res[g], offsets_out + lo, idx + base);
-                if (rc != LAPPER_OK) {
-                    free(idx);
-                    throw Error(rc, g_last_error);
-                }
-                if (base)
-                    for (uint64_t j = 0; j <= m; j++) offsets_out[lo + j] += base;
-                base += res[g]->total;
-            }
-            offsets_out[nq] = total;
+            for_each_replica(grp, [&](size_t g) {
+                const uint64_t lo = nq * g / G;
+                const lapper_result_t *r = res[g];
+                DeviceGuard dg(r->device);
+                StreamOwner st;
+                const uint64_t cnt = r->nq + (g + 1 == G ? 1 : 0);  // the last shard also writes offsets[nq]
+                Scratch<uint64_t> tmp(cnt, st.s);
+                launch_rebase_offsets(r->d_offsets, tmp.p, cnt, base[g], st.s);
+                LAPPER_CUDA_CHECK(cudaMemcpyAsync(offsets_out + lo, tmp.p, cnt * 8, cudaMemcpyDeviceToHost, st.s));
+                if (r->total)
+                    LAPPER_CUDA_CHECK(cudaMemcpyAsync(idx + base[g], r->d_indices, r->total * 4, cudaMemcpyDeviceToHost, st.s));
+                tmp.release();
+                LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+            });
             *indices_out = idx;
             *total_out = total;
         } catch (...) {
+            free(idx);
             cleanup();
             throw;
         }

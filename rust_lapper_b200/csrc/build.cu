@@ -135,25 +135,54 @@ void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, uint64
     }
 }
 
-struct BuildStats {
-    uint32_t max_len;
-    uint32_t inverted;
-};
-
-// max_len = max over intervals of stop.checked_sub(start).unwrap_or(0)   (src/lib.rs:218-227)
-__global__ void stats_kernel(const uint32_t *__restrict__ s, const uint32_t *__restrict__ e, uint64_t n,
-                             BuildStats *__restrict__ out) {
-    uint32_t mx = 0, inv = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t a = s[i], b = e[i];
-        mx = max(mx, b >= a ? b - a : 0u);
+// One pass over the sorted intervals: max_len (src/lib.rs:218-227), the inverted flag, the histogram of lengths by
+// bit length (what the length classes are chosen from), the largest input position, and the end points the table
+// shapes depend on.
+__global__ void __launch_bounds__(kThreads) stats_kernel(const uint32_t *__restrict__ s, const uint32_t *__restrict__ e,
+                                                         const uint32_t *__restrict__ e_sorted,
+                                                         const uint32_t *__restrict__ perm, uint64_t n,
+                                                         BuildStats *__restrict__ out) {
+    __shared__ uint32_t cnt[33];
+    __shared__ uint32_t mx[33];
+    for (int i = threadIdx.x; i < 33; i += blockDim.x) cnt[i] = 0, mx[i] = 0;
+    __syncthreads();
+    uint32_t inv = 0, pmax = 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    // (warp-uniform trip count: the loop runs on the warp's first index)
+    for (uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + (threadIdx.x & ~31u); i0 < n; i0 += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t i = i0 + lane;
+        const bool live = i < n;
+        const uint32_t a = live ? s[i] : 0u, b = live ? e[i] : 0u;
+        const uint32_t len = b > a ? b - a : 0u;
+        const uint32_t bin = len ? 32u - __clz(len) : 0u;
+        // lanes of a warp mostly share a bin: one shared-memory atomic per distinct bin
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, live ? bin : 64u + lane);
+        const uint32_t len_max = __reduce_max_sync(peers, len);
+        if (live && lane == (uint32_t)(__ffs(peers) - 1)) {
+            atomicAdd(&cnt[bin], (uint32_t)__popc(peers));
+            atomicMax(&mx[bin], len_max);
+        }
         inv |= (b < a);
+        if (live) pmax = max(pmax, perm[i]);
     }
-    mx = __reduce_max_sync(0xFFFFFFFFu, mx);
     inv = __reduce_or_sync(0xFFFFFFFFu, inv);
+    pmax = __reduce_max_sync(0xFFFFFFFFu, pmax);
     if ((threadIdx.x & 31) == 0) {
-        if (mx) atomicMax(&out->max_len, mx);
         if (inv) atomicOr(&out->inverted, 1u);
+        if (pmax) atomicMax(&out->max_perm, pmax);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 33; i += blockDim.x) {
+        if (cnt[i]) {
+            atomicAdd(&out->count[i], (unsigned long long)cnt[i]);
+            atomicMax(&out->maxlen[i], mx[i]);
+            atomicMax(&out->max_len, mx[i]);
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        out->first_start = s[0];
+        out->last_start = s[n - 1];
+        out->last_stop = e_sorted[n - 1];
     }
 }
 
@@ -289,34 +318,6 @@ __global__ void __launch_bounds__(kThreads) block_max_kernel(const uint32_t *__r
     if (lane == 0) out[warp] = v;
 }
 
-struct LenHist {
-    unsigned long long count[33];
-    uint32_t maxlen[33];
-};
-
-// histogram of interval lengths by bit length (bin 0 = length 0 or inverted) + the longest per bin
-__global__ void len_hist_kernel(const uint32_t *__restrict__ s, const uint32_t *__restrict__ e, uint64_t n,
-                                LenHist *__restrict__ out) {
-    __shared__ uint32_t cnt[33];
-    __shared__ uint32_t mx[33];
-    for (int i = threadIdx.x; i < 33; i += blockDim.x) cnt[i] = 0, mx[i] = 0;
-    __syncthreads();
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t a = s[i], b = e[i];
-        const uint32_t len = b > a ? b - a : 0u;
-        const uint32_t bin = len ? 32u - __clz(len) : 0u;
-        atomicAdd(&cnt[bin], 1u);
-        atomicMax(&mx[bin], len);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 33; i += blockDim.x) {
-        if (cnt[i]) {
-            atomicAdd(&out->count[i], (unsigned long long)cnt[i]);
-            atomicMax(&out->maxlen[i], mx[i]);
-        }
-    }
-}
-
 // rank of each bucket's first coordinate in every class (one uint4 per bucket)
 __global__ void fill_class_dir_kernel(const uint32_t *__restrict__ cs, uint32_t off0, uint32_t n0, uint32_t off1,
                                       uint32_t n1, uint32_t off2, uint32_t n2, uint32_t off3, uint32_t n3,
@@ -334,15 +335,6 @@ __global__ void fill_class_dir_kernel(const uint32_t *__restrict__ cs, uint32_t 
         r.w = lower_bound_u32(cs + off3, 0, n3, base);
     }
     dir[B] = r;
-}
-
-template <typename T>
-T *dev_alloc(uint64_t count, uint64_t &bytes) {
-    T *p = nullptr;
-    uint64_t b = (count ? count : 1) * sizeof(T);
-    LAPPER_CUDA_CHECK(cudaMalloc((void **)&p, b));
-    bytes += b;
-    return p;
 }
 
 uint32_t grid_for(uint64_t n) { return (uint32_t)div_up(n ? n : 1, kThreads); }
@@ -433,7 +425,7 @@ bool choose_dense_shape(uint64_t n, uint32_t max_coord, uint32_t flags, uint64_t
 // Choose up to kMaxClasses contiguous groups of length bins minimising the expected number of
 // interval slots find() has to look at per query: sum_c n_c * (maxlen_c + q) / span + kappa per class
 // (each class costs two directory lookups).  33 bins, a tiny DP on the host.
-void choose_classes(const LenHist &h, uint64_t span, uint8_t class_of_bin[33], uint32_t &ncls, uint32_t cls_n[4],
+void choose_classes(const BuildStats &h, uint64_t span, uint8_t class_of_bin[33], uint32_t &ncls, uint32_t cls_n[4],
                     uint32_t cls_maxlen[4]) {
     const double kQueryLen = 256.0, kKappa = 12.0;
     int bins[33], nbins = 0;
@@ -509,28 +501,18 @@ void choose_classes(const LenHist &h, uint64_t span, uint8_t class_of_bin[33], u
 
 void build_find_classes(DeviceIndex &ix, cudaStream_t stream) {
     const uint64_t n = ix.n;
-    Scratch<LenHist> d_hist(1, stream);
-    LAPPER_CUDA_CHECK(cudaMemsetAsync(d_hist.p, 0, sizeof(LenHist), stream));
-    const uint32_t g = (uint32_t)std::min<uint64_t>(div_up(n, kThreads), 148 * 8);
-    len_hist_kernel<<<g, kThreads, 0, stream>>>(ix.starts, ix.stops_by_iv, n, d_hist.p);
-    LAPPER_CUDA_CHECK(cudaGetLastError());
-    LenHist h;
-    uint32_t first_start = 0, last_start = 0;
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&h, d_hist.p, sizeof(h), cudaMemcpyDeviceToHost, stream));
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&first_start, ix.starts, 4, cudaMemcpyDeviceToHost, stream));
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&last_start, ix.starts + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
-    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const uint32_t first_start = ix.stats.first_start, last_start = ix.stats.last_start;
     uint8_t class_of_bin[33];
-    choose_classes(h, (uint64_t)last_start - first_start + 1, class_of_bin, ix.ncls, ix.cls_n, ix.cls_maxlen);
+    choose_classes(ix.stats, (uint64_t)last_start - first_start + 1, class_of_bin, ix.ncls, ix.cls_n, ix.cls_maxlen);
     uint32_t off = 0;
     for (uint32_t c = 0; c < 4; c++) {
         ix.cls_off[c] = off;
         off += ix.cls_n[c];
     }
 
-    ix.cls_starts = dev_alloc<uint32_t>(n, ix.bytes);
-    ix.cls_stops = dev_alloc<uint32_t>(n, ix.bytes);
-    ix.cls_gidx = dev_alloc<uint32_t>(n, ix.bytes);
+    ix.cls_starts = pool_alloc<uint32_t>(n, ix.bytes, stream);
+    ix.cls_stops = pool_alloc<uint32_t>(n, ix.bytes, stream);
+    ix.cls_gidx = pool_alloc<uint32_t>(n, ix.bytes, stream);
     launch_class_partition(ix, class_of_bin, stream);
     // directory: about one bucket per six intervals, at least 2^4 coordinates wide
     uint32_t k = 0;
@@ -538,7 +520,7 @@ void build_find_classes(DeviceIndex &ix, cudaStream_t stream) {
     while (k < 31 && ((uint64_t)(last_start >> k) + 1) > target) k++;
     ix.cls_shift = k;
     ix.cls_nb = (uint64_t)(last_start >> k) + 1;
-    ix.cls_dir = dev_alloc<uint4>(ix.cls_nb + 1, ix.bytes);
+    ix.cls_dir = pool_alloc<uint4>(ix.cls_nb + 1, ix.bytes, stream);
     fill_class_dir_kernel<<<grid_for(ix.cls_nb + 1), kThreads, 0, stream>>>(
         ix.cls_starts, ix.cls_off[0], ix.cls_n[0], ix.cls_off[1], ix.cls_n[1], ix.cls_off[2], ix.cls_n[2], ix.cls_off[3],
         ix.cls_n[3], k, ix.cls_nb, ix.cls_dir);
@@ -551,111 +533,122 @@ void launch_sort_u32(uint32_t *keys, uint32_t *tmp, uint64_t n, cudaStream_t str
     if (n > 1) radix_sort<uint32_t, false>(keys, tmp, nullptr, nullptr, n, 32, stream);
 }
 
-void free_index(DeviceIndex &ix) {
-    cudaFree(ix.cls_starts);
-    cudaFree(ix.cls_stops);
-    cudaFree(ix.cls_gidx);
-    cudaFree(ix.cls_dir);
-    cudaFree(ix.blkmax32);
-    cudaFree(ix.blkmax1024);
-    cudaFree(ix.starts);
-    cudaFree(ix.stops_by_iv);
-    cudaFree(ix.stops_sorted);
-    cudaFree(ix.perm);
-    cudaFree(ix.prefix_max);
-    cudaFree(ix.buckets);
-    cudaFree(ix.pool);
-    cudaFree(ix.dense);
+void free_index(DeviceIndex &ix, cudaStream_t stream) {
+    void *arrays[] = {ix.cls_starts, ix.cls_stops, ix.cls_gidx, ix.cls_dir, ix.blkmax32, ix.blkmax1024, ix.starts,
+                      ix.stops_by_iv, ix.stops_sorted, ix.perm, ix.prefix_max, ix.buckets, ix.pool, ix.dense};
+    for (void *p : arrays) pool_free(p, stream);
     ix = DeviceIndex();
 }
 
-void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stream) {
+static void free_query_tables(DeviceIndex &ix, cudaStream_t stream) {
+    void *arrays[] = {ix.cls_starts, ix.cls_stops, ix.cls_gidx, ix.cls_dir, ix.blkmax32, ix.blkmax1024, ix.buckets, ix.pool, ix.dense};
+    for (void *p : arrays) pool_free(p, stream);
+    ix.cls_starts = ix.cls_stops = ix.cls_gidx = nullptr;
+    ix.cls_dir = nullptr;
+    ix.blkmax32 = ix.blkmax1024 = nullptr;
+    ix.buckets = ix.pool = ix.dense = nullptr;
+    ix.shift = 0xFFFFFFFFu;
+    ix.nbuckets = ix.npool = ix.dense_nb = 0;
+    ix.margin = 0;
+    ix.ncls = 0;
+    ix.dense_w = ix.dense_m = ix.dense_magic = 0;
+    ix.dense_overflow = 0;
+    ix.tables_ready = false;
+}
+
+// One host sync: the scalars every later decision depends on come back together.
+void finish_index_core(DeviceIndex &ix, cudaStream_t stream) {
     const uint64_t n = ix.n;
     ix.max_len = 0;
     ix.has_inverted = false;
     ix.max_coord = 0;
-    ix.shift = 0xFFFFFFFFu;
-    ix.nbuckets = 0;
-    ix.npool = 0;
-    ix.margin = 0;
-    ix.ncls = 0;
-    ix.dense_nb = 0;
-    ix.dense_w = ix.dense_m = ix.dense_magic = 0;
-    ix.dense_overflow = 0;
-    if (n == 0) return;
-
+    ix.stats = BuildStats();
+    ix.tables_ready = false;
+    if (n == 0) {
+        ix.tables_ready = true;  // nothing to build
+        return;
+    }
     Scratch<BuildStats> d_stats(1, stream);
     LAPPER_CUDA_CHECK(cudaMemsetAsync(d_stats.p, 0, sizeof(BuildStats), stream));
-    uint32_t g = (uint32_t)std::min<uint64_t>(div_up(n, kThreads), 148 * 16);
-    stats_kernel<<<g, kThreads, 0, stream>>>(ix.starts, ix.stops_by_iv, n, d_stats.p);
+    const uint32_t g = (uint32_t)std::min<uint64_t>(div_up(n, kThreads), (uint64_t)sm_count() * 8);
+    stats_kernel<<<g, kThreads, 0, stream>>>(ix.starts, ix.stops_by_iv, ix.stops_sorted, ix.perm, n, d_stats.p);
     LAPPER_CUDA_CHECK(cudaGetLastError());
-
-    ix.prefix_max = dev_alloc<uint32_t>(n, ix.bytes);
+    if (!ix.prefix_max) ix.prefix_max = pool_alloc<uint32_t>(n, ix.bytes, stream);
     launch_prefix_max(ix.stops_by_iv, ix.prefix_max, n, stream);
-
-    BuildStats st;
-    uint32_t last_start = 0, last_stop = 0;
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&st, d_stats.p, sizeof(st), cudaMemcpyDeviceToHost, stream));
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&last_start, ix.starts + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&last_stop, ix.stops_sorted + (n - 1), 4, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&ix.stats, d_stats.p, sizeof(BuildStats), cudaMemcpyDeviceToHost, stream));
     LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
-    ix.max_len = st.max_len;
-    ix.has_inverted = st.inverted != 0;
-    ix.max_coord = std::max(last_start, last_stop);
+    ix.max_len = ix.stats.max_len;
+    ix.has_inverted = ix.stats.inverted != 0;
+    ix.max_coord = std::max(ix.stats.last_start, ix.stats.last_stop);
+}
 
-    build_find_classes(ix, stream);
-    {
-        const uint64_t nb32 = div_up(n, 32), nb1024 = div_up(nb32, 32);
-        ix.blkmax32 = dev_alloc<uint32_t>(nb32, ix.bytes);
-        ix.blkmax1024 = dev_alloc<uint32_t>(nb1024, ix.bytes);
-        block_max_kernel<<<(uint32_t)div_up(nb32 * 32, kThreads), kThreads, 0, stream>>>(ix.stops_by_iv, n, ix.blkmax32, nb32);
-        block_max_kernel<<<(uint32_t)div_up(nb1024 * 32, kThreads), kThreads, 0, stream>>>(ix.blkmax32, nb32, ix.blkmax1024, nb1024);
-        LAPPER_CUDA_CHECK(cudaGetLastError());
+void build_query_tables(DeviceIndex &ix, uint32_t flags, cudaStream_t stream) {
+    const uint64_t n = ix.n;
+    if (ix.tables_ready) return;
+    if (n == 0) {
+        ix.tables_ready = true;
+        return;
     }
-
-    uint32_t shift = 0;
-    if (choose_shift(n, ix.max_coord, flags, shift)) {
-        ix.shift = shift;
-        ix.margin = shift >= 2 ? (1u << shift) / 4 : 0;
-        ix.nbuckets = (uint64_t)(ix.max_coord >> shift) + 1;
-        LAPPER_REQUIRE(ix.nbuckets < (1ull << 31), "bucket table too large");
-        ix.buckets = dev_alloc<Sector>(ix.nbuckets + 1, ix.bytes);
-        Scratch<unsigned long long> d_pool_count(1, stream);
-        LAPPER_CUDA_CHECK(cudaMemsetAsync(d_pool_count.p, 0, 8, stream));
-        fill_buckets_kernel<<<grid_for(ix.nbuckets + 1), kThreads, 0, stream>>>(
-            ix.starts, ix.stops_sorted, (uint32_t)n, shift, ix.margin, ix.nbuckets, ix.buckets, d_pool_count.p);
-        LAPPER_CUDA_CHECK(cudaGetLastError());
-        unsigned long long npool = 0;
-        LAPPER_CUDA_CHECK(cudaMemcpyAsync(&npool, d_pool_count.p, 8, cudaMemcpyDeviceToHost, stream));
-        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
-        LAPPER_REQUIRE(npool < 0xFFFFFFFFull, "child sector pool too large");
-        ix.npool = npool;
-        if (npool) {
-            ix.pool = dev_alloc<Sector>(npool, ix.bytes);
-            fill_children_kernel<<<grid_for(ix.nbuckets + 1), kThreads, 0, stream>>>(
-                ix.starts, ix.stops_sorted, (uint32_t)n, shift, ix.nbuckets, ix.buckets, ix.pool);
+    try {
+        uint32_t shift = 0;
+        const bool with_buckets = choose_shift(n, ix.max_coord, flags, shift);
+        Scratch<unsigned long long> d_counters(2, stream);  // child sectors reserved, packed sectors overflowed
+        if (with_buckets) {
+            // the sector table first: the number of child sectors it reserves is the one value the host has to wait
+            // for, and the class / blkmax kernels below run while it does
+            ix.shift = shift;
+            ix.margin = shift >= 2 ? (1u << shift) / 4 : 0;
+            ix.nbuckets = (uint64_t)(ix.max_coord >> shift) + 1;
+            LAPPER_REQUIRE(ix.nbuckets < (1ull << 31), "bucket table too large");
+            ix.buckets = pool_alloc<Sector>(ix.nbuckets + 1, ix.bytes, stream);
+            LAPPER_CUDA_CHECK(cudaMemsetAsync(d_counters.p, 0, 16, stream));
+            fill_buckets_kernel<<<grid_for(ix.nbuckets + 1), kThreads, 0, stream>>>(
+                ix.starts, ix.stops_sorted, (uint32_t)n, shift, ix.margin, ix.nbuckets, ix.buckets, d_counters.p);
             LAPPER_CUDA_CHECK(cudaGetLastError());
         }
-        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
-
-        uint32_t dw = 0, dm = 0;
-        if (choose_dense_shape(n, ix.max_coord, flags, (ix.nbuckets + 1 + ix.npool) * sizeof(Sector), ix.margin, dw, dm)) {
-            const PackedParams pp = packed_params(dw, ix.max_coord, dm);
-            ix.dense_w = pp.w;
-            ix.dense_m = pp.m;
-            ix.dense_magic = pp.magic;
-            ix.dense_nb = pp.nb;
-            ix.dense = dev_alloc<Sector>(ix.dense_nb + 1, ix.bytes);
-            Scratch<unsigned long long> d_over(1, stream);
-            LAPPER_CUDA_CHECK(cudaMemsetAsync(d_over.p, 0, 8, stream));
-            fill_dense_kernel<<<grid_for(ix.dense_nb + 1), kThreads, 0, stream>>>(
-                ix.starts, ix.stops_sorted, (uint32_t)n, pp, ix.dense, d_over.p);
+        build_find_classes(ix, stream);
+        {
+            const uint64_t nb32 = div_up(n, 32), nb1024 = div_up(nb32, 32);
+            ix.blkmax32 = pool_alloc<uint32_t>(nb32, ix.bytes, stream);
+            ix.blkmax1024 = pool_alloc<uint32_t>(nb1024, ix.bytes, stream);
+            block_max_kernel<<<(uint32_t)div_up(nb32 * 32, kThreads), kThreads, 0, stream>>>(ix.stops_by_iv, n, ix.blkmax32, nb32);
+            block_max_kernel<<<(uint32_t)div_up(nb1024 * 32, kThreads), kThreads, 0, stream>>>(ix.blkmax32, nb32, ix.blkmax1024, nb1024);
             LAPPER_CUDA_CHECK(cudaGetLastError());
-            unsigned long long nover = 0;
-            LAPPER_CUDA_CHECK(cudaMemcpyAsync(&nover, d_over.p, 8, cudaMemcpyDeviceToHost, stream));
+        }
+        if (with_buckets) {
+            unsigned long long npool = 0;
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(&npool, d_counters.p, 8, cudaMemcpyDeviceToHost, stream));
             LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
-            ix.dense_overflow = nover;
+            LAPPER_REQUIRE(npool < 0xFFFFFFFFull, "child sector pool too large");
+            ix.npool = npool;
+            if (npool) {
+                ix.pool = pool_alloc<Sector>(npool, ix.bytes, stream);
+                fill_children_kernel<<<grid_for(ix.nbuckets + 1), kThreads, 0, stream>>>(
+                    ix.starts, ix.stops_sorted, (uint32_t)n, shift, ix.nbuckets, ix.buckets, ix.pool);
+                LAPPER_CUDA_CHECK(cudaGetLastError());
+            }
+            uint32_t dw = 0, dm = 0;
+            if (choose_dense_shape(n, ix.max_coord, flags, (ix.nbuckets + 1 + ix.npool) * sizeof(Sector), ix.margin, dw, dm)) {
+                const PackedParams pp = packed_params(dw, ix.max_coord, dm);
+                ix.dense_w = pp.w;
+                ix.dense_m = pp.m;
+                ix.dense_magic = pp.magic;
+                ix.dense_nb = pp.nb;
+                ix.dense = pool_alloc<Sector>(ix.dense_nb + 1, ix.bytes, stream);
+                fill_dense_kernel<<<grid_for(ix.dense_nb + 1), kThreads, 0, stream>>>(
+                    ix.starts, ix.stops_sorted, (uint32_t)n, pp, ix.dense, d_counters.p + 1);
+                LAPPER_CUDA_CHECK(cudaGetLastError());
+                unsigned long long nover = 0;
+                LAPPER_CUDA_CHECK(cudaMemcpyAsync(&nover, d_counters.p + 1, 8, cudaMemcpyDeviceToHost, stream));
+                LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+                ix.dense_overflow = nover;
+            }
         }
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));  // the tables are complete when tables_ready says so
+        ix.tables_ready = true;
+    } catch (...) {
+        free_query_tables(ix, stream);
+        throw;
     }
 }
 
@@ -665,14 +658,14 @@ void build_index_from_unsorted(DeviceIndex &ix, const uint32_t *d_starts, const 
     ix = DeviceIndex();
     ix.n = n;
     if (n == 0) {
-        finish_index_from_sorted(ix, flags, stream);
+        finish_index_core(ix, stream);
         return;
     }
     try {
-        ix.starts = dev_alloc<uint32_t>(n, ix.bytes);
-        ix.stops_by_iv = dev_alloc<uint32_t>(n, ix.bytes);
-        ix.stops_sorted = dev_alloc<uint32_t>(n, ix.bytes);
-        ix.perm = dev_alloc<uint32_t>(n, ix.bytes);
+        ix.starts = pool_alloc<uint32_t>(n, ix.bytes, stream);
+        ix.stops_by_iv = pool_alloc<uint32_t>(n, ix.bytes, stream);
+        ix.stops_sorted = pool_alloc<uint32_t>(n, ix.bytes, stream);
+        ix.perm = pool_alloc<uint32_t>(n, ix.bytes, stream);
         {
             Scratch<uint64_t> keys(n, stream), keys_tmp(n, stream);
             Scratch<uint32_t> pos_tmp(n, stream), stops_tmp(n, stream);
@@ -686,9 +679,10 @@ void build_index_from_unsorted(DeviceIndex &ix, const uint32_t *d_starts, const 
             LAPPER_CUDA_CHECK(cudaMemcpyAsync(ix.stops_sorted, d_stops, n * 4, cudaMemcpyDeviceToDevice, stream));
             radix_sort<uint32_t, false>(ix.stops_sorted, stops_tmp.p, nullptr, nullptr, n, 32, stream);
         }
-        finish_index_from_sorted(ix, flags, stream);
+        finish_index_core(ix, stream);
+        build_query_tables(ix, flags, stream);
     } catch (...) {
-        free_index(ix);
+        free_index(ix, stream);
         throw;
     }
 }

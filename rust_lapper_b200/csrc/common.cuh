@@ -56,6 +56,9 @@ struct DeviceGuard {
 // "never": a batch call that needs 400 MB of scratch gets it back from the pool on the next call
 // instead of from the driver (which costs about a millisecond per call).
 cudaMemPool_t scratch_pool();  // api.cu
+// number of SMs of the current device (cudaDevAttrMultiProcessorCount, cached per device): persistent grids are sized
+// as a multiple of it (148 on B200)
+uint32_t sm_count();  // api.cu
 
 template <typename T>
 struct Scratch {

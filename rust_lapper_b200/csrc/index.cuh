@@ -44,6 +44,17 @@ constexpr uint32_t kNoChild = 0xFFFFFFFFu;
 
 // The packed ("dense") table in front of this one: packed_sector.cuh.
 
+// histogram of interval lengths by bit length (bin 0 = length 0 or inverted) + the longest per bin, and the other
+// scalars of one pass over the sorted intervals (finish_index_core)
+struct BuildStats {
+    unsigned long long count[33];
+    uint32_t maxlen[33];
+    uint32_t max_len;      // max over intervals of stop.checked_sub(start).unwrap_or(0)   (src/lib.rs:218-227)
+    uint32_t inverted;     // some interval has stop < start
+    uint32_t first_start, last_start, last_stop;  // S[0], S[n-1], sorted stops [n-1]
+    uint32_t max_perm;     // max input position
+};
+
 struct DeviceIndex {
     uint64_t n = 0;
     uint32_t *starts = nullptr;
@@ -66,6 +77,10 @@ struct DeviceIndex {
     uint32_t max_coord = 0;
     bool has_inverted = false;
     uint64_t bytes = 0;
+    // the query tables (buckets / pool / dense, length classes, blkmax) are derived data: built at once by
+    // lapper_build_*, lazily -- on the first count / find -- after merge_overlaps and insert (build_query_tables)
+    bool tables_ready = false;
+    BuildStats stats = {};  // host copy (finish_index_core)
 
     // ---- find: length classes (build.cu::build_find_classes).  The sorted intervals are split,
     // order-preserving, into up to kMaxClasses groups by length; class c occupies
@@ -99,6 +114,8 @@ constexpr uint32_t kMaxClasses = 4;
 struct lapper {
     int device = 0;
     lap::DeviceIndex ix;
+    std::mutex tables_mu;  // serialises the lazy build of ix's query tables between concurrent const calls
+    std::atomic<bool> tables_flag{false};  // ix.tables_ready, readable without the mutex
     bool overlaps_merged = false;
     bool cov_is_some = false;
     uint32_t cov = 0;
@@ -106,7 +123,7 @@ struct lapper {
     uint64_t next_input_id = 0;  // input position handed to the next inserted interval
 };
 
-struct lapper_result {
+struct lapper_result {  // device CSR of one find_batch call (pool memory)
     int device = 0;
     uint64_t nq = 0;
     uint64_t total = 0;
@@ -120,9 +137,27 @@ namespace lap {
 // Sort (start, stop) pairs (stable, by (start, stop)) and derive every array of DeviceIndex.
 void build_index_from_unsorted(DeviceIndex &ix, const uint32_t *d_starts, const uint32_t *d_stops, uint64_t n,
                                uint32_t flags, cudaStream_t stream);
-// Arrays already sorted (import / after merge_overlaps).  Takes ownership of the four arrays.
-void finish_index_from_sorted(DeviceIndex &ix, uint32_t flags, cudaStream_t stream);
-void free_index(DeviceIndex &ix);
+// Arrays already sorted (import / after merge_overlaps / insert); ix owns the four sorted arrays (pool memory).
+// finish_index_core: max_len, has_inverted, max_coord, prefix_max (what cov / merge / the accessors need; one host
+// sync).  build_query_tables: everything count / find need on top of that (length classes, blkmax, BITS sectors,
+// packed table); sets ix.tables_ready.
+void finish_index_core(DeviceIndex &ix, cudaStream_t stream);
+void build_query_tables(DeviceIndex &ix, uint32_t flags, cudaStream_t stream);
+// every array of the index goes back to the library pool, stream-ordered on `stream`
+void free_index(DeviceIndex &ix, cudaStream_t stream);
+// index memory: stream-ordered allocations from the library pool (common.cuh) -- a rebuilt index reuses the
+// memory of the one it replaces instead of going through cudaMalloc / cudaFree (milliseconds per call at 50 M)
+template <typename T>
+T *pool_alloc(uint64_t count, uint64_t &bytes, cudaStream_t stream) {
+    T *p = nullptr;
+    const uint64_t b = (count ? count : 1) * sizeof(T);
+    LAPPER_CUDA_CHECK(cudaMallocFromPoolAsync((void **)&p, b, scratch_pool(), stream));
+    bytes += b;
+    return p;
+}
+inline void pool_free(void *p, cudaStream_t stream) {
+    if (p) cudaFreeAsync(p, stream);
+}
 // in-place ascending sort of n u32 keys (hand-written LSD radix sort); tmp holds n keys
 void launch_sort_u32(uint32_t *keys, uint32_t *tmp, uint64_t n, cudaStream_t stream);
 
@@ -134,8 +169,13 @@ void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d
 // writes d_offsets[nq+1]; returns total hits (synchronises the stream)
 uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
                              uint64_t *d_offsets, cudaStream_t stream);
+// total = offsets[nq] when the caller knows it (saves a device round trip), kTotalUnknown otherwise
+constexpr uint64_t kTotalUnknown = ~0ull;
 void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
-                      const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream);
+                      const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream,
+                      uint64_t total = kTotalUnknown);
+// out[j] = in[j] + base for j < count (CSR offsets of a shard / chunk -> offsets of the whole batch)
+void launch_rebase_offsets(const uint64_t *in, uint64_t *out, uint64_t count, uint64_t base, cudaStream_t stream);
 
 // setops.cu --------------------------------------------------------------------------------------
 // order-preserving split of the sorted intervals into length classes (fills ix.cls_starts/stops/gidx)
@@ -145,11 +185,11 @@ void launch_exclusive_sum(const uint32_t *in, uint32_t *out, uint64_t n, cudaStr
 // inclusive prefix max of `in` (n elements) into `out`
 void launch_prefix_max(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream);
 uint32_t compute_cov(const DeviceIndex &ix, cudaStream_t stream);
-// merged (start, stop, head perm) arrays; returns m.  Outputs are cudaMalloc'ed (m may be 0).
+// merged (start, stop, head perm) arrays; returns m.  Outputs are pool memory (pool_free; m may be 0).
 uint64_t compute_merged(const DeviceIndex &ix, uint32_t **m_starts, uint32_t **m_stops, uint32_t **m_perm,
                         cudaStream_t stream);
-// depth(): maximal runs of equal coverage depth (src/lib.rs:576-598, :735-784).  Device arrays (cudaMalloc),
-// returns the number of runs.
+// depth(): maximal runs of equal coverage depth (src/lib.rs:576-598, :735-784).  Device arrays (pool memory,
+// pool_free), returns the number of runs.
 uint64_t compute_depth(const DeviceIndex &ix, uint32_t **d_starts, uint32_t **d_stops, uint32_t **d_depth,
                        cudaStream_t stream);
 // measure of (union of a) intersected with (union of b), wrapping u32

@@ -692,7 +692,7 @@ __global__ void __launch_bounds__(1024) scan_super_sums_kernel(uint64_t *__restr
 __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t *__restrict__ counts,
                                                                  const uint64_t *__restrict__ tile_sums,
                                                                  const uint64_t *__restrict__ super_sums, uint64_t nq,
-                                                                 uint64_t *__restrict__ offsets) {
+                                                                 uint64_t *__restrict__ offsets, bool vec) {
     __shared__ uint64_t warp_tot[kThreads / 32];
     const uint64_t tile_base = super_sums[blockIdx.x / kSuperTiles] + tile_sums[blockIdx.x];
     const uint64_t base = (uint64_t)blockIdx.x * kFindTile + (uint64_t)threadIdx.x * kFindQPT;
@@ -716,7 +716,7 @@ __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t 
 #pragma unroll
     for (int i = 0; i < kThreads / 32; i++) wbase += (i < w) ? warp_tot[i] : 0;
     uint64_t run = tile_base + wbase + inc - local;
-    if (base + kFindQPT <= nq) {  // 32 contiguous bytes per thread: two 128-bit stores
+    if (vec && base + kFindQPT <= nq) {  // 32 contiguous bytes per thread: two 128-bit stores (offsets 16-byte aligned)
         const uint64_t r0 = run, r1 = r0 + c[0], r2 = r1 + c[1], r3 = r2 + c[2];
         ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(offsets + base);
         dst[0] = make_ulonglong2(r0, r1);
@@ -1794,7 +1794,7 @@ FindView make_find_view(const DeviceIndex &ix) {
 
 uint32_t capped_grid(uint64_t work_items, int per_block, int waves) {
     uint64_t g = div_up(work_items ? work_items : 1, per_block);
-    const uint64_t cap = 148ull * waves;
+    const uint64_t cap = (uint64_t)sm_count() * waves;
     return (uint32_t)(g < cap ? g : cap);
 }
 
@@ -1822,12 +1822,12 @@ void launch_count_buckets(const DeviceIndex &ix, const uint32_t *d_qs, const uin
                            reinterpret_cast<uintptr_t>(out)) & 31u) == 0;
     const uint64_t ntiles = aligned ? nq / kTileQ : 0;
     if (ntiles) {
-        // persistent grids: 148 SMs x resident CTAs of 256 threads.  Large batches over an index that has both paths:
+        // persistent grids: SMs (148 on B200) x resident CTAs of 256 threads.  Large batches over an index that has both paths:
         // the 4-CTA build for start-sorted batches and the 3-CTA build for the rest, selected on the device.
         const bool dual = ntiles >= 4096 && v.dense != nullptr && v.local_span != 0 && !count_dual_disabled();
         const auto launch = [&](auto ctas, int mode) {
             constexpr int kCtas = decltype(ctas)::value;
-            const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, 148 * kCtas);
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)sm_count() * kCtas);
             if (tile_sums)
                 g_query_launches++, count_bucket_kernel<false, true, kCtas><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, tile_sums, mode);
             else if (out64)
@@ -1945,7 +1945,8 @@ uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const 
     LAPPER_CUDA_CHECK(cudaGetLastError());
     g_query_launches++, scan_super_sums_kernel<<<1, 1024, 0, stream>>>(super_sums.p, nsuper, d_offsets + nq);
     LAPPER_CUDA_CHECK(cudaGetLastError());
-    g_query_launches++, write_offsets_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(counts.p, tile_sums.p, super_sums.p, nq, d_offsets);
+    g_query_launches++, write_offsets_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(
+        counts.p, tile_sums.p, super_sums.p, nq, d_offsets, (reinterpret_cast<uintptr_t>(d_offsets) & 15u) == 0);
     LAPPER_CUDA_CHECK(cudaGetLastError());
     uint64_t total = 0;
     LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
@@ -1962,15 +1963,27 @@ static bool find_tile_disabled() {
     return off;
 }
 
+__global__ void rebase_offsets_kernel(const uint64_t *__restrict__ in, uint64_t *__restrict__ out, uint64_t count, uint64_t base) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = in[i] + base;
+}
+
+void launch_rebase_offsets(const uint64_t *in, uint64_t *out, uint64_t count, uint64_t base, cudaStream_t stream) {
+    if (count == 0) return;
+    rebase_offsets_kernel<<<capped_grid(count, kThreads, 8), kThreads, 0, stream>>>(in, out, count, base);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
-                      const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream) {
+                      const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream, uint64_t total) {
     if (nq == 0 || ix.n == 0) return;
     LAPPER_REQUIRE(nq < (1ull << 32), "find_batch: at most 2^32 - 1 queries per call");
     const FindView f = make_find_view(ix);
     // heavy queries (>= kHeavyHits hits): at most total / kHeavyHits of them; the total is offsets[nq]
-    uint64_t total = 0;
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
-    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    if (total == kTotalUnknown) {
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    }
     // the heavy list: queries with >= kHeavyHits hits (at most total / kHeavyHits) + light queries with long class
     // windows, admitted up to a sixteenth of the batch
     const uint32_t max_admitted = (uint32_t)std::min<uint64_t>(nq, nq / 16 + 1024);
@@ -1996,7 +2009,7 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
                                                    cudaSharedmemCarveoutMaxShared));
             prepared[dev].store(true, std::memory_order_release);
         }
-        const uint32_t tgrid = (uint32_t)std::min<uint64_t>(ntiles, 148 * LAPPER_TILE_CTAS);
+        const uint32_t tgrid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)sm_count() * LAPPER_TILE_CTAS);
         g_query_launches++, find_fill_tile_kernel<<<tgrid, kTT, kTSmemWords * sizeof(uint32_t), stream>>>(
             f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2, counters.p + 3, max_admitted);
         LAPPER_CUDA_CHECK(cudaGetLastError());
@@ -2009,7 +2022,7 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
     LAPPER_CUDA_CHECK(cudaGetLastError());
     {
         // persistent warps; exits at once when the list is empty (it may also hold light queries with long windows)
-        g_query_launches++, find_heavy_kernel<<<148 * 8, kThreads, 0, stream>>>(f, d_qs, d_qe, d_offsets, d_indices, heavy.p, counters.p, counters.p + 1);
+        g_query_launches++, find_heavy_kernel<<<sm_count() * 8, kThreads, 0, stream>>>(f, d_qs, d_qe, d_offsets, d_indices, heavy.p, counters.p, counters.p + 1);
         LAPPER_CUDA_CHECK(cudaGetLastError());
     }
 }

@@ -317,15 +317,24 @@ __global__ void __launch_bounds__(kThreads) intersect_kernel(const uint32_t *__r
 
 uint32_t reduce_grid(uint64_t n) {
     uint64_t g = div_up(n ? n : 1, kThreads);
-    return (uint32_t)(g < 148 * 8 ? g : 148 * 8);
+    const uint64_t cap = (uint64_t)sm_count() * 8;
+    return (uint32_t)(g < cap ? g : cap);
 }
 
-struct DevArrays {
+struct DevArrays {  // three pool arrays, returned to the pool (stream-ordered) unless handed on
     uint32_t *s = nullptr, *e = nullptr, *perm = nullptr;
+    cudaStream_t stream;
+    explicit DevArrays(cudaStream_t st) : stream(st) {}
+    void alloc(uint64_t count) {
+        uint64_t bytes = 0;
+        s = pool_alloc<uint32_t>(count, bytes, stream);
+        e = pool_alloc<uint32_t>(count, bytes, stream);
+        perm = pool_alloc<uint32_t>(count, bytes, stream);
+    }
     ~DevArrays() {
-        cudaFree(s);
-        cudaFree(e);
-        cudaFree(perm);
+        pool_free(s, stream);
+        pool_free(e, stream);
+        pool_free(perm, stream);
     }
 };
 
@@ -379,14 +388,11 @@ uint64_t compute_merged(const DeviceIndex &ix, uint32_t **m_starts, uint32_t **m
     uint32_t m = 0;
     LAPPER_CUDA_CHECK(cudaMemcpyAsync(&m, d_total.p, 4, cudaMemcpyDeviceToHost, stream));
     LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
-    DevArrays out;
-    LAPPER_CUDA_CHECK(cudaMalloc((void **)&out.s, (uint64_t)m * 4));
-    LAPPER_CUDA_CHECK(cudaMalloc((void **)&out.e, (uint64_t)m * 4));
-    LAPPER_CUDA_CHECK(cudaMalloc((void **)&out.perm, (uint64_t)m * 4));
+    DevArrays out(stream);
+    out.alloc(m);
     MergeSink sink{ix.starts, ix.prefix_max, ix.perm, n, out.s, out.e, out.perm};
     tile_apply_kernel<AddOp, HeadFlag, MergeSink><<<(uint32_t)ntiles, kThreads, 0, stream>>>(flags, n, agg.p, sink);
     LAPPER_CUDA_CHECK(cudaGetLastError());
-    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
     *m_starts = out.s;
     *m_stops = out.e;
     *m_perm = out.perm;
@@ -429,10 +435,8 @@ uint64_t compute_depth(const DeviceIndex &ix, uint32_t **d_starts, uint32_t **d_
         LAPPER_CUDA_CHECK(cudaGetLastError());
         LAPPER_CUDA_CHECK(cudaMemcpyAsync(&nr, d_count.p, 4, cudaMemcpyDeviceToHost, stream));
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
-        DevArrays out;
-        LAPPER_CUDA_CHECK(cudaMalloc((void **)&out.s, std::max<uint64_t>(nr, 1) * 4));
-        LAPPER_CUDA_CHECK(cudaMalloc((void **)&out.e, std::max<uint64_t>(nr, 1) * 4));
-        LAPPER_CUDA_CHECK(cudaMalloc((void **)&out.perm, std::max<uint64_t>(nr, 1) * 4));
+        DevArrays out(stream);
+        out.alloc(nr);
         tile_apply_kernel<AddOp, RunFlag, RunSink><<<(uint32_t)ntiles, kThreads, 0, stream>>>(
             rf, ne, agg.p, RunSink{eu.p, ed.p, ez.p, out.s, out.e, out.perm});
         LAPPER_CUDA_CHECK(cudaGetLastError());
@@ -447,7 +451,7 @@ uint64_t compute_depth(const DeviceIndex &ix, uint32_t **d_starts, uint32_t **d_
 
 uint32_t compute_intersect_measure(const DeviceIndex &a, const DeviceIndex &b, cudaStream_t stream) {
     if (a.n == 0 || b.n == 0) return 0;
-    DevArrays ma, mb;
+    DevArrays ma(stream), mb(stream);
     const uint64_t na = compute_merged(a, &ma.s, &ma.e, &ma.perm, stream);
     const uint64_t nb = compute_merged(b, &mb.s, &mb.e, &mb.perm, stream);
     Scratch<uint32_t> cum(nb, stream), d_out(1, stream);

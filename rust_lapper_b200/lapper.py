@@ -33,8 +33,19 @@ class Interval(NamedTuple):
 
 
 def _u32(a) -> np.ndarray:
-    arr = np.ascontiguousarray(np.asarray(a, dtype=np.uint32))
-    return arr.reshape(-1)
+    """Coordinates as a contiguous u32 array.  Values outside [0, 2^32) are an error, never wrapped: the engine is
+    I = u32 (the reference would not compile `Interval<u32, _>` with such a literal either)."""
+    arr = np.asarray(a)
+    if arr.dtype != np.uint32:
+        if arr.size and arr.dtype.kind not in "iub":
+            if arr.dtype.kind == "f" and np.all(np.isfinite(arr)) and np.all(arr == np.floor(arr)):
+                arr = arr.astype(np.float64)
+            else:
+                raise ValueError(f"coordinates must be integers, got dtype {arr.dtype}")
+        if arr.size and (arr.min() < 0 or arr.max() > 0xFFFFFFFF):
+            raise ValueError("coordinate out of range for u32 (0 <= x <= 4294967295)")
+        arr = arr.astype(np.uint32)
+    return np.ascontiguousarray(arr).reshape(-1)
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -168,6 +179,8 @@ class Lapper:
 
     def count_batch_c32(self, q_start, q_stop) -> np.ndarray:
         qs, qe = _u32(q_start), _u32(q_stop)
+        if qs.shape != qe.shape:
+            raise ValueError("q_start and q_stop differ in length")
         out = np.empty(qs.size, np.uint32)
         _ffi.check(self._lib.lapper_count_batch_u32_c32(self._h, _ptr(qs), _ptr(qe), qs.size, _ptr(out)))
         return out
@@ -187,6 +200,24 @@ class Lapper:
         finally:
             self._lib.lapper_result_free(res)
         return offsets, indices
+
+    def find_batch_into(self, q_start, q_stop, offsets_out: np.ndarray, indices_out: Optional[np.ndarray]) -> int:
+        """find_batch straight into caller-owned host buffers (pinned ones give full PCIe speed) through the pipelined
+        one-call entry point; returns the total.  indices_out=None asks for offsets and the total only; a buffer that
+        is too small raises LapperError(ERR_CAPACITY) after offsets_out has been filled."""
+        qs, qe = _u32(q_start), _u32(q_stop)
+        if qs.shape != qe.shape:
+            raise ValueError("q_start and q_stop differ in length")
+        if offsets_out.dtype != np.uint64 or offsets_out.size < qs.size + 1 or not offsets_out.flags.c_contiguous:
+            raise ValueError("offsets_out must be a contiguous uint64 array of nq + 1 entries")
+        if indices_out is not None and (indices_out.dtype != np.uint32 or not indices_out.flags.c_contiguous):
+            raise ValueError("indices_out must be a contiguous uint32 array")
+        total = C.c_uint64(0)
+        cap = 0 if indices_out is None else indices_out.size
+        ip = C.c_void_p(indices_out.ctypes.data) if indices_out is not None and indices_out.size else C.c_void_p(0)
+        _ffi.check(self._lib.lapper_find_batch_u32_host(self._h, _ptr(qs), _ptr(qe), qs.size, C.c_void_p(offsets_out.ctypes.data),
+                                                        ip, cap, C.byref(total)))
+        return int(total.value)
 
     # ---------------------------------------------------------------- per-query API of the reference
     def count(self, start: int, stop: int) -> int:  # src/lib.rs:610-618
@@ -292,12 +323,16 @@ class LapperGroup:
 
     def count_batch(self, q_start, q_stop) -> np.ndarray:
         qs, qe = _u32(q_start), _u32(q_stop)
+        if qs.shape != qe.shape:
+            raise ValueError("q_start and q_stop differ in length")
         out = np.empty(qs.size, np.uint64)
         _ffi.check(self._lib.lapper_group_count_batch_u32(self._h, _ptr(qs), _ptr(qe), qs.size, _ptr(out)))
         return out
 
     def find_batch(self, q_start, q_stop) -> Tuple[np.ndarray, np.ndarray]:
         qs, qe = _u32(q_start), _u32(q_stop)
+        if qs.shape != qe.shape:
+            raise ValueError("q_start and q_stop differ in length")
         offsets = np.empty(qs.size + 1, np.uint64)
         idx_p, total = C.c_void_p(0), C.c_uint64(0)
         _ffi.check(self._lib.lapper_group_find_batch_u32(self._h, _ptr(qs), _ptr(qe), qs.size, _ptr(offsets),

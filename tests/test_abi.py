@@ -96,3 +96,18 @@ def test_synth_host_and_torch_agree():
         assert np.all(a[1].astype(np.int64) >= a[0].astype(np.int64))
     s, _ = synth.queries_sorted_fixed_len(45, 5000, synth.GRCH38, 150)
     assert np.all(np.diff(s.astype(np.int64)) >= 0)
+
+
+def test_python_mirror_rejects_out_of_range_coordinates():
+    """int64 / negative inputs used to wrap modulo 2^32 silently."""
+    import numpy as np
+    import pytest
+
+    from rust_lapper_b200.lapper import _u32
+
+    assert _u32([0, 4294967295]).dtype == np.uint32
+    assert _u32(np.array([5, 7], dtype=np.int64)).tolist() == [5, 7]
+    assert _u32(np.array([], dtype=np.int64)).size == 0
+    for bad in ([-1, 3], [1 << 32], np.array([2**40], dtype=np.int64), [1.5]):
+        with pytest.raises(ValueError):
+            _u32(bad)

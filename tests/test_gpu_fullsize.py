@@ -208,3 +208,90 @@ def test_tile_with_more_than_2_pow_32_hits():
         assert bool((want == hits[nq_big:]).all())
     finally:
         lib.lapper_free(h)
+
+
+def test_cfg5_sized_set_auto_selected_tables(oracle):
+    """cfg 5's interval set at its real size (50 M): only n >~ 20 M reaches the third branch of choose_dense_shape
+    (build.cu) -- bucket width ~200, hundreds of thousands of overflowed sectors -- and `local_span = 0` (query.cu), which
+    sends start-sorted batches through the packed path too.  Random, start-sorted, long and inverted queries; a 200 k
+    sample against the oracle for count and find, bit for bit; sum(count) == |CSR| on the whole batches."""
+    import torch
+
+    from rust_lapper_b200 import _ffi, synth
+
+    dev = torch.device("cuda", 0)
+    lib = _ffi.lib()
+    U = synth.GRCH38
+    n = 50_000_000
+    s, e = synth.intervals_uniform(42, n, U, 50, 5000, device=dev)
+    hs, he = synth.intervals_uniform(42, n, U, 50, 5000)
+    h, sp = _build(lib, s, e, dev)
+    del s, e
+    try:
+        w, ns, no = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        _ffi.check(lib.lapper_packed_table_info(h, C.byref(w), C.byref(ns), C.byref(no)))
+        assert w.value and w.value < 400, "the auto-selected packed table of the dense regime was not built"
+        assert no.value > 10_000  # the regime the test is about: many overflowed sectors
+        cpu = oracle.OracleLapper(starts=hs, stops=he)
+        host_s, host_e, host_p = (np.empty(n, np.uint32) for _ in range(3))
+        _ffi.check(lib.lapper_get_intervals(h, C.c_void_p(host_s.ctypes.data), C.c_void_p(host_e.ctypes.data),
+                                            C.c_void_p(host_p.ctypes.data)))
+        cs, ce, cp = cpu.intervals_soa()
+        assert np.array_equal(cs, host_s) and np.array_equal(ce, host_e) and np.array_equal(cp, host_p)
+        assert int(lib.lapper_max_len(h)) == cpu.max_len
+        del host_s, host_e, host_p, cs, ce, cp
+        rng = np.random.default_rng(5)
+        nq = 20_000_000
+        batches = {
+            "random": synth.queries_fixed_len(43, nq, U, 150, device=dev),
+            "sorted": synth.queries_sorted_fixed_len(45, nq, U, 150, device=dev),
+        }
+        # long (beyond any margin), zero-length and inverted queries mixed into a random batch
+        ms, me = synth.queries_fixed_len(48, nq, U, 150, device=dev)
+        kind = torch.arange(nq, device=dev) % 8
+        me = torch.where(kind == 1, ms + 3000, me)
+        me = torch.where(kind == 2, ms, me)
+        me = torch.where(kind == 3, ms - 100, me)
+        batches["mixed"] = (ms.contiguous(), me.to(torch.int32).contiguous())
+        for name, (qs, qe) in batches.items():
+            counts = _count(lib, h, qs, qe, sp)
+            pick = np.sort(rng.choice(nq, 200_000, replace=False))
+            pick_t = torch.from_numpy(pick).to(dev)
+            sq, se = synth.to_numpy_u32(qs[pick_t]), synth.to_numpy_u32(qe[pick_t])
+            want = cpu.count_batch(sq, se, 8)
+            got = counts[pick_t].cpu().numpy().view(np.uint32).astype(np.uint64)
+            assert np.array_equal(got, want & 0xFFFFFFFF), name
+            # find on a prefix (43 hits per query: 2 M queries ~ 86 M positions)
+            k = 2_000_000
+            off, idx, total = _find(lib, h, qs[:k].contiguous(), qe[:k].contiguous(), sp)
+            if name != "mixed":  # |find| == count needs non-empty queries
+                assert total == int((counts[:k].to(torch.int64) & 0xFFFFFFFF).sum()), name
+            sub = np.sort(rng.choice(k, 100_000, replace=False))
+            fq, fe = synth.to_numpy_u32(qs[:k])[sub], synth.to_numpy_u32(qe[:k])[sub]
+            woff, widx = cpu.find_batch(fq, fe, 8)
+            off_c = off.cpu().numpy()
+            idx_c = idx.cpu().numpy().view(np.uint32)
+            hits = (off_c[1:] - off_c[:-1])[sub]
+            assert np.array_equal(hits.astype(np.uint64), np.diff(woff)), name
+            for t in rng.choice(sub.size, 3000, replace=False):
+                j = int(sub[t])
+                assert np.array_equal(idx_c[off_c[j]:off_c[j + 1]], widx[int(woff[t]):int(woff[t + 1])]), name
+            del counts, off, idx
+        # merge_overlaps + cov at this size, and a count against the merged set (lazy tables)
+        cov = C.c_uint32(0)
+        _ffi.check(lib.lapper_cov(h, C.byref(cov)))
+        assert int(cov.value) == cpu.cov()
+        _ffi.check(lib.lapper_merge_overlaps(h))
+        cpu.merge_overlaps()
+        m = int(lib.lapper_len(h))
+        assert m == len(cpu)
+        ms_, me_ = np.empty(m, np.uint32), np.empty(m, np.uint32)
+        _ffi.check(lib.lapper_get_intervals(h, C.c_void_p(ms_.ctypes.data), C.c_void_p(me_.ctypes.data), None))
+        assert np.array_equal(ms_, cpu.intervals_soa()[0]) and np.array_equal(me_, cpu.intervals_soa()[1])
+        assert int(lib.lapper_max_len(h)) == cpu.max_len
+        qs, qe = batches["random"]
+        counts = _count(lib, h, qs[:1_000_000].contiguous(), qe[:1_000_000].contiguous(), sp)
+        want = cpu.count_batch(synth.to_numpy_u32(qs[:1_000_000]), synth.to_numpy_u32(qe[:1_000_000]), 8)
+        assert np.array_equal(counts.cpu().numpy().view(np.uint32).astype(np.uint64), want)
+    finally:
+        lib.lapper_free(h)

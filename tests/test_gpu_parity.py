@@ -409,3 +409,147 @@ def test_concurrent_const_calls_from_host_threads(oracle):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+# ------------------------------------------------------------------------------------------------ round 2
+def _dev_find(lib, h, qs, qe, off, sp):
+    """two-phase device find into the caller's offsets tensor (any alignment); returns (offsets, indices) on the host"""
+    import ctypes as C
+
+    import torch
+
+    from rust_lapper_b200 import _ffi
+
+    nq = qs.numel()
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    total = C.c_uint64(0)
+    _ffi.check(lib.lapper_find_batch_offsets_u32_dev(h, vp(qs), vp(qe), nq, vp(off), C.byref(total), sp))
+    idx = torch.empty(max(int(total.value), 1), dtype=torch.int32, device=qs.device)
+    _ffi.check(lib.lapper_find_batch_fill_total_u32_dev(h, vp(qs), vp(qe), nq, vp(off), int(total.value), vp(idx), sp))
+    torch.cuda.synchronize()
+    return off.cpu().numpy().view(np.uint64), idx[: int(total.value)].cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize("skew", [0, 1, 3])
+def test_find_offsets_buffer_at_any_alignment(oracle, skew):
+    """lapper_find_batch_offsets_u32_dev used to store offsets through 16-byte vectors whatever the
+    caller's pointer; an 8-byte-aligned d_offsets (a tensor slice at an odd index) and query arrays at odd word
+    offsets must work and give the same CSR."""
+    import ctypes as C
+
+    import torch
+
+    from rust_lapper_b200 import _ffi, synth
+
+    dev = torch.device("cuda", 0)
+    lib = _ffi.lib()
+    s, e = synth.intervals_gene_exon(44, 300_000, 60_000_000)
+    qs, qe = synth.queries_sorted_fixed_len(45, 50_000, 60_000_000, 150)
+    cpu = oracle.OracleLapper(starts=s, stops=e)
+    want_o, want_i = cpu.find_batch(qs, qe, 4)
+    h = C.c_void_p(0)
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ts = torch.from_numpy(s.view(np.int32)).to(dev)
+    te = torch.from_numpy(e.view(np.int32)).to(dev)
+    _ffi.check(lib.lapper_build_u32_dev(C.c_void_p(ts.data_ptr()), C.c_void_p(te.data_ptr()), len(s), 0, 0, sp, C.byref(h)))
+    try:
+        nq = len(qs)
+        big_s = torch.zeros(nq + 8, dtype=torch.int32, device=dev)
+        big_e = torch.zeros(nq + 8, dtype=torch.int32, device=dev)
+        big_s[skew:skew + nq] = torch.from_numpy(qs.view(np.int32)).to(dev)
+        big_e[skew:skew + nq] = torch.from_numpy(qe.view(np.int32)).to(dev)
+        off_buf = torch.empty(nq + 1 + 4, dtype=torch.int64, device=dev)
+        off = off_buf[(1 if skew else 0):][: nq + 1]  # 8-byte aligned only when skewed
+        got_o, got_i = _dev_find(lib, h, big_s[skew:skew + nq], big_e[skew:skew + nq], off, sp)
+        assert np.array_equal(got_o, want_o) and np.array_equal(got_i, want_i)
+    finally:
+        lib.lapper_free(h)
+
+
+@pytest.mark.parametrize("capacity_mode", ["exact", "size_query", "too_small"])
+def test_find_batch_host_pipeline(oracle, capacity_mode):
+    """lapper_find_batch_u32_host: host queries -> host CSR through the chunk pipeline (several chunks of 4 M queries,
+    ragged last chunk), pinned and pageable buffers, the size-query and capacity-error protocols."""
+    import ctypes as C
+
+    from rust_lapper_b200 import Lapper, _ffi, synth
+
+    lib = _ffi.lib()
+    s, e = synth.intervals_gene_exon(44, 400_000, 300_000_000)
+    nq = 9_000_017  # three chunks
+    qs, qe = synth.queries_sorted_fixed_len(45, nq, 300_000_000, 150)
+    qs[5::100_003] = 0xFFFFFFFF  # a few inverted queries at u32::MAX
+    lap = Lapper(starts=s, stops=e)
+    cpu = oracle.OracleLapper(starts=s, stops=e)
+    want_o, want_i = cpu.find_batch(qs, qe, 8)
+    total = C.c_uint64(0)
+    off = np.empty(nq + 1, np.uint64)
+    p = lambda a: C.c_void_p(a.ctypes.data)  # noqa: E731
+    if capacity_mode == "size_query":
+        _ffi.check(lib.lapper_find_batch_u32_host(lap.handle, p(qs), p(qe), nq, p(off), None, 0, C.byref(total)))
+        assert int(total.value) == int(want_o[-1]) and np.array_equal(off, want_o)
+    elif capacity_mode == "too_small":
+        idx = np.zeros(int(want_o[-1]) // 2, np.uint32)
+        rc = lib.lapper_find_batch_u32_host(lap.handle, p(qs), p(qe), nq, p(off), p(idx), idx.size, C.byref(total))
+        assert rc == _ffi.ERR_CAPACITY and int(total.value) == int(want_o[-1]) and np.array_equal(off, want_o)
+    else:
+        idx = np.empty(int(want_o[-1]), np.uint32)
+        _ffi.check(lib.lapper_find_batch_u32_host(lap.handle, p(qs), p(qe), nq, p(off), p(idx), idx.size, C.byref(total)))
+        assert int(total.value) == int(want_o[-1])
+        assert np.array_equal(off, want_o) and np.array_equal(idx, want_i)
+        # empty batch
+        off0 = np.full(1, 7, np.uint64)
+        _ffi.check(lib.lapper_find_batch_u32_host(lap.handle, None, None, 0, p(off0), None, 0, C.byref(total)))
+        assert int(off0[0]) == 0 and int(total.value) == 0
+
+
+def test_query_tables_are_rebuilt_lazily_after_mutation(oracle):
+    """merge_overlaps and insert replace the sorted arrays at once and leave the query tables (sectors, packed table,
+    length classes) to the first count / find; the accessors and every query path must see the new set."""
+    from rust_lapper_b200 import Lapper, _ffi
+
+    rng = np.random.default_rng(11)
+    s = rng.integers(0, 5_000_000, 200_000).astype(np.uint32)
+    e = (s + rng.integers(1, 30, 200_000)).astype(np.uint32)
+    qs = rng.integers(0, 5_000_000, 50_000).astype(np.uint32)
+    qe = (qs + rng.integers(0, 200, 50_000)).astype(np.uint32)
+    lap = Lapper(starts=s, stops=e, flags=_ffi.BUILD_FORCE_BUCKETS | _ffi.BUILD_FORCE_DENSE)
+    cpu = oracle.OracleLapper(starts=s, stops=e)
+    for step in range(3):
+        assert np.array_equal(lap.count_batch(qs, qe), cpu.count_batch(qs, qe)), step
+        go, gi = lap.find_batch(qs, qe)
+        co, ci = cpu.find_batch(qs, qe)
+        assert np.array_equal(go, co) and np.array_equal(gi, ci), step
+        assert lap.bucket_shift is not None and lap.packed_table is not None
+        assert lap.max_len == cpu.max_len and len(lap) == len(cpu)
+        if step == 0:
+            lap.merge_overlaps()
+            cpu.merge_overlaps()
+            assert lap.max_len == cpu.max_len and len(lap) == len(cpu) and lap.cov() == cpu.cov()
+        elif step == 1:
+            for a, b in ((17, 90_000), (4_999_999, 5_000_400), (0, 1)):
+                lap.insert(a, b)
+                cpu.insert(a, b)
+            assert lap.max_len == cpu.max_len
+
+
+def test_replica_of_merged_set_issues_fresh_input_positions():
+    """after merge_overlaps perm keeps original input positions (which may exceed the run count); a replica or
+    an imported handle must not hand one of them to the next inserted interval."""
+    from rust_lapper_b200 import Lapper, LapperGroup
+
+    ivs = [(10 * i, 10 * i + 15, i) for i in range(50)] + [(1000, 1010, 50), (2000, 2010, 51)]
+    lap = Lapper(ivs)
+    lap.merge_overlaps()
+    _, _, perm = lap.intervals_soa()
+    assert len(lap) == 3 and perm.max() == 51
+    grp = LapperGroup(lap, [0])
+    import ctypes as C
+
+    from rust_lapper_b200 import _ffi
+
+    rep = _ffi.lib().lapper_group_replica(grp._h, 0)
+    pos = C.c_uint64(0)
+    _ffi.check(_ffi.lib().lapper_insert_u32(C.c_void_p(rep), 3000, 3005, C.byref(pos)))
+    assert int(pos.value) == 52
+    grp.close()
