@@ -212,9 +212,18 @@ uint64_t find_host(const lapper_t *l, const uint32_t *qs, const uint32_t *qe, ui
                    uint32_t *indices_out, uint64_t capacity, uint64_t offsets_base) {
     check_handle(l);
     DeviceGuard dg(l->device);
-    constexpr int kSlots = 3;
-    constexpr uint64_t kChunk = 1ull << 22;  // 4 M queries: 32 MB in, ~ 32 MB + 4 B/hit out per chunk
-    StreamOwner st[kSlots];
+    static constexpr int kMaxSlots = 4;
+    // 4 M queries per chunk: 32 MB in, ~ 32 MB + 4 B/hit out (experiments: LAPPER_FIND_CHUNK_LOG2, LAPPER_FIND_SLOTS)
+    static const uint64_t kChunk = [] {
+        const char *e = std::getenv("LAPPER_FIND_CHUNK_LOG2");
+        const int k = e ? atoi(e) : 22;
+        return 1ull << std::min(std::max(k, 10), 30);
+    }();
+    static const int kSlots = [] {
+        const char *e = std::getenv("LAPPER_FIND_SLOTS");
+        return std::min(std::max(e ? atoi(e) : 3, 2), kMaxSlots);
+    }();
+    StreamOwner st[kMaxSlots];
     ensure_tables(l, st[0].s);
     if (nq == 0) {
         offsets_out[0] = offsets_base;
@@ -222,8 +231,8 @@ uint64_t find_host(const lapper_t *l, const uint32_t *qs, const uint32_t *qe, ui
     }
     const uint64_t chunk = std::min(nq, kChunk);
     const uint64_t nchunks = div_up(nq, chunk);
-    Scratch<uint32_t> d_qs[kSlots], d_qe[kSlots], d_idx[kSlots];
-    Scratch<uint64_t> d_off[kSlots], d_goff[kSlots];
+    Scratch<uint32_t> d_qs[kMaxSlots], d_qe[kMaxSlots], d_idx[kMaxSlots];
+    Scratch<uint64_t> d_off[kMaxSlots], d_goff[kMaxSlots];
     const int used = (int)std::min<uint64_t>(kSlots, nchunks);
     for (int s = 0; s < used; s++) {
         d_qs[s].alloc(chunk, st[s].s);
