@@ -64,6 +64,13 @@ uint64_t lapper_query_kernel_launches(void);
 /* builds with -DLAPPER_DEBUG_CHECKS carry bounds checks in the query kernels (compute-sanitizer is not available on
  * every GPU pool): the number of violated checks on the current device so far; -1 in normal builds */
 long long lapper_debug_violations(void);
+/* test hook: batches of at least this many queries are offered to the sorted-run kernel (count_sorted.cu), which the
+ * batch probe then selects on the device; default 4 Mi (below that the probe's 32 samples say little).  Returns the
+ * previous value.  The answers never depend on it. */
+uint64_t lapper_debug_set_sorted_min_queries(uint64_t min_queries);
+/* runs of 256 queries the sorted-run kernel has answered on the current device since the last reset: out2[0] by
+ * ranking the run against the sorted arrays, out2[1] query by query (runs that do not qualify); synchronises the device */
+int lapper_debug_sorted_run_stats(uint64_t *out2, int reset);
 
 /* ---- Lapper::new (src/lib.rs:196-236): stable sort by (start, stop), sorted starts, sorted stops,
  *      max_len.  Built on `device` by a radix sort + reductions.  n may be 0. */

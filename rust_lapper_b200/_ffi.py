@@ -57,6 +57,8 @@ SIGNATURES = {
     "lapper_device_count": (_int, [C.POINTER(_int)]),
     "lapper_query_kernel_launches": (_u64, []),
     "lapper_debug_violations": (C.c_longlong, []),
+    "lapper_debug_set_sorted_min_queries": (_u64, [_u64]),
+    "lapper_debug_sorted_run_stats": (_int, [_vp, _int]),
     "lapper_build_u32": (_int, [_vp, _vp, _u64, _int, _pvp]),
     "lapper_build_u32_ex": (_int, [_vp, _vp, _u64, _int, _u32, _pvp]),
     "lapper_build_u32_dev": (_int, [_vp, _vp, _u64, _int, _u32, _vp, _pvp]),

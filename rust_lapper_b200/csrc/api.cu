@@ -513,6 +513,17 @@ uint64_t lapper_query_kernel_launches(void) { return lap::g_query_launches.load(
  * (synchronises it); -1 in normal builds */
 long long lapper_debug_violations(void) { return lap::debug_violations(); }
 
+int lapper_debug_sorted_run_stats(uint64_t *out2, int reset) {
+    return guarded([&] {
+        LAPPER_REQUIRE(out2, "null pointer");
+        lap::sorted_run_stats(out2, reset != 0);
+    });
+}
+
+uint64_t lapper_debug_set_sorted_min_queries(uint64_t min_queries) {
+    return lap::g_sorted_min_queries.exchange(std::max<uint64_t>(min_queries, 32 * 1024), std::memory_order_relaxed);
+}
+
 int lapper_packed_table_info(const lapper_t *l, uint32_t *width_out, uint64_t *sectors_out, uint64_t *overflowed_out) {
     return guarded([&] {
         check_handle(l);

@@ -163,7 +163,10 @@ void launch_sort_u32(uint32_t *keys, uint32_t *tmp, uint64_t n, cudaStream_t str
 
 // query.cu ---------------------------------------------------------------------------------------
 extern std::atomic<uint64_t> g_query_launches;  // kernels launched by launch_count / launch_find_* in this process
-long long debug_violations();  // LAPPER_DEBUG_CHECKS builds: violated LAPPER_CHECKs so far; -1 otherwise
+extern std::atomic<uint64_t> g_sorted_min_queries;  // lapper_debug_set_sorted_min_queries()
+long long debug_violations();
+// count_sorted.cu: runs of 256 queries answered by ranking / per query on the current device since the last reset
+void sorted_run_stats(uint64_t out[2], bool reset);  // LAPPER_DEBUG_CHECKS builds: violated LAPPER_CHECKs so far; -1 otherwise
 void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, uint32_t *d_out32,
                   uint64_t *d_out64, cudaStream_t stream);
 // writes d_offsets[nq+1]; returns total hits (synchronises the stream)

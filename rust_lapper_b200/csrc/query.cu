@@ -13,18 +13,20 @@
 #include <cstdlib>
 #include <type_traits>
 
-#include "index.cuh"
+#include "query_views.cuh"
 
 namespace lap {
 
 // kernels launched by the query path in this process (lapper_query_kernel_launches(): what bench.py reports as
 // `gpu_launches`, counted rather than derived)
 std::atomic<uint64_t> g_query_launches{0};
+std::atomic<uint64_t> g_sorted_min_queries{4096ull * 1024};
 #ifdef LAPPER_DEBUG_CHECKS
 __device__ unsigned long long g_debug_violations = 0;
 #endif
 
 namespace {
+
 
 #ifndef LAPPER_MIN_CTAS
 #define LAPPER_MIN_CTAS 3
@@ -35,222 +37,6 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kQPT = LAPPER_QPT;                   // queries per thread: eight independent sector gathers in flight
 constexpr int kTileQ = kThreads * kQPT;   // queries per CTA tile
-
-struct BucketView {
-    const Sector *buckets;
-    const uint32_t *S;
-    const uint32_t *E;
-    uint32_t n;
-    const Sector *pool;
-    uint32_t shift;
-    uint32_t margin;
-    uint32_t nb;  // index of the sentinel bucket
-    // packed table in front of the sector table (index.cuh); dense == nullptr when there is none
-    const Sector *dense;
-    PackedParams pk;
-    uint32_t local_span;  // a warp whose threads each see their queries within this span stays on the sector-table path
-};
-
-// bytes 1 and 3 of t0 and of t1 (the high byte of every 16-bit lane), each replaced by its sign bit
-// replicated: 0xFF where the lane's guard bit survived the subtraction, 0x00 where it did not
-__device__ __forceinline__ uint32_t guard_bytes(uint32_t t0, uint32_t t1) {
-    uint32_t r;
-    asm("prmt.b32 %0, %1, %2, 0xFDB9;" : "=r"(r) : "r"(t0), "r"(t1));
-    return r;
-}
-
-// acc - #{16-bit lanes of w[2..7] whose value is >= x}; x2 = x replicated in both halves.
-// One packed subtract per word, one PRMT per two words, one IDP.4A (bytes are 0 or -1) per PRMT.
-__device__ __forceinline__ int sub_lanes_ge(const Sector &s, uint32_t x2, int acc) {
-    acc = __dp4a((int)guard_bytes(s.w[2] - x2, s.w[3] - x2), 0x01010101, acc);
-    acc = __dp4a((int)guard_bytes(s.w[4] - x2, s.w[5] - x2), 0x01010101, acc);
-    acc = __dp4a((int)guard_bytes(s.w[6] - x2, s.w[7] - x2), 0x01010101, acc);
-    return acc;
-}
-
-__device__ __forceinline__ bool sector_overflow(const Sector &s) { return s.w[7] == 0xFFFFFFFFu; }
-
-// lower_bound / upper_bound inside one overflowing bucket's slice of a sorted array: bisect down to a
-// short range, then count it with independent (not dependent) loads -- one memory round trip
-__device__ __forceinline__ uint32_t count_lt_range(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi,
-                                                   uint32_t key) {
-    while (hi - lo > 32) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (__ldg(a + mid) < key)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    uint32_t c = lo;
-#pragma unroll 8
-    for (uint32_t i = lo; i < hi; i++) c += (__ldg(a + i) < key);
-    return c;
-}
-__device__ __forceinline__ uint32_t count_le_range(const uint32_t *__restrict__ a, uint32_t lo, uint32_t hi,
-                                                   uint32_t key) {
-    while (hi - lo > 32) {
-        const uint32_t mid = lo + ((hi - lo) >> 1);
-        if (__ldg(a + mid) <= key)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    uint32_t c = lo;
-#pragma unroll 8
-    for (uint32_t i = lo; i < hi; i++) c += (__ldg(a + i) <= key);
-    return c;
-}
-
-// lane counts of a (non-overflowing) sector of width w
-__device__ __forceinline__ uint32_t sector_lb(const Sector &s, uint32_t b_rel) {
-    return s.w[0] + kBucketLanes + (uint32_t)sub_lanes_ge(s, b_rel * 0x10001u, 0);
-}
-__device__ __forceinline__ uint32_t sector_ub(const Sector &s, uint32_t w, uint32_t a_rel_plus_margin) {
-    return s.w[1] + (uint32_t)sub_lanes_ge(s, (w + a_rel_plus_margin + 1u) * 0x10001u, 0);
-}
-
-// lower_bound(starts, key) from the sector of key's own bucket, following the refinement if any
-__device__ __forceinline__ uint32_t lb_from_sector(const BucketView &v, const Sector &s, uint32_t key) {
-    const uint32_t low = key & ((1u << v.shift) - 1u);
-    if (__builtin_expect(!sector_overflow(s), 1)) return sector_lb(s, low);
-    if (s.w[2] != kNoChild) {
-        const uint32_t cshift = v.shift - s.w[3];
-        const Sector c = ld_sector_cached(v.pool + s.w[2] + (low >> cshift));
-        if (!sector_overflow(c)) return sector_lb(c, low & ((1u << cshift) - 1u));
-        return count_lt_range(v.S, c.w[0], c.w[4], key);
-    }
-    return count_lt_range(v.S, s.w[0], s.w[4], key);
-}
-
-// upper_bound(stops_sorted, key) from the sector of key's own bucket
-__device__ __forceinline__ uint32_t ub_from_sector(const BucketView &v, const Sector &s, uint32_t key) {
-    const uint32_t w = 1u << v.shift, low = key & (w - 1u);
-    if (__builtin_expect(!sector_overflow(s), 1)) return sector_ub(s, w, low + v.margin);
-    if (s.w[2] != kNoChild) {
-        const uint32_t cshift = v.shift - s.w[3];
-        const Sector c = ld_sector_cached(v.pool + s.w[2] + (low >> cshift));
-        if (!sector_overflow(c)) return sector_ub(c, 1u << cshift, low & ((1u << cshift) - 1u));
-        return count_le_range(v.E, c.w[5], c.w[1], key);
-    }
-    return count_le_range(v.E, s.w[5], s.w[1], key);
-}
-
-__device__ __forceinline__ uint32_t bucket_of(const BucketView &v, uint32_t x) { return min(x >> v.shift, v.nb); }
-
-// Lapper::count for one query, any case: each side from its own bucket
-__device__ __forceinline__ void bits_count_slow(const BucketView &v, uint32_t a, uint32_t b, uint32_t &lb,
-                                                uint32_t &ub) {
-    const uint32_t bb = bucket_of(v, b), ba = bucket_of(v, a);
-    const Sector sb = ld_sector_cached(v.buckets + bb);
-    lb = lb_from_sector(v, sb, b);
-    if (ba == bb) {
-        ub = ub_from_sector(v, sb, a);
-    } else {
-        const Sector sa = ld_sector_cached(v.buckets + ba);
-        ub = ub_from_sector(v, sa, a);
-    }
-    // src/lib.rs:614: `start + one` wraps to 0 when start == u32::MAX, so `first` is 0 there.
-    if (a == 0xFFFFFFFFu) ub = 0;
-}
-
-template <bool kOut64>
-__device__ __forceinline__ void store_count(uint32_t *o32, uint64_t *o64, uint64_t j, uint32_t lb, uint32_t ub) {
-    // len - first - (len - last) in wrapping usize == last - first (mod 2^64)
-    if (kOut64)
-        st_stream_u64(o64 + j, (uint64_t)lb - (uint64_t)ub);
-    else
-        st_stream_u32(o32 + j, lb - ub);
-}
-
-// ------------------------------------------------------------------------------------- find
-// find(a, b) = ascending i with start_i < b and stop_i > a (src/lib.rs:704-717; the start offset
-// :632-635 and the early break :712-713 only prune).  The reference scans one window
-// [lower_bound(a - max_len), lower_bound(b)) of the whole sorted vector, which a single long interval
-// stretches to everything before b (src/lib.rs:36-47).  Here the sorted vector is also kept split by
-// length class (index.cuh): per class the window is [lower_bound_c(a - maxlen_c), lower_bound_c(b)),
-// the class hit streams are ascending in global position, and a per-query k-way merge emits them in
-// exactly the reference's order.
-struct FindView {
-    BucketView bv;
-    bool has_buckets;
-    const uint32_t *S;
-    const uint32_t *Eiv;  // stops paired with S
-    const uint32_t *E;    // sorted stops
-    uint32_t n;
-    uint32_t max_len;
-    bool has_inverted;
-    // length classes
-    uint32_t ncls;
-    uint32_t cls_off[4], cls_n[4], cls_maxlen[4];
-    const uint32_t *cs, *ce, *cg;
-    const uint4 *dir;
-    uint32_t cls_shift, cls_nb;
-    // heavy queries
-    const uint32_t *pmax, *blkmax32, *blkmax1024;
-};
-
-__device__ __forceinline__ uint32_t rank_lb_starts(const FindView &f, uint32_t key) {
-    if (f.has_buckets) {
-        const uint32_t bk = bucket_of(f.bv, key);
-        const Sector s = ld_sector_cached(f.bv.buckets + bk);
-        return lb_from_sector(f.bv, s, key);
-    }
-    return lower_bound_u32(f.S, 0, f.n, key);
-}
-__device__ __forceinline__ uint32_t rank_ub_stops(const FindView &f, uint32_t key) {
-    if (f.has_buckets) {
-        const uint32_t bk = bucket_of(f.bv, key);
-        const Sector s = ld_sector_cached(f.bv.buckets + bk);
-        return ub_from_sector(f.bv, s, key);
-    }
-    return upper_bound_u32(f.E, 0, f.n, key);
-}
-
-__device__ __forceinline__ uint32_t dir_get(const uint4 &d, int c) { return c == 0 ? d.x : c == 1 ? d.y : c == 2 ? d.z : d.w; }
-
-// lower_bound of `key` among the starts of class c: directory rank, then a short forward walk
-__device__ __forceinline__ uint32_t class_lb(const FindView &f, int c, uint32_t key) {
-    const uint32_t B = min(key >> f.cls_shift, f.cls_nb);
-    const uint4 d0 = __ldg(f.dir + B);
-    uint32_t r = dir_get(d0, c);
-    if (B < f.cls_nb) {
-        const uint32_t hi = dir_get(__ldg(f.dir + B + 1), c);
-        const uint32_t *cs = f.cs + f.cls_off[c];
-        if (hi - r > 16) return lower_bound_u32(cs, r, hi, key);
-        while (r < hi && __ldg(cs + r) < key) r++;
-    }
-    return r;
-}
-
-// per-class scan windows of one query; returns the class-relative [lo, hi)
-__device__ __forceinline__ void class_window(const FindView &f, int c, uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi) {
-    hi = class_lb(f, c, b);
-    lo = class_lb(f, c, a >= f.cls_maxlen[c] ? a - f.cls_maxlen[c] : 0u);
-    if (lo > hi) lo = hi;
-}
-
-// number of positions find(a, b) yields, by the predicate (any input)
-__device__ __forceinline__ uint32_t find_count_scan(const FindView &f, uint32_t a, uint32_t b) {
-    uint32_t total = 0;
-    for (int c = 0; c < (int)f.ncls; c++) {
-        uint32_t lo, hi;
-        class_window(f, c, a, b, lo, hi);
-        const uint32_t *ce = f.ce + f.cls_off[c];
-        for (uint32_t i = lo; i < hi; i++) total += (__ldg(ce + i) > a);
-    }
-    return total;
-}
-
-__device__ __forceinline__ uint32_t find_count_one(const FindView &f, uint32_t a, uint32_t b) {
-    if (f.n == 0) return 0;
-    if (a < b && !f.has_inverted) {
-        // |find| == count when every interval has start <= stop and the query is non-empty
-        // (SURVEY Appendix A.4); a == u32::MAX cannot happen here because a < b.
-        return rank_lb_starts(f, b) - rank_ub_stops(f, a);
-    }
-    return find_count_scan(f, a, b);
-}
-
 
 // ---- count, bucket path, full tiles.  Persistent CTAs walk tiles of 2048 queries; each thread owns
 // eight consecutive queries: two 256-bit loads (starts, stops), eight independent sector gathers
@@ -315,23 +101,14 @@ __device__ __forceinline__ void load_queries(const uint32_t *__restrict__ qs, co
 // For large batches both are launched back to back and every CTA of both takes the same decision from the same 32
 // sampled query groups (`batch_looks_sorted`), so exactly one of them does the work and the other exits at once:
 // no host round trip, no extra pass over the queries.
-constexpr int kRunAlways = 0, kRunIfSorted = 1, kRunIfNotSorted = 2;
-__device__ __forceinline__ bool batch_looks_sorted(const BucketView &v, const uint32_t *__restrict__ qe, uint64_t ntiles) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint64_t j = (ntiles * lane / 32) * kTileQ + 4 * lane;  // one group of four consecutive queries per lane
-    const uint32_t d = __ldg(qe + j + 3) - __ldg(qe + j);
-    const bool local = d + v.local_span < 2u * v.local_span;
-    return __popc(__ballot_sync(0xFFFFFFFFu, local)) >= 28;
-}
-
 template <bool kOut64, bool kFind, int kCtas>
 __global__ void __launch_bounds__(kThreads, kCtas) count_bucket_kernel(BucketView v, const FindView f,
                                                                    const uint32_t *__restrict__ qs,
                                                                    const uint32_t *__restrict__ qe, uint64_t ntiles,
                                                                    uint32_t *__restrict__ o32,
                                                                    uint64_t *__restrict__ o64,
-                                                                   uint64_t *__restrict__ tile_sums, int run_mode) {
-    if (run_mode != kRunAlways && batch_looks_sorted(v, qe, ntiles) != (run_mode == kRunIfSorted)) return;
+                                                                   uint64_t *__restrict__ tile_sums, const BatchProbe probe) {
+    if (!batch_accepted(probe)) return;
     __shared__ uint32_t wqueue[kWarps][kWQCap * 3];  // (relative query index, start, stop) per entry
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t *const wq = wqueue[warp];
@@ -1742,62 +1519,6 @@ __global__ void __launch_bounds__(kThreads) find_heavy_kernel(FindView f, const 
     }
 }
 
-BucketView make_bucket_view(const DeviceIndex &ix) {
-    BucketView v;
-    v.buckets = ix.buckets;
-    v.pool = ix.pool;
-    v.margin = ix.margin;
-    v.S = ix.starts;
-    v.E = ix.stops_sorted;
-    v.n = (uint32_t)ix.n;
-    v.shift = ix.shift;
-    v.nb = (uint32_t)ix.nbuckets;
-    v.dense = ix.dense;
-    v.pk.w = ix.dense_w;
-    v.pk.m = ix.dense_m;
-    v.pk.magic = ix.dense_magic;
-    v.pk.nb = (uint32_t)ix.dense_nb;
-    v.local_span = ix.shift <= kMaxBucketShift ? 4u << ix.shift : 0u;  // (no sector table: no packed table either)
-    // dense sets: the packed table's margin covers longer queries than the sector table's and fewer of its sectors
-    // overflow, so it serves start-sorted batches better too -- every warp takes the packed path
-    if (ix.dense && ix.dense_m > ix.margin) v.local_span = 0;
-    return v;
-}
-
-FindView make_find_view(const DeviceIndex &ix) {
-    FindView f;
-    f.has_buckets = ix.buckets != nullptr;
-    f.bv = make_bucket_view(ix);
-    f.S = ix.starts;
-    f.Eiv = ix.stops_by_iv;
-    f.E = ix.stops_sorted;
-    f.n = (uint32_t)ix.n;
-    f.max_len = ix.max_len;
-    f.has_inverted = ix.has_inverted;
-    f.ncls = ix.ncls;
-    for (int c = 0; c < 4; c++) {
-        f.cls_off[c] = ix.cls_off[c];
-        f.cls_n[c] = ix.cls_n[c];
-        f.cls_maxlen[c] = ix.cls_maxlen[c];
-    }
-    f.cs = ix.cls_starts;
-    f.ce = ix.cls_stops;
-    f.cg = ix.cls_gidx;
-    f.dir = ix.cls_dir;
-    f.cls_shift = ix.cls_shift;
-    f.cls_nb = (uint32_t)ix.cls_nb;
-    f.pmax = ix.prefix_max;
-    f.blkmax32 = ix.blkmax32;
-    f.blkmax1024 = ix.blkmax1024;
-    return f;
-}
-
-uint32_t capped_grid(uint64_t work_items, int per_block, int waves) {
-    uint64_t g = div_up(work_items ? work_items : 1, per_block);
-    const uint64_t cap = (uint64_t)sm_count() * waves;
-    return (uint32_t)(g < cap ? g : cap);
-}
-
 }  // namespace
 
 namespace {
@@ -1811,37 +1532,71 @@ static bool count_dual_disabled() {
     return off;
 }
 
+// How a batch over the bucket table is split between the kernels (decided once per call, shared by every launch of it).
+struct BucketPlan {
+    uint64_t ntiles;   // full tiles of kTileQ queries that the tiled kernels take (0: pointers not 32-byte aligned)
+    bool dual;         // both register builds of count_bucket_kernel, selected on the device
+    bool sorted;       // count_sorted_kernel on offer for the tiled part
+    BatchProbe probe;  // .accept is filled in per launch
+};
+static_assert(kProbeTile == (uint32_t)kTileQ, "the batch probe samples the count kernel's tiles");
+
+BucketPlan plan_buckets(const BucketView &v, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, const void *out,
+                        bool sorted_possible) {
+    BucketPlan p;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_qs) | reinterpret_cast<uintptr_t>(d_qe) |
+                           reinterpret_cast<uintptr_t>(out)) & 31u) == 0;
+    p.ntiles = aligned ? nq / kTileQ : 0;
+    const bool big = p.ntiles >= 4096;  // enough queries for the probe's 32 samples to mean something
+    p.dual = big && v.dense != nullptr && v.local_span != 0 && !count_dual_disabled();
+    // (>= 32 tiles: the probe takes one sample per 32nd of the batch)
+    // (fewer than 2^31 intervals: the sorted-run kernel sign-extends 32-bit rank differences)
+    p.sorted = p.ntiles * kTileQ >= g_sorted_min_queries.load(std::memory_order_relaxed) && sorted_possible && v.n < (1u << 31) &&
+               !count_sorted_disabled();
+    p.probe.qs = d_qs, p.probe.qe = d_qe, p.probe.ntiles = p.ntiles;
+    p.probe.n = v.n, p.probe.shift = v.shift, p.probe.nb = v.nb, p.probe.local_span = v.local_span;
+    p.probe.sorted_ok = p.sorted ? 1u : 0u;
+    p.probe.accept = kAcceptAll;
+    return p;
+}
+BatchProbe probe_for(const BucketPlan &p, uint32_t accept) {
+    BatchProbe b = p.probe;
+    b.accept = (p.dual || p.sorted) ? accept : kAcceptAll;
+    return b;
+}
+
 // count over the bucket table.  tile_sums != nullptr selects find mode (u32 counts + per-tile sums).
-void launch_count_buckets(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
+void launch_count_buckets(const DeviceIndex &ix, const BucketPlan &plan, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
                           uint32_t *d_out32, uint64_t *d_out64, uint64_t *tile_sums, cudaStream_t stream) {
     const BucketView v = make_bucket_view(ix);
     const FindView f = make_find_view(ix);
     const bool out64 = d_out64 != nullptr;
-    const void *out = out64 ? (const void *)d_out64 : (const void *)d_out32;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(d_qs) | reinterpret_cast<uintptr_t>(d_qe) |
-                           reinterpret_cast<uintptr_t>(out)) & 31u) == 0;
-    const uint64_t ntiles = aligned ? nq / kTileQ : 0;
+    const uint64_t ntiles = plan.ntiles;
+    constexpr uint32_t kRandom = 1u << kBatchRandom, kLocal = 1u << kBatchLocal, kSorted = 1u << kBatchSortedDense;
     if (ntiles) {
-        // persistent grids: SMs (148 on B200) x resident CTAs of 256 threads.  Large batches over an index that has both paths:
-        // the 4-CTA build for start-sorted batches and the 3-CTA build for the rest, selected on the device.
-        const bool dual = ntiles >= 4096 && v.dense != nullptr && v.local_span != 0 && !count_dual_disabled();
-        const auto launch = [&](auto ctas, int mode) {
+        // persistent grids: SMs (148 on B200) x resident CTAs of 256 threads.  Large batches: the 4-CTA build for batches
+        // with local queries, the 3-CTA build for order-less ones, count_sorted_kernel for sorted dense ones -- all
+        // launched, the batch probe lets exactly one of them work.
+        const auto launch = [&](auto ctas, uint32_t accept) {
             constexpr int kCtas = decltype(ctas)::value;
+            const BatchProbe pb = probe_for(plan, accept);
             const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)sm_count() * kCtas);
             if (tile_sums)
-                g_query_launches++, count_bucket_kernel<false, true, kCtas><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, tile_sums, mode);
+                g_query_launches++, count_bucket_kernel<false, true, kCtas><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, tile_sums, pb);
             else if (out64)
-                g_query_launches++, count_bucket_kernel<true, false, kCtas><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, nullptr, d_out64, nullptr, mode);
+                g_query_launches++, count_bucket_kernel<true, false, kCtas><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, nullptr, d_out64, nullptr, pb);
             else
-                g_query_launches++, count_bucket_kernel<false, false, kCtas><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, nullptr, mode);
+                g_query_launches++, count_bucket_kernel<false, false, kCtas><<<grid, kThreads, 0, stream>>>(v, f, d_qs, d_qe, ntiles, d_out32, nullptr, nullptr, pb);
             LAPPER_CUDA_CHECK(cudaGetLastError());
         };
-        if (dual) {
-            launch(std::integral_constant<int, 4>{}, kRunIfSorted);
-            launch(std::integral_constant<int, LAPPER_MIN_CTAS>{}, kRunIfNotSorted);
+        if (plan.dual) {
+            launch(std::integral_constant<int, 4>{}, kLocal);
+            launch(std::integral_constant<int, LAPPER_MIN_CTAS>{}, kRandom);
         } else {
-            launch(std::integral_constant<int, LAPPER_MIN_CTAS>{}, kRunAlways);
+            launch(std::integral_constant<int, LAPPER_MIN_CTAS>{}, kRandom | kLocal);
         }
+        if (plan.sorted)
+            launch_count_sorted(ix, d_qs, d_qe, ntiles * (kTileQ / kProbeRun), d_out32, d_out64, tile_sums, probe_for(plan, kSorted), stream);
     }
     const uint64_t done = ntiles * kTileQ, rest = nq - done;
     if (rest) {
@@ -1872,7 +1627,9 @@ void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d
     }
     const bool out64 = d_out64 != nullptr;
     if (ix.buckets) {
-        launch_count_buckets(ix, d_qs, d_qe, nq, d_out32, d_out64, nullptr, stream);
+        const void *out = out64 ? (const void *)d_out64 : (const void *)d_out32;
+        const BucketPlan plan = plan_buckets(make_bucket_view(ix), d_qs, d_qe, nq, out, true);
+        launch_count_buckets(ix, plan, d_qs, d_qe, nq, d_out32, d_out64, nullptr, stream);
     } else {
         PlainView v;
         v.S = ix.starts;
@@ -1933,8 +1690,9 @@ uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const 
         // every interval has start <= stop: the BITS count IS the number of hits of a non-empty query, so
         // the count kernel runs in find mode (it also accumulates the tile sums and recounts start >= stop
         // queries by the predicate)
+        const BucketPlan plan = plan_buckets(f.bv, d_qs, d_qe, nq, counts.p, true);
         LAPPER_CUDA_CHECK(cudaMemsetAsync(tile_sums.p, 0, ntiles * sizeof(uint64_t), stream));
-        launch_count_buckets(ix, d_qs, d_qe, nq, counts.p, nullptr, tile_sums.p, stream);
+        launch_count_buckets(ix, plan, d_qs, d_qe, nq, counts.p, nullptr, tile_sums.p, stream);
     } else {
         g_query_launches++, find_count_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, counts.p, tile_sums.p);
     }

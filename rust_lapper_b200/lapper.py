@@ -116,6 +116,11 @@ class Lapper:
         return bool(self._lib.lapper_overlaps_merged(self._h))
 
     @property
+    def has_inverted(self) -> bool:
+        """some interval has stop < start (count is defined for such sets, src/lib.rs:610-618; cov / union are not)"""
+        return bool(self._lib.lapper_has_inverted(self._h))
+
+    @property
     def bucket_shift(self) -> Optional[int]:
         k = int(self._lib.lapper_bucket_shift(self._h))
         return None if k == 0xFFFFFFFF else k

@@ -28,8 +28,14 @@ print(f"flags {flags}: sector-table shift {lib.lapper_bucket_shift(h)}, packed t
       f"{ns.value} sectors ({ns.value * 32 / 1e6:.1f} MB), {no.value} overflowed ({100.0 * no.value / max(ns.value, 1):.2f} %)")
 out = torch.empty(nq, dtype=torch.int32, device=dev)
 qlen = int(os.environ.get("QLEN", 150))
-for name, (qs, qe) in (("random", synth.queries_fixed_len(43, nq, synth.GRCH38, qlen, device=dev)),
-                       ("sorted", synth.queries_sorted_fixed_len(45, nq, synth.GRCH38, qlen, device=dev))):
+only = os.environ.get("ONLY", "")
+cases = []
+if only in ("", "random"):
+    cases.append(("random", synth.queries_fixed_len(43, nq, synth.GRCH38, qlen, device=dev)))
+if only in ("", "sorted"):
+    cases.append(("sorted", synth.queries_sorted_fixed_len(45, nq, synth.GRCH38, qlen, device=dev)))
+stats = (C.c_uint64 * 2)()
+for name, (qs, qe) in cases:
     for _ in range(int(os.environ.get("WARM", 2))):
         _ffi.check(lib.lapper_count_batch_u32_dev(h, C.c_void_p(qs.data_ptr()), C.c_void_p(qe.data_ptr()), nq,
                                                   C.c_void_p(out.data_ptr()), sp))
@@ -41,5 +47,7 @@ for name, (qs, qe) in (("random", synth.queries_fixed_len(43, nq, synth.GRCH38, 
                                                   C.c_void_p(out.data_ptr()), sp))
     b.record()
     torch.cuda.synchronize()
-    print(f"{name}: {a.elapsed_time(b) / reps:.3f} ms per launch, checksum {int(out.to(torch.int64).sum())}")
+    lib.lapper_debug_sorted_run_stats(stats, 1)
+    print(f"{name}: {a.elapsed_time(b) / reps:.3f} ms per launch, checksum {int(out.to(torch.int64).sum())}; "
+          f"sorted-run kernel: {stats[0]} runs ranked, {stats[1]} per query")
 lib.lapper_free(h)

@@ -60,7 +60,9 @@ for _ in range(reps):
 b.record()
 torch.cuda.synchronize()
 ms_fill = a.elapsed_time(b) / reps
-print(f"  offsets phase {ms_off:.3f} ms, fill phase {ms_fill:.3f} ms")
+stats = (C.c_uint64 * 2)()
+lib.lapper_debug_sorted_run_stats(stats, 1)
+print(f"  offsets phase {ms_off:.3f} ms, fill phase {ms_fill:.3f} ms; sorted-run kernel so far: {stats[0]} runs ranked, {stats[1]} per query")
 print(f"find {order}: {ms:.3f} ms per pass, {int(total.value)} hits ({int(total.value) / nq:.2f}/query), "
       f"{nq / ms / 1e6:.2f} Gq/s, {int(total.value) / ms / 1e6:.1f} Ghits/s, checksum {int(idx[: int(total.value)].to(torch.int64).sum())}")
 if os.environ.get("EMIT_STATS"):
