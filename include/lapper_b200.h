@@ -150,6 +150,19 @@ int lapper_find_batch_u32_host(const lapper_t *l, const uint32_t *q_start, const
                                uint64_t *offsets_out, uint32_t *indices_out, uint64_t indices_capacity,
                                uint64_t *total_out);
 
+/* ONE call, caller-allocated device buffers of known size (a steady-state pipeline re-uses them): count pass, scan and
+ * emit are enqueued back to back -- the emit kernel derives the offsets from the counts itself, so there is no separate
+ * offsets pass and no host round trip between the phases; `stream` is synchronised once, at the end, to return the total.
+ * d_offsets[nq + 1] is always written in full and *total_out = d_offsets[nq]:
+ *   - total <= indices_capacity: d_indices[0 .. total) written, LAPPER_OK;
+ *   - otherwise LAPPER_ERR_CAPACITY and d_indices is untouched (call again with a larger buffer, or pass the offsets
+ *     to lapper_find_batch_fill_total_u32_dev).
+ * d_indices == NULL (indices_capacity 0) is the size query: offsets and total only, LAPPER_OK.  Same results as the
+ * two-phase calls below. */
+int lapper_find_batch_u32_dev(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop, uint64_t nq,
+                              uint64_t *d_offsets, uint32_t *d_indices, uint64_t indices_capacity, uint64_t *total_out,
+                              void *stream);
+
 /* two-phase, caller-allocated device buffers: phase 1 writes d_offsets[nq+1] and returns the total
  * (synchronises `stream`); phase 2 fills d_indices[total].  No alignment is required of any buffer (16-byte aligned
  * d_offsets and 32-byte aligned query arrays -- what cudaMalloc and every tensor allocator give -- take the vectorised

@@ -86,6 +86,7 @@ SIGNATURES = {
     "lapper_result_copy": (_int, [_vp, _vp, _vp]),
     "lapper_result_dev": (_int, [_vp, _pvp, _pvp]),
     "lapper_result_free": (None, [_vp]),
+    "lapper_find_batch_u32_dev": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64), _vp]),
     "lapper_find_batch_offsets_u32_dev": (_int, [_vp, _vp, _vp, _u64, _vp, C.POINTER(_u64), _vp]),
     "lapper_find_batch_fill_u32_dev": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _vp]),
     "lapper_find_batch_fill_total_u32_dev": (_int, [_vp, _vp, _vp, _u64, _vp, _u64, _vp, _vp]),

@@ -191,9 +191,30 @@ lapper_result_t *find_on_device(const lapper_t *l, const uint32_t *d_qs, const u
     try {
         uint64_t bytes = 0;
         r->d_offsets = pool_alloc<uint64_t>(nq + 1, bytes, stream);
-        r->total = launch_find_offsets(l->ix, d_qs, d_qe, nq, r->d_offsets, stream);
-        r->d_indices = pool_alloc<uint32_t>(r->total, bytes, stream);
-        launch_find_fill(l->ix, d_qs, d_qe, nq, r->d_offsets, r->d_indices, stream, r->total);
+        // Both phases in one enqueue when the size of the answer can be guessed: from the handle's previous batch
+        // (+ 1/8), or 16 positions per query for a first batch that is small (<= 64 Mi positions).  A wrong guess costs
+        // nothing but the buffer: the offsets are complete, and the emit runs again into a buffer of the right size.
+        const uint64_t ratio = l->find_hits_per_query_x256.load(std::memory_order_relaxed);
+        uint64_t guess = 0;
+        if (ratio)
+            guess = (uint64_t)(((unsigned __int128)nq * ratio) >> 8) / 8 * 9 + 4096;
+        else if (nq <= (64ull << 20) / 16)
+            guess = nq * 16;
+        if (guess && nq) {
+            r->d_indices = pool_alloc<uint32_t>(guess, bytes, stream);
+            r->total = launch_find(l->ix, d_qs, d_qe, nq, r->d_offsets, r->d_indices, guess, stream);
+            if (r->total > guess) {
+                pool_free(r->d_indices, stream);
+                r->d_indices = nullptr;
+                r->d_indices = pool_alloc<uint32_t>(r->total, bytes, stream);
+                launch_find_fill(l->ix, d_qs, d_qe, nq, r->d_offsets, r->d_indices, stream, r->total);
+            }
+        } else {
+            r->total = launch_find_offsets(l->ix, d_qs, d_qe, nq, r->d_offsets, stream);
+            r->d_indices = pool_alloc<uint32_t>(r->total, bytes, stream);
+            launch_find_fill(l->ix, d_qs, d_qe, nq, r->d_offsets, r->d_indices, stream, r->total);
+        }
+        if (nq) l->find_hits_per_query_x256.store(std::max<uint64_t>(div_up(r->total * 256, nq), 1), std::memory_order_relaxed);
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
     } catch (...) {
         free_result_arrays(r.get(), stream);
@@ -699,6 +720,24 @@ int lapper_find_batch_offsets_u32_dev(const lapper_t *l, const uint32_t *d_q_sta
         ensure_tables(l, (cudaStream_t)stream);
         const uint64_t t = launch_find_offsets(l->ix, d_q_start, d_q_stop, nq, d_offsets, (cudaStream_t)stream);
         if (total_out) *total_out = t;
+    });
+}
+
+int lapper_find_batch_u32_dev(const lapper_t *l, const uint32_t *d_q_start, const uint32_t *d_q_stop, uint64_t nq,
+                              uint64_t *d_offsets, uint32_t *d_indices, uint64_t indices_capacity, uint64_t *total_out,
+                              void *stream) {
+    return guarded([&] {
+        check_handle(l);
+        LAPPER_REQUIRE(d_offsets && total_out && (nq == 0 || (d_q_start && d_q_stop)), "find_batch_dev: null pointer");
+        LAPPER_REQUIRE(d_indices || indices_capacity == 0, "find_batch_dev: null position buffer with a capacity");
+        DeviceGuard dg(l->device);
+        ensure_tables(l, (cudaStream_t)stream);
+        *total_out = 0;
+        const uint64_t total = launch_find(l->ix, d_q_start, d_q_stop, nq, d_offsets, d_indices, indices_capacity, (cudaStream_t)stream);
+        *total_out = total;
+        if (d_indices && total > indices_capacity)
+            throw Error(LAPPER_ERR_CAPACITY, "find_batch_dev: " + std::to_string(total) + " positions do not fit the buffer of " +
+                                                 std::to_string(indices_capacity) + " (offsets and *total_out are complete)");
     });
 }
 

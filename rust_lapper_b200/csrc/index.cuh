@@ -121,6 +121,9 @@ struct lapper {
     uint32_t cov = 0;
     uint32_t build_flags = 0;
     uint64_t next_input_id = 0;  // input position handed to the next inserted interval
+    // hits per query (x 256, rounded up) of the last find_batch on this handle; 0: none yet.  find_batch sizes its
+    // position buffer from it and runs both phases in one enqueue (launch_find)
+    mutable std::atomic<uint64_t> find_hits_per_query_x256{0};
 };
 
 struct lapper_result {  // device CSR of one find_batch call (pool memory)
@@ -172,6 +175,9 @@ void launch_count(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d
 // writes d_offsets[nq+1]; returns total hits (synchronises the stream)
 uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
                              uint64_t *d_offsets, cudaStream_t stream);
+// one enqueue for both phases (query.cu): returns the total; d_indices is written only when the total fits `capacity`
+uint64_t launch_find(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, uint64_t *d_offsets,
+                     uint32_t *d_indices, uint64_t capacity, cudaStream_t stream);
 // total = offsets[nq] when the caller knows it (saves a device round trip), kTotalUnknown otherwise
 constexpr uint64_t kTotalUnknown = ~0ull;
 void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,

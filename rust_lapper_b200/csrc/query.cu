@@ -408,7 +408,8 @@ __global__ void __launch_bounds__(kThreads) find_count_kernel(FindView f, const 
 // tiles ("super-tile") turns its tile sums into exclusive prefixes within the super-tile and emits its total;
 // (b) one block scans the few hundred super-tile totals.  A tile's base is then super_base[tile / 256] + tile_sums[tile].
 constexpr int kSuperTiles = 256;
-__global__ void __launch_bounds__(kSuperTiles) super_sums_kernel(uint64_t *__restrict__ tile_sums, uint64_t ntiles,
+// (tile_base may be tile_sums itself: in place)
+__global__ void __launch_bounds__(kSuperTiles) super_sums_kernel(const uint64_t *tile_sums, uint64_t ntiles, uint64_t *tile_base,
                                                                  uint64_t *__restrict__ super_sums) {
     __shared__ uint64_t warp_tot[kSuperTiles / 32];
     const uint64_t t = (uint64_t)blockIdx.x * kSuperTiles + threadIdx.x;
@@ -428,7 +429,7 @@ __global__ void __launch_bounds__(kSuperTiles) super_sums_kernel(uint64_t *__res
         wbase += (i < w) ? warp_tot[i] : 0;
         all += warp_tot[i];
     }
-    if (t < ntiles) tile_sums[t] = wbase + inc - mine;  // exclusive within the super-tile
+    if (t < ntiles) tile_base[t] = wbase + inc - mine;  // exclusive within the super-tile
     if (threadIdx.x == 0) super_sums[blockIdx.x] = all;
 }
 
@@ -465,21 +466,30 @@ __global__ void __launch_bounds__(1024) scan_super_sums_kernel(uint64_t *__restr
     if (threadIdx.x == 0) *total_out = carry_s;
 }
 
-// pass 3: offsets[j] = tile base + exclusive scan of the tile's counts
-__global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t *__restrict__ counts,
-                                                                 const uint64_t *__restrict__ tile_sums,
-                                                                 const uint64_t *__restrict__ super_sums, uint64_t nq,
-                                                                 uint64_t *__restrict__ offsets, bool vec) {
-    __shared__ uint64_t warp_tot[kThreads / 32];
+// pass 3: offsets[j] = tile base + exclusive scan of the tile's counts.  128 threads per tile, eight counts each (32 bytes
+// of loads and 64 bytes of stores in flight per thread: the kernel only streams, so bytes in flight are what it needs).
+constexpr int kWoThreads = 128;
+constexpr int kWoQPT = kFindTile / kWoThreads;
+static_assert(kWoQPT == 8, "write_offsets_kernel: eight counts per thread");
+__global__ void __launch_bounds__(kWoThreads, 16) write_offsets_kernel(const uint32_t *__restrict__ counts,
+                                                                       const uint64_t *__restrict__ tile_sums,
+                                                                       const uint64_t *__restrict__ super_sums, uint64_t nq,
+                                                                       uint64_t *__restrict__ offsets, bool vec) {
+    __shared__ uint64_t warp_tot[kWoThreads / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kFindTile + (uint64_t)threadIdx.x * kWoQPT;
+    uint32_t c[kWoQPT];
+    const bool whole = base + kWoQPT <= nq;
+    if (whole) {  // (counts is the library's own scratch: 16-byte aligned)
+        const uint4 c0 = ld_stream_v4(counts + base), c1 = ld_stream_v4(counts + base + 4);
+        c[0] = c0.x, c[1] = c0.y, c[2] = c0.z, c[3] = c0.w, c[4] = c1.x, c[5] = c1.y, c[6] = c1.z, c[7] = c1.w;
+    } else {
+#pragma unroll
+        for (int k = 0; k < kWoQPT; k++) c[k] = base + k < nq ? counts[base + k] : 0u;
+    }
     const uint64_t tile_base = super_sums[blockIdx.x / kSuperTiles] + tile_sums[blockIdx.x];
-    const uint64_t base = (uint64_t)blockIdx.x * kFindTile + (uint64_t)threadIdx.x * kFindQPT;
-    uint32_t c[kFindQPT];
     uint64_t local = 0;
 #pragma unroll
-    for (int k = 0; k < kFindQPT; k++) {
-        c[k] = base + k < nq ? counts[base + k] : 0u;
-        local += c[k];
-    }
+    for (int k = 0; k < kWoQPT; k++) local += c[k];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     uint64_t inc = local;
 #pragma unroll
@@ -491,16 +501,19 @@ __global__ void __launch_bounds__(kThreads) write_offsets_kernel(const uint32_t 
     __syncthreads();
     uint64_t wbase = 0;
 #pragma unroll
-    for (int i = 0; i < kThreads / 32; i++) wbase += (i < w) ? warp_tot[i] : 0;
+    for (int i = 0; i < kWoThreads / 32; i++) wbase += (i < w) ? warp_tot[i] : 0;
     uint64_t run = tile_base + wbase + inc - local;
-    if (vec && base + kFindQPT <= nq) {  // 32 contiguous bytes per thread: two 128-bit stores (offsets 16-byte aligned)
-        const uint64_t r0 = run, r1 = r0 + c[0], r2 = r1 + c[1], r3 = r2 + c[2];
+    if (vec && whole) {  // 64 contiguous bytes per thread: four 128-bit stores (offsets 16-byte aligned)
         ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(offsets + base);
-        dst[0] = make_ulonglong2(r0, r1);
-        dst[1] = make_ulonglong2(r2, r3);
+#pragma unroll
+        for (int k = 0; k < kWoQPT / 2; k++) {
+            const uint64_t r0 = run, r1 = r0 + c[2 * k];
+            dst[k] = make_ulonglong2(r0, r1);
+            run = r1 + c[2 * k + 1];
+        }
     } else {
 #pragma unroll
-        for (int k = 0; k < kFindQPT; k++) {
+        for (int k = 0; k < kWoQPT; k++) {
             if (base + k < nq) offsets[base + k] = run;
             run += c[k];
         }
@@ -939,6 +952,7 @@ constexpr int kTCtlWords = 32;
 constexpr int kTSmemWords = 4 * kTCand + kTW * kTWarpWords + kTRelWords + kTCtlWords;
 static_assert(3 * kTCand <= kTW * kTWarpWords, "the raw candidate list aliases the warps' areas");
 static_assert(kTQPT == 4 || kTQPT == 8, "tile prologue: 4 or 8 queries per thread");
+static_assert(kTW <= 8, "ctl[16 + warp] and ctl[24 + warp]");
 
 __device__ __forceinline__ uint32_t smem_lower_bound(const uint32_t *a, uint32_t n, uint32_t key) {
     uint32_t lo = 0, hi = n;
@@ -952,9 +966,23 @@ __device__ __forceinline__ uint32_t smem_lower_bound(const uint32_t *a, uint32_t
     return lo;
 }
 
+// The fused form (kFromCounts, lapper_find_batch_u32_dev): the tile's offsets do not exist yet -- the kernel derives them
+// from the count pass's u32 counts and the scanned tile sums (one block scan per tile, which it needs anyway for its
+// tile-relative offsets), writes them out for the caller and the later kernels, and emits nothing at all when the
+// grand total exceeds the room in `indices`.  That replaces write_offsets_kernel and its 12 bytes per query.
+struct TileCounts {
+    const uint32_t *counts;      // per query (the count pass)
+    const uint64_t *tile_sums;   // per tile: sum of its counts
+    const uint64_t *tile_base;   // per tile: exclusive prefix within its super-tile
+    const uint64_t *super_base;  // per super-tile: exclusive prefix
+    uint64_t *offsets_out;       // offsets[j] for every j < nq are written here (offsets[nq] by scan_super_sums_kernel)
+    uint64_t capacity;           // room in `indices`
+};
+
+template <bool kFromCounts>
 __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(FindView f, const uint32_t *__restrict__ qs,
                                                                     const uint32_t *__restrict__ qe, uint64_t nq,
-                                                                    const uint64_t *__restrict__ offsets,
+                                                                    const uint64_t *offsets, const TileCounts tc,
                                                                     uint32_t *__restrict__ indices,
                                                                     uint32_t *__restrict__ heavy_list,
                                                                     unsigned int *__restrict__ heavy_count,
@@ -967,22 +995,25 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
     uint32_t *const warp_area = tsm + 4 * kTCand;            // per warp: stage, then its candidate list
     uint32_t *const rel = warp_area + kTW * kTWarpWords;     // tile-relative offsets [0, nqt]
     // ctl: [0..3] class lo, [4..7] class window size, [8..11] kept per class, [12] amin, [13] bmax, [14] tile hits >> 32,
-    // [16..] warp counts
+    // [16..] warp counts, [24..] the warps' count totals (fused form)
     uint32_t *const ctl = rel + kTRelWords;
     uint32_t *const rawg = warp_area, *const raws = warp_area + kTCand, *const rawe = warp_area + 2 * kTCand;
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t *const stage = warp_area + warp * kTWarpWords;
     uint4 *const wlist = reinterpret_cast<uint4 *>(stage + kTStage);
     const uint64_t ntiles = div_up(nq, kFindTile);
+    const bool over_capacity = kFromCounts && tc.offsets_out[nq] > tc.capacity;
     for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const uint64_t q0 = tile * kFindTile;
         const uint32_t nqt = (uint32_t)min((uint64_t)kFindTile, nq - q0);
         const uint32_t jt = threadIdx.x * kTQPT;
-        {   // the next tile's offsets and queries on their way into L2 while this tile is emitted
+        {   // the next tile's offsets (counts) and queries on their way into L2 while this tile is emitted
             const uint64_t qn = q0 + (uint64_t)gridDim.x * kFindTile + jt;
             if (qn + kTQPT <= nq) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(offsets + qn));
+                if (!kFromCounts)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(offsets + qn));
                 if ((threadIdx.x & 3u) == 0) {
+                    if (kFromCounts) asm volatile("prefetch.global.L2 [%0];" ::"l"(tc.counts + qn));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(qs + qn));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(qe + qn));
                 }
@@ -992,16 +1023,10 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
         if (threadIdx.x < 14) ctl[threadIdx.x] = threadIdx.x == 12 ? 0xFFFFFFFFu : 0u;  // [14] is written below
         // ---- 1. the tile's offsets (thread t: queries t*kTQPT .. and the offset after them), heavy queries,
         //         smallest start / largest stop over the queries this kernel emits
-        const uint64_t tile_o0 = offsets[q0];
+        uint64_t tile_o0;
         uint32_t r[kTQPT + 1], qa[kTQPT], qb[kTQPT];
-        if (nqt == (uint32_t)kFindTile) {
-            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(offsets + q0 + jt);
-#pragma unroll
-            for (int k = 0; k < kTQPT / 2; k++) {
-                const ulonglong2 u = src[k];
-                r[2 * k] = (uint32_t)(u.x - tile_o0), r[2 * k + 1] = (uint32_t)(u.y - tile_o0);
-            }
-            r[kTQPT] = (uint32_t)(offsets[q0 + jt + kTQPT] - tile_o0);
+        const bool full = nqt == (uint32_t)kFindTile;
+        if (full) {
 #pragma unroll
             for (int k = 0; k < kTQPT / 4; k++) {
                 // (normal caching, not evict-first: the groups read their queries again a few microseconds later, from L2)
@@ -1012,12 +1037,82 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
             }
         } else {
 #pragma unroll
-            for (int k = 0; k <= kTQPT; k++) r[k] = (uint32_t)(offsets[q0 + min(jt + k, nqt)] - tile_o0);
-#pragma unroll
             for (int k = 0; k < kTQPT; k++) {
                 const bool live = jt + k < nqt;
                 qa[k] = live ? ld_stream_u32(qs + q0 + jt + k) : 0xFFFFFFFFu;
                 qb[k] = live ? ld_stream_u32(qe + q0 + jt + k) : 0u;
+            }
+        }
+        uint32_t inc = 0, last = 0;  // kFromCounts: the warp's inclusive scan of the threads' sums, the thread's own sum
+        uint64_t tile_total = 0;
+        if (kFromCounts) {
+            tile_total = tc.tile_sums[tile];
+            tile_o0 = tc.super_base[tile / kSuperTiles] + tc.tile_base[tile];
+            uint32_t c[kTQPT];
+            if (full) {
+#pragma unroll
+                for (int k = 0; k < kTQPT / 4; k++) {
+                    const uint4 v = ld_stream_v4(tc.counts + q0 + jt + 4 * k);
+                    c[4 * k] = v.x, c[4 * k + 1] = v.y, c[4 * k + 2] = v.z, c[4 * k + 3] = v.w;
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kTQPT; k++) c[k] = jt + k < nqt ? ld_stream_u32(tc.counts + q0 + jt + k) : 0u;
+            }
+            // r[k + 1] for now: the thread's own inclusive prefix
+            r[0] = 0;
+#pragma unroll
+            for (int k = 0; k < kTQPT; k++) r[k + 1] = r[k] + c[k];
+            last = r[kTQPT];
+            inc = last;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+                if (lane >= (uint32_t)o) inc += y;
+            }
+            if (lane == 31) ctl[24 + warp] = inc;
+        } else {
+            tile_o0 = offsets[q0];
+            if (full) {
+                const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(offsets + q0 + jt);
+#pragma unroll
+                for (int k = 0; k < kTQPT / 2; k++) {
+                    const ulonglong2 u = src[k];
+                    r[2 * k] = (uint32_t)(u.x - tile_o0), r[2 * k + 1] = (uint32_t)(u.y - tile_o0);
+                }
+                r[kTQPT] = (uint32_t)(offsets[q0 + jt + kTQPT] - tile_o0);
+            } else {
+#pragma unroll
+                for (int k = 0; k <= kTQPT; k++) r[k] = (uint32_t)(offsets[q0 + min(jt + k, nqt)] - tile_o0);
+            }
+            if (threadIdx.x == kTT - 1) tile_total = offsets[q0 + nqt] - tile_o0;
+        }
+        if (kFromCounts) {
+            __syncthreads();  // ctl initialised, the warps' totals are there
+            uint32_t ex = inc - last;
+#pragma unroll
+            for (int w = 0; w < kTW; w++) ex += w < (int)warp ? ctl[24 + w] : 0u;
+#pragma unroll
+            for (int k = 0; k <= kTQPT; k++) r[k] += ex;
+            // the offsets leave for the caller (and for find_fill_kernel / find_heavy_kernel, which run after this kernel)
+            if ((tile_total >> 32) == 0) {
+                if (full) {
+                    ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tc.offsets_out + q0 + jt);
+#pragma unroll
+                    for (int k = 0; k < kTQPT / 2; k++) dst[k] = make_ulonglong2(tile_o0 + r[2 * k], tile_o0 + r[2 * k + 1]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < kTQPT; k++)
+                        if (jt + k < nqt) tc.offsets_out[q0 + jt + k] = tile_o0 + r[k];
+                }
+            } else if (threadIdx.x == 0) {
+                // 2^32 or more hits in one tile (possible only over millions of mutually overlapping intervals): 64-bit
+                // prefixes, serially; the tile itself is left to find_fill_kernel below (ctl[14] != 0)
+                uint64_t run = tile_o0;
+                for (uint32_t k = 0; k < nqt; k++) {
+                    tc.offsets_out[q0 + k] = run;
+                    run += tc.counts[q0 + k];
+                }
             }
         }
         uint32_t hmask = 0, amin = 0xFFFFFFFFu, bmax = 0;
@@ -1035,16 +1130,17 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
         if (threadIdx.x == kTT - 1) {
             rel[kFindTile] = r[kTQPT];
             // tile-relative offsets are 32-bit: a tile with 2^32 or more hits is left to find_fill_kernel (64-bit offsets)
-            ctl[14] = (uint32_t)((offsets[q0 + nqt] - tile_o0) >> 32);
+            ctl[14] = (uint32_t)(tile_total >> 32);
         }
         amin = __reduce_min_sync(0xFFFFFFFFu, amin);
         bmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
-        __syncthreads();  // ctl initialised
+        if (!kFromCounts) __syncthreads();  // ctl initialised
         if (lane == 0) {
             atomicMin(&ctl[12], amin);
             atomicMax(&ctl[13], bmax);
         }
         __syncthreads();
+        if (kFromCounts && over_capacity) continue;  // (uniform; the offsets are complete, nothing is emitted)
         if (rel[nqt] == 0 && ctl[14] == 0) continue;
         amin = ctl[12], bmax = ctl[13];
         // ---- 2. class windows of the tile (warp 0; four lanes per bound, as in find_fill_kernel)
@@ -1699,11 +1795,11 @@ uint64_t launch_find_offsets(const DeviceIndex &ix, const uint32_t *d_qs, const 
     LAPPER_CUDA_CHECK(cudaGetLastError());
     const uint64_t nsuper = div_up(ntiles, kSuperTiles);
     Scratch<uint64_t> super_sums(nsuper, stream);
-    g_query_launches++, super_sums_kernel<<<(uint32_t)nsuper, kSuperTiles, 0, stream>>>(tile_sums.p, ntiles, super_sums.p);
+    g_query_launches++, super_sums_kernel<<<(uint32_t)nsuper, kSuperTiles, 0, stream>>>(tile_sums.p, ntiles, tile_sums.p, super_sums.p);
     LAPPER_CUDA_CHECK(cudaGetLastError());
     g_query_launches++, scan_super_sums_kernel<<<1, 1024, 0, stream>>>(super_sums.p, nsuper, d_offsets + nq);
     LAPPER_CUDA_CHECK(cudaGetLastError());
-    g_query_launches++, write_offsets_kernel<<<(uint32_t)ntiles, kThreads, 0, stream>>>(
+    g_query_launches++, write_offsets_kernel<<<(uint32_t)ntiles, kWoThreads, 0, stream>>>(
         counts.p, tile_sums.p, super_sums.p, nq, d_offsets, (reinterpret_cast<uintptr_t>(d_offsets) & 15u) == 0);
     LAPPER_CUDA_CHECK(cudaGetLastError());
     uint64_t total = 0;
@@ -1732,6 +1828,58 @@ void launch_rebase_offsets(const uint64_t *in, uint64_t *out, uint64_t count, ui
     LAPPER_CUDA_CHECK(cudaGetLastError());
 }
 
+namespace {
+// the emit kernels over offsets that exist (tc == nullptr) or that the tile kernel derives from the counts (fused form)
+void launch_emit(const FindView &f, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, uint64_t *d_offsets,
+                 uint32_t *d_indices, uint64_t heavy_bound, const TileCounts *tc, bool tiled, cudaStream_t stream) {
+    // the heavy list: queries with >= kHeavyHits hits (at most heavy_bound / kHeavyHits) + light queries with long class
+    // windows, admitted up to a sixteenth of the batch
+    const uint32_t max_admitted = (uint32_t)std::min<uint64_t>(nq, nq / 16 + 1024);
+    const uint64_t cap = std::min<uint64_t>(heavy_bound / kHeavyHits + 1, nq) + max_admitted;
+    const uint64_t ntiles = div_up(nq, kFindTile);
+    Scratch<uint32_t> heavy(cap, stream);
+    Scratch<uint32_t> fallback(ntiles, stream);
+    Scratch<unsigned int> counters(4, stream);  // heavy queries, next heavy query, fallback tiles, admitted long-window queries
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned int), stream));
+    const uint32_t grid = capped_grid(nq, kThreads, LAPPER_EMIT_MIN_CTAS * 8);
+    if (tiled) {
+        // tile form first; the tiles it cannot take (no locality) are left to the per-warp kernel
+        // once per device: all of the SM's L1/shared array as shared memory, so that LAPPER_TILE_CTAS tiles are resident
+        static std::atomic<bool> prepared[64];
+        int dev = 0;
+        LAPPER_CUDA_CHECK(cudaGetDevice(&dev));
+        if (dev >= 0 && dev < 64 && !prepared[dev].load(std::memory_order_acquire)) {
+            LAPPER_CUDA_CHECK(cudaFuncSetAttribute(find_fill_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   kTSmemWords * (int)sizeof(uint32_t)));
+            LAPPER_CUDA_CHECK(cudaFuncSetAttribute(find_fill_tile_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                   cudaSharedmemCarveoutMaxShared));
+            LAPPER_CUDA_CHECK(cudaFuncSetAttribute(find_fill_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   kTSmemWords * (int)sizeof(uint32_t)));
+            LAPPER_CUDA_CHECK(cudaFuncSetAttribute(find_fill_tile_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                   cudaSharedmemCarveoutMaxShared));
+            prepared[dev].store(true, std::memory_order_release);
+        }
+        const uint32_t tgrid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)sm_count() * LAPPER_TILE_CTAS);
+        if (tc)
+            g_query_launches++, find_fill_tile_kernel<true><<<tgrid, kTT, kTSmemWords * sizeof(uint32_t), stream>>>(
+                f, d_qs, d_qe, nq, d_offsets, *tc, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2, counters.p + 3, max_admitted);
+        else
+            g_query_launches++, find_fill_tile_kernel<false><<<tgrid, kTT, kTSmemWords * sizeof(uint32_t), stream>>>(
+                f, d_qs, d_qe, nq, d_offsets, TileCounts{}, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2, counters.p + 3, max_admitted);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        g_query_launches++, find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p,
+                                                        fallback.p, counters.p + 2, counters.p + 3, max_admitted);
+    } else {
+        g_query_launches++, find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, nullptr,
+                                                        nullptr, counters.p + 3, max_admitted);
+    }
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    // persistent warps; exits at once when the list is empty (it may also hold light queries with long windows)
+    g_query_launches++, find_heavy_kernel<<<sm_count() * 8, kThreads, 0, stream>>>(f, d_qs, d_qe, d_offsets, d_indices, heavy.p, counters.p, counters.p + 1);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+}
+}  // namespace
+
 void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq,
                       const uint64_t *d_offsets, uint32_t *d_indices, cudaStream_t stream, uint64_t total) {
     if (nq == 0 || ix.n == 0) return;
@@ -1742,47 +1890,44 @@ void launch_find_fill(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_
         LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
-    // the heavy list: queries with >= kHeavyHits hits (at most total / kHeavyHits) + light queries with long class
-    // windows, admitted up to a sixteenth of the batch
-    const uint32_t max_admitted = (uint32_t)std::min<uint64_t>(nq, nq / 16 + 1024);
-    const uint64_t cap = std::min<uint64_t>(total / kHeavyHits + 1, nq) + max_admitted;
-    const uint64_t ntiles = div_up(nq, kFindTile);
-    Scratch<uint32_t> heavy(cap, stream);
-    Scratch<uint32_t> fallback(ntiles, stream);
-    Scratch<unsigned int> counters(4, stream);  // heavy queries, next heavy query, fallback tiles, admitted long-window queries
-    LAPPER_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned int), stream));
-    const uint32_t grid = capped_grid(nq, kThreads, LAPPER_EMIT_MIN_CTAS * 8);
     const bool tiled = ((reinterpret_cast<uintptr_t>(d_offsets) | reinterpret_cast<uintptr_t>(d_qs) |
                          reinterpret_cast<uintptr_t>(d_qe)) & 15u) == 0 && !find_tile_disabled();
-    if (tiled) {
-        // tile form first; the tiles it cannot take (no locality) are left to the per-warp kernel
-        // once per device: all of the SM's L1/shared array as shared memory, so that LAPPER_TILE_CTAS tiles are resident
-        static std::atomic<bool> prepared[64];
-        int dev = 0;
-        LAPPER_CUDA_CHECK(cudaGetDevice(&dev));
-        if (dev >= 0 && dev < 64 && !prepared[dev].load(std::memory_order_acquire)) {
-            LAPPER_CUDA_CHECK(cudaFuncSetAttribute(find_fill_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                   kTSmemWords * (int)sizeof(uint32_t)));
-            LAPPER_CUDA_CHECK(cudaFuncSetAttribute(find_fill_tile_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                   cudaSharedmemCarveoutMaxShared));
-            prepared[dev].store(true, std::memory_order_release);
-        }
-        const uint32_t tgrid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)sm_count() * LAPPER_TILE_CTAS);
-        g_query_launches++, find_fill_tile_kernel<<<tgrid, kTT, kTSmemWords * sizeof(uint32_t), stream>>>(
-            f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2, counters.p + 3, max_admitted);
-        LAPPER_CUDA_CHECK(cudaGetLastError());
-        g_query_launches++, find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p,
-                                                        fallback.p, counters.p + 2, counters.p + 3, max_admitted);
-    } else {
-        g_query_launches++, find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, nullptr,
-                                                        nullptr, counters.p + 3, max_admitted);
+    launch_emit(f, d_qs, d_qe, nq, const_cast<uint64_t *>(d_offsets), d_indices, total, nullptr, tiled, stream);
+}
+
+// find_batch in one enqueue: count pass, scan of the tile sums, emit -- the tile kernel derives the offsets from the
+// counts (no write_offsets pass, no host round trip between the phases).  Returns the total (synchronises the stream
+// once, at the end); nothing is written to d_indices when it exceeds `capacity` (the offsets are complete either way).
+uint64_t launch_find(const DeviceIndex &ix, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, uint64_t *d_offsets,
+                     uint32_t *d_indices, uint64_t capacity, cudaStream_t stream) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(d_offsets) | reinterpret_cast<uintptr_t>(d_qs) |
+                           reinterpret_cast<uintptr_t>(d_qe)) & 31u) == 0;
+    if (nq == 0 || ix.n == 0 || ix.has_inverted || !ix.buckets || nq >= (1ull << 31) || !aligned || find_tile_disabled()) {
+        // shapes the fused form does not cover: the two phases, one after the other
+        const uint64_t total = launch_find_offsets(ix, d_qs, d_qe, nq, d_offsets, stream);
+        if (total <= capacity && total) launch_find_fill(ix, d_qs, d_qe, nq, d_offsets, d_indices, stream, total);
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+        return total;
     }
+    const FindView f = make_find_view(ix);
+    const uint64_t ntiles = div_up(nq, kFindTile), nsuper = div_up(ntiles, kSuperTiles);
+    Scratch<uint32_t> counts(nq, stream);
+    Scratch<uint64_t> tile_sums(ntiles, stream), tile_base(ntiles, stream), super_sums(nsuper, stream);
+    const BucketPlan plan = plan_buckets(f.bv, d_qs, d_qe, nq, counts.p, true);
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(tile_sums.p, 0, ntiles * sizeof(uint64_t), stream));
+    launch_count_buckets(ix, plan, d_qs, d_qe, nq, counts.p, nullptr, tile_sums.p, stream);
+    g_query_launches++, super_sums_kernel<<<(uint32_t)nsuper, kSuperTiles, 0, stream>>>(tile_sums.p, ntiles, tile_base.p, super_sums.p);
     LAPPER_CUDA_CHECK(cudaGetLastError());
-    {
-        // persistent warps; exits at once when the list is empty (it may also hold light queries with long windows)
-        g_query_launches++, find_heavy_kernel<<<sm_count() * 8, kThreads, 0, stream>>>(f, d_qs, d_qe, d_offsets, d_indices, heavy.p, counters.p, counters.p + 1);
-        LAPPER_CUDA_CHECK(cudaGetLastError());
-    }
+    g_query_launches++, scan_super_sums_kernel<<<1, 1024, 0, stream>>>(super_sums.p, nsuper, d_offsets + nq);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    TileCounts tc;
+    tc.counts = counts.p, tc.tile_sums = tile_sums.p, tc.tile_base = tile_base.p, tc.super_base = super_sums.p;
+    tc.offsets_out = d_offsets, tc.capacity = capacity;
+    launch_emit(f, d_qs, d_qe, nq, d_offsets, d_indices, capacity, &tc, true, stream);
+    uint64_t total = 0;
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return total;
 }
 
 }  // namespace lap

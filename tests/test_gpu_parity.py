@@ -553,3 +553,98 @@ def test_replica_of_merged_set_issues_fresh_input_positions():
     _ffi.check(_ffi.lib().lapper_insert_u32(C.c_void_p(rep), 3000, 3005, C.byref(pos)))
     assert int(pos.value) == 52
     grp.close()
+
+
+# ------------------------------------------------------------------------------------------------ one-call device find
+def _dev_find_one_call(lib, h, qs, qe, capacity, sp, fill=0x5A5A5A5A):
+    """lapper_find_batch_u32_dev into caller buffers; returns (status, total, offsets, indices-buffer) on the host"""
+    import ctypes as C
+
+    import torch
+
+    nq = qs.numel()
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    off = torch.empty(nq + 1, dtype=torch.int64, device=qs.device)
+    idx = torch.full((max(capacity, 1),), fill, dtype=torch.int32, device=qs.device)
+    total = C.c_uint64(0)
+    st = lib.lapper_find_batch_u32_dev(h, vp(qs), vp(qe), nq, vp(off), vp(idx) if capacity else C.c_void_p(0), capacity,
+                                       C.byref(total), sp)
+    torch.cuda.synchronize()
+    return st, int(total.value), off.cpu().numpy().view(np.uint64), idx.cpu().numpy().view(np.uint32)
+
+
+@pytest.mark.parametrize("shape", ["sorted", "random", "ragged", "heavy", "inverted_set", "tiny"])
+def test_find_one_call_device_api(oracle, shape):
+    """lapper_find_batch_u32_dev (count pass, scan and emit in one enqueue; the emit kernel derives the offsets from the
+    counts): same CSR as the oracle for start-sorted batches (tile kernel), random-order ones (every tile falls back to
+    the per-warp kernel), a ragged last tile, heavy queries (>= 256 hits: find_heavy_kernel reads the offsets the tile
+    kernel wrote), sets the fused form does not cover (inverted intervals: two-phase inside the call), plus the
+    capacity protocol: exact fit, room to spare, too small (LAPPER_ERR_CAPACITY, offsets complete, positions untouched)
+    and the size query."""
+    import ctypes as C
+
+    import torch
+
+    from rust_lapper_b200 import _ffi, synth
+
+    dev = torch.device("cuda", 0)
+    lib = _ffi.lib()
+    U = 60_000_000
+    rng = np.random.default_rng(5)
+    if shape == "heavy":
+        s, e = synth.intervals_uniform(42, 40_000, 2_000_000, 500, 80_000)  # ~ 800 hits per query
+        qs, qe = synth.queries_sorted_fixed_len(45, 5_000, 2_000_000, 150)
+    else:
+        s, e = synth.intervals_gene_exon(44, 300_000, U)
+        if shape == "inverted_set":
+            s, e = s.copy(), e.copy()
+            k = rng.choice(s.size, 1000, replace=False)
+            s[k], e[k] = e[k], s[k]
+        nq = {"ragged": 70_001, "tiny": 37}.get(shape, 64 * 1024)
+        if shape == "random":
+            qs, qe = synth.queries_fixed_len(43, nq, U, 150)
+        else:
+            qs, qe = synth.queries_sorted_fixed_len(45, nq, U, 150)
+    cpu = oracle.OracleLapper(starts=s, stops=e)
+    want_o, want_i = cpu.find_batch(qs, qe, 4)
+    total = int(want_o[-1])
+    h = C.c_void_p(0)
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    ts = torch.from_numpy(s.view(np.int32)).to(dev)
+    te = torch.from_numpy(e.view(np.int32)).to(dev)
+    _ffi.check(lib.lapper_build_u32_dev(C.c_void_p(ts.data_ptr()), C.c_void_p(te.data_ptr()), len(s), 0, 0, sp, C.byref(h)))
+    try:
+        tq = torch.from_numpy(qs.view(np.int32)).to(dev)
+        tqe = torch.from_numpy(qe.view(np.int32)).to(dev)
+        for capacity in (total, total + 12345):
+            st, got_t, got_o, got_i = _dev_find_one_call(lib, h, tq, tqe, capacity, sp)
+            assert st == _ffi.OK, lib.lapper_last_error()
+            assert got_t == total and np.array_equal(got_o, want_o)
+            assert np.array_equal(got_i[:total], want_i)
+            assert np.all(got_i[total:] == 0x5A5A5A5A)  # nothing written past the result
+        if total > 1:
+            st, got_t, got_o, got_i = _dev_find_one_call(lib, h, tq, tqe, total - 1, sp)
+            assert st == _ffi.ERR_CAPACITY
+            assert got_t == total and np.array_equal(got_o, want_o)
+            assert np.all(got_i == 0x5A5A5A5A)  # untouched
+        st, got_t, got_o, _ = _dev_find_one_call(lib, h, tq, tqe, 0, sp)
+        assert st == _ffi.OK  # the size query
+        assert got_t == total and np.array_equal(got_o, want_o)
+    finally:
+        lib.lapper_free(h)
+
+
+def test_find_batch_guesses_the_result_size_from_the_previous_batch(oracle):
+    """find_batch on a handle sizes its position buffer from the handle's previous batch and runs one enqueue; a batch
+    with far more hits per query than the previous one (guess too small) and one with far fewer must both be exact."""
+    from rust_lapper_b200 import Lapper, synth
+
+    U = 30_000_000
+    s, e = synth.intervals_gene_exon(44, 200_000, U)
+    gpu, cpu = Lapper(starts=s, stops=e), oracle.OracleLapper(starts=s, stops=e)
+    short = synth.queries_sorted_fixed_len(45, 40_000, U, 10)
+    long_ = synth.queries_sorted_fixed_len(46, 40_000, U, 200_000)
+    for qs, qe in (short, long_, short, long_, long_):
+        go, gi = gpu.find_batch(qs, qe)
+        co, ci = cpu.find_batch(qs, qe, 4)
+        assert np.array_equal(go, co) and np.array_equal(gi, ci)

@@ -4,6 +4,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <cuda_runtime.h>
 
 struct __align__(32) Sector { uint32_t w[8]; };
@@ -20,12 +21,25 @@ __device__ __forceinline__ uint32_t mix(uint64_t x) {
 }
 
 // each thread performs `iters` rounds of K independent gathers; also streams `stream_bytes_per_gather` optional
+// g_split: 0 = every CTA gathers from the whole table; otherwise a CTA gathers from ONE half of it only, chosen by
+// 1 = parity of %smid, 2 = %smid below / above half the SM count, 3 = parity of blockIdx.x (control: no relation to
+// where the CTA runs), 4 = (%smid / 2) parity (TPC pairs).  Tests whether a table half that is only ever read by the SMs
+// of one die doubles the L2 capacity that is effective for the table.
+__constant__ int g_split;
 template <int K, bool STREAM>
 __global__ void gather_kernel(const Sector* __restrict__ table, uint32_t nsect, int iters, uint32_t* __restrict__ out,
                               const uint4* __restrict__ stream_in, uint32_t* __restrict__ stream_out) {
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nthreads = (uint64_t)gridDim.x * blockDim.x;
     uint32_t acc = 0;
+    if (g_split) {
+        uint32_t smid, nsm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        const uint32_t half = g_split == 1 ? (smid & 1u) : g_split == 2 ? (smid >= nsm / 2 ? 1u : 0u) : g_split == 3 ? (blockIdx.x & 1u) : ((smid >> 1) & 1u);
+        nsect /= 2;
+        table += (size_t)half * nsect;
+    }
     for (int it = 0; it < iters; it++) {
         const uint64_t q0 = ((uint64_t)it * nthreads + tid) * K;
         uint32_t extra = 0;
@@ -73,6 +87,38 @@ int main(int argc, char** argv) {
     uint32_t* out; cudaMalloc(&out, 4);
     uint4* sin; uint32_t* sout; cudaMalloc(&sin, total * 8 + 4096); cudaMalloc(&sout, total * 4 + 4096);
     cudaMemset(sin, 1, total * 8);
+    if (argc > 1 && !strcmp(argv[1], "one")) {
+        // mb_gather one <MB> <split>: a single configuration (4 gathers in flight per thread, query / result streams,
+        // 4 CTAs of 256 threads per SM) -- the one to put under ncu
+        const double mb = argc > 2 ? atof(argv[2]) : 75;
+        const int split = argc > 3 ? atoi(argv[3]) : 0;
+        cudaMemcpyToSymbol(g_split, &split, sizeof(int));
+        uint32_t nsect = (uint32_t)(mb * 1e6 / 32);
+        Sector* table; cudaMalloc(&table, (size_t)nsect * 32); cudaMemset(table, 1, (size_t)nsect * 32);
+        int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+        printf("== table %.0f MB (%u sectors), split mode %d\n", mb, nsect, split);
+        run<4, true>(table, nsect, total, 256, nsm * 4, out, sin, sout);
+        return 0;
+    }
+    if (argc > 1 && !strcmp(argv[1], "split")) {
+        // the die-split experiment: table sizes around and beyond the L2 knee, every split mode, with and without streams
+        int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+        double sizes[] = {48, 75, 97, 128, 150, 194};
+        for (double mb : sizes) {
+            uint32_t nsect = (uint32_t)(mb * 1e6 / 32);
+            Sector* table; cudaMalloc(&table, (size_t)nsect * 32); cudaMemset(table, 1, (size_t)nsect * 32);
+            for (int split = 0; split <= 4; split++) {
+                cudaMemcpyToSymbol(g_split, &split, sizeof(int));
+                printf("== table %.0f MB, split mode %d: ", mb, split);
+                run<4, false>(table, nsect, total, 256, nsm * 4, out, sin, sout);
+                printf("== table %.0f MB, split mode %d: ", mb, split);
+                run<4, true>(table, nsect, total, 256, nsm * 4, out, sin, sout);
+            }
+            cudaFree(table);
+        }
+        return 0;
+    }
+    { const int zero = 0; cudaMemcpyToSymbol(g_split, &zero, sizeof(int)); }
     double sizes_mb[] = {12, 24, 48, 64, 80, 97, 194, 485};
     for (double mb : sizes_mb) {
         uint32_t nsect = (uint32_t)(mb * 1e6 / 32);

@@ -65,6 +65,24 @@ lib.lapper_debug_sorted_run_stats(stats, 1)
 print(f"  offsets phase {ms_off:.3f} ms, fill phase {ms_fill:.3f} ms; sorted-run kernel so far: {stats[0]} runs ranked, {stats[1]} per query")
 print(f"find {order}: {ms:.3f} ms per pass, {int(total.value)} hits ({int(total.value) / nq:.2f}/query), "
       f"{nq / ms / 1e6:.2f} Gq/s, {int(total.value) / ms / 1e6:.1f} Ghits/s, checksum {int(idx[: int(total.value)].to(torch.int64).sum())}")
+# the one-call form: count pass, scan and emit in one enqueue (the emit kernel derives the offsets)
+off2 = torch.empty_like(off)
+idx2 = torch.empty_like(idx)
+cap = int(total.value)
+for _ in range(2):
+    t = C.c_uint64(0)
+    _ffi.check(lib.lapper_find_batch_u32_dev(h, vp(qs), vp(qe), nq, vp(off2), vp(idx2), cap, C.byref(t), sp))
+torch.cuda.synchronize()
+a.record()
+for _ in range(reps):
+    t = C.c_uint64(0)
+    _ffi.check(lib.lapper_find_batch_u32_dev(h, vp(qs), vp(qe), nq, vp(off2), vp(idx2), cap, C.byref(t), sp))
+b.record()
+torch.cuda.synchronize()
+ms1 = a.elapsed_time(b) / reps
+same = bool(torch.equal(off, off2)) and bool(torch.equal(idx[:cap], idx2[:cap]))
+print(f"find {order}, one call: {ms1:.3f} ms per pass, {nq / ms1 / 1e6:.2f} Gq/s, {cap / ms1 / 1e6:.1f} Ghits/s, "
+      f"same CSR as the two-phase calls: {same}")
 if os.environ.get("EMIT_STATS"):
     import ctypes
     raw = ctypes.CDLL(_ffi.LIB_PATH)
