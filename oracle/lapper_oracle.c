@@ -57,34 +57,34 @@ static void iv_stable_sort(lo_interval *a, size_t n) {
 }
 
 static int u32_cmp(const void *a, const void *b) {
-    uint32_t x = *(const uint32_t *)a, y = *(const uint32_t *)b;
+    lo_coord x = *(const lo_coord *)a, y = *(const lo_coord *)b;
     return (x > y) - (x < y);
 }
 
 /* src/lib.rs:203-227 (and :393-415): unzip, sort starts and stops, max_len with checked_sub -> 0 */
 static void rebuild_aux(lo_lapper *l) {
-    uint32_t max_len = 0;
+    lo_coord max_len = 0;
     for (size_t i = 0; i < l->len; i++) {
         l->starts[i] = l->intervals[i].start;
         l->stops[i] = l->intervals[i].stop;
     }
-    qsort(l->starts, l->len, sizeof(uint32_t), u32_cmp);
-    qsort(l->stops, l->len, sizeof(uint32_t), u32_cmp);
+    qsort(l->starts, l->len, sizeof(lo_coord), u32_cmp);
+    qsort(l->stops, l->len, sizeof(lo_coord), u32_cmp);
     for (size_t i = 0; i < l->len; i++) {
         const lo_interval *iv = &l->intervals[i];
-        uint32_t i_len = iv->stop >= iv->start ? iv->stop - iv->start : 0; /* checked_sub.unwrap_or(0) */
+        lo_coord i_len = iv->stop >= iv->start ? iv->stop - iv->start : 0; /* checked_sub.unwrap_or(0) */
         if (i_len > max_len) max_len = i_len;
     }
     l->max_len = max_len;
 }
 
-lo_lapper *lo_new(const uint32_t *starts, const uint32_t *stops, const uint32_t *vals, size_t n) {
+lo_lapper *lo_new(const lo_coord *starts, const lo_coord *stops, const uint32_t *vals, size_t n) {
     lo_lapper *l = (lo_lapper *)xmalloc(sizeof(lo_lapper));
     l->len = n;
     l->cap = n ? n : 1;
     l->intervals = (lo_interval *)xmalloc(l->cap * sizeof(lo_interval));
-    l->starts = (uint32_t *)xmalloc(l->cap * sizeof(uint32_t));
-    l->stops = (uint32_t *)xmalloc(l->cap * sizeof(uint32_t));
+    l->starts = (lo_coord *)xmalloc(l->cap * sizeof(lo_coord));
+    l->stops = (lo_coord *)xmalloc(l->cap * sizeof(lo_coord));
     for (size_t i = 0; i < n; i++) {
         l->intervals[i].start = starts[i];
         l->intervals[i].stop = stops[i];
@@ -106,18 +106,18 @@ void lo_free(lo_lapper *l) {
     free(l);
 }
 
-uint32_t lo_interval_intersect(uint32_t s1, uint32_t e1, uint32_t s2, uint32_t e2) {
+lo_coord lo_interval_intersect(lo_coord s1, lo_coord e1, lo_coord s2, lo_coord e2) {
     /* :133-135  min(stops).checked_sub(max(starts)).unwrap_or(0) */
-    uint32_t mn = e1 < e2 ? e1 : e2;
-    uint32_t mx = s1 > s2 ? s1 : s2;
+    lo_coord mn = e1 < e2 ? e1 : e2;
+    lo_coord mx = s1 > s2 ? s1 : s2;
     return mn >= mx ? mn - mx : 0;
 }
 
-int lo_interval_overlap(const lo_interval *iv, uint32_t start, uint32_t stop) {
+int lo_interval_overlap(const lo_interval *iv, lo_coord start, lo_coord stop) {
     return iv->start < stop && iv->stop > start; /* :141 */
 }
 
-size_t lo_lower_bound(uint32_t start, const lo_interval *intervals, size_t n) {
+size_t lo_lower_bound(lo_coord start, const lo_interval *intervals, size_t n) {
     /* :424-436 */
     size_t size = n;
     size_t low = 0;
@@ -133,7 +133,7 @@ size_t lo_lower_bound(uint32_t start, const lo_interval *intervals, size_t n) {
     return low;
 }
 
-size_t lo_bsearch_seq(uint32_t key, const uint32_t *elems, size_t n) {
+size_t lo_bsearch_seq(lo_coord key, const lo_coord *elems, size_t n) {
     /* :452-465 */
     if (n == 0 || elems[0] >= key) {
         return 0;
@@ -167,26 +167,26 @@ static size_t bsearch_seq_iv(const lo_interval *key, const lo_interval *elems, s
     return cursor;
 }
 
-void lo_insert(lo_lapper *l, uint32_t start, uint32_t stop, uint32_t val) {
+void lo_insert(lo_lapper *l, lo_coord start, lo_coord stop, uint32_t val) {
     /* :261-272 */
     lo_interval elem = {start, stop, val};
     size_t starts_insert_index = lo_bsearch_seq(start, l->starts, l->len);
     size_t stops_insert_index = lo_bsearch_seq(stop, l->stops, l->len);
     size_t intervals_insert_index = bsearch_seq_iv(&elem, l->intervals, l->len);
-    uint32_t i_len = stop >= start ? stop - start : 0;
+    lo_coord i_len = stop >= start ? stop - start : 0;
     if (i_len > l->max_len) l->max_len = i_len;
     if (l->len + 1 > l->cap) {
         l->cap = l->cap * 2 + 1;
         l->intervals = (lo_interval *)realloc(l->intervals, l->cap * sizeof(lo_interval));
-        l->starts = (uint32_t *)realloc(l->starts, l->cap * sizeof(uint32_t));
-        l->stops = (uint32_t *)realloc(l->stops, l->cap * sizeof(uint32_t));
+        l->starts = (lo_coord *)realloc(l->starts, l->cap * sizeof(lo_coord));
+        l->stops = (lo_coord *)realloc(l->stops, l->cap * sizeof(lo_coord));
         if (!l->intervals || !l->starts || !l->stops) abort();
     }
     memmove(&l->starts[starts_insert_index + 1], &l->starts[starts_insert_index],
-            (l->len - starts_insert_index) * sizeof(uint32_t));
+            (l->len - starts_insert_index) * sizeof(lo_coord));
     l->starts[starts_insert_index] = start;
     memmove(&l->stops[stops_insert_index + 1], &l->stops[stops_insert_index],
-            (l->len - stops_insert_index) * sizeof(uint32_t));
+            (l->len - stops_insert_index) * sizeof(lo_coord));
     l->stops[stops_insert_index] = stop;
     memmove(&l->intervals[intervals_insert_index + 1], &l->intervals[intervals_insert_index],
             (l->len - intervals_insert_index) * sizeof(lo_interval));
@@ -196,16 +196,16 @@ void lo_insert(lo_lapper *l, uint32_t start, uint32_t stop, uint32_t val) {
     l->overlaps_merged = 0;
 }
 
-uint64_t lo_count(const lo_lapper *l, uint32_t start, uint32_t stop) {
+uint64_t lo_count(const lo_lapper *l, lo_coord start, lo_coord stop) {
     /* :612-617; `start + one` wraps like a release build when start == u32::MAX */
     uint64_t len = (uint64_t)l->len;
-    uint64_t first = (uint64_t)lo_bsearch_seq((uint32_t)(start + 1u), l->stops, l->len);
+    uint64_t first = (uint64_t)lo_bsearch_seq((lo_coord)(start + 1u), l->stops, l->len);
     uint64_t last = (uint64_t)lo_bsearch_seq(stop, l->starts, l->len);
     uint64_t num_cant_after = len - last;
     return len - first - num_cant_after; /* wrapping usize */
 }
 
-lo_iter_find lo_find(const lo_lapper *l, uint32_t start, uint32_t stop) {
+lo_iter_find lo_find(const lo_lapper *l, lo_coord start, lo_coord stop) {
     /* :630-638 */
     lo_iter_find it;
     it.inner = l;
@@ -215,9 +215,9 @@ lo_iter_find lo_find(const lo_lapper *l, uint32_t start, uint32_t stop) {
     return it;
 }
 
-lo_iter_find lo_seek(const lo_lapper *l, uint32_t start, uint32_t stop, size_t *cursor) {
+lo_iter_find lo_seek(const lo_lapper *l, lo_coord start, lo_coord stop, size_t *cursor) {
     /* :658-678 */
-    uint32_t floor = start >= l->max_len ? start - l->max_len : 0;
+    lo_coord floor = start >= l->max_len ? start - l->max_len : 0;
     if (*cursor == 0 || (*cursor < l->len && l->intervals[*cursor].start > start)) {
         *cursor = lo_lower_bound(floor, l->intervals, l->len);
     }
@@ -246,10 +246,10 @@ int64_t lo_iter_find_next(lo_iter_find *it) {
     return -1;
 }
 
-uint32_t lo_calculate_coverage(const lo_lapper *l) {
+lo_coord lo_calculate_coverage(const lo_lapper *l) {
     /* :328-349; u32 arithmetic wraps like a release build */
     lo_interval moving = {0, 0, 0};
-    uint32_t cov = 0;
+    lo_coord cov = 0;
     for (size_t i = 0; i < l->len; i++) {
         const lo_interval *interval = &l->intervals[i];
         if (lo_interval_overlap(&moving, interval->start, interval->stop)) {
@@ -265,12 +265,12 @@ uint32_t lo_calculate_coverage(const lo_lapper *l) {
     return cov;
 }
 
-uint32_t lo_cov(const lo_lapper *l) {
+lo_coord lo_cov(const lo_lapper *l) {
     return l->cov_is_some ? l->cov : lo_calculate_coverage(l); /* :311-316 */
 }
 
-uint32_t lo_set_cov(lo_lapper *l) {
-    uint32_t cov = lo_calculate_coverage(l); /* :320-324 */
+lo_coord lo_set_cov(lo_lapper *l) {
+    lo_coord cov = lo_calculate_coverage(l); /* :320-324 */
     l->cov_is_some = 1;
     l->cov = cov;
     return cov;
@@ -299,14 +299,14 @@ void lo_merge_overlaps(lo_lapper *l) {
     rebuild_aux(l); /* :393-415 */
 }
 
-void lo_union_and_intersect(const lo_lapper *self, const lo_lapper *other, uint32_t *union_out,
-                            uint32_t *intersect_out) {
+void lo_union_and_intersect(const lo_lapper *self, const lo_lapper *other, lo_coord *union_out,
+                            lo_coord *intersect_out) {
     /* :514-544 */
     size_t cursor = 0;
     if (!self->overlaps_merged || !other->overlaps_merged) {
         size_t cap = 16, cnt = 0;
-        uint32_t *is = (uint32_t *)xmalloc(cap * sizeof(uint32_t));
-        uint32_t *ie = (uint32_t *)xmalloc(cap * sizeof(uint32_t));
+        lo_coord *is = (lo_coord *)xmalloc(cap * sizeof(lo_coord));
+        lo_coord *ie = (lo_coord *)xmalloc(cap * sizeof(lo_coord));
         for (size_t i = 0; i < self->len; i++) {
             const lo_interval *self_iv = &self->intervals[i];
             lo_iter_find it = lo_seek(other, self_iv->start, self_iv->stop, &cursor);
@@ -315,8 +315,8 @@ void lo_union_and_intersect(const lo_lapper *self, const lo_lapper *other, uint3
                 const lo_interval *other_iv = &other->intervals[j];
                 if (cnt == cap) {
                     cap *= 2;
-                    is = (uint32_t *)realloc(is, cap * sizeof(uint32_t));
-                    ie = (uint32_t *)realloc(ie, cap * sizeof(uint32_t));
+                    is = (lo_coord *)realloc(is, cap * sizeof(lo_coord));
+                    ie = (lo_coord *)realloc(ie, cap * sizeof(lo_coord));
                     if (!is || !ie) abort();
                 }
                 is[cnt] = self_iv->start > other_iv->start ? self_iv->start : other_iv->start;
@@ -327,14 +327,14 @@ void lo_union_and_intersect(const lo_lapper *self, const lo_lapper *other, uint3
         lo_lapper *temp = lo_new(is, ie, NULL, cnt);
         lo_merge_overlaps(temp);
         lo_set_cov(temp);
-        uint32_t u = lo_cov(self) + lo_cov(other) - lo_cov(temp);
+        lo_coord u = lo_cov(self) + lo_cov(other) - lo_cov(temp);
         *union_out = u;
         *intersect_out = lo_cov(temp);
         lo_free(temp);
         free(is);
         free(ie);
     } else {
-        uint32_t intersect = 0;
+        lo_coord intersect = 0;
         for (size_t i = 0; i < self->len; i++) {
             const lo_interval *c1 = &self->intervals[i];
             lo_iter_find it = lo_seek(other, c1->start, c1->stop, &cursor);
@@ -351,8 +351,8 @@ void lo_union_and_intersect(const lo_lapper *self, const lo_lapper *other, uint3
 
 lo_iter_depth lo_depth(const lo_lapper *l) {
     /* :578-597 */
-    uint32_t *s = (uint32_t *)xmalloc(l->len * sizeof(uint32_t));
-    uint32_t *e = (uint32_t *)xmalloc(l->len * sizeof(uint32_t));
+    lo_coord *s = (lo_coord *)xmalloc(l->len * sizeof(lo_coord));
+    lo_coord *e = (lo_coord *)xmalloc(l->len * sizeof(lo_coord));
     for (size_t i = 0; i < l->len; i++) {
         s[i] = l->intervals[i].start;
         e[i] = l->intervals[i].stop;
@@ -371,14 +371,14 @@ lo_iter_depth lo_depth(const lo_lapper *l) {
     return it;
 }
 
-static size_t seek_count(const lo_lapper *l, uint32_t start, uint32_t stop, size_t *cursor) {
+static size_t seek_count(const lo_lapper *l, lo_coord start, lo_coord stop, size_t *cursor) {
     lo_iter_find it = lo_seek(l, start, stop, cursor);
     size_t c = 0;
     while (lo_iter_find_next(&it) >= 0) c++;
     return c;
 }
 
-int lo_iter_depth_next(lo_iter_depth *it, uint32_t *start_out, uint32_t *stop_out, uint32_t *val_out) {
+int lo_iter_depth_next(lo_iter_depth *it, lo_coord *start_out, lo_coord *stop_out, uint32_t *val_out) {
     /* :743-783 */
     if (it->curr_pos >= it->merged->len) {
         fprintf(stderr, "lapper_oracle: depth() index out of bounds (the reference panics, src/lib.rs:744)\n");
@@ -397,7 +397,7 @@ int lo_iter_depth_next(lo_iter_depth *it, uint32_t *start_out, uint32_t *stop_ou
             return 0;
         }
     }
-    uint32_t start = it->curr_merged_pos;
+    lo_coord start = it->curr_merged_pos;
     size_t depth_at_point = seek_count(it->inner, it->curr_merged_pos, it->curr_merged_pos + 1u, &it->cursor);
     size_t new_depth_at_point = depth_at_point;
     while (new_depth_at_point == depth_at_point && it->curr_merged_pos < interval->stop) {
@@ -419,7 +419,7 @@ void lo_iter_depth_free(lo_iter_depth *it) {
 
 typedef struct {
     const lo_lapper *l;
-    const uint32_t *qs, *qe;
+    const lo_coord *qs, *qe;
     size_t lo, hi;
     int mode; /* 0 count, 1 find-count into counts, 2 find-fill, 3 find-count sum */
     uint64_t *counts;
@@ -477,7 +477,7 @@ static uint64_t run_batch(batch_job proto, size_t nq, int nthreads) {
     return sum;
 }
 
-void lo_count_batch(const lo_lapper *l, const uint32_t *q_start, const uint32_t *q_stop, size_t nq,
+void lo_count_batch(const lo_lapper *l, const lo_coord *q_start, const lo_coord *q_stop, size_t nq,
                     uint64_t *counts_out, int nthreads) {
     batch_job p;
     memset(&p, 0, sizeof(p));
@@ -489,7 +489,7 @@ void lo_count_batch(const lo_lapper *l, const uint32_t *q_start, const uint32_t 
     run_batch(p, nq, nthreads);
 }
 
-uint64_t lo_find_batch_offsets(const lo_lapper *l, const uint32_t *q_start, const uint32_t *q_stop,
+uint64_t lo_find_batch_offsets(const lo_lapper *l, const lo_coord *q_start, const lo_coord *q_stop,
                                size_t nq, uint64_t *offsets_out, int nthreads) {
     batch_job p;
     memset(&p, 0, sizeof(p));
@@ -509,7 +509,7 @@ uint64_t lo_find_batch_offsets(const lo_lapper *l, const uint32_t *q_start, cons
     return run;
 }
 
-void lo_find_batch_fill(const lo_lapper *l, const uint32_t *q_start, const uint32_t *q_stop, size_t nq,
+void lo_find_batch_fill(const lo_lapper *l, const lo_coord *q_start, const lo_coord *q_stop, size_t nq,
                         const uint64_t *offsets, uint32_t *indices_out, int nthreads) {
     batch_job p;
     memset(&p, 0, sizeof(p));
@@ -522,7 +522,7 @@ void lo_find_batch_fill(const lo_lapper *l, const uint32_t *q_start, const uint3
     run_batch(p, nq, nthreads);
 }
 
-void lo_seek_batch_fill(const lo_lapper *l, const uint32_t *q_start, const uint32_t *q_stop, size_t nq,
+void lo_seek_batch_fill(const lo_lapper *l, const lo_coord *q_start, const lo_coord *q_stop, size_t nq,
                         const uint64_t *offsets, uint32_t *indices_out) {
     size_t cursor = 0;
     for (size_t q = 0; q < nq; q++) {
@@ -538,7 +538,7 @@ void lo_seek_batch_fill(const lo_lapper *l, const uint32_t *q_start, const uint3
     }
 }
 
-uint64_t lo_find_count_sum(const lo_lapper *l, const uint32_t *q_start, const uint32_t *q_stop, size_t nq,
+uint64_t lo_find_count_sum(const lo_lapper *l, const lo_coord *q_start, const lo_coord *q_stop, size_t nq,
                            int nthreads) {
     batch_job p;
     memset(&p, 0, sizeof(p));

@@ -18,18 +18,20 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "liblapper_oracle.so")
+_SO64 = os.path.join(_HERE, "liblapper_oracle64.so")  # the same source with I = u64 (-DLO_COORD_BITS=64)
 
 
-def build(force: bool = False) -> str:
+def build(force: bool = False, coord_bits: int = 32) -> str:
     """Compile the oracle with gcc (plain C, no CUDA)."""
+    so = _SO64 if coord_bits == 64 else _SO
     src = os.path.join(_HERE, "lapper_oracle.c")
     hdr = os.path.join(_HERE, "lapper_oracle.h")
-    stale = (not os.path.exists(_SO)) or any(
-        os.path.getmtime(f) > os.path.getmtime(_SO) for f in (src, hdr) if os.path.exists(f)
+    stale = (not os.path.exists(so)) or any(
+        os.path.getmtime(f) > os.path.getmtime(so) for f in (src, hdr) if os.path.exists(f)
     )
     if force or stale:
-        subprocess.check_call(["make", "-s", "-C", _HERE, "liblapper_oracle.so"] + (["-B"] if force else []))
-    return _SO
+        subprocess.check_call(["make", "-s", "-C", _HERE, os.path.basename(so)] + (["-B"] if force else []))
+    return so
 
 
 def build_native(out_path: str) -> Optional[str]:
@@ -41,88 +43,114 @@ def build_native(out_path: str) -> Optional[str]:
         return None
 
 
-class _Iv(C.Structure):
-    _fields_ = [("start", C.c_uint32), ("stop", C.c_uint32), ("val", C.c_uint32)]
+class _Binding:
+    """ctypes view of one build of the oracle: the struct layouts and prototypes for I = u32 or I = u64"""
 
+    def __init__(self, bits: int):
+        self.bits = bits
+        ct = C.c_uint64 if bits == 64 else C.c_uint32
+        self.ct = ct
+        self.np = np.uint64 if bits == 64 else np.uint32
+        self.p = C.POINTER(ct)
+        # lo_interval {I start; I stop; u32 val} (8-byte aligned, so padded to 24 bytes, when I = u64)
+        self.iv_dtype = (np.dtype([("start", "<u8"), ("stop", "<u8"), ("val", "<u4"), ("pad", "<u4")]) if bits == 64 else
+                         np.dtype([("start", "<u4"), ("stop", "<u4"), ("val", "<u4")]))
 
-class _Lapper(C.Structure):
-    _fields_ = [
-        ("intervals", C.POINTER(_Iv)),
-        ("starts", C.POINTER(C.c_uint32)),
-        ("stops", C.POINTER(C.c_uint32)),
-        ("len", C.c_size_t),
-        ("cap", C.c_size_t),
-        ("max_len", C.c_uint32),
-        ("cov_is_some", C.c_int),
-        ("cov", C.c_uint32),
-        ("overlaps_merged", C.c_int),
-    ]
+        class Iv(C.Structure):
+            _fields_ = [("start", ct), ("stop", ct), ("val", C.c_uint32)]
 
+        class Lapper(C.Structure):
+            _fields_ = [
+                ("intervals", C.POINTER(Iv)),
+                ("starts", C.POINTER(ct)),
+                ("stops", C.POINTER(ct)),
+                ("len", C.c_size_t),
+                ("cap", C.c_size_t),
+                ("max_len", ct),
+                ("cov_is_some", C.c_int),
+                ("cov", ct),
+                ("overlaps_merged", C.c_int),
+            ]
 
-class _IterFind(C.Structure):
-    _fields_ = [("inner", C.POINTER(_Lapper)), ("off", C.c_size_t), ("start", C.c_uint32), ("stop", C.c_uint32)]
+        class IterFind(C.Structure):
+            _fields_ = [("inner", C.POINTER(Lapper)), ("off", C.c_size_t), ("start", ct), ("stop", ct)]
 
+        class IterDepth(C.Structure):
+            _fields_ = [
+                ("inner", C.POINTER(Lapper)),
+                ("merged", C.POINTER(Lapper)),
+                ("curr_merged_pos", ct),
+                ("curr_pos", C.c_size_t),
+                ("cursor", C.c_size_t),
+                ("end", C.c_size_t),
+            ]
 
-class _IterDepth(C.Structure):
-    _fields_ = [
-        ("inner", C.POINTER(_Lapper)),
-        ("merged", C.POINTER(_Lapper)),
-        ("curr_merged_pos", C.c_uint32),
-        ("curr_pos", C.c_size_t),
-        ("cursor", C.c_size_t),
-        ("end", C.c_size_t),
-    ]
+        assert C.sizeof(Iv) == self.iv_dtype.itemsize
+        self.Iv, self.Lapper, self.IterFind, self.IterDepth = Iv, Lapper, IterFind, IterDepth
+        self.lib = None
+
+    def bind(self, lib):
+        ct, cp = self.ct, self.p
+        LP = C.POINTER(self.Lapper)
+        lib.lo_new.restype = LP
+        lib.lo_new.argtypes = [cp, cp, _u32p, C.c_size_t]
+        lib.lo_free.argtypes = [LP]
+        lib.lo_insert.argtypes = [LP, ct, ct, C.c_uint32]
+        lib.lo_interval_intersect.restype = ct
+        lib.lo_interval_intersect.argtypes = [ct] * 4
+        lib.lo_lower_bound.restype = C.c_size_t
+        lib.lo_lower_bound.argtypes = [ct, C.POINTER(self.Iv), C.c_size_t]
+        lib.lo_bsearch_seq.restype = C.c_size_t
+        lib.lo_bsearch_seq.argtypes = [ct, cp, C.c_size_t]
+        lib.lo_count.restype = C.c_uint64
+        lib.lo_count.argtypes = [LP, ct, ct]
+        lib.lo_find.restype = self.IterFind
+        lib.lo_find.argtypes = [LP, ct, ct]
+        lib.lo_seek.restype = self.IterFind
+        lib.lo_seek.argtypes = [LP, ct, ct, C.POINTER(C.c_size_t)]
+        lib.lo_iter_find_next.restype = C.c_int64
+        lib.lo_iter_find_next.argtypes = [C.POINTER(self.IterFind)]
+        for f in ("lo_calculate_coverage", "lo_cov", "lo_set_cov"):
+            getattr(lib, f).restype = ct
+            getattr(lib, f).argtypes = [LP]
+        lib.lo_merge_overlaps.argtypes = [LP]
+        lib.lo_union_and_intersect.argtypes = [LP, LP, cp, cp]
+        lib.lo_depth.restype = self.IterDepth
+        lib.lo_depth.argtypes = [LP]
+        lib.lo_iter_depth_next.restype = C.c_int
+        lib.lo_iter_depth_next.argtypes = [C.POINTER(self.IterDepth), cp, cp, _u32p]
+        lib.lo_iter_depth_free.argtypes = [C.POINTER(self.IterDepth)]
+        lib.lo_count_batch.argtypes = [LP, cp, cp, C.c_size_t, _u64p, C.c_int]
+        lib.lo_find_batch_offsets.restype = C.c_uint64
+        lib.lo_find_batch_offsets.argtypes = [LP, cp, cp, C.c_size_t, _u64p, C.c_int]
+        lib.lo_find_batch_fill.argtypes = [LP, cp, cp, C.c_size_t, _u64p, _u32p, C.c_int]
+        lib.lo_seek_batch_fill.argtypes = [LP, cp, cp, C.c_size_t, _u64p, _u32p]
+        lib.lo_find_count_sum.restype = C.c_uint64
+        lib.lo_find_count_sum.argtypes = [LP, cp, cp, C.c_size_t, C.c_int]
+        lib._binding = self
+        return lib
+
+    def arr(self, a) -> np.ndarray:
+        return np.ascontiguousarray(np.asarray(a, dtype=self.np))
+
+    def ptr(self, a: np.ndarray):
+        return a.ctypes.data_as(self.p)
 
 
 _u32p = C.POINTER(C.c_uint32)
 _u64p = C.POINTER(C.c_uint64)
-_lib = None
+_bindings = {32: _Binding(32), 64: _Binding(64)}
+_IterFind = _bindings[32].IterFind
 
 
-def load(path: Optional[str] = None):
-    global _lib
-    if _lib is not None and path is None:
-        return _lib
-    lib = C.CDLL(path or build())
-    LP = C.POINTER(_Lapper)
-    lib.lo_new.restype = LP
-    lib.lo_new.argtypes = [_u32p, _u32p, _u32p, C.c_size_t]
-    lib.lo_free.argtypes = [LP]
-    lib.lo_insert.argtypes = [LP, C.c_uint32, C.c_uint32, C.c_uint32]
-    lib.lo_interval_intersect.restype = C.c_uint32
-    lib.lo_interval_intersect.argtypes = [C.c_uint32] * 4
-    lib.lo_lower_bound.restype = C.c_size_t
-    lib.lo_lower_bound.argtypes = [C.c_uint32, C.POINTER(_Iv), C.c_size_t]
-    lib.lo_bsearch_seq.restype = C.c_size_t
-    lib.lo_bsearch_seq.argtypes = [C.c_uint32, _u32p, C.c_size_t]
-    lib.lo_count.restype = C.c_uint64
-    lib.lo_count.argtypes = [LP, C.c_uint32, C.c_uint32]
-    lib.lo_find.restype = _IterFind
-    lib.lo_find.argtypes = [LP, C.c_uint32, C.c_uint32]
-    lib.lo_seek.restype = _IterFind
-    lib.lo_seek.argtypes = [LP, C.c_uint32, C.c_uint32, C.POINTER(C.c_size_t)]
-    lib.lo_iter_find_next.restype = C.c_int64
-    lib.lo_iter_find_next.argtypes = [C.POINTER(_IterFind)]
-    for f in ("lo_calculate_coverage", "lo_cov", "lo_set_cov"):
-        getattr(lib, f).restype = C.c_uint32
-        getattr(lib, f).argtypes = [LP]
-    lib.lo_merge_overlaps.argtypes = [LP]
-    lib.lo_union_and_intersect.argtypes = [LP, LP, _u32p, _u32p]
-    lib.lo_depth.restype = _IterDepth
-    lib.lo_depth.argtypes = [LP]
-    lib.lo_iter_depth_next.restype = C.c_int
-    lib.lo_iter_depth_next.argtypes = [C.POINTER(_IterDepth), _u32p, _u32p, _u32p]
-    lib.lo_iter_depth_free.argtypes = [C.POINTER(_IterDepth)]
-    lib.lo_count_batch.argtypes = [LP, _u32p, _u32p, C.c_size_t, _u64p, C.c_int]
-    lib.lo_find_batch_offsets.restype = C.c_uint64
-    lib.lo_find_batch_offsets.argtypes = [LP, _u32p, _u32p, C.c_size_t, _u64p, C.c_int]
-    lib.lo_find_batch_fill.argtypes = [LP, _u32p, _u32p, C.c_size_t, _u64p, _u32p, C.c_int]
-    lib.lo_seek_batch_fill.argtypes = [LP, _u32p, _u32p, C.c_size_t, _u64p, _u32p]
-    lib.lo_find_count_sum.restype = C.c_uint64
-    lib.lo_find_count_sum.argtypes = [LP, _u32p, _u32p, C.c_size_t, C.c_int]
+def load(path: Optional[str] = None, coord_bits: int = 32):
+    """The oracle library for I = u32 (default) or I = u64; `path` loads another build of the u32 one."""
+    b = _bindings[coord_bits]
     if path is None:
-        _lib = lib
-    return lib
+        if b.lib is None:
+            b.lib = b.bind(C.CDLL(build(coord_bits=coord_bits)))
+        return b.lib
+    return _Binding(coord_bits).bind(C.CDLL(path))
 
 
 def _as_u32(a) -> np.ndarray:
@@ -138,20 +166,22 @@ def _p64(a: np.ndarray):
 
 
 class OracleLapper:
-    """`Lapper<u32,u32>` of the reference, restated on the CPU (src/lib.rs:182-680)."""
+    """`Lapper<u32,u32>` (coord_bits=64: `Lapper<u64,u32>`) of the reference, restated on the CPU (src/lib.rs:182-680)."""
 
-    def __init__(self, intervals: Iterable[Tuple[int, int]] = (), *, starts=None, stops=None, vals=None, lib=None):
-        self._lib = lib or load()
+    def __init__(self, intervals: Iterable[Tuple[int, int]] = (), *, starts=None, stops=None, vals=None, lib=None,
+                 coord_bits: int = 32):
+        self._lib = lib or load(coord_bits=coord_bits)
+        self._b = self._lib._binding
         if starts is None:
             ivs = list(intervals)
             starts = [iv[0] for iv in ivs]
             stops = [iv[1] for iv in ivs]
             if ivs and len(ivs[0]) > 2:
                 vals = [iv[2] for iv in ivs]
-        s, e = _as_u32(starts), _as_u32(stops)
+        s, e = self._b.arr(starts), self._b.arr(stops)
         assert s.shape == e.shape
         v = _as_u32(vals) if vals is not None else None
-        self._h = self._lib.lo_new(_p32(s), _p32(e), _p32(v) if v is not None else None, s.size)
+        self._h = self._lib.lo_new(self._b.ptr(s), self._b.ptr(e), _p32(v) if v is not None else None, s.size)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -176,7 +206,7 @@ class OracleLapper:
     def _arr(self, field: str) -> np.ndarray:
         n = len(self)
         if n == 0:
-            return np.zeros(0, np.uint32)
+            return np.zeros(0, self._b.np)
         return np.ctypeslib.as_array(getattr(self._h.contents, field), shape=(n,)).copy()
 
     @property
@@ -190,10 +220,10 @@ class OracleLapper:
     def intervals_soa(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         n = len(self)
         if n == 0:
-            z = np.zeros(0, np.uint32)
-            return z, z.copy(), z.copy()
-        raw = np.ctypeslib.as_array(C.cast(self._h.contents.intervals, _u32p), shape=(n, 3)).copy()
-        return raw[:, 0].copy(), raw[:, 1].copy(), raw[:, 2].copy()
+            return np.zeros(0, self._b.np), np.zeros(0, self._b.np), np.zeros(0, np.uint32)
+        nbytes = n * self._b.iv_dtype.itemsize
+        raw = np.frombuffer(C.string_at(self._h.contents.intervals, nbytes), dtype=self._b.iv_dtype)
+        return raw["start"].copy(), raw["stop"].copy(), raw["val"].copy()
 
     @property
     def intervals(self) -> List[Tuple[int, int]]:
@@ -210,7 +240,7 @@ class OracleLapper:
     def count(self, start: int, stop: int) -> int:
         return int(self._lib.lo_count(self._h, start, stop))
 
-    def _drain(self, it: _IterFind) -> List[int]:
+    def _drain(self, it) -> List[int]:
         out = []
         while True:
             p = self._lib.lo_iter_find_next(C.byref(it))
@@ -247,7 +277,7 @@ class OracleLapper:
         self._lib.lo_merge_overlaps(self._h)
 
     def union_and_intersect(self, other: "OracleLapper") -> Tuple[int, int]:
-        u, i = C.c_uint32(0), C.c_uint32(0)
+        u, i = self._b.ct(0), self._b.ct(0)
         self._lib.lo_union_and_intersect(self._h, other._h, C.byref(u), C.byref(i))
         return int(u.value), int(i.value)
 
@@ -262,7 +292,7 @@ class OracleLapper:
             raise IndexError("depth() on an empty lapper panics in the reference (src/lib.rs:744)")
         it = self._lib.lo_depth(self._h)
         out = []
-        s, e, v = C.c_uint32(0), C.c_uint32(0), C.c_uint32(0)
+        s, e, v = self._b.ct(0), self._b.ct(0), C.c_uint32(0)
         while self._lib.lo_iter_depth_next(C.byref(it), C.byref(s), C.byref(e), C.byref(v)):
             out.append((int(s.value), int(e.value), int(v.value)))
         self._lib.lo_iter_depth_free(C.byref(it))
@@ -270,29 +300,29 @@ class OracleLapper:
 
     # -- batch drivers
     def count_batch(self, q_start, q_stop, nthreads: int = 1) -> np.ndarray:
-        qs, qe = _as_u32(q_start), _as_u32(q_stop)
+        qs, qe = self._b.arr(q_start), self._b.arr(q_stop)
         out = np.empty(qs.size, np.uint64)
-        self._lib.lo_count_batch(self._h, _p32(qs), _p32(qe), qs.size, _p64(out), nthreads)
+        self._lib.lo_count_batch(self._h, self._b.ptr(qs), self._b.ptr(qe), qs.size, _p64(out), nthreads)
         return out
 
     def find_batch(self, q_start, q_stop, nthreads: int = 1) -> Tuple[np.ndarray, np.ndarray]:
-        qs, qe = _as_u32(q_start), _as_u32(q_stop)
+        qs, qe = self._b.arr(q_start), self._b.arr(q_stop)
         offsets = np.empty(qs.size + 1, np.uint64)
-        total = int(self._lib.lo_find_batch_offsets(self._h, _p32(qs), _p32(qe), qs.size, _p64(offsets), nthreads))
+        total = int(self._lib.lo_find_batch_offsets(self._h, self._b.ptr(qs), self._b.ptr(qe), qs.size, _p64(offsets), nthreads))
         indices = np.empty(total, np.uint32)
-        self._lib.lo_find_batch_fill(self._h, _p32(qs), _p32(qe), qs.size, _p64(offsets), _p32(indices), nthreads)
+        self._lib.lo_find_batch_fill(self._h, self._b.ptr(qs), self._b.ptr(qe), qs.size, _p64(offsets), _p32(indices), nthreads)
         return offsets, indices
 
     def seek_batch(self, q_start, q_stop, offsets: np.ndarray) -> np.ndarray:
-        qs, qe = _as_u32(q_start), _as_u32(q_stop)
+        qs, qe = self._b.arr(q_start), self._b.arr(q_stop)
         offsets = np.ascontiguousarray(offsets, dtype=np.uint64)
         indices = np.full(int(offsets[-1]), 0xFFFFFFFF, np.uint32)
-        self._lib.lo_seek_batch_fill(self._h, _p32(qs), _p32(qe), qs.size, _p64(offsets), _p32(indices))
+        self._lib.lo_seek_batch_fill(self._h, self._b.ptr(qs), self._b.ptr(qe), qs.size, _p64(offsets), _p32(indices))
         return indices
 
     def find_count_sum(self, q_start, q_stop, nthreads: int = 1) -> int:
-        qs, qe = _as_u32(q_start), _as_u32(q_stop)
-        return int(self._lib.lo_find_count_sum(self._h, _p32(qs), _p32(qe), qs.size, nthreads))
+        qs, qe = self._b.arr(q_start), self._b.arr(q_stop)
+        return int(self._lib.lo_find_count_sum(self._h, self._b.ptr(qs), self._b.ptr(qe), qs.size, nthreads))
 
 
 def interval_intersect(a: Sequence[int], b: Sequence[int]) -> int:
