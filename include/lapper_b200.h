@@ -238,6 +238,50 @@ int lapper_from_sorted_dev(const uint32_t *d_starts, const uint32_t *d_stops_by_
 int lapper_host_alloc_pinned(uint64_t bytes, void **out);
 void lapper_host_free_pinned(void *p);
 
+/* =====================================================================================================
+ * Lapper<I, T> with I = u64 (src/lib.rs:88-100: the coordinate is any PrimInt + Unsigned; the README's examples use
+ * usize).  The second instantiation of the query path (csrc/engine64.cu): the same contracts as the u32 entry points
+ * above with 64-bit coordinates -- count wraps in u64 like usize, positions stay u32 (at most 2^32 - 2 intervals),
+ * find results come back as the same lapper_result_t.  Plain bisection under a shared-memory key directory instead of
+ * the u32 engine's sector tables.  Not instantiated for u64: insert, depth, the seek cursor, groups (seek yields
+ * find's sequence).
+ * ===================================================================================================== */
+typedef struct lapper64 lapper64_t;
+
+/* Lapper::new (src/lib.rs:196-236); host arrays / device arrays + stream (synchronised before returning) */
+int lapper64_build(const uint64_t *starts, const uint64_t *stops, uint64_t n, int device, lapper64_t **out);
+int lapper64_build_dev(const uint64_t *d_starts, const uint64_t *d_stops, uint64_t n, int device, void *stream,
+                       lapper64_t **out);
+void lapper64_free(lapper64_t *l);
+uint64_t lapper64_len(const lapper64_t *l);          /* src/lib.rs:284-287 */
+uint64_t lapper64_max_len(const lapper64_t *l);      /* src/lib.rs:218-227 */
+int lapper64_overlaps_merged(const lapper64_t *l);   /* src/lib.rs:122 */
+int lapper64_has_inverted(const lapper64_t *l);
+/* the sorted `intervals` vector as SoA + perm (sorted position -> input position); any pointer may be NULL */
+int lapper64_get_intervals(const lapper64_t *l, uint64_t *starts_out, uint64_t *stops_out, uint32_t *perm_out);
+/* the private sorted `stops` (src/lib.rs:116) */
+int lapper64_get_sorted_stops(const lapper64_t *l, uint64_t *stops_sorted_out);
+
+/* Lapper::count (src/lib.rs:610-618), batched; u64 counts wrap like the reference's usize arithmetic */
+int lapper64_count_batch(const lapper64_t *l, const uint64_t *q_start, const uint64_t *q_stop, uint64_t nq,
+                         uint64_t *counts_out);
+int lapper64_count_batch_dev(const lapper64_t *l, const uint64_t *d_q_start, const uint64_t *d_q_stop, uint64_t nq,
+                             uint64_t *d_counts_out, void *stream);
+
+/* Lapper::find + IterFind::next (src/lib.rs:628-639, :695-718), batched CSR (see lapper_find_batch_u32 /
+ * lapper_find_batch_u32_dev for the contracts, incl. LAPPER_ERR_CAPACITY and the size query) */
+int lapper64_find_batch(const lapper64_t *l, const uint64_t *q_start, const uint64_t *q_stop, uint64_t nq,
+                        lapper_result_t **out);
+int lapper64_find_batch_dev(const lapper64_t *l, const uint64_t *d_q_start, const uint64_t *d_q_stop, uint64_t nq,
+                            uint64_t *d_offsets, uint32_t *d_indices, uint64_t indices_capacity, uint64_t *total_out,
+                            void *stream);
+
+/* cov / set_cov (src/lib.rs:310-350), merge_overlaps (:361-416), union_and_intersect (:512-559) */
+int lapper64_cov(const lapper64_t *l, uint64_t *cov_out);
+int lapper64_set_cov(lapper64_t *l, uint64_t *cov_out);
+int lapper64_merge_overlaps(lapper64_t *l);
+int lapper64_union_and_intersect(const lapper64_t *a, const lapper64_t *b, uint64_t *union_out, uint64_t *intersect_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,24 @@ SIGNATURES = {
     "lapper_group_find_batch_u32": (_int, [_vp, _vp, _vp, _u64, _vp, _pvp, C.POINTER(_u64)]),
     "lapper_from_sorted_dev": (_int, [_vp, _vp, _vp, _vp, _u64, _int, _int, _u32, _vp, _pvp]),
     "lapper_host_alloc_pinned": (_int, [_u64, _pvp]),
+    # I = u64 (csrc/engine64.cu)
+    "lapper64_build": (_int, [_vp, _vp, _u64, _int, _pvp]),
+    "lapper64_build_dev": (_int, [_vp, _vp, _u64, _int, _vp, _pvp]),
+    "lapper64_free": (None, [_vp]),
+    "lapper64_len": (_u64, [_vp]),
+    "lapper64_max_len": (_u64, [_vp]),
+    "lapper64_overlaps_merged": (_int, [_vp]),
+    "lapper64_has_inverted": (_int, [_vp]),
+    "lapper64_get_intervals": (_int, [_vp, _vp, _vp, _vp]),
+    "lapper64_get_sorted_stops": (_int, [_vp, _vp]),
+    "lapper64_count_batch": (_int, [_vp, _vp, _vp, _u64, _vp]),
+    "lapper64_count_batch_dev": (_int, [_vp, _vp, _vp, _u64, _vp, _vp]),
+    "lapper64_find_batch": (_int, [_vp, _vp, _vp, _u64, _pvp]),
+    "lapper64_find_batch_dev": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64), _vp]),
+    "lapper64_cov": (_int, [_vp, C.POINTER(_u64)]),
+    "lapper64_set_cov": (_int, [_vp, C.POINTER(_u64)]),
+    "lapper64_merge_overlaps": (_int, [_vp]),
+    "lapper64_union_and_intersect": (_int, [_vp, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "lapper_host_free_pinned": (None, [_vp]),
 }
 

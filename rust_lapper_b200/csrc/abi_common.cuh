@@ -1,0 +1,45 @@
+// abi_common.cuh -- what the files that define C-ABI entry points share (api.cu: I = u32, engine64.cu: I = u64): the
+// exception -> status code boundary, the per-thread error text behind lapper_last_error(), device checks.
+#pragma once
+
+#include <new>
+#include <string>
+
+#include "common.cuh"
+
+namespace lap {
+
+std::string &last_error_slot();  // api.cu: the calling thread's last error text
+void require_device_index(int device);  // api.cu: throws LAPPER_ERR_NO_DEVICE / LAPPER_ERR_INVALID_ARG
+
+template <typename F>
+int guarded_call(F &&f) {
+    try {
+        f();
+        return LAPPER_OK;
+    } catch (const Error &e) {
+        last_error_slot() = e.what();
+        return e.code;
+    } catch (const std::bad_alloc &) {
+        last_error_slot() = "host allocation failed";
+        return LAPPER_ERR_OOM;
+    } catch (const std::exception &e) {
+        last_error_slot() = e.what();
+        return LAPPER_ERR_CUDA;
+    } catch (...) {
+        last_error_slot() = "unknown error";
+        return LAPPER_ERR_CUDA;
+    }
+}
+
+struct OwnedStream {
+    cudaStream_t s = nullptr;
+    OwnedStream() { LAPPER_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+    ~OwnedStream() {
+        if (s) cudaStreamDestroy(s);
+    }
+    OwnedStream(const OwnedStream &) = delete;
+    OwnedStream &operator=(const OwnedStream &) = delete;
+};
+
+}  // namespace lap

@@ -9,6 +9,7 @@
 #include <thread>
 #include <vector>
 
+#include "abi_common.cuh"
 #include "index.cuh"
 
 using namespace lap;
@@ -53,6 +54,13 @@ uint32_t sm_count() {
 namespace {
 
 thread_local std::string g_last_error;
+void require_device(int device);
+}  // namespace
+namespace lap {
+std::string &last_error_slot() { return g_last_error; }
+void require_device_index(int device) { require_device(device); }
+}  // namespace lap
+namespace {
 
 template <typename F>
 int guarded(F &&f) {

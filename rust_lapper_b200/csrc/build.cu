@@ -529,6 +529,14 @@ void build_find_classes(DeviceIndex &ix, cudaStream_t stream) {
 
 }  // namespace
 
+void launch_sort_u64(uint64_t *keys, uint64_t *tmp, uint64_t n, cudaStream_t stream) {
+    if (n) radix_sort<uint64_t, false>(keys, tmp, nullptr, nullptr, n, 64, stream);
+}
+
+void launch_sort_pairs_u64(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, uint64_t n, cudaStream_t stream) {
+    if (n) radix_sort<uint64_t, true>(keys, keys_tmp, vals, vals_tmp, n, 64, stream);
+}
+
 void launch_sort_u32(uint32_t *keys, uint32_t *tmp, uint64_t n, cudaStream_t stream) {
     if (n > 1) radix_sort<uint32_t, false>(keys, tmp, nullptr, nullptr, n, 32, stream);
 }

@@ -1,0 +1,805 @@
+// engine64.cu -- Lapper<I, T> with I = u64 (src/lib.rs:88-100: any PrimInt + Unsigned coordinate; the README's examples
+// use usize).  The second instantiation of the query path: same C-ABI shape as the u32 engine (lapper64_* in
+// include/lapper_b200.h), checked by the same CPU restatement built with I = u64 and the same parity suite
+// (tests/test_gpu_u64.py).
+//
+// The u32 engine's tables (BITS sectors with 16-bit lanes, the packed 12-bit table, length classes) are formats for
+// 32-bit coordinates in a GRCh38-sized universe.  64-bit coordinates get the plain form of the same algorithms:
+//   build   (src/lib.rs:196-236)  two stable LSD radix sorts (by stop, then by start: (start, stop) order, ties in
+//                                 input order like Vec::sort), sorted stops, max_len / inverted flag, prefix max of stops
+//   count   (src/lib.rs:610-618)  lower_bound(starts, stop) - upper_bound(stops, start) by bisection under a
+//                                 1024-entry sampled directory of each array in shared memory (the top ten levels)
+//   find    (src/lib.rs:628-639, :695-718)  count pass (the BITS identity where it holds, the predicate elsewhere),
+//                                 u64 exclusive scan, emit: one warp per query scans the window
+//                                 [max(lower_bound(start - max_len), first i with prefix_max_i > start), lower_bound(stop))
+//                                 32 intervals per step and ballot-compacts the hits -- ascending positions, the
+//                                 reference iterator's order
+//   cov, merge_overlaps, union_and_intersect (src/lib.rs:310-350, :361-416, :512-559)  the prefix-max closed forms of
+//                                 setops.cu on u64 values
+// seek yields find's sequence (no cursor crosses the ABI); insert and depth are not instantiated for u64 (the u32
+// engine has them).  At most 2^32 - 1 intervals (positions are u32, as in the u32 engine).
+#include <algorithm>
+#include <memory>
+
+#include "abi_common.cuh"
+#include "index.cuh"
+
+struct lapper64 {
+    int device = 0;
+    uint64_t n = 0;
+    uint64_t *S = nullptr;    // starts, sorted by (start, stop)
+    uint64_t *Eiv = nullptr;  // stops paired with S
+    uint64_t *E = nullptr;    // stops, sorted on their own (the reference's private `stops`)
+    uint64_t *P = nullptr;    // prefix max of Eiv
+    uint32_t *perm = nullptr; // sorted position -> input position
+    uint64_t max_len = 0;
+    bool has_inverted = false;
+    bool overlaps_merged = false;
+    bool cov_is_some = false;
+    uint64_t cov = 0;
+};
+
+namespace lap {
+namespace {
+
+constexpr int kT = 256;
+constexpr int kItems = 8;
+constexpr int kTile64 = kT * kItems;  // items per tile of the scans
+
+uint32_t grid_for(uint64_t n, int per_block = kT) { return (uint32_t)div_up(n ? n : 1, per_block); }
+uint32_t capped(uint64_t n, int waves = 8) {
+    const uint64_t g = div_up(n ? n : 1, kT), cap = (uint64_t)sm_count() * waves;
+    return (uint32_t)std::min(g, cap);
+}
+
+__device__ __forceinline__ uint64_t lb64(const uint64_t *__restrict__ a, uint64_t lo, uint64_t hi, uint64_t key) {
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(a + mid) < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+__device__ __forceinline__ uint64_t ub64(const uint64_t *__restrict__ a, uint64_t lo, uint64_t hi, uint64_t key) {
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        if (__ldg(a + mid) <= key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------ build
+__global__ void iota_kernel(uint32_t *__restrict__ v, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (uint32_t)i;
+}
+__global__ void gather64_kernel(uint64_t *__restrict__ out, const uint64_t *__restrict__ in, const uint32_t *__restrict__ idx,
+                                uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[idx[i]];
+}
+// max_len with checked_sub -> 0 (src/lib.rs:218-227) and the inverted flag; out[0] = max_len, out[1] = inverted
+__global__ void __launch_bounds__(kT) stats64_kernel(const uint64_t *__restrict__ s, const uint64_t *__restrict__ e, uint64_t n,
+                                                     unsigned long long *__restrict__ out) {
+    unsigned long long mx = 0, inv = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t a = s[i], b = e[i];
+        mx = max(mx, (unsigned long long)(b > a ? b - a : 0ull));
+        inv |= (b < a) ? 1ull : 0ull;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
+        inv |= __shfl_xor_sync(0xFFFFFFFFu, inv, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (mx) atomicMax(out, mx);
+        if (inv) atomicOr(out + 1, 1ull);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ scans over u64 values
+// Three kernels: per-tile aggregate, one block scans the aggregates (exclusive, in place; total out), per-tile scan
+// with the carry applied, results handed to a sink functor as (index, inclusive, exclusive, value).
+struct Max64 {
+    static __device__ __forceinline__ uint64_t id() { return 0; }
+    static __device__ __forceinline__ uint64_t op(uint64_t a, uint64_t b) { return a > b ? a : b; }
+};
+struct Add64 {
+    static __device__ __forceinline__ uint64_t id() { return 0; }
+    static __device__ __forceinline__ uint64_t op(uint64_t a, uint64_t b) { return a + b; }
+};
+
+template <typename Op>
+__device__ __forceinline__ uint64_t block_scan_incl(uint64_t x, uint64_t *warp_tot, uint64_t &block_total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint64_t inc = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc = Op::op(y, inc);
+    }
+    __syncthreads();  // warp_tot may still be read from the previous use
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    uint64_t before = Op::id(), all = Op::id();
+#pragma unroll
+    for (int i = 0; i < kT / 32; i++) {
+        if (i < w) before = Op::op(before, warp_tot[i]);
+        all = Op::op(all, warp_tot[i]);
+    }
+    block_total = all;
+    return Op::op(before, inc);
+}
+
+template <typename Op, typename In>
+__global__ void __launch_bounds__(kT) tile_reduce64_kernel(In in, uint64_t n, uint64_t *__restrict__ agg) {
+    __shared__ uint64_t warp_tot[kT / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kTile64 + (uint64_t)threadIdx.x * kItems;
+    uint64_t x = Op::id();
+#pragma unroll
+    for (int k = 0; k < kItems; k++)
+        if (base + k < n) x = Op::op(x, in(base + k));
+    uint64_t total;
+    block_scan_incl<Op>(x, warp_tot, total);
+    if (threadIdx.x == 0) agg[blockIdx.x] = total;
+}
+
+template <typename Op>
+__global__ void __launch_bounds__(kT) tile_scan64_kernel(uint64_t *__restrict__ agg, uint64_t ntiles, uint64_t *__restrict__ total_out) {
+    __shared__ uint64_t warp_tot[kT / 32];
+    uint64_t carry = Op::id();
+    for (uint64_t t0 = 0; t0 < ntiles; t0 += kT) {
+        const uint64_t t = t0 + threadIdx.x;
+        const uint64_t x = t < ntiles ? agg[t] : Op::id();
+        uint64_t total;
+        const uint64_t inc = block_scan_incl<Op>(x, warp_tot, total);
+        // exclusive = carry op (everything before t in this round)
+        const uint64_t prev = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+        uint64_t ex;
+        if ((threadIdx.x & 31) == 0) {
+            ex = Op::id();
+            for (int i = 0; i < (int)(threadIdx.x >> 5); i++) ex = Op::op(ex, warp_tot[i]);
+        } else {
+            ex = prev;
+        }
+        if (t < ntiles) agg[t] = Op::op(carry, ex);
+        carry = Op::op(carry, total);
+    }
+    if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+template <typename Op, typename In, typename Sink>
+__global__ void __launch_bounds__(kT) tile_apply64_kernel(In in, uint64_t n, const uint64_t *__restrict__ tile_excl, Sink sink) {
+    __shared__ uint64_t warp_tot[kT / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * kTile64 + (uint64_t)threadIdx.x * kItems;
+    uint64_t v[kItems], x = Op::id();
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        v[k] = base + k < n ? in(base + k) : Op::id();
+        x = Op::op(x, v[k]);
+    }
+    uint64_t total;
+    const uint64_t inc = block_scan_incl<Op>(x, warp_tot, total);
+    // exclusive prefix of this thread's first item: everything before it in the tile, and the tiles before
+    const uint64_t prev = __shfl_up_sync(0xFFFFFFFFu, inc, 1);
+    uint64_t ex;
+    if ((threadIdx.x & 31) == 0) {
+        ex = Op::id();
+        for (int i = 0; i < (int)(threadIdx.x >> 5); i++) ex = Op::op(ex, warp_tot[i]);
+    } else {
+        ex = prev;
+    }
+    uint64_t run = Op::op(tile_excl[blockIdx.x], ex);
+#pragma unroll
+    for (int k = 0; k < kItems; k++) {
+        const uint64_t incl = Op::op(run, v[k]);
+        if (base + k < n) sink(base + k, incl, run, v[k]);
+        run = incl;
+    }
+}
+
+template <typename Op, typename In, typename Sink>
+void scan64(In in, uint64_t n, Sink sink, uint64_t *d_total, cudaStream_t stream) {
+    if (n == 0) {
+        if (d_total) LAPPER_CUDA_CHECK(cudaMemsetAsync(d_total, 0, 8, stream));
+        return;
+    }
+    const uint64_t ntiles = div_up(n, kTile64);
+    Scratch<uint64_t> agg(ntiles, stream);
+    tile_reduce64_kernel<Op, In><<<(uint32_t)ntiles, kT, 0, stream>>>(in, n, agg.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    tile_scan64_kernel<Op><<<1, kT, 0, stream>>>(agg.p, ntiles, d_total);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    tile_apply64_kernel<Op, In, Sink><<<(uint32_t)ntiles, kT, 0, stream>>>(in, n, agg.p, sink);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+}
+
+struct Load64 {
+    const uint64_t *a;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return a[i]; }
+};
+struct Load32 {
+    const uint32_t *a;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return a[i]; }
+};
+struct StoreIncl {
+    uint64_t *out;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t incl, uint64_t, uint64_t) const { out[i] = incl; }
+};
+struct StoreExcl {
+    uint64_t *out;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t, uint64_t excl, uint64_t) const { out[i] = excl; }
+};
+// merge_overlaps (src/lib.rs:364-381): a run starts where the running max of the stops before it is below the start
+struct Head64 {
+    const uint64_t *S, *P;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return (i == 0 || P[i - 1] < S[i]) ? 1ull : 0ull; }
+};
+struct MergeSink64 {
+    const uint64_t *S, *P;
+    const uint32_t *perm;
+    uint64_t n;
+    uint64_t *ms, *me;
+    uint32_t *mperm;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t incl, uint64_t, uint64_t flag) const {
+        if (flag) ms[incl - 1] = S[i], mperm[incl - 1] = perm[i];  // the head gives start and val (src/lib.rs:383-390)
+        if (i + 1 == n || P[i] < S[i + 1]) me[incl - 1] = P[i];    // the run's last interval: its stop is the running max
+    }
+};
+struct RunLen64 {
+    const uint64_t *s, *e;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return e[i] - s[i]; }
+};
+
+// ------------------------------------------------------------------------------------------ count
+constexpr int kDir = 1024;  // sampled keys per array in shared memory: the top ten levels of each bisection
+
+struct View64 {
+    const uint64_t *S, *Eiv, *E, *P;
+    uint64_t n, max_len;
+    uint64_t stride;  // directory sample i is element min(i * stride, n - 1)
+    bool has_inverted;
+};
+
+__device__ __forceinline__ void load_dir(const View64 &v, uint64_t *dS, uint64_t *dE) {
+    for (int i = threadIdx.x; i < kDir; i += blockDim.x) {
+        const uint64_t at = min((uint64_t)i * v.stride, v.n - 1);
+        dS[i] = v.S[at];
+        dE[i] = v.E[at];
+    }
+    __syncthreads();
+}
+// #{x in a : x < key} with the directory narrowing the range first
+__device__ __forceinline__ uint64_t dir_lb(const uint64_t *__restrict__ a, const uint64_t *dir, const View64 &v, uint64_t key) {
+    // samples below key: all elements up to the last such sample are below key
+    int lo = 0, hi = kDir;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (dir[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    // lo samples are < key: elements [0, (lo - 1) * stride] are < key; the answer is at most lo * stride
+    const uint64_t from = lo ? min((uint64_t)(lo - 1) * v.stride + 1, v.n) : 0;
+    const uint64_t to = min((uint64_t)lo * v.stride, v.n);
+    return lb64(a, from, to, key);
+}
+__device__ __forceinline__ uint64_t dir_ub(const uint64_t *__restrict__ a, const uint64_t *dir, const View64 &v, uint64_t key) {
+    int lo = 0, hi = kDir;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (dir[mid] <= key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    const uint64_t from = lo ? min((uint64_t)(lo - 1) * v.stride + 1, v.n) : 0;
+    const uint64_t to = min((uint64_t)lo * v.stride, v.n);
+    return ub64(a, from, to, key);
+}
+
+// Lapper::count (src/lib.rs:611-617): len - first - (len - last) in wrapping usize == last - first (mod 2^64);
+// `start + 1` wraps to 0 at I::MAX in a release build, so first = 0 there.
+__global__ void __launch_bounds__(kT) count64_kernel(const View64 v, const uint64_t *__restrict__ qs, const uint64_t *__restrict__ qe,
+                                                     uint64_t nq, uint64_t *__restrict__ out) {
+    __shared__ uint64_t dS[kDir], dE[kDir];
+    load_dir(v, dS, dE);
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t a = qs[j], b = qe[j];
+        const uint64_t last = dir_lb(v.S, dS, v, b);
+        const uint64_t first = a == ~0ull ? 0ull : dir_ub(v.E, dE, v, a);
+        out[j] = last - first;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ find
+// the scan window of one query: the reference's [lower_bound(start - max_len), first interval with start >= stop)
+// (src/lib.rs:632-635, :712-713), its front tightened by the running max of the stops (nothing before the first
+// position whose prefix max exceeds `start` can end after `start`)
+__device__ __forceinline__ void window64(const View64 &v, uint64_t a, uint64_t b, uint64_t &lo, uint64_t &hi) {
+    hi = lb64(v.S, 0, v.n, b);
+    const uint64_t floor_key = a >= v.max_len ? a - v.max_len : 0ull;
+    lo = lb64(v.S, 0, hi, floor_key);
+    const uint64_t tight = ub64(v.P, 0, hi, a);
+    lo = max(lo, tight);
+    if (lo > hi) lo = hi;
+}
+
+// number of positions find(a, b) yields
+__global__ void __launch_bounds__(kT) find64_count_kernel(const View64 v, const uint64_t *__restrict__ qs,
+                                                          const uint64_t *__restrict__ qe, uint64_t nq, uint32_t *__restrict__ counts) {
+    __shared__ uint64_t dS[kDir], dE[kDir];
+    load_dir(v, dS, dE);
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t a = qs[j], b = qe[j];
+        uint32_t c;
+        if (a < b && !v.has_inverted) {
+            // |find| == count when every interval has start <= stop and the query is non-empty
+            c = (uint32_t)(dir_lb(v.S, dS, v, b) - dir_ub(v.E, dE, v, a));
+        } else {
+            uint64_t lo, hi;
+            window64(v, a, b, lo, hi);
+            c = 0;
+            for (uint64_t i = lo; i < hi; i++) c += __ldg(v.Eiv + i) > a;
+        }
+        counts[j] = c;
+    }
+}
+
+// one warp per query: 32 intervals of the window per step, hits ballot-compacted into the query's slice of `indices`
+__global__ void __launch_bounds__(kT) find64_emit_kernel(const View64 v, const uint64_t *__restrict__ qs, const uint64_t *__restrict__ qe,
+                                                         uint64_t nq, const uint64_t *__restrict__ offsets, uint32_t *__restrict__ indices,
+                                                         uint64_t capacity) {
+    if (offsets[nq] > capacity) return;  // nothing is written when the result does not fit
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t nwarps = (uint64_t)gridDim.x * (kT / 32);
+    for (uint64_t j = (uint64_t)blockIdx.x * (kT / 32) + (threadIdx.x >> 5); j < nq; j += nwarps) {
+        const uint64_t o0 = offsets[j], room = offsets[j + 1] - o0;
+        if (room == 0) continue;
+        const uint64_t a = __ldg(qs + j), b = __ldg(qe + j);
+        uint64_t lo, hi;
+        window64(v, a, b, lo, hi);
+        uint64_t written = 0;
+        for (uint64_t i0 = lo; i0 < hi && written < room; i0 += 32) {
+            const uint64_t i = i0 + lane;
+            const bool hit = i < hi && __ldg(v.Eiv + i) > a;  // start_i < b holds for every i < hi (src/lib.rs:140-142)
+            const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+            const uint64_t at = written + __popc(m & ((1u << lane) - 1u));
+            if (hit && at < room) indices[o0 + at] = (uint32_t)i;
+            written += __popc(m);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ set operations
+// cov = sum_{last of run} P_i - sum_{head} S_i (wrapping u64), runs of calculate_coverage (src/lib.rs:327-350)
+__global__ void __launch_bounds__(kT) cov64_kernel(const uint64_t *__restrict__ S, const uint64_t *__restrict__ P, uint64_t n,
+                                                   unsigned long long *__restrict__ out) {
+    unsigned long long acc = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t s = S[i], p = P[i];
+        if (i == 0 || P[i - 1] < s) acc -= s;
+        if (i + 1 == n || p < S[i + 1]) acc += p;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+// covered length of union(B) below x; B given as disjoint sorted runs with exclusive prefix lengths
+__device__ __forceinline__ uint64_t covered_below64(const uint64_t *__restrict__ bs, const uint64_t *__restrict__ be,
+                                                    const uint64_t *__restrict__ cum, uint64_t m, uint64_t x) {
+    const uint64_t j = lb64(bs, 0, m, x);  // runs starting below x
+    if (j == 0) return 0;
+    const uint64_t s = bs[j - 1], e = be[j - 1];
+    return cum[j - 1] + (min(x, e) - s);
+}
+__global__ void __launch_bounds__(kT) intersect64_kernel(const uint64_t *__restrict__ as, const uint64_t *__restrict__ ae, uint64_t ma,
+                                                         const uint64_t *__restrict__ bs, const uint64_t *__restrict__ be,
+                                                         const uint64_t *__restrict__ cum, uint64_t mb,
+                                                         unsigned long long *__restrict__ out) {
+    unsigned long long acc = 0;
+    for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < ma; r += (uint64_t)gridDim.x * blockDim.x)
+        acc += covered_below64(bs, be, cum, mb, ae[r]) - covered_below64(bs, be, cum, mb, as[r]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+// ------------------------------------------------------------------------------------------ host side
+View64 view_of(const lapper64 *l) {
+    View64 v;
+    v.S = l->S, v.Eiv = l->Eiv, v.E = l->E, v.P = l->P;
+    v.n = l->n, v.max_len = l->max_len;
+    v.stride = std::max<uint64_t>(div_up(l->n ? l->n : 1, kDir), 1);
+    v.has_inverted = l->has_inverted;
+    return v;
+}
+
+void free_arrays(lapper64 *l, cudaStream_t stream) {
+    pool_free(l->S, stream), pool_free(l->Eiv, stream), pool_free(l->E, stream), pool_free(l->P, stream), pool_free(l->perm, stream);
+    l->S = l->Eiv = l->E = l->P = nullptr;
+    l->perm = nullptr;
+}
+
+// max_len, inverted flag and prefix max from the sorted arrays (S, Eiv set; P allocated here)
+void finish_from_sorted(lapper64 *l, cudaStream_t stream) {
+    uint64_t bytes = 0;
+    l->max_len = 0, l->has_inverted = false;
+    if (l->n == 0) return;
+    l->P = pool_alloc<uint64_t>(l->n, bytes, stream);
+    Scratch<unsigned long long> st(2, stream);
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(st.p, 0, 16, stream));
+    stats64_kernel<<<capped(l->n), kT, 0, stream>>>(l->S, l->Eiv, l->n, st.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    scan64<Max64>(Load64{l->Eiv}, l->n, StoreIncl{l->P}, nullptr, stream);
+    unsigned long long h[2] = {0, 0};
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(h, st.p, 16, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    l->max_len = h[0];
+    l->has_inverted = h[1] != 0;
+}
+
+void build_from_device(lapper64 *l, const uint64_t *d_s, const uint64_t *d_e, uint64_t n, cudaStream_t stream) {
+    LAPPER_REQUIRE(n < 0xFFFFFFFFull, "lapper64: at most 2^32 - 2 intervals (positions are u32)");
+    l->n = n;
+    if (n == 0) return;
+    uint64_t bytes = 0;
+    l->S = pool_alloc<uint64_t>(n, bytes, stream);
+    l->Eiv = pool_alloc<uint64_t>(n, bytes, stream);
+    l->E = pool_alloc<uint64_t>(n, bytes, stream);
+    l->perm = pool_alloc<uint32_t>(n, bytes, stream);
+    Scratch<uint64_t> ktmp(n, stream);
+    Scratch<uint32_t> vtmp(n, stream);
+    // stable sort by stop, then stable sort by start: (start, stop) order, equal intervals in input order
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(l->E, d_e, n * 8, cudaMemcpyDeviceToDevice, stream));
+    iota_kernel<<<grid_for(n), kT, 0, stream>>>(l->perm, n);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    launch_sort_pairs_u64(l->E, ktmp.p, l->perm, vtmp.p, n, stream);  // E: stops ascending (= the sorted stops), perm: their inputs
+    gather64_kernel<<<grid_for(n), kT, 0, stream>>>(l->S, d_s, l->perm, n);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    launch_sort_pairs_u64(l->S, ktmp.p, l->perm, vtmp.p, n, stream);
+    gather64_kernel<<<grid_for(n), kT, 0, stream>>>(l->Eiv, d_e, l->perm, n);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    finish_from_sorted(l, stream);
+}
+
+uint64_t cov_of(const lapper64 *l, cudaStream_t stream) {
+    if (l->n == 0) return 0;
+    Scratch<unsigned long long> d(1, stream);
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(d.p, 0, 8, stream));
+    cov64_kernel<<<capped(l->n), kT, 0, stream>>>(l->S, l->P, l->n, d.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    unsigned long long h = 0;
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&h, d.p, 8, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    return h;
+}
+
+struct Merged64 {
+    uint64_t m = 0;
+    uint64_t *s = nullptr, *e = nullptr;
+    uint32_t *perm = nullptr;
+    cudaStream_t stream;
+    explicit Merged64(cudaStream_t st) : stream(st) {}
+    ~Merged64() { pool_free(s, stream), pool_free(e, stream), pool_free(perm, stream); }
+    Merged64(const Merged64 &) = delete;
+    Merged64 &operator=(const Merged64 &) = delete;
+};
+
+void merged_of(const lapper64 *l, Merged64 &out, cudaStream_t stream) {
+    if (l->n == 0) return;
+    const uint64_t n = l->n, ntiles = div_up(n, kTile64);
+    const Head64 flags{l->S, l->P};
+    Scratch<uint64_t> agg(ntiles, stream), d_total(1, stream);
+    tile_reduce64_kernel<Add64, Head64><<<(uint32_t)ntiles, kT, 0, stream>>>(flags, n, agg.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    tile_scan64_kernel<Add64><<<1, kT, 0, stream>>>(agg.p, ntiles, d_total.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    uint64_t m = 0;
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&m, d_total.p, 8, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    uint64_t bytes = 0;
+    out.m = m;
+    out.s = pool_alloc<uint64_t>(m, bytes, stream);
+    out.e = pool_alloc<uint64_t>(m, bytes, stream);
+    out.perm = pool_alloc<uint32_t>(m, bytes, stream);
+    tile_apply64_kernel<Add64, Head64, MergeSink64><<<(uint32_t)ntiles, kT, 0, stream>>>(
+        flags, n, agg.p, MergeSink64{l->S, l->P, l->perm, n, out.s, out.e, out.perm});
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+}
+
+void need_valid(const lapper64 *l, const char *what) {
+    if (l->has_inverted)
+        throw Error(LAPPER_ERR_PRECONDITION, std::string(what) + ": an interval has stop < start (the reference's arithmetic is "
+                                                                "undefined there; the closed form needs start <= stop)");
+}
+
+// offsets[0 .. nq] from the count pass; returns nothing (the total is offsets[nq])
+void find_offsets64(const lapper64 *l, const uint64_t *d_qs, const uint64_t *d_qe, uint64_t nq, uint64_t *d_offsets, cudaStream_t stream) {
+    if (nq == 0 || l->n == 0) {
+        LAPPER_CUDA_CHECK(cudaMemsetAsync(d_offsets, 0, (nq + 1) * 8, stream));
+        return;
+    }
+    Scratch<uint32_t> counts(nq, stream);
+    find64_count_kernel<<<capped(nq), kT, 0, stream>>>(view_of(l), d_qs, d_qe, nq, counts.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    scan64<Add64>(Load32{counts.p}, nq, StoreExcl{d_offsets}, d_offsets + nq, stream);
+}
+
+void find_emit64(const lapper64 *l, const uint64_t *d_qs, const uint64_t *d_qe, uint64_t nq, const uint64_t *d_offsets,
+                 uint32_t *d_indices, uint64_t capacity, cudaStream_t stream) {
+    if (nq == 0 || l->n == 0) return;
+    find64_emit_kernel<<<(uint32_t)std::min<uint64_t>(div_up(nq, kT / 32), (uint64_t)sm_count() * 16), kT, 0, stream>>>(
+        view_of(l), d_qs, d_qe, nq, d_offsets, d_indices, capacity);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+}
+
+void check64(const lapper64 *l) { LAPPER_REQUIRE(l != nullptr, "null lapper64 handle"); }
+
+}  // namespace
+}  // namespace lap
+
+using namespace lap;
+
+extern "C" {
+
+int lapper64_build_dev(const uint64_t *d_starts, const uint64_t *d_stops, uint64_t n, int device, void *stream, lapper64_t **out) {
+    return guarded_call([&] {
+        LAPPER_REQUIRE(out, "null output handle");
+        *out = nullptr;
+        LAPPER_REQUIRE(n == 0 || (d_starts && d_stops), "lapper64_build: null pointer");
+        require_device_index(device);
+        DeviceGuard dg(device);
+        std::unique_ptr<lapper64> l(new lapper64());
+        l->device = device;
+        try {
+            build_from_device(l.get(), d_starts, d_stops, n, (cudaStream_t)stream);
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+        } catch (...) {
+            free_arrays(l.get(), (cudaStream_t)stream);
+            throw;
+        }
+        *out = l.release();
+    });
+}
+
+int lapper64_build(const uint64_t *starts, const uint64_t *stops, uint64_t n, int device, lapper64_t **out) {
+    return guarded_call([&] {
+        LAPPER_REQUIRE(out, "null output handle");
+        *out = nullptr;
+        LAPPER_REQUIRE(n == 0 || (starts && stops), "lapper64_build: null pointer");
+        require_device_index(device);
+        DeviceGuard dg(device);
+        OwnedStream st;
+        Scratch<uint64_t> ds(n, st.s), de(n, st.s);
+        if (n) {
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(ds.p, starts, n * 8, cudaMemcpyHostToDevice, st.s));
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(de.p, stops, n * 8, cudaMemcpyHostToDevice, st.s));
+        }
+        std::unique_ptr<lapper64> l(new lapper64());
+        l->device = device;
+        try {
+            build_from_device(l.get(), ds.p, de.p, n, st.s);
+            ds.release(), de.release();
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+        } catch (...) {
+            free_arrays(l.get(), st.s);
+            cudaStreamSynchronize(st.s);
+            throw;
+        }
+        *out = l.release();
+    });
+}
+
+void lapper64_free(lapper64_t *l) {
+    if (!l) return;
+    int prev = -1;
+    cudaGetDevice(&prev);
+    cudaSetDevice(l->device);
+    free_arrays(l, nullptr);
+    cudaStreamSynchronize(nullptr);
+    if (prev >= 0) cudaSetDevice(prev);
+    delete l;
+}
+
+uint64_t lapper64_len(const lapper64_t *l) { return l ? l->n : 0; }
+uint64_t lapper64_max_len(const lapper64_t *l) { return l ? l->max_len : 0; }
+int lapper64_overlaps_merged(const lapper64_t *l) { return l && l->overlaps_merged; }
+int lapper64_has_inverted(const lapper64_t *l) { return l && l->has_inverted; }
+
+int lapper64_get_intervals(const lapper64_t *l, uint64_t *starts_out, uint64_t *stops_out, uint32_t *perm_out) {
+    return guarded_call([&] {
+        check64(l);
+        if (l->n == 0) return;
+        DeviceGuard dg(l->device);
+        if (starts_out) LAPPER_CUDA_CHECK(cudaMemcpy(starts_out, l->S, l->n * 8, cudaMemcpyDeviceToHost));
+        if (stops_out) LAPPER_CUDA_CHECK(cudaMemcpy(stops_out, l->Eiv, l->n * 8, cudaMemcpyDeviceToHost));
+        if (perm_out) LAPPER_CUDA_CHECK(cudaMemcpy(perm_out, l->perm, l->n * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+int lapper64_get_sorted_stops(const lapper64_t *l, uint64_t *stops_sorted_out) {
+    return guarded_call([&] {
+        check64(l);
+        LAPPER_REQUIRE(stops_sorted_out || l->n == 0, "null pointer");
+        DeviceGuard dg(l->device);
+        if (l->n) LAPPER_CUDA_CHECK(cudaMemcpy(stops_sorted_out, l->E, l->n * 8, cudaMemcpyDeviceToHost));
+    });
+}
+
+int lapper64_count_batch_dev(const lapper64_t *l, const uint64_t *d_q_start, const uint64_t *d_q_stop, uint64_t nq,
+                             uint64_t *d_counts_out, void *stream) {
+    return guarded_call([&] {
+        check64(l);
+        LAPPER_REQUIRE(nq == 0 || (d_q_start && d_q_stop && d_counts_out), "count_batch: null pointer");
+        if (nq == 0) return;
+        DeviceGuard dg(l->device);
+        if (l->n == 0) {
+            LAPPER_CUDA_CHECK(cudaMemsetAsync(d_counts_out, 0, nq * 8, (cudaStream_t)stream));
+            return;
+        }
+        g_query_launches++, count64_kernel<<<capped(nq), kT, 0, (cudaStream_t)stream>>>(view_of(l), d_q_start, d_q_stop, nq, d_counts_out);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+    });
+}
+
+int lapper64_count_batch(const lapper64_t *l, const uint64_t *q_start, const uint64_t *q_stop, uint64_t nq, uint64_t *counts_out) {
+    return guarded_call([&] {
+        check64(l);
+        LAPPER_REQUIRE(nq == 0 || (q_start && q_stop && counts_out), "count_batch: null pointer");
+        if (nq == 0) return;
+        DeviceGuard dg(l->device);
+        OwnedStream st;
+        Scratch<uint64_t> dqs(nq, st.s), dqe(nq, st.s), dout(nq, st.s);
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqs.p, q_start, nq * 8, cudaMemcpyHostToDevice, st.s));
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqe.p, q_stop, nq * 8, cudaMemcpyHostToDevice, st.s));
+        const int rc = lapper64_count_batch_dev(l, dqs.p, dqe.p, nq, dout.p, st.s);
+        if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(counts_out, dout.p, nq * 8, cudaMemcpyDeviceToHost, st.s));
+        dqs.release(), dqe.release(), dout.release();
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+    });
+}
+
+int lapper64_find_batch_dev(const lapper64_t *l, const uint64_t *d_q_start, const uint64_t *d_q_stop, uint64_t nq,
+                            uint64_t *d_offsets, uint32_t *d_indices, uint64_t indices_capacity, uint64_t *total_out, void *stream) {
+    return guarded_call([&] {
+        check64(l);
+        LAPPER_REQUIRE(d_offsets && total_out && (nq == 0 || (d_q_start && d_q_stop)), "find_batch_dev: null pointer");
+        LAPPER_REQUIRE(d_indices || indices_capacity == 0, "find_batch_dev: null position buffer with a capacity");
+        DeviceGuard dg(l->device);
+        cudaStream_t s = (cudaStream_t)stream;
+        *total_out = 0;
+        find_offsets64(l, d_q_start, d_q_stop, nq, d_offsets, s);
+        if (d_indices) find_emit64(l, d_q_start, d_q_stop, nq, d_offsets, d_indices, indices_capacity, s);
+        uint64_t total = 0;
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(&total, d_offsets + nq, 8, cudaMemcpyDeviceToHost, s));
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(s));
+        *total_out = total;
+        if (d_indices && total > indices_capacity)
+            throw Error(LAPPER_ERR_CAPACITY, "find_batch_dev: " + std::to_string(total) + " positions do not fit the buffer of " +
+                                                 std::to_string(indices_capacity) + " (offsets and *total_out are complete)");
+    });
+}
+
+int lapper64_find_batch(const lapper64_t *l, const uint64_t *q_start, const uint64_t *q_stop, uint64_t nq, lapper_result_t **out) {
+    return guarded_call([&] {
+        check64(l);
+        LAPPER_REQUIRE(out, "null result handle");
+        *out = nullptr;
+        LAPPER_REQUIRE(nq == 0 || (q_start && q_stop), "find_batch: null pointer");
+        DeviceGuard dg(l->device);
+        OwnedStream st;
+        Scratch<uint64_t> dqs(nq, st.s), dqe(nq, st.s);
+        if (nq) {
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqs.p, q_start, nq * 8, cudaMemcpyHostToDevice, st.s));
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqe.p, q_stop, nq * 8, cudaMemcpyHostToDevice, st.s));
+        }
+        std::unique_ptr<lapper_result_t> r(new lapper_result_t());
+        r->device = l->device;
+        r->nq = nq;
+        uint64_t bytes = 0;
+        try {
+            r->d_offsets = pool_alloc<uint64_t>(nq + 1, bytes, st.s);
+            find_offsets64(l, dqs.p, dqe.p, nq, r->d_offsets, st.s);
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(&r->total, r->d_offsets + nq, 8, cudaMemcpyDeviceToHost, st.s));
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+            r->d_indices = pool_alloc<uint32_t>(r->total, bytes, st.s);
+            find_emit64(l, dqs.p, dqe.p, nq, r->d_offsets, r->d_indices, r->total, st.s);
+            dqs.release(), dqe.release();
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+        } catch (...) {
+            pool_free(r->d_offsets, st.s), pool_free(r->d_indices, st.s);
+            cudaStreamSynchronize(st.s);
+            throw;
+        }
+        *out = r.release();
+    });
+}
+
+int lapper64_cov(const lapper64_t *l, uint64_t *cov_out) {
+    return guarded_call([&] {
+        check64(l);
+        LAPPER_REQUIRE(cov_out, "null pointer");
+        if (l->cov_is_some) {  // src/lib.rs:311-316
+            *cov_out = l->cov;
+            return;
+        }
+        need_valid(l, "cov");
+        DeviceGuard dg(l->device);
+        OwnedStream st;
+        *cov_out = cov_of(l, st.s);
+    });
+}
+
+int lapper64_set_cov(lapper64_t *l, uint64_t *cov_out) {
+    return guarded_call([&] {
+        check64(l);
+        need_valid(l, "set_cov");
+        DeviceGuard dg(l->device);
+        OwnedStream st;
+        l->cov = cov_of(l, st.s);  // src/lib.rs:320-324
+        l->cov_is_some = true;
+        if (cov_out) *cov_out = l->cov;
+    });
+}
+
+int lapper64_merge_overlaps(lapper64_t *l) {
+    return guarded_call([&] {
+        check64(l);
+        need_valid(l, "merge_overlaps");
+        if (l->n == 0) return;  // src/lib.rs:366: overlaps_merged is set only when there is a first interval
+        DeviceGuard dg(l->device);
+        OwnedStream st;
+        Merged64 mg(st.s);
+        merged_of(l, mg, st.s);
+        uint64_t bytes = 0;
+        // the merged runs are disjoint and ascending: their stops are sorted, and the prefix max is the stops themselves
+        uint64_t *E = pool_alloc<uint64_t>(mg.m, bytes, st.s);
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(E, mg.e, mg.m * 8, cudaMemcpyDeviceToDevice, st.s));
+        free_arrays(l, st.s);
+        l->n = mg.m;
+        l->S = mg.s, l->Eiv = mg.e, l->perm = mg.perm, l->E = E;
+        mg.s = mg.e = nullptr, mg.perm = nullptr;
+        finish_from_sorted(l, st.s);
+        l->overlaps_merged = true;
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+    });
+}
+
+int lapper64_union_and_intersect(const lapper64_t *a, const lapper64_t *b, uint64_t *union_out, uint64_t *intersect_out) {
+    return guarded_call([&] {
+        check64(a), check64(b);
+        LAPPER_REQUIRE(a->device == b->device, "union_and_intersect: both lappers must live on the same device");
+        need_valid(a, "union_and_intersect"), need_valid(b, "union_and_intersect");
+        DeviceGuard dg(a->device);
+        OwnedStream st;
+        uint64_t x = 0;
+        if (a->n && b->n) {
+            Merged64 ma(st.s), mb(st.s);
+            merged_of(a, ma, st.s), merged_of(b, mb, st.s);
+            Scratch<uint64_t> cum(mb.m, st.s);
+            Scratch<unsigned long long> d(1, st.s);
+            scan64<Add64>(RunLen64{mb.s, mb.e}, mb.m, StoreExcl{cum.p}, nullptr, st.s);
+            LAPPER_CUDA_CHECK(cudaMemsetAsync(d.p, 0, 8, st.s));
+            intersect64_kernel<<<capped(ma.m), kT, 0, st.s>>>(ma.s, ma.e, ma.m, mb.s, mb.e, cum.p, mb.m, d.p);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(&x, d.p, 8, cudaMemcpyDeviceToHost, st.s));
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+        }
+        const uint64_t ca = a->cov_is_some ? a->cov : cov_of(a, st.s);
+        const uint64_t cb = b->cov_is_some ? b->cov : cov_of(b, st.s);
+        if (union_out) *union_out = ca + cb - x;  // src/lib.rs:532 / :542
+        if (intersect_out) *intersect_out = x;
+    });
+}
+
+}  // extern "C"

@@ -163,6 +163,9 @@ inline void pool_free(void *p, cudaStream_t stream) {
 }
 // in-place ascending sort of n u32 keys (hand-written LSD radix sort); tmp holds n keys
 void launch_sort_u32(uint32_t *keys, uint32_t *tmp, uint64_t n, cudaStream_t stream);
+// the same sort on u64 keys, alone or with u32 payloads (stable: equal keys keep their order); tmp arrays hold n items
+void launch_sort_u64(uint64_t *keys, uint64_t *tmp, uint64_t n, cudaStream_t stream);
+void launch_sort_pairs_u64(uint64_t *keys, uint64_t *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, uint64_t n, cudaStream_t stream);
 
 // query.cu ---------------------------------------------------------------------------------------
 extern std::atomic<uint64_t> g_query_launches;  // kernels launched by launch_count / launch_find_* in this process

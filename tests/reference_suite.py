@@ -275,12 +275,13 @@ def py_bsearch_seq(key, elems):
     return cursor
 
 
-def py_count(intervals, a, b):
-    """Lapper::count (src/lib.rs:611-618) with u32 `start + 1` and usize subtraction wrapping (release build)."""
+def py_count(intervals, a, b, bits=32):
+    """Lapper::count (src/lib.rs:611-618) with `start + 1` wrapping in I (u32; bits=64: u64) and usize subtraction
+    wrapping (release build)."""
     starts = sorted(s for s, _ in intervals)
     stops = sorted(e for _, e in intervals)
     n = len(intervals)
-    first = py_bsearch_seq((a + 1) & 0xFFFFFFFF, stops)
+    first = py_bsearch_seq((a + 1) & ((1 << bits) - 1), stops)
     last = py_bsearch_seq(b, starts)
     return (n - first - (n - last)) % (1 << 64)
 
@@ -308,9 +309,9 @@ def py_find(intervals, a, b):
     return out
 
 
-def edge_case_vectors():
-    """(intervals, query) pairs from SURVEY Appendix B; expectations come from py_count / py_find."""
-    X = 0xFFFFFFFF
+def edge_case_vectors(bits=32):
+    """(intervals, query) pairs from SURVEY Appendix B; expectations come from py_count / py_find.  X = I::MAX."""
+    X = (1 << bits) - 1
     return [
         ([(8, 8)], (7, 9)),                 # zero-length interval strictly straddled
         ([(5, 10)], (7, 7)),                # zero-length query strictly inside

@@ -14,7 +14,7 @@ HEADER = os.path.join(ROOT, "include", "lapper_b200.h")
 def declared_symbols():
     text = open(HEADER).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(lapper_[a-z0-9_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(lapper(?:64)?_[a-z0-9_]+)\s*\(", text)))
 
 
 @pytest.fixture(scope="module")
@@ -31,7 +31,9 @@ def lib():
 def test_header_declares_the_reference_api():
     syms = declared_symbols()
     for must in ("lapper_build_u32", "lapper_count_batch_u32", "lapper_find_batch_u32", "lapper_merge_overlaps",
-                 "lapper_cov", "lapper_set_cov", "lapper_union_and_intersect", "lapper_seek_cursor", "lapper_free"):
+                 "lapper_cov", "lapper_set_cov", "lapper_union_and_intersect", "lapper_seek_cursor", "lapper_free",
+                 "lapper_find_batch_u32_dev", "lapper64_build", "lapper64_count_batch", "lapper64_find_batch",
+                 "lapper64_merge_overlaps", "lapper64_cov", "lapper64_union_and_intersect"):
         assert must in syms
 
 

@@ -1,0 +1,236 @@
+"""The u64 engine (lapper64_* / rust_lapper_b200.Lapper64, csrc/engine64.cu) against the same checker as the u32
+engine: the reference's known-answer tests (reference_suite.py), and the C oracle built with I = u64
+(oracle/liblapper_oracle64.so) on seeded random sets whose coordinates do not fit 32 bits -- counts (u64, wrapping),
+CSR offsets and positions, the sorted structure incl. tie order, cov / merge_overlaps / union_and_intersect, the
+capacity protocol of the one-call device entry point -- always bit for bit."""
+import numpy as np
+import pytest
+
+import reference_suite as rs
+
+pytestmark = pytest.mark.gpu
+
+U64_MAX = (1 << 64) - 1
+
+
+@pytest.fixture(scope="module")
+def oracle64():
+    from oracle import lapper_oracle
+
+    lapper_oracle.load(coord_bits=64)
+    return lambda **kw: lapper_oracle.OracleLapper(coord_bits=64, **kw)
+
+
+@pytest.fixture(scope="module")
+def make():
+    from rust_lapper_b200 import Lapper64
+
+    return lambda ivs: Lapper64(ivs)
+
+
+# the known-answer checks that need only the methods the u64 engine instantiates (no insert / depth)
+U64_CHECKS = [c for c in rs.CORE_CHECKS if c.__name__ not in ("check_depth",)]
+
+
+@pytest.mark.parametrize("check", U64_CHECKS, ids=lambda f: f.__name__)
+def test_reference_known_answers_u64(make, check):
+    check(make)
+
+
+def test_reference_known_answers_shifted_beyond_32_bits(make):
+    """the same vectors translated by 2^40: every coordinate needs more than 32 bits"""
+    sh = 1 << 40
+    ivs = [(s + sh, e + sh) for s, e in rs.badlapper()]
+    lap = make(ivs)
+    assert lap.find(15 + sh, 20 + sh) == [(14 + sh, 16 + sh)]  # src/lib.rs:1368-1385 shape
+    assert lap.count(8 + sh, 20 + sh) == 4
+    assert lap.find(0, sh) == [] and lap.count(0, sh) == 0
+    assert lap.cov() == 73  # examples/ex1.rs:104, translation-invariant
+    lap.merge_overlaps()
+    assert lap.intervals == [(10 + sh, 16 + sh), (40 + sh, 45 + sh), (50 + sh, 55 + sh), (60 + sh, 65 + sh), (68 + sh, 120 + sh)]
+
+
+def test_edge_cases_match_reference_semantics_u64(make):
+    for ivs, (a, b) in rs.edge_case_vectors(64) + rs.edge_case_vectors(32):
+        lap = make(ivs)
+        assert lap.count(a, b) == rs.py_count(ivs, a, b, 64), (ivs, a, b)
+        assert lap.find_idx(a, b) == rs.py_find(ivs, a, b), (ivs, a, b)
+
+
+def test_stable_ties_keep_input_order_u64(make):
+    ivs = [(5, 9), (1, 3), (5, 9), (5, 8), (1, 3), (5, 9)]
+    s, e, p = make(ivs).intervals_soa()
+    assert list(zip(s.tolist(), e.tolist())) == sorted(ivs)
+    assert p.tolist() == [1, 4, 3, 0, 2, 5]
+
+
+def _random_set(rng, n, universe, max_len, long_frac=0.0):
+    s = rng.integers(0, universe, n, dtype=np.uint64)
+    ln = rng.integers(0, max_len, n, dtype=np.uint64)
+    if long_frac:
+        k = rng.random(n) < long_frac
+        ln[k] = rng.integers(universe // 4, universe // 2, int(k.sum()), dtype=np.uint64)
+    return s, s + ln
+
+
+def _same(gpu, cpu, qs, qe):
+    assert np.array_equal(gpu.count_batch(qs, qe), cpu.count_batch(qs, qe, 4))
+    go, gi = gpu.find_batch(qs, qe)
+    co, ci = cpu.find_batch(qs, qe, 4)
+    assert np.array_equal(go, co)
+    assert np.array_equal(gi, ci)
+
+
+@pytest.mark.parametrize("n,universe,max_len,long_frac", [
+    (1, 1 << 50, 1 << 20, 0.0),
+    (1000, 1 << 45, 1 << 30, 0.0),
+    (200_000, 1 << 60, 1 << 44, 0.0),
+    (200_000, 1 << 40, 1 << 24, 0.01),   # a few very long intervals: max_len stretches the reference's window
+    (50_000, 1 << 20, 1 << 8, 0.0),      # many duplicates and ties
+    (2049, 3_000_000_000, 5000, 0.0),    # sizes around the scan tile
+])
+def test_random_sets_u64(oracle64, n, universe, max_len, long_frac):
+    from rust_lapper_b200 import Lapper64
+
+    rng = np.random.default_rng(n ^ 0xABCD)
+    s, e = _random_set(rng, n, universe, max_len, long_frac)
+    gpu, cpu = Lapper64(starts=s, stops=e), oracle64(starts=s, stops=e)
+    gs, ge, gp = gpu.intervals_soa()
+    cs, ce, cv = cpu.intervals_soa()
+    assert np.array_equal(gs, cs) and np.array_equal(ge, ce) and np.array_equal(gp, cv)  # val = input position
+    assert np.array_equal(gpu.stops, cpu.stops) and gpu.max_len == cpu.max_len
+    nq = 30_000
+    qs = rng.integers(0, universe + universe // 8, nq, dtype=np.uint64)
+    qe = qs + rng.integers(0, max(max_len, 2), nq, dtype=np.uint64)
+    # a tenth of the queries empty (a == b) or inverted, some at the ends of the coordinate range
+    k = rng.choice(nq, nq // 10, replace=False)
+    qe[k] = qs[k] - rng.integers(0, 3, k.size, dtype=np.uint64).clip(max=qs[k])
+    qs[:4] = [0, 0, U64_MAX, U64_MAX - 5]
+    qe[:4] = [0, U64_MAX, U64_MAX, U64_MAX]
+    _same(gpu, cpu, qs, qe)
+    _same(gpu, cpu, np.sort(qs), np.sort(qs) + np.uint64(150))
+    assert gpu.cov() == cpu.cov()
+    assert gpu.set_cov() == cpu.set_cov()
+
+
+def test_coordinates_at_the_ends_of_u64(oracle64):
+    from rust_lapper_b200 import Lapper64
+
+    s = np.array([0, 0, 1, U64_MAX - 10, U64_MAX - 1, U64_MAX, 1 << 63, (1 << 63) - 1], dtype=np.uint64)
+    e = np.array([0, U64_MAX, 1, U64_MAX, U64_MAX, U64_MAX, (1 << 63) + 5, 1 << 63], dtype=np.uint64)
+    gpu, cpu = Lapper64(starts=s, stops=e), oracle64(starts=s, stops=e)
+    pts = np.array([0, 1, 2, (1 << 63) - 1, 1 << 63, (1 << 63) + 5, U64_MAX - 10, U64_MAX - 1, U64_MAX], dtype=np.uint64)
+    qs, qe = np.meshgrid(pts, pts)
+    _same(gpu, cpu, qs.reshape(-1).copy(), qe.reshape(-1).copy())
+    assert gpu.max_len == cpu.max_len == U64_MAX
+
+
+def test_inverted_intervals_u64(oracle64):
+    """count and find have no precondition on the intervals (src/lib.rs:610-639); cov / merge / union refuse"""
+    from rust_lapper_b200 import Lapper64, LapperError, _ffi
+
+    rng = np.random.default_rng(3)
+    s, e = _random_set(rng, 20_000, 1 << 42, 1 << 28)
+    k = rng.choice(s.size, 500, replace=False)
+    s[k], e[k] = e[k], s[k]
+    gpu, cpu = Lapper64(starts=s, stops=e), oracle64(starts=s, stops=e)
+    assert gpu.has_inverted
+    qs = rng.integers(0, 1 << 42, 20_000, dtype=np.uint64)
+    _same(gpu, cpu, qs, qs + rng.integers(0, 1 << 29, qs.size, dtype=np.uint64))
+    for call in (gpu.cov, gpu.merge_overlaps):
+        with pytest.raises(LapperError) as ei:
+            call()
+        assert ei.value.code == _ffi.ERR_PRECONDITION
+
+
+def test_empty_u64():
+    from rust_lapper_b200 import Lapper64
+
+    lap = Lapper64([])
+    assert len(lap) == 0 and lap.is_empty() and lap.max_len == 0
+    assert lap.count(1, 100) == 0 and lap.find(1, 100) == []
+    assert lap.count_batch([], []).size == 0
+    off, idx = lap.find_batch([5, 6], [7, 8])
+    assert off.tolist() == [0, 0, 0] and idx.size == 0
+    assert lap.cov() == 0
+    lap.merge_overlaps()
+    assert not lap.overlaps_merged  # src/lib.rs:366: set only when there is a first interval
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_set_operations_u64(oracle64, seed):
+    from rust_lapper_b200 import Lapper64
+
+    rng = np.random.default_rng(seed)
+    U = 1 << 44
+    a_s, a_e = _random_set(rng, 30_000, U, 1 << 31, 0.001)
+    b_s, b_e = _random_set(rng, 20_000, U, 1 << 30)
+    ga, gb = Lapper64(starts=a_s, stops=a_e), Lapper64(starts=b_s, stops=b_e)
+    ca, cb = oracle64(starts=a_s, stops=a_e), oracle64(starts=b_s, stops=b_e)
+    assert ga.cov() == ca.cov() and gb.cov() == cb.cov()
+    # the reference's unmerged branch materialises every pairwise intersection: keep the oracle's work bounded by
+    # comparing on the merged sets (both branches give the same values, src/lib.rs:497-510)
+    ga.merge_overlaps(), gb.merge_overlaps(), ca.merge_overlaps(), cb.merge_overlaps()
+    for g, c in ((ga, ca), (gb, cb)):
+        gs, ge, gp = g.intervals_soa()
+        cs, ce, cv = c.intervals_soa()
+        assert np.array_equal(gs, cs) and np.array_equal(ge, ce) and np.array_equal(gp, cv)
+        assert np.array_equal(g.stops, c.stops) and g.max_len == c.max_len
+        assert g.overlaps_merged and c.overlaps_merged
+    assert ga.union_and_intersect(gb) == ca.union_and_intersect(cb)
+    assert gb.union_and_intersect(ga) == cb.union_and_intersect(ca)
+    ga.set_cov(), ca.set_cov()
+    assert ga.union_and_intersect(gb) == ca.union_and_intersect(cb)
+    qs = np.sort(rng.integers(0, U, 20_000, dtype=np.uint64))
+    _same(ga, ca, qs, qs + np.uint64(1 << 20))
+
+
+def test_find_one_call_device_api_u64(oracle64):
+    """lapper64_find_batch_dev: exact fit, room to spare, too small (LAPPER_ERR_CAPACITY, offsets complete, positions
+    untouched), the size query; lapper64_count_batch_dev on device buffers"""
+    import ctypes as C
+
+    import torch
+
+    from rust_lapper_b200 import _ffi
+
+    lib = _ffi.lib()
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(9)
+    s, e = _random_set(rng, 100_000, 1 << 46, 1 << 32)
+    qs = np.sort(rng.integers(0, 1 << 46, 40_000, dtype=np.uint64))
+    qe = qs + np.uint64(1 << 30)
+    cpu = oracle64(starts=s, stops=e)
+    want_o, want_i = cpu.find_batch(qs, qe, 4)
+    total = int(want_o[-1])
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    ts, te = torch.from_numpy(s.view(np.int64)).to(dev), torch.from_numpy(e.view(np.int64)).to(dev)
+    tq, tqe = torch.from_numpy(qs.view(np.int64)).to(dev), torch.from_numpy(qe.view(np.int64)).to(dev)
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    h = C.c_void_p(0)
+    _ffi.check(lib.lapper64_build_dev(vp(ts), vp(te), len(s), 0, sp, C.byref(h)))
+    try:
+        nq = len(qs)
+        cnt = torch.empty(nq, dtype=torch.int64, device=dev)
+        _ffi.check(lib.lapper64_count_batch_dev(h, vp(tq), vp(tqe), nq, vp(cnt), sp))
+        torch.cuda.synchronize()
+        assert np.array_equal(cnt.cpu().numpy().view(np.uint64), cpu.count_batch(qs, qe, 4))
+        for cap, want_st in ((total, _ffi.OK), (total + 999, _ffi.OK), (total - 1, _ffi.ERR_CAPACITY)):
+            off = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+            idx = torch.full((cap,), 0x5A5A5A5A, dtype=torch.int32, device=dev)
+            t = C.c_uint64(0)
+            st = lib.lapper64_find_batch_dev(h, vp(tq), vp(tqe), nq, vp(off), vp(idx), cap, C.byref(t), sp)
+            torch.cuda.synchronize()
+            assert st == want_st and int(t.value) == total
+            assert np.array_equal(off.cpu().numpy().view(np.uint64), want_o)
+            got = idx.cpu().numpy().view(np.uint32)
+            if st == _ffi.OK:
+                assert np.array_equal(got[:total], want_i) and np.all(got[total:] == 0x5A5A5A5A)
+            else:
+                assert np.all(got == 0x5A5A5A5A)
+        off = torch.empty(nq + 1, dtype=torch.int64, device=dev)
+        t = C.c_uint64(0)
+        assert lib.lapper64_find_batch_dev(h, vp(tq), vp(tqe), nq, vp(off), C.c_void_p(0), 0, C.byref(t), sp) == _ffi.OK
+        assert int(t.value) == total
+    finally:
+        lib.lapper64_free(h)
