@@ -761,15 +761,27 @@ int lapper64_merge_overlaps(lapper64_t *l) {
         OwnedStream st;
         Merged64 mg(st.s);
         merged_of(l, mg, st.s);
-        uint64_t bytes = 0;
-        // the merged runs are disjoint and ascending: their stops are sorted, and the prefix max is the stops themselves
-        uint64_t *E = pool_alloc<uint64_t>(mg.m, bytes, st.s);
-        LAPPER_CUDA_CHECK(cudaMemcpyAsync(E, mg.e, mg.m * 8, cudaMemcpyDeviceToDevice, st.s));
-        free_arrays(l, st.s);
-        l->n = mg.m;
-        l->S = mg.s, l->Eiv = mg.e, l->perm = mg.perm, l->E = E;
+        // the new index is completed aside and swapped in only when nothing can fail any more
+        lapper64 next;
+        next.device = l->device;
+        next.n = mg.m;
+        next.S = mg.s, next.Eiv = mg.e, next.perm = mg.perm;
         mg.s = mg.e = nullptr, mg.perm = nullptr;
-        finish_from_sorted(l, st.s);
+        try {
+            uint64_t bytes = 0;
+            // the merged runs are disjoint and ascending: their stops are sorted, and the prefix max is the stops themselves
+            next.E = pool_alloc<uint64_t>(next.n, bytes, st.s);
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(next.E, next.Eiv, next.n * 8, cudaMemcpyDeviceToDevice, st.s));
+            finish_from_sorted(&next, st.s);
+        } catch (...) {
+            free_arrays(&next, st.s);
+            cudaStreamSynchronize(st.s);
+            throw;
+        }
+        free_arrays(l, st.s);
+        l->n = next.n;
+        l->S = next.S, l->Eiv = next.Eiv, l->E = next.E, l->P = next.P, l->perm = next.perm;
+        l->max_len = next.max_len, l->has_inverted = next.has_inverted;
         l->overlaps_merged = true;
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
     });

@@ -946,6 +946,11 @@ constexpr uint32_t kTRawMax = 4096;        // class-window slots a tile is willi
 #define LAPPER_TILE_STAGE 1024
 #endif
 constexpr int kTStage = LAPPER_TILE_STAGE;  // staged output words per warp
+#ifndef LAPPER_TILE_QL
+#define LAPPER_TILE_QL 2
+#endif
+constexpr int kTQL = LAPPER_TILE_QL;        // queries per lane in a group
+constexpr uint32_t kTG = 32u * kTQL;        // queries per group
 constexpr int kTWarpWords = kTStage + 4 * kEmitCand;  // + the warp's own candidate list (64 x uint4)
 constexpr int kTRelWords = kFindTile + 4;
 constexpr int kTCtlWords = 32;
@@ -1254,15 +1259,15 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
             }
         }
         __syncthreads();  // cand complete; the raw list (aliasing the warps' areas) is dead
-        // ---- 5. 64-query groups
-        for (uint32_t gq = warp * 64; gq < nqt; gq += kTW * 64) {
-            const uint32_t gq_end = min(gq + 64u, nqt);
+        // ---- 5. groups of kTG consecutive queries, kTQL per lane
+        for (uint32_t gq = warp * kTG; gq < nqt; gq += kTW * kTG) {
+            const uint32_t gq_end = min(gq + kTG, nqt);
             const uint32_t gbase = rel[gq];
             if (rel[gq_end] == gbase) continue;
-            uint32_t ro0[kEmitQ], ro1[kEmitQ], a[kEmitQ], b[kEmitQ];
-            bool mine[kEmitQ];
+            uint32_t ro0[kTQL], ro1[kTQL], a[kTQL], b[kTQL];
+            bool mine[kTQL];
 #pragma unroll
-            for (int q = 0; q < kEmitQ; q++) {
+            for (int q = 0; q < kTQL; q++) {
                 const uint32_t jl = min(gq + q * 32 + lane, nqt);  // beyond the tile: rel[nqt] twice = no hits
                 ro0[q] = rel[jl];
                 ro1[q] = rel[min(jl + 1, nqt)];
@@ -1274,7 +1279,9 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                     b[q] = __ldg(qe + q0 + jl);
                 }
             }
-            uint32_t gamin = min(a[0], a[1]), gbmax = max(b[0], b[1]);
+            uint32_t gamin = a[0], gbmax = b[0];
+#pragma unroll
+            for (int q = 1; q < kTQL; q++) gamin = min(gamin, a[q]), gbmax = max(gbmax, b[q]);
             gamin = __reduce_min_sync(0xFFFFFFFFu, gamin);
             gbmax = __reduce_max_sync(0xFFFFFFFFu, gbmax);
             // the group's candidates: tile candidates that start before its largest stop and end after its smallest
@@ -1305,7 +1312,7 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                     // largest sub_hi with rel[sub_hi] - sbase + pad <= kTStage (rel is non-decreasing)
                     sub_hi = sub_lo;
 #pragma unroll
-                    for (int q = 0; q < kEmitQ; q++) {
+                    for (int q = 0; q < kTQL; q++) {
                         const uint32_t idx = sub_lo + 1 + q * 32 + lane;
                         const bool ok = idx <= gq_end && rel[min(idx, nqt)] - sbase + pad <= (uint32_t)kTStage;
                         sub_hi += __popc(__ballot_sync(0xFFFFFFFFu, ok));
@@ -1320,10 +1327,10 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                 if (wtotal) {
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // previous slice has left the stage
                     __syncwarp();
-                    uint32_t sa[kEmitQ], sb[kEmitQ];
-                    bool act[kEmitQ];
+                    uint32_t sa[kTQL], sb[kTQL];
+                    bool act[kTQL];
 #pragma unroll
-                    for (int q = 0; q < kEmitQ; q++) {
+                    for (int q = 0; q < kTQL; q++) {
                         const uint32_t jl = gq + q * 32 + lane;
                         act[q] = mine[q] && jl >= sub_lo && jl < sub_hi;
                         sa[q] = act[q] ? a[q] : 0xFFFFFFFFu;
@@ -1332,22 +1339,38 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                     if (fits) {
                         EMIT_STAT(4, 1);
                         EMIT_STAT(5, T);
-                        uint32_t *wp[kEmitQ];
+                        // write cursors as shared-memory addresses; per candidate and query: two compares, one
+                        // predicated store, one predicated add (inline PTX: the compiler's own form spends two
+                        // instructions on the predicated cursor update)
+                        uint32_t wp[kTQL];
 #pragma unroll
-                        for (int q = 0; q < kEmitQ; q++) wp[q] = stage + pad + (ro0[q] - sbase);
+                        for (int q = 0; q < kTQL; q++) wp[q] = (uint32_t)__cvta_generic_to_shared(stage + pad + (ro0[q] - sbase));
                         for (uint32_t x = 0; x < T; x++) {
                             const uint4 c = wlist[x];  // one broadcast LDS.128: (start, stop, position)
 #pragma unroll
-                            for (int q = 0; q < kEmitQ; q++)
-                                if (c.x < sb[q] && c.y > sa[q]) {  // src/lib.rs:140-142
-                                    LAPPER_CHECK(wp[q] >= stage + pad && wp[q] < stage + pad + wtotal);
-                                    *wp[q]++ = c.z;
+                            for (int q = 0; q < kTQL; q++) {
+#ifdef LAPPER_DEBUG_CHECKS
+                                if (c.x < sb[q] && c.y > sa[q]) {
+                                    const uint32_t lo_a = (uint32_t)__cvta_generic_to_shared(stage + pad);
+                                    LAPPER_CHECK(wp[q] >= lo_a && wp[q] < lo_a + 4u * wtotal);
                                 }
+#endif
+                                // src/lib.rs:140-142: start_i < q_stop && stop_i > q_start
+                                asm volatile(
+                                    "{ .reg .pred p;\n"
+                                    "  setp.lt.u32 p, %2, %3;\n"
+                                    "  setp.gt.and.u32 p, %4, %5, p;\n"
+                                    "  @p st.shared.u32 [%0], %1;\n"
+                                    "  @p add.u32 %0, %0, 4; }"
+                                    : "+r"(wp[q])
+                                    : "r"(c.z), "r"(c.x), "r"(sb[q]), "r"(c.y), "r"(sa[q])
+                                    : "memory");
+                            }
                         }
                     } else {
                         EMIT_STAT(6, 1);
 #pragma unroll
-                        for (int q = 0; q < kEmitQ; q++)
+                        for (int q = 0; q < kTQL; q++)
                             if (act[q])
                                 emit_one_query(f, a[q], b[q], stage + pad + (ro0[q] - sbase), ro1[q] - ro0[q], heavy,
                                                q0 + gq + q * 32 + lane);

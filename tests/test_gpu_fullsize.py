@@ -295,3 +295,66 @@ def test_cfg5_sized_set_auto_selected_tables(oracle):
         assert np.array_equal(counts.cpu().numpy().view(np.uint32).astype(np.uint64), want)
     finally:
         lib.lapper_free(h)
+
+
+def test_north_star_10m_intervals_x_1b_queries(oracle):
+    """BASELINE.json's target size: 10 M intervals x 1 B queries, bit-exact.  The oracle cannot count a billion queries
+    in test time, so the billion is covered by two independent engines agreeing: ten batches of 100 M random-order
+    queries are counted by the packed-table kernel, then sorted on the device and counted again by the sorted-run
+    kernel (a different algorithm over different arrays: ranks against the sorted starts / stops instead of one table
+    sector per query) -- the two answers must be equal query for query -- and find's CSR over the sorted batch must
+    have exactly those counts as its row lengths (one-call device API).  20 k queries of every batch are compared with
+    the oracle itself, so 200 k oracle answers anchor the agreement."""
+    import torch
+
+    from rust_lapper_b200 import _ffi, synth
+
+    dev = torch.device("cuda", 0)
+    lib = _ffi.lib()
+    U = synth.GRCH38
+    s, e = synth.intervals_uniform(42, N_IV, U, 50, 5000, device=dev)
+    hs, he = synth.intervals_uniform(42, N_IV, U, 50, 5000)
+    cpu = oracle.OracleLapper(starts=hs, stops=he)
+    h, sp = _build(lib, s, e, dev)
+    stats = (C.c_uint64 * 2)()
+    try:
+        lib.lapper_debug_sorted_run_stats(stats, 1)
+        grand = 0
+        for batch in range(10):
+            qs, qe = synth.queries_fixed_len(1000 + batch, NQ, U, 150, device=dev)
+            c_random = _count(lib, h, qs, qe, sp)
+            order = torch.argsort(qs.to(torch.int64) & 0xFFFFFFFF)
+            qs_s, qe_s = qs[order].contiguous(), qe[order].contiguous()
+            c_sorted = _count(lib, h, qs_s, qe_s, sp)
+            assert bool(torch.equal(c_sorted, c_random[order])), f"batch {batch}: the two count engines disagree"
+            # find over the sorted batch: row lengths == counts, total == their sum
+            total = int(c_sorted.to(torch.int64).sum())
+            off = torch.empty(NQ + 1, dtype=torch.int64, device=dev)
+            idx = torch.empty(total, dtype=torch.int32, device=dev)
+            t = C.c_uint64(0)
+            _ffi.check(lib.lapper_find_batch_u32_dev(h, _vp(qs_s), _vp(qe_s), NQ, _vp(off), _vp(idx), total, C.byref(t), sp))
+            torch.cuda.synchronize()
+            assert int(t.value) == total
+            assert bool(torch.equal(off[1:] - off[:-1], c_sorted.to(torch.int64)))
+            grand += total
+            # the oracle on a sample of this batch (random-order positions)
+            pick = torch.randint(0, NQ, (20_000,), device=dev, generator=torch.Generator(device=dev).manual_seed(batch))
+            a = qs[pick].cpu().numpy().view(np.uint32)
+            b = qe[pick].cpu().numpy().view(np.uint32)
+            want = cpu.count_batch(a, b, 4)
+            assert np.array_equal(c_random[pick].cpu().numpy().view(np.uint32).astype(np.uint64), want)
+            # ... and find's rows for the same queries in the sorted batch
+            inv = torch.empty_like(order)
+            inv[order] = torch.arange(NQ, device=dev)
+            rows = inv[pick]
+            wo, wi = cpu.find_batch(a, b, 4)
+            lo = off[rows].cpu().numpy()
+            got = np.concatenate([idx[int(x): int(x) + int(n)].cpu().numpy().view(np.uint32) for x, n in
+                                  zip(lo[:2000], np.diff(wo)[:2000])]) if len(lo) else np.zeros(0, np.uint32)
+            assert np.array_equal(got, wi[: int(wo[2000])])
+            del qs, qe, qs_s, qe_s, c_random, c_sorted, off, idx, order, inv
+        lib.lapper_debug_sorted_run_stats(stats, 0)
+        assert stats[0] >= 10 * (NQ // 256) * 2 - 10 * 8  # count + find's count pass went through the sorted-run kernel
+        assert grand > 0
+    finally:
+        lib.lapper_free(h)

@@ -29,6 +29,18 @@ _ffi.check(lib.lapper_find_batch_offsets_u32_dev(h, vp(qs), vp(qe), nq, vp(off),
 idx = torch.empty(max(int(total.value), 1), dtype=torch.int32, device=dev)
 
 
+if os.environ.get("ONE_CALL_ONLY"):
+    # the one-call form alone (for ncu: every kernel of one lapper_find_batch_u32_dev call, after one warm-up call)
+    off2, idx2, cap = torch.empty_like(off), torch.empty_like(idx), int(total.value)
+    for _ in range(2):
+        t = C.c_uint64(0)
+        _ffi.check(lib.lapper_find_batch_u32_dev(h, vp(qs), vp(qe), nq, vp(off2), vp(idx2), cap, C.byref(t), sp))
+    torch.cuda.synchronize()
+    print(f"one call: {int(t.value)} hits, same CSR as the two-phase calls: {bool(torch.equal(off, off2))}")
+    lib.lapper_free(h)
+    sys.exit(0)
+
+
 def step():
     t = C.c_uint64(0)
     _ffi.check(lib.lapper_find_batch_offsets_u32_dev(h, vp(qs), vp(qe), nq, vp(off), C.byref(t), sp))
