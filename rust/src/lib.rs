@@ -33,6 +33,13 @@ extern "C" {
     fn lapper_cov(l: *const LapperHandle, out: *mut u32) -> c_int;
     fn lapper_set_cov(l: *mut LapperHandle, out: *mut u32) -> c_int;
     fn lapper_union_and_intersect(a: *const LapperHandle, b: *const LapperHandle, u: *mut u32, i: *mut u32) -> c_int;
+    fn lapper_insert_u32(l: *mut LapperHandle, start: u32, stop: u32, input_position_out: *mut u64) -> c_int;
+    fn lapper_depth(l: *const LapperHandle, n: *mut u64, starts: *mut *mut u32, stops: *mut *mut u32, depth: *mut *mut u32) -> c_int;
+    fn lapper_host_free(p: *mut c_void);
+    fn lapper_find_batch_u32_host(l: *const LapperHandle, qs: *const u32, qe: *const u32, nq: u64, offsets: *mut u64,
+                                  indices: *mut u32, capacity: u64, total: *mut u64) -> c_int;
+    fn lapper_get_cached_state(l: *const LapperHandle, cov_is_some: *mut c_int, cov: *mut u32, overlaps_merged: *mut c_int) -> c_int;
+    fn lapper_restore_cached_state(l: *mut LapperHandle, cov_is_some: c_int, cov: u32, overlaps_merged: c_int) -> c_int;
 }
 
 fn check(rc: c_int) {
@@ -128,6 +135,71 @@ impl<T: Eq + Clone + Send + Sync> Lapper<T> {
     }
     pub fn intersect(&self, other: &Self) -> u32 { self.union_and_intersect(other).1 }
     pub fn union(&self, other: &Self) -> u32 { self.union_and_intersect(other).0 }
+
+    /// src/lib.rs:260-273.  O(n) like the reference; the engine hands back the input position it gave the interval.
+    pub fn insert(&mut self, elem: Interval<T>) {
+        let mut pos = 0u64;
+        check(unsafe { lapper_insert_u32(self.h, elem.start, elem.stop, &mut pos) });
+        debug_assert_eq!(pos as usize, self.input.len());
+        self.input.push(elem);
+        self.refresh();
+    }
+
+    /// src/lib.rs:576-598: maximal runs of equal coverage depth, as `Interval<u32>` with `val` = depth.
+    /// Panics on an empty lapper like the reference (src/lib.rs:744).
+    pub fn depth(&self) -> impl Iterator<Item = Interval<u32>> {
+        let (mut n, mut s, mut e, mut d) = (0u64, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut());
+        check(unsafe { lapper_depth(self.h, &mut n, &mut s, &mut e, &mut d) });
+        let n = n as usize;
+        let out: Vec<Interval<u32>> = (0..n)
+            .map(|i| unsafe { Interval { start: *s.add(i), stop: *e.add(i), val: *d.add(i) } })
+            .collect();
+        unsafe {
+            lapper_host_free(s as *mut c_void);
+            lapper_host_free(e as *mut c_void);
+            lapper_host_free(d as *mut c_void);
+        }
+        out.into_iter()
+    }
+
+    /// find_batch straight into caller-owned buffers through the pipelined host entry point; returns the total.
+    /// `Err(total)` when `indices` is too small (offsets are complete; call again with `total` slots).
+    pub fn find_batch_into(&self, qs: &[u32], qe: &[u32], offsets: &mut [u64], indices: &mut [u32]) -> Result<u64, u64> {
+        assert!(qs.len() == qe.len() && offsets.len() > qs.len());
+        let mut total = 0u64;
+        let rc = unsafe {
+            lapper_find_batch_u32_host(self.h, qs.as_ptr(), qe.as_ptr(), qs.len() as u64, offsets.as_mut_ptr(),
+                                       indices.as_mut_ptr(), indices.len() as u64, &mut total)
+        };
+        match rc {
+            0 => Ok(total),
+            6 => Err(total), // LAPPER_ERR_CAPACITY
+            _ => { check(rc); unreachable!() }
+        }
+    }
+
+    /// The `with_serde` feature (src/lib.rs:85-86): serialise `intervals` + the cached `cov` / `overlaps_merged`
+    /// (lapper_get_cached_state), rebuild the index on load and restore the cache (lapper_restore_cached_state).
+    /// rust_lapper_b200/bincode_io.py is the exercised implementation of that layout.
+    pub fn cached_state(&self) -> (Option<u32>, bool) {
+        let (mut some, mut cov, mut merged) = (0, 0u32, 0);
+        check(unsafe { lapper_get_cached_state(self.h, &mut some, &mut cov, &mut merged) });
+        (if some != 0 { Some(cov) } else { None }, merged != 0)
+    }
+    pub fn restore_cached_state(&mut self, cov: Option<u32>, overlaps_merged: bool) {
+        check(unsafe { lapper_restore_cached_state(self.h, cov.is_some() as c_int, cov.unwrap_or(0), overlaps_merged as c_int) });
+    }
+}
+/// src/lib.rs:785-849: `IntoIterator` for `Lapper` and `&Lapper` walk the sorted `intervals` vector.
+impl<T: Eq + Clone + Send + Sync> IntoIterator for Lapper<T> {
+    type Item = Interval<T>;
+    type IntoIter = std::vec::IntoIter<Interval<T>>;
+    fn into_iter(mut self) -> Self::IntoIter { std::mem::take(&mut self.intervals).into_iter() }
+}
+impl<'a, T: Eq + Clone + Send + Sync> IntoIterator for &'a Lapper<T> {
+    type Item = &'a Interval<T>;
+    type IntoIter = std::slice::Iter<'a, Interval<T>>;
+    fn into_iter(self) -> Self::IntoIter { self.intervals.iter() }
 }
 impl<T: Eq + Clone + Send + Sync> Drop for Lapper<T> {
     fn drop(&mut self) { unsafe { lapper_free(self.h) } }
