@@ -525,6 +525,13 @@ def run_ours(args):
         "api": "lapper_count_batch_u32_c32 (host pointers, pinned; 3-slot chunked H2D/kernel/D2H pipeline)",
         "matches_device_run": e2e_ok,
     }
+    # what the host side delivers when all N GPUs copy the step's bytes at once (800 MB in + 400 MB out per GPU, nothing
+    # else running): measured by tools/mb_pcie.py / tools/mb_pcie_multi.py on this pool's boxes, logs under profiles/
+    ceiling_ms = PCIE_MIX_MS.get(world)
+    if ceiling_ms and nq == 100_000_000:
+        e2e["concurrent_copy_ceiling_ms"] = ceiling_ms
+        e2e["frac_of_concurrent_copy_ceiling"] = ceiling_ms / e2e["ms_per_step"]
+        e2e["ceiling_source"] = PCIE_MIX_SOURCE
     del hq_s, hq_e, h_out
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) + parity of the timed outputs on the sample
@@ -626,6 +633,12 @@ def timed_events(cx, fn, steps, warm=3):
     ms = a.elapsed_time(b) / steps
     cx.barrier()
     return ms
+
+
+# ms for one count e2e step's copies (800 MB H2D + 400 MB D2H per GPU, all GPUs at once, pinned memory), by GPU count
+PCIE_MIX_MS = {1: 16.1, 2: 19.19, 4: 32.24}
+PCIE_MIX_SOURCE = ("profiles/r1_mb_pcie.log (N=1), profiles/r2_mb_pcie_2gpu.log, profiles/r2_mb_pcie_4gpu.log: 'pinned, H2D + D2H'; "
+                   "the host side does not scale with N (one NUMA node, shared root complex), so neither can e2e")
 
 
 def find_device(cx, h, qs, qe, nq, offsets, indices=None):
