@@ -636,9 +636,11 @@ def timed_events(cx, fn, steps, warm=3):
 
 
 # ms for one count e2e step's copies (800 MB H2D + 400 MB D2H per GPU, all GPUs at once, pinned memory), by GPU count
-PCIE_MIX_MS = {1: 16.1, 2: 19.19, 4: 32.24}
-PCIE_MIX_SOURCE = ("profiles/r1_mb_pcie.log (N=1), profiles/r2_mb_pcie_2gpu.log, profiles/r2_mb_pcie_4gpu.log: 'pinned, H2D + D2H'; "
-                   "the host side does not scale with N (one NUMA node, shared root complex), so neither can e2e")
+PCIE_MIX_MS = {1: 16.1, 2: 19.19, 4: 32.24, 8: 71.09}
+PCIE_MIX_SOURCE = ("profiles/r1_mb_pcie.log (N=1), profiles/r2_mb_pcie_{2,4,8}gpu.log: 'pinned, H2D + D2H' (every GPU starts both "
+                   "copies of the whole step at once; the library's staggered chunk pipeline can come in slightly under it); the host "
+                   "side does not scale with N (one NUMA node, shared root complex: ~100 GB/s in + ~50 GB/s out for the whole box "
+                   "from N = 4 on), so neither can e2e")
 
 
 def find_device(cx, h, qs, qe, nq, offsets, indices=None):
