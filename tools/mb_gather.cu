@@ -65,6 +65,118 @@ __global__ void gather_kernel(const Sector* __restrict__ table, uint32_t nsect, 
     if (acc == 0x12345678u) out[0] = acc;
 }
 
+// The same work with the streams moved by the TMA path instead of LSU instructions: a CTA's tile of 1024 "queries"
+// (8 B each) arrives in shared memory by one bulk copy, the results (4 B each) leave by one bulk store; only the
+// gathers go through the L1TEX tag stage.  Tests whether the sector rate of that stage (one per clock per SM) is what
+// the streams' LDG / STG instructions compete for.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int K>
+__global__ void __launch_bounds__(256) gather_tma_kernel(const Sector* __restrict__ table, uint32_t nsect, int iters,
+                                                         uint32_t* __restrict__ out, const uint4* __restrict__ stream_in,
+                                                         uint32_t* __restrict__ stream_out) {
+    // per-warp pipelines (no CTA barrier): a warp's 32 * K queries = one bulk load of 32 * K * 8 bytes, two stages;
+    // its 32 * K results = one bulk store, two buffers.  Streams carry the L2 evict-first policy like the real kernel's.
+    struct __align__(128) WarpBuf {
+        uint32_t qin[2][32 * K * 2];
+        uint32_t res[2][32 * K];
+        uint64_t full[2];
+        uint64_t pad[14];
+    };
+    __shared__ WarpBuf bufs[8];
+    WarpBuf& wb = bufs[threadIdx.x >> 5];
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warp_global = (uint64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const uint64_t nwarps = (uint64_t)gridDim.x * 8;
+    uint32_t acc = 0;
+    if (g_split) {
+        uint32_t smid, nsm;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u32 %0, %%nsmid;" : "=r"(nsm));
+        const uint32_t half = g_split == 1 ? (smid & 1u) : (smid >= nsm / 2 ? 1u : 0u);
+        nsect /= 2;
+        table += (size_t)half * nsect;
+    }
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    if (lane == 0) {
+        for (int s = 0; s < 2; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&wb.full[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const uint32_t tile_bytes = 32 * K * 8;
+    auto fetch = [&](int it) {
+        const uint64_t q0 = ((uint64_t)it * nwarps + warp_global) * (32 * K);
+        const int s = it & 1;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(&wb.full[s])), "r"(tile_bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                         smem_addr(wb.qin[s])),
+                     "l"((const char*)stream_in + q0 * 8), "r"(tile_bytes), "r"(smem_addr(&wb.full[s])), "l"(pol)
+                     : "memory");
+    };
+    if (lane == 0) fetch(0);
+    for (int it = 0; it < iters; it++) {
+        const int s = it & 1;
+        if (lane == 0 && it + 1 < iters) fetch(it + 1);
+        {
+            uint32_t ok;
+            const uint32_t parity = (it >> 1) & 1;
+            do {
+                asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                             : "=r"(ok) : "r"(smem_addr(&wb.full[s])), "r"(parity) : "memory");
+            } while (!ok);
+        }
+        const uint64_t q0 = ((uint64_t)it * nwarps + warp_global) * (32 * K) + lane * K;
+        uint32_t extra = 0;
+#pragma unroll
+        for (int k = 0; k < K / 2; k++) {
+            const uint4 v = *reinterpret_cast<const uint4*>(&wb.qin[s][(lane * K + 2 * k) * 2]);
+            extra += v.x ^ v.y ^ v.z ^ v.w;
+        }
+        Sector sc[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            uint32_t idx = (uint32_t)(((uint64_t)mix(q0 + k) * nsect) >> 32);
+            sc[k] = ld256(table + idx);
+        }
+#pragma unroll
+        for (int k = 0; k < K; k++) acc += sc[k].w[0] + sc[k].w[7];
+        acc += extra;
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        uint4 r;
+        r.x = acc, r.y = acc + 1, r.z = acc + 2, r.w = acc + 3;
+        static_assert(K == 4, "one 128-bit result store per thread");
+        *reinterpret_cast<uint4*>(&wb.res[s][lane * K]) = r;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+            const uint64_t o0 = ((uint64_t)it * nwarps + warp_global) * (32 * K);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(stream_out + o0),
+                         "r"(smem_addr(wb.res[s])), "r"(32 * K * 4), "l"(pol)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    if (acc == 0x12345678u) out[0] = acc;
+}
+
+float run_tma(const Sector* table, uint32_t nsect, uint64_t total_gathers, int blocks, uint32_t* out, const uint4* sin, uint32_t* sout) {
+    const int K = 4, threads = 256;
+    int iters = (int)(total_gathers / ((uint64_t)threads * blocks * K));
+    if (iters < 1) iters = 1;
+    cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
+    gather_tma_kernel<K><<<blocks, threads>>>(table, nsect, iters, out, sin, sout);
+    cudaEventRecord(a);
+    for (int r = 0; r < 3; r++) gather_tma_kernel<K><<<blocks, threads>>>(table, nsect, iters, out, sin, sout);
+    cudaEventRecord(b); cudaEventSynchronize(b);
+    float ms; cudaEventElapsedTime(&ms, a, b); ms /= 3;
+    double g = (double)iters * threads * blocks * K;
+    printf("K=%d stream=TMA threads=%d blocks=%d : %.3f ms  %.1f Ggather/s  %.1f GB/s(sector bytes)  [%s]\n", K, threads, blocks, ms,
+           g / ms * 1e-6, g * 32 / ms * 1e-6, cudaGetErrorString(cudaGetLastError()));
+    return ms;
+}
+
 template <int K, bool STREAM>
 float run(const Sector* table, uint32_t nsect, uint64_t total_gathers, int threads, int blocks, uint32_t* out,
           const uint4* sin, uint32_t* sout) {
@@ -98,6 +210,24 @@ int main(int argc, char** argv) {
         int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
         printf("== table %.0f MB (%u sectors), split mode %d\n", mb, nsect, split);
         run<4, true>(table, nsect, total, 256, nsm * 4, out, sin, sout);
+        return 0;
+    }
+    if (argc > 1 && !strcmp(argv[1], "tma")) {
+        // streams by LSU instructions vs by bulk copies (TMA), table sizes on both sides of the L2 knee
+        int nsm = 148; cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, 0);
+        { const int zero = 0; cudaMemcpyToSymbol(g_split, &zero, sizeof(int)); }
+        double sizes[] = {12, 48, 64, 75, 97};
+        for (double mb : sizes) {
+            uint32_t nsect = (uint32_t)(mb * 1e6 / 32);
+            Sector* table; cudaMalloc(&table, (size_t)nsect * 32); cudaMemset(table, 1, (size_t)nsect * 32);
+            for (int occ : {3, 4, 6, 8}) {
+                printf("== table %.0f MB, %d CTAs/SM: ", mb, occ);
+                run<4, true>(table, nsect, total, 256, nsm * occ, out, sin, sout);
+                printf("== table %.0f MB, %d CTAs/SM: ", mb, occ);
+                run_tma(table, nsect, total, nsm * occ, out, sin, sout);
+            }
+            cudaFree(table);
+        }
         return 0;
     }
     if (argc > 1 && !strcmp(argv[1], "split")) {
