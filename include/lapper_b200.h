@@ -243,8 +243,7 @@ void lapper_host_free_pinned(void *p);
  * usize).  The second instantiation of the query path (csrc/engine64.cu): the same contracts as the u32 entry points
  * above with 64-bit coordinates -- count wraps in u64 like usize, positions stay u32 (at most 2^32 - 2 intervals),
  * find results come back as the same lapper_result_t.  Plain bisection under a shared-memory key directory instead of
- * the u32 engine's sector tables.  Not instantiated for u64: insert, depth, the seek cursor, groups (seek yields
- * find's sequence).
+ * the u32 engine's sector tables.  Not instantiated for u64: replica groups, the bincode cache accessors.
  * ===================================================================================================== */
 typedef struct lapper64 lapper64_t;
 
@@ -281,6 +280,11 @@ int lapper64_cov(const lapper64_t *l, uint64_t *cov_out);
 int lapper64_set_cov(lapper64_t *l, uint64_t *cov_out);
 int lapper64_merge_overlaps(lapper64_t *l);
 int lapper64_union_and_intersect(const lapper64_t *a, const lapper64_t *b, uint64_t *union_out, uint64_t *intersect_out);
+/* insert (src/lib.rs:260-273), the seek cursor (:658-671) and depth (:576-598, :720-784; arrays freed with
+ * lapper_host_free, depth values are u32) -- the contracts of lapper_insert_u32 / lapper_seek_cursor / lapper_depth */
+int lapper64_insert(lapper64_t *l, uint64_t start, uint64_t stop, uint64_t *input_position_out);
+int lapper64_seek_cursor(const lapper64_t *l, uint64_t start, uint64_t *cursor);
+int lapper64_depth(const lapper64_t *l, uint64_t *n_out, uint64_t **starts_out, uint64_t **stops_out, uint32_t **depth_out);
 
 #ifdef __cplusplus
 }

@@ -127,6 +127,9 @@ SIGNATURES = {
     "lapper64_set_cov": (_int, [_vp, C.POINTER(_u64)]),
     "lapper64_merge_overlaps": (_int, [_vp]),
     "lapper64_union_and_intersect": (_int, [_vp, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
+    "lapper64_insert": (_int, [_vp, _u64, _u64, C.POINTER(_u64)]),
+    "lapper64_seek_cursor": (_int, [_vp, _u64, C.POINTER(_u64)]),
+    "lapper64_depth": (_int, [_vp, C.POINTER(_u64), _pvp, _pvp, _pvp]),
     "lapper_host_free_pinned": (None, [_vp]),
 }
 

@@ -16,9 +16,11 @@
 //                                 reference iterator's order
 //   cov, merge_overlaps, union_and_intersect (src/lib.rs:310-350, :361-416, :512-559)  the prefix-max closed forms of
 //                                 setops.cu on u64 values
-// seek yields find's sequence (no cursor crosses the ABI); insert and depth are not instantiated for u64 (the u32
-// engine has them).  At most 2^32 - 1 intervals (positions are u32, as in the u32 engine).
+//   insert, depth, the seek cursor (src/lib.rs:260-273, :576-598 + :720-784, :658-671)  as in the u32 engine: sorted insert at
+//                                 the reference's positions, depth in closed form over the sorted unique event coordinates
+// At most 2^32 - 2 intervals (positions are u32, as in the u32 engine).  Replica groups exist for u32 only.
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 
 #include "abi_common.cuh"
@@ -37,6 +39,7 @@ struct lapper64 {
     bool overlaps_merged = false;
     bool cov_is_some = false;
     uint64_t cov = 0;
+    uint64_t next_input_id = 0;  // input position handed to the next inserted interval
 };
 
 namespace lap {
@@ -413,6 +416,98 @@ __global__ void __launch_bounds__(kT) intersect64_kernel(const uint64_t *__restr
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+// ------------------------------------------------------------------------------------------ depth, insert, seek
+// depth() in closed form (the same one as setops.cu, see compute_depth there): over the sorted unique event
+// coordinates u_t with D_t = #{start <= u_t} - #{stop <= u_t}, a run starts wherever D changes to a positive value and
+// ends at the next change; a zero-length merged run is reported as (u, u, 0) unless it is the first run of the set.
+struct Unique64 {
+    const uint64_t *X;
+    __device__ __forceinline__ uint64_t operator()(uint64_t i) const { return (i == 0 || X[i] != X[i - 1]) ? 1ull : 0ull; }
+};
+struct UniqueSink64 {
+    const uint64_t *X;
+    uint64_t *U;
+    __device__ __forceinline__ void operator()(uint64_t i, uint64_t incl, uint64_t, uint64_t flag) const {
+        if (flag) U[incl - 1] = X[i];
+    }
+};
+__global__ void __launch_bounds__(kT) depth_eval64_kernel(const uint64_t *__restrict__ S, const uint64_t *__restrict__ E, uint64_t n,
+                                                          const uint64_t *__restrict__ U, uint64_t m, uint32_t *__restrict__ D,
+                                                          uint32_t *__restrict__ has_start) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m; t += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t u = U[t];
+        const uint64_t ub_s = ub64(S, 0, n, u);
+        D[t] = (uint32_t)(ub_s - ub64(E, 0, n, u));
+        has_start[t] = lb64(S, 0, n, u) < ub_s ? 1u : 0u;
+    }
+}
+struct EmitPoint64 {
+    const uint32_t *D, *has_start;
+    __device__ __forceinline__ bool zero_run(uint64_t t) const { return t > 0 && D[t] == 0 && D[t - 1] == 0 && has_start[t]; }
+    __device__ __forceinline__ uint64_t operator()(uint64_t t) const {
+        return (t == 0 || D[t] != D[t - 1] || zero_run(t)) ? 1ull : 0ull;
+    }
+};
+struct EmitPointSink64 {
+    const uint64_t *U;
+    EmitPoint64 f;
+    uint64_t *eu;
+    uint32_t *ed, *ez;
+    __device__ __forceinline__ void operator()(uint64_t t, uint64_t incl, uint64_t, uint64_t flag) const {
+        if (flag) eu[incl - 1] = U[t], ed[incl - 1] = f.D[t], ez[incl - 1] = f.zero_run(t) ? 1u : 0u;
+    }
+};
+struct Run64 {
+    const uint32_t *ed, *ez;
+    __device__ __forceinline__ uint64_t operator()(uint64_t q) const { return (ed[q] > 0 || ez[q]) ? 1ull : 0ull; }
+};
+struct RunSink64 {
+    const uint64_t *eu;
+    const uint32_t *ed, *ez;
+    uint64_t *os, *oe;
+    uint32_t *od;
+    __device__ __forceinline__ void operator()(uint64_t q, uint64_t incl, uint64_t, uint64_t flag) const {
+        if (flag) {
+            const uint64_t r = incl - 1;
+            os[r] = eu[q];
+            oe[r] = ez[q] ? eu[q] : eu[q + 1];  // a positive-depth run ends at the next emit point, always a depth change
+            od[r] = ed[q];
+        }
+    }
+};
+
+// positions the reference's insert() picks (src/lib.rs:261-263): lower_bound of the interval among the sorted
+// intervals by (start, stop), and of its stop among the sorted stops
+__global__ void insert_positions64_kernel(const uint64_t *__restrict__ S, const uint64_t *__restrict__ Eiv,
+                                          const uint64_t *__restrict__ E, uint64_t n, uint64_t start, uint64_t stop,
+                                          uint64_t *__restrict__ out) {
+    uint64_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint64_t mid = lo + ((hi - lo) >> 1);
+        const uint64_t s = S[mid], e = Eiv[mid];
+        if (s < start || (s == start && e < stop))
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    out[0] = lo;
+    out[1] = lb64(E, 0, n, stop);
+}
+template <typename T>
+__global__ void insert_into64_kernel(T *__restrict__ dst, const T *__restrict__ src, uint64_t n, uint64_t pos, T value) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x)
+        dst[i] = i < pos ? src[i] : i == pos ? value : src[i - 1];
+}
+// Lapper::seek's cursor update (src/lib.rs:658-671) with the advancing while-loop in closed form
+__global__ void seek_cursor64_kernel(const uint64_t *__restrict__ S, uint64_t n, uint64_t max_len, uint64_t start,
+                                     uint64_t cursor_in, uint64_t *__restrict__ cursor_out) {
+    const uint64_t floor_key = start >= max_len ? start - max_len : 0ull;
+    uint64_t c = cursor_in;
+    if (c == 0 || (c < n && S[c] > start)) c = lb64(S, 0, n, floor_key);
+    if (c + 1 < n && S[c + 1] < floor_key) c = lb64(S, 0, n, floor_key) - 1;
+    *cursor_out = c;
+}
+
 // ------------------------------------------------------------------------------------------ host side
 View64 view_of(const lapper64 *l) {
     View64 v;
@@ -562,6 +657,7 @@ int lapper64_build_dev(const uint64_t *d_starts, const uint64_t *d_stops, uint64
         l->device = device;
         try {
             build_from_device(l.get(), d_starts, d_stops, n, (cudaStream_t)stream);
+            l->next_input_id = n;
             LAPPER_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
         } catch (...) {
             free_arrays(l.get(), (cudaStream_t)stream);
@@ -588,6 +684,7 @@ int lapper64_build(const uint64_t *starts, const uint64_t *stops, uint64_t n, in
         l->device = device;
         try {
             build_from_device(l.get(), ds.p, de.p, n, st.s);
+            l->next_input_id = n;
             ds.release(), de.release();
             LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
         } catch (...) {
@@ -811,6 +908,139 @@ int lapper64_union_and_intersect(const lapper64_t *a, const lapper64_t *b, uint6
         const uint64_t cb = b->cov_is_some ? b->cov : cov_of(b, st.s);
         if (union_out) *union_out = ca + cb - x;  // src/lib.rs:532 / :542
         if (intersect_out) *intersect_out = x;
+    });
+}
+
+int lapper64_insert(lapper64_t *l, uint64_t start, uint64_t stop, uint64_t *input_position_out) {
+    return guarded_call([&] {
+        check64(l);
+        DeviceGuard dg(l->device);
+        OwnedStream st;
+        const uint64_t n = l->n;
+        LAPPER_REQUIRE(n + 1 < 0xFFFFFFF0ull && l->next_input_id < 0xFFFFFFF0ull, "lapper64_insert: too many intervals");
+        uint64_t pos[2] = {0, 0};
+        if (n) {
+            Scratch<uint64_t> d_pos(2, st.s);
+            insert_positions64_kernel<<<1, 1, 0, st.s>>>(l->S, l->Eiv, l->E, n, start, stop, d_pos.p);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(pos, d_pos.p, 16, cudaMemcpyDeviceToHost, st.s));
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+        }
+        const uint64_t id = l->next_input_id;
+        // the new index is completed aside: a failure leaves the handle as it was
+        lapper64 next;
+        next.device = l->device;
+        next.n = n + 1;
+        try {
+            uint64_t bytes = 0;
+            next.S = pool_alloc<uint64_t>(n + 1, bytes, st.s);
+            next.Eiv = pool_alloc<uint64_t>(n + 1, bytes, st.s);
+            next.E = pool_alloc<uint64_t>(n + 1, bytes, st.s);
+            next.perm = pool_alloc<uint32_t>(n + 1, bytes, st.s);
+            const uint32_t g = capped(n + 1);
+            insert_into64_kernel<uint64_t><<<g, kT, 0, st.s>>>(next.S, l->S, n, pos[0], start);
+            insert_into64_kernel<uint64_t><<<g, kT, 0, st.s>>>(next.Eiv, l->Eiv, n, pos[0], stop);
+            insert_into64_kernel<uint64_t><<<g, kT, 0, st.s>>>(next.E, l->E, n, pos[1], stop);
+            insert_into64_kernel<uint32_t><<<g, kT, 0, st.s>>>(next.perm, l->perm, n, pos[0], (uint32_t)id);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+            finish_from_sorted(&next, st.s);  // max_len (src/lib.rs:264-267) falls out of it
+        } catch (...) {
+            free_arrays(&next, st.s);
+            cudaStreamSynchronize(st.s);
+            throw;
+        }
+        free_arrays(l, st.s);
+        l->n = next.n;
+        l->S = next.S, l->Eiv = next.Eiv, l->E = next.E, l->P = next.P, l->perm = next.perm;
+        l->max_len = next.max_len, l->has_inverted = next.has_inverted;
+        l->next_input_id = id + 1;
+        l->cov_is_some = false;      // src/lib.rs:271
+        l->overlaps_merged = false;  // src/lib.rs:272
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+        if (input_position_out) *input_position_out = id;
+    });
+}
+
+int lapper64_seek_cursor(const lapper64_t *l, uint64_t start, uint64_t *cursor) {
+    return guarded_call([&] {
+        check64(l);
+        LAPPER_REQUIRE(cursor, "null cursor");
+        if (l->n == 0) return;  // lower_bound over an empty vector is 0 and the while-loop never runs (src/lib.rs:658-671)
+        DeviceGuard dg(l->device);
+        OwnedStream st;
+        Scratch<uint64_t> d_c(1, st.s);
+        seek_cursor64_kernel<<<1, 1, 0, st.s>>>(l->S, l->n, l->max_len, start, *cursor, d_c.p);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(cursor, d_c.p, 8, cudaMemcpyDeviceToHost, st.s));
+        d_c.release();
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+    });
+}
+
+int lapper64_depth(const lapper64_t *l, uint64_t *n_out, uint64_t **starts_out, uint64_t **stops_out, uint32_t **depth_out) {
+    return guarded_call([&] {
+        check64(l);
+        LAPPER_REQUIRE(n_out && starts_out && stops_out && depth_out, "lapper64_depth: null pointer");
+        *n_out = 0;
+        *starts_out = *stops_out = nullptr;
+        *depth_out = nullptr;
+        LAPPER_REQUIRE(l->n > 0, "depth() on an empty lapper: the reference panics here (src/lib.rs:744)");
+        need_valid(l, "depth");
+        DeviceGuard dg(l->device);
+        OwnedStream st;
+        cudaStream_t s = st.s;
+        const uint64_t n = l->n, n2 = 2 * n;
+        Scratch<uint64_t> X(n2, s), tmp(n2, s), U(n2, s), d_count(1, s);
+        Scratch<uint32_t> D(n2, s), HS(n2, s);
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(X.p, l->S, n * 8, cudaMemcpyDeviceToDevice, s));
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(X.p + n, l->E, n * 8, cudaMemcpyDeviceToDevice, s));
+        launch_sort_u64(X.p, tmp.p, n2, s);
+        uint64_t m = 0, ne = 0, nr = 0;
+        scan64<Add64>(Unique64{X.p}, n2, UniqueSink64{X.p, U.p}, d_count.p, s);
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(&m, d_count.p, 8, cudaMemcpyDeviceToHost, s));
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(s));
+        depth_eval64_kernel<<<capped(m), kT, 0, s>>>(l->S, l->E, n, U.p, m, D.p, HS.p);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        Scratch<uint64_t> eu(m + 1, s);
+        Scratch<uint32_t> ed(m + 1, s), ez(m + 1, s);
+        const EmitPoint64 epf{D.p, HS.p};
+        scan64<Add64>(epf, m, EmitPointSink64{U.p, epf, eu.p, ed.p, ez.p}, d_count.p, s);
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(&ne, d_count.p, 8, cudaMemcpyDeviceToHost, s));
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(s));
+        // the runs: counted first (the outputs are sized from the count), then written
+        const Run64 rf{ed.p, ez.p};
+        const uint64_t ntiles = div_up(ne ? ne : 1, kTile64);
+        Scratch<uint64_t> agg(ntiles, s);
+        if (ne) {
+            tile_reduce64_kernel<Add64, Run64><<<(uint32_t)ntiles, kT, 0, s>>>(rf, ne, agg.p);
+            tile_scan64_kernel<Add64><<<1, kT, 0, s>>>(agg.p, ntiles, d_count.p);
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(&nr, d_count.p, 8, cudaMemcpyDeviceToHost, s));
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(s));
+        }
+        Scratch<uint64_t> os(nr, s), oe(nr, s);
+        Scratch<uint32_t> od(nr, s);
+        if (nr) {
+            tile_apply64_kernel<Add64, Run64, RunSink64><<<(uint32_t)ntiles, kT, 0, s>>>(rf, ne, agg.p,
+                                                                                        RunSink64{eu.p, ed.p, ez.p, os.p, oe.p, od.p});
+            LAPPER_CUDA_CHECK(cudaGetLastError());
+        }
+        uint64_t *hs = (uint64_t *)malloc(std::max<uint64_t>(nr, 1) * 8), *he = (uint64_t *)malloc(std::max<uint64_t>(nr, 1) * 8);
+        uint32_t *hd = (uint32_t *)malloc(std::max<uint64_t>(nr, 1) * 4);
+        try {
+            if (!hs || !he || !hd) throw std::bad_alloc();
+            if (nr) {
+                LAPPER_CUDA_CHECK(cudaMemcpyAsync(hs, os.p, nr * 8, cudaMemcpyDeviceToHost, s));
+                LAPPER_CUDA_CHECK(cudaMemcpyAsync(he, oe.p, nr * 8, cudaMemcpyDeviceToHost, s));
+                LAPPER_CUDA_CHECK(cudaMemcpyAsync(hd, od.p, nr * 4, cudaMemcpyDeviceToHost, s));
+            }
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(s));
+        } catch (...) {
+            free(hs), free(he), free(hd);
+            throw;
+        }
+        *n_out = nr;
+        *starts_out = hs, *stops_out = he, *depth_out = hd;  // freed with lapper_host_free
     });
 }
 

@@ -1,6 +1,6 @@
 """`Lapper<u64, T>`: the host-side mirror of the reference's Lapper (src/lib.rs:182-680) over the u64 entry points
 of include/lapper_b200.h (csrc/engine64.cu).  Same method names and meaning as `rust_lapper_b200.Lapper`; `val`
-stays on the host, results are positions in the sorted interval vector.  Not instantiated for u64: insert, depth."""
+stays on the host, results are positions in the sorted interval vector."""
 from __future__ import annotations
 
 import ctypes as C
@@ -149,9 +149,41 @@ class Lapper64:
         ivs = self.intervals
         return [ivs[i] for i in self.find_idx(start, stop)]
 
-    def seek(self, start: int, stop: int, cursor: List[int]) -> List[Tuple[int, int]]:  # src/lib.rs:656-679
-        """the same sequence as find for start-sorted queries; the cursor is left alone (no cursor crosses the ABI)"""
-        return self.find(start, stop)
+    def seek_idx(self, start: int, stop: int, cursor: List[int]) -> List[int]:
+        """src/lib.rs:656-679: the cursor (a one-element list standing in for `&mut usize`) is updated exactly as the
+        reference updates it; the positions are find's from the cursor on."""
+        c = C.c_uint64(cursor[0])
+        _ffi.check(self._lib.lapper64_seek_cursor(self._h, start, C.byref(c)))
+        cursor[0] = int(c.value)
+        return [i for i in self.find_idx(start, stop) if i >= cursor[0]]
+
+    def seek(self, start: int, stop: int, cursor: List[int]) -> List[Tuple[int, int]]:
+        ivs = self.intervals
+        return [ivs[i] for i in self.seek_idx(start, stop, cursor)]
+
+    def insert(self, start: int, stop: int, val: Any = None) -> None:
+        """src/lib.rs:260-273: sorted insert (before equal intervals); clears cov and overlaps_merged."""
+        pos = C.c_uint64(0)
+        _ffi.check(self._lib.lapper64_insert(self._h, start, stop, C.byref(pos)))
+        if self._vals is not None:
+            while len(self._vals) < int(pos.value):
+                self._vals.append(None)
+            self._vals.append(val)
+
+    def depth(self) -> List[Tuple[int, int, int]]:
+        """src/lib.rs:576-598: maximal runs of equal coverage depth as (start, stop, depth), in iterator order"""
+        n = C.c_uint64(0)
+        ps, pe, pd = C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)
+        _ffi.check(self._lib.lapper64_depth(self._h, C.byref(n), C.byref(ps), C.byref(pe), C.byref(pd)))
+        k = int(n.value)
+        try:
+            s = np.ctypeslib.as_array(C.cast(ps, C.POINTER(C.c_uint64)), shape=(k,)).tolist() if k else []
+            e = np.ctypeslib.as_array(C.cast(pe, C.POINTER(C.c_uint64)), shape=(k,)).tolist() if k else []
+            d = np.ctypeslib.as_array(C.cast(pd, C.POINTER(C.c_uint32)), shape=(k,)).tolist() if k else []
+        finally:
+            for p in (ps, pe, pd):
+                self._lib.lapper_host_free(p)
+        return list(zip(s, e, d))
 
     # ---------------------------------------------------------------- set operations
     def merge_overlaps(self) -> None:  # src/lib.rs:361-416

@@ -28,13 +28,55 @@ def make():
     return lambda ivs: Lapper64(ivs)
 
 
-# the known-answer checks that need only the methods the u64 engine instantiates (no insert / depth)
-U64_CHECKS = [c for c in rs.CORE_CHECKS if c.__name__ not in ("check_depth",)]
-
-
-@pytest.mark.parametrize("check", U64_CHECKS, ids=lambda f: f.__name__)
+@pytest.mark.parametrize("check", rs.CORE_CHECKS + [rs.check_depth], ids=lambda f: f.__name__)
 def test_reference_known_answers_u64(make, check):
     check(make)
+
+
+@pytest.mark.parametrize(
+    "data",
+    [rs.nonoverlapping(), rs.overlapping(), rs.badlapper(), rs.single()],
+    ids=["nonoverlapping", "overlapping", "badlapper", "single"],
+)
+def test_insert_equality_u64(make, data):  # src/lib.rs:907-948, :976-1019
+    new_lapper = make(data)
+    insert_lapper = make([])
+    for s, e in data:
+        insert_lapper.insert(s, e)
+    assert new_lapper.starts.tolist() == insert_lapper.starts.tolist()
+    assert new_lapper.stops.tolist() == insert_lapper.stops.tolist()
+    assert new_lapper.intervals == insert_lapper.intervals
+    assert new_lapper.max_len == insert_lapper.max_len
+
+
+def test_insert_depth_seek_against_the_oracle_u64(oracle64):
+    """insert (positions before equal intervals, perm of the new interval), depth and the seek cursor protocol on
+    coordinates beyond 32 bits, against the oracle built with I = u64"""
+    from rust_lapper_b200 import Lapper64
+
+    rng = np.random.default_rng(17)
+    sh = 1 << 41
+    s = (rng.integers(0, 5000, 400).astype(np.uint64) + np.uint64(sh))
+    e = s + rng.integers(0, 300, 400).astype(np.uint64)
+    gpu, cpu = Lapper64(starts=s[:300], stops=e[:300]), oracle64(starts=s[:300], stops=e[:300])
+    for a, b in zip(s[300:].tolist(), e[300:].tolist()):
+        gpu.insert(a, b)
+        cpu.insert(a, b, len(cpu))  # val = input position, like the engine's perm
+    gs, ge, gp = gpu.intervals_soa()
+    cs, ce, cv = cpu.intervals_soa()
+    assert np.array_equal(gs, cs) and np.array_equal(ge, ce) and np.array_equal(gp, cv)
+    assert np.array_equal(gpu.stops, cpu.stops) and gpu.max_len == cpu.max_len
+    assert gpu.depth() == cpu.depth()
+    qs = np.sort(rng.integers(sh - 100, sh + 5400, 300).astype(np.uint64))
+    cg, cc = [0], [0]
+    for a in qs.tolist():
+        assert gpu.seek_idx(a, a + 40, cg) == cpu.seek_idx(a, a + 40, cc)
+        assert cg == cc
+    # unsorted queries: the cursor protocol differs from find and must still match the reference
+    cg, cc = [0], [0]
+    for a in rng.permutation(qs).tolist()[:150]:
+        assert gpu.seek_idx(a, a + 40, cg) == cpu.seek_idx(a, a + 40, cc)
+        assert cg == cc
 
 
 def test_reference_known_answers_shifted_beyond_32_bits(make):
