@@ -596,8 +596,9 @@ def run_ours(args):
             "e2e": e2e,
             "gpu_launches": world * launches_timed,
             "gpu_launches_note": "kernels launched by the library inside the headline's timed region, counted by "
-                                 "lapper_query_kernel_launches(); per step: count_bucket_kernel at 4 CTAs/SM (runs for start-sorted "
-                                 "batches, else exits at once), count_bucket_kernel at 3 CTAs/SM (the reverse), "
+                                 "lapper_query_kernel_launches(); per step: count_bucket_kernel at 3 CTAs/SM (does the work for "
+                                 "order-less batches like this one), its 4-CTAs/SM build and count_sorted_kernel (for local / sorted "
+                                 "dense batches; both read the same on-device batch probe and exit at once here), "
                                  "count_bucket_tail_kernel for the ragged tail",
             "clocks": cx.clocks.summary(),
             "checksum": checksum,
