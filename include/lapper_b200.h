@@ -227,6 +227,12 @@ int lapper_group_count_batch_u32(const lapper_group_t *grp, const uint32_t *q_st
 int lapper_group_find_batch_u32(const lapper_group_t *grp, const uint32_t *q_start, const uint32_t *q_stop,
                                 uint64_t nq, uint64_t *offsets_out /* nq+1 */, uint32_t **indices_out /* lapper_host_free */,
                                 uint64_t *total_out);
+/* set operations over a group: cov as the sum of the replicas' chunk sums (each replica covers a contiguous chunk of
+ * the sorted vector; the cached value of src/lib.rs:311-316 is honoured and set on every replica by _set_cov),
+ * merge_overlaps on every replica at once (the replicas stay identical) */
+int lapper_group_cov(const lapper_group_t *grp, uint32_t *cov_out);
+int lapper_group_set_cov(lapper_group_t *grp, uint32_t *cov_out);
+int lapper_group_merge_overlaps(lapper_group_t *grp);
 
 /* ---- index import/export for one-process-per-GPU deployments (torch.distributed broadcast of the
  *      built arrays): build a handle from already-sorted device arrays without re-sorting. */

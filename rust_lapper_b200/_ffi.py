@@ -107,6 +107,9 @@ SIGNATURES = {
     "lapper_group_replica": (_vp, [_vp, _int]),
     "lapper_group_count_batch_u32": (_int, [_vp, _vp, _vp, _u64, _vp]),
     "lapper_group_find_batch_u32": (_int, [_vp, _vp, _vp, _u64, _vp, _pvp, C.POINTER(_u64)]),
+    "lapper_group_cov": (_int, [_vp, C.POINTER(_u32)]),
+    "lapper_group_set_cov": (_int, [_vp, C.POINTER(_u32)]),
+    "lapper_group_merge_overlaps": (_int, [_vp]),
     "lapper_from_sorted_dev": (_int, [_vp, _vp, _vp, _vp, _u64, _int, _int, _u32, _vp, _pvp]),
     "lapper_host_alloc_pinned": (_int, [_u64, _pvp]),
     # I = u64 (csrc/engine64.cu)

@@ -197,6 +197,8 @@ void launch_exclusive_sum(const uint32_t *in, uint32_t *out, uint64_t n, cudaStr
 // inclusive prefix max of `in` (n elements) into `out`
 void launch_prefix_max(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream_t stream);
 uint32_t compute_cov(const DeviceIndex &ix, cudaStream_t stream);
+// the share of cov contributed by the sorted positions [lo, hi) (wrapping u32; the shares of a partition add up to cov)
+uint32_t compute_cov_range(const DeviceIndex &ix, uint64_t lo, uint64_t hi, cudaStream_t stream);
 // merged (start, stop, head perm) arrays; returns m.  Outputs are pool memory (pool_free; m may be 0).
 uint64_t compute_merged(const DeviceIndex &ix, uint32_t **m_starts, uint32_t **m_stops, uint32_t **m_perm,
                         cudaStream_t stream);

@@ -280,10 +280,12 @@ void scan3(In in, uint64_t n, Sink sink, uint32_t *d_total, cudaStream_t stream)
 }
 
 // cov = sum_{last of run} P_i - sum_{head} S_i  (wrapping u32)
+// (over positions [lo, hi) of the n intervals: the prefix max is global, so a chunk's partial sum needs nothing from
+// the other chunks -- the multi-GPU form of cov is the sum of the replicas' chunk sums)
 __global__ void __launch_bounds__(kThreads) cov_kernel(const uint32_t *__restrict__ S, const uint32_t *__restrict__ P,
-                                                       uint64_t n, uint32_t *__restrict__ out) {
+                                                       uint64_t n, uint64_t lo, uint64_t hi, uint32_t *__restrict__ out) {
     uint32_t acc = 0;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t s = S[i], p = P[i];
         const bool head = (i == 0) || (P[i - 1] < s);
         const bool last = (i + 1 == n) || (p < S[i + 1]);
@@ -359,11 +361,14 @@ void launch_prefix_max(const uint32_t *in, uint32_t *out, uint64_t n, cudaStream
     scan3<MaxOp>(LoadArray{in}, n, StoreSink{out}, nullptr, stream);
 }
 
-uint32_t compute_cov(const DeviceIndex &ix, cudaStream_t stream) {
-    if (ix.n == 0) return 0;
+uint32_t compute_cov(const DeviceIndex &ix, cudaStream_t stream) { return compute_cov_range(ix, 0, ix.n, stream); }
+
+uint32_t compute_cov_range(const DeviceIndex &ix, uint64_t lo, uint64_t hi, cudaStream_t stream) {
+    hi = std::min<uint64_t>(hi, ix.n);
+    if (ix.n == 0 || lo >= hi) return 0;
     Scratch<uint32_t> d_out(1, stream);
     LAPPER_CUDA_CHECK(cudaMemsetAsync(d_out.p, 0, 4, stream));
-    cov_kernel<<<reduce_grid(ix.n), kThreads, 0, stream>>>(ix.starts, ix.prefix_max, ix.n, d_out.p);
+    cov_kernel<<<reduce_grid(hi - lo), kThreads, 0, stream>>>(ix.starts, ix.prefix_max, ix.n, lo, hi, d_out.p);
     LAPPER_CUDA_CHECK(cudaGetLastError());
     uint32_t cov = 0;
     LAPPER_CUDA_CHECK(cudaMemcpyAsync(&cov, d_out.p, 4, cudaMemcpyDeviceToHost, stream));

@@ -348,3 +348,29 @@ class LapperGroup:
         finally:
             self._lib.lapper_host_free(idx_p)
         return offsets, indices
+
+    # ---------------------------------------------------------------- set operations over the group
+    def cov(self) -> int:
+        """cov as the sum of the replicas' chunk sums (replica g covers positions [g n/G, (g+1) n/G) of the sorted vector)"""
+        out = C.c_uint32(0)
+        _ffi.check(self._lib.lapper_group_cov(self._h, C.byref(out)))
+        return int(out.value)
+
+    def set_cov(self) -> int:
+        out = C.c_uint32(0)
+        _ffi.check(self._lib.lapper_group_set_cov(self._h, C.byref(out)))
+        return int(out.value)
+
+    def merge_overlaps(self) -> None:
+        """every replica merges its own copy, all at once; the replicas stay identical"""
+        _ffi.check(self._lib.lapper_group_merge_overlaps(self._h))
+
+    def replica_intervals(self, g: int) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(starts, stops, perm) of replica g's sorted vector (a borrowed handle: the group owns it)"""
+        h = self._lib.lapper_group_replica(self._h, g)
+        if not h:
+            raise IndexError(g)
+        n = int(self._lib.lapper_len(h))
+        s, e, p = np.empty(n, np.uint32), np.empty(n, np.uint32), np.empty(n, np.uint32)
+        _ffi.check(self._lib.lapper_get_intervals(h, _ptr(s), _ptr(e), _ptr(p)))
+        return s, e, p
