@@ -794,7 +794,8 @@ def bench_find(cx):
         def e2e_step():
             _ffi.check(lib.lapper_find_batch_u32_host(h3, _vp(hq_s), _vp(hq_e), nq, _vp(h_off), _vp(h_idx), h_idx.numel(), C.byref(tot)))
 
-        e2e_step()
+        for _ in range(2):  # (the first call grows the library's memory pool, the second settles its chunk buffers)
+            e2e_step()
         cx.barrier()
         e2e_steps = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
@@ -805,6 +806,32 @@ def bench_find(cx):
         cx.barrier()
         ok = int(tot.value) == hits and bool(torch.equal(h_off, offsets.cpu())) and bool(torch.equal(h_idx[:hits], indices[:hits].cpu()))
         d2h = (nq + 1) * 8 + hits * 4
+        # what the link delivers for the same bytes on THIS box, now: the step's D2H bytes in 192 MB pieces with the
+        # step's H2D beside it, plain copies on two streams (all ranks at once, max over ranks)
+        link_ms = None
+        if hits:
+            s_out, s_in = torch.cuda.Stream(), torch.cuda.Stream()
+            piece = 48_000_000
+
+            def link_step():
+                with torch.cuda.stream(s_out):
+                    for lo in range(0, hits, piece):
+                        h_idx[lo:lo + piece].copy_(indices[lo:lo + piece], non_blocking=True)
+                    h_off.copy_(offsets, non_blocking=True)
+                with torch.cuda.stream(s_in):
+                    qs.copy_(hq_s, non_blocking=True)
+                    qe.copy_(hq_e, non_blocking=True)
+
+            torch.cuda.synchronize()
+            link_step()
+            torch.cuda.synchronize()
+            cx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(2):
+                link_step()
+            torch.cuda.synchronize()
+            link_ms = 1e3 * cx.max_over_ranks(time.perf_counter() - t0) / 2
+            cx.barrier()
         e2e = {
             "value": world * nq * e2e_steps / e2e_s, "unit": UNIT, "hits_per_s": hits_all * e2e_steps / e2e_s,
             "h2d_bytes_per_step": world * nq * 8, "d2h_bytes_per_step": world * d2h if world == 1 else None,
@@ -813,6 +840,10 @@ def bench_find(cx):
             "api": "lapper_find_batch_u32_host (host pointers, pinned; 3-slot chunk pipeline: H2D queries | offsets + emit | D2H offsets + positions)",
             "matches_device_run": cx.all_true(ok),
             "pcie_floor_ms_at_55GBps": 1e3 * d2h / 55e9,
+            "link_ms_same_bytes": link_ms,
+            "frac_of_link": (link_ms / (1e3 * e2e_s / e2e_steps)) if link_ms else None,
+            "link_note": "link_ms_same_bytes = plain cudaMemcpyAsync of the step's D2H bytes (192 MB pieces) with its H2D bytes beside "
+                         "them, timed in this process right after the e2e steps (max over ranks, all ranks copying at once)",
         }
         if world > 1:
             t = torch.tensor([d2h], dtype=torch.int64, device=dev)

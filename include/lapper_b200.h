@@ -291,6 +291,12 @@ int lapper64_union_and_intersect(const lapper64_t *a, const lapper64_t *b, uint6
 int lapper64_insert(lapper64_t *l, uint64_t start, uint64_t stop, uint64_t *input_position_out);
 int lapper64_seek_cursor(const lapper64_t *l, uint64_t start, uint64_t *cursor);
 int lapper64_depth(const lapper64_t *l, uint64_t *n_out, uint64_t **starts_out, uint64_t **stops_out, uint32_t **depth_out);
+/* Narrowing: a u64 set whose coordinates all fit 32 bits (<= 2^32 - 3) has its count / find batches answered by the
+ * u32 engine's tables and kernels (same results bit for bit: csrc/engine64.cu, "narrowing"); the u32 index is built on
+ * the first batch of >= 4096 queries and dropped by insert / merge_overlaps.  lapper64_is_narrow: 1 once it exists.
+ * lapper64_debug_set_narrow_mode (tests): 0 = never, 1 = default, 2 = from the first batch on; returns the old mode. */
+int lapper64_is_narrow(const lapper64_t *l);
+int lapper64_debug_set_narrow_mode(int mode);
 
 #ifdef __cplusplus
 }

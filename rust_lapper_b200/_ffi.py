@@ -133,6 +133,8 @@ SIGNATURES = {
     "lapper64_insert": (_int, [_vp, _u64, _u64, C.POINTER(_u64)]),
     "lapper64_seek_cursor": (_int, [_vp, _u64, C.POINTER(_u64)]),
     "lapper64_depth": (_int, [_vp, C.POINTER(_u64), _pvp, _pvp, _pvp]),
+    "lapper64_is_narrow": (_int, [_vp]),
+    "lapper64_debug_set_narrow_mode": (_int, [_int]),
     "lapper_host_free_pinned": (None, [_vp]),
 }
 

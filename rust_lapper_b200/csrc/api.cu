@@ -262,6 +262,7 @@ uint64_t find_host(const lapper_t *l, const uint32_t *qs, const uint32_t *qe, ui
     const uint64_t nchunks = div_up(nq, chunk);
     Scratch<uint32_t> d_qs[kMaxSlots], d_qe[kMaxSlots], d_idx[kMaxSlots];
     Scratch<uint64_t> d_off[kMaxSlots], d_goff[kMaxSlots];
+    uint64_t idx_cap[kMaxSlots] = {};
     const int used = (int)std::min<uint64_t>(kSlots, nchunks);
     for (int s = 0; s < used; s++) {
         d_qs[s].alloc(chunk, st[s].s);
@@ -286,7 +287,12 @@ uint64_t find_host(const lapper_t *l, const uint32_t *qs, const uint32_t *qe, ui
         launch_rebase_offsets(d_off[s].p, d_goff[s].p, m + (last ? 1 : 0), offsets_base + base, st[s].s);
         LAPPER_CUDA_CHECK(cudaMemcpyAsync(offsets_out + lo, d_goff[s].p, (m + (last ? 1 : 0)) * 8, cudaMemcpyDeviceToHost, st[s].s));
         if (indices_out && base + t <= capacity && t) {
-            d_idx[s].alloc(t, st[s].s);  // (the previous chunk's buffer of this slot goes back to the pool in stream order)
+            // the slot keeps its position buffer while the chunks fit it (+ 1/8 of headroom when it has to grow): the
+            // pool sees a handful of allocations per call, of sizes that repeat from call to call
+            if (t > idx_cap[s]) {
+                idx_cap[s] = t + t / 8;
+                d_idx[s].alloc(idx_cap[s], st[s].s);  // (the old buffer goes back to the pool in stream order)
+            }
             launch_find_fill(l->ix, d_qs[s].p, d_qe[s].p, m, d_off[s].p, d_idx[s].p, st[s].s, t);
             LAPPER_CUDA_CHECK(cudaMemcpyAsync(indices_out + base, d_idx[s].p, t * 4, cudaMemcpyDeviceToHost, st[s].s));
         }

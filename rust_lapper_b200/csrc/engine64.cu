@@ -20,8 +20,10 @@
 //                                 the reference's positions, depth in closed form over the sorted unique event coordinates
 // At most 2^32 - 2 intervals (positions are u32, as in the u32 engine).  Replica groups exist for u32 only.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <memory>
+#include <mutex>
 
 #include "abi_common.cuh"
 #include "index.cuh"
@@ -40,6 +42,11 @@ struct lapper64 {
     bool cov_is_some = false;
     uint64_t cov = 0;
     uint64_t next_input_id = 0;  // input position handed to the next inserted interval
+    uint64_t max_coord = 0;      // largest start or stop
+    // The u32 engine over the same sorted intervals (see "narrowing" below): built on the first batch that is worth it
+    // when every coordinate fits, dropped by insert / merge_overlaps.
+    mutable std::atomic<lapper_t *> narrow{nullptr};
+    mutable std::mutex narrow_mu;
 };
 
 namespace lap {
@@ -86,23 +93,27 @@ __global__ void gather64_kernel(uint64_t *__restrict__ out, const uint64_t *__re
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[idx[i]];
 }
-// max_len with checked_sub -> 0 (src/lib.rs:218-227) and the inverted flag; out[0] = max_len, out[1] = inverted
+// max_len with checked_sub -> 0 (src/lib.rs:218-227), the inverted flag and the largest coordinate;
+// out[0] = max_len, out[1] = inverted, out[2] = max(start, stop)
 __global__ void __launch_bounds__(kT) stats64_kernel(const uint64_t *__restrict__ s, const uint64_t *__restrict__ e, uint64_t n,
                                                      unsigned long long *__restrict__ out) {
-    unsigned long long mx = 0, inv = 0;
+    unsigned long long mx = 0, inv = 0, top = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t a = s[i], b = e[i];
         mx = max(mx, (unsigned long long)(b > a ? b - a : 0ull));
         inv |= (b < a) ? 1ull : 0ull;
+        top = max(top, (unsigned long long)max(a, b));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
         inv |= __shfl_xor_sync(0xFFFFFFFFu, inv, o);
+        top = max(top, __shfl_xor_sync(0xFFFFFFFFu, top, o));
     }
     if ((threadIdx.x & 31) == 0) {
         if (mx) atomicMax(out, mx);
         if (inv) atomicOr(out + 1, 1ull);
+        if (top) atomicMax(out + 2, top);
     }
 }
 
@@ -527,19 +538,20 @@ void free_arrays(lapper64 *l, cudaStream_t stream) {
 // max_len, inverted flag and prefix max from the sorted arrays (S, Eiv set; P allocated here)
 void finish_from_sorted(lapper64 *l, cudaStream_t stream) {
     uint64_t bytes = 0;
-    l->max_len = 0, l->has_inverted = false;
+    l->max_len = 0, l->has_inverted = false, l->max_coord = 0;
     if (l->n == 0) return;
     l->P = pool_alloc<uint64_t>(l->n, bytes, stream);
-    Scratch<unsigned long long> st(2, stream);
-    LAPPER_CUDA_CHECK(cudaMemsetAsync(st.p, 0, 16, stream));
+    Scratch<unsigned long long> st(3, stream);
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(st.p, 0, 24, stream));
     stats64_kernel<<<capped(l->n), kT, 0, stream>>>(l->S, l->Eiv, l->n, st.p);
     LAPPER_CUDA_CHECK(cudaGetLastError());
     scan64<Max64>(Load64{l->Eiv}, l->n, StoreIncl{l->P}, nullptr, stream);
-    unsigned long long h[2] = {0, 0};
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(h, st.p, 16, cudaMemcpyDeviceToHost, stream));
+    unsigned long long h[3] = {0, 0, 0};
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(h, st.p, 24, cudaMemcpyDeviceToHost, stream));
     LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
     l->max_len = h[0];
     l->has_inverted = h[1] != 0;
+    l->max_coord = h[2];
 }
 
 void build_from_device(lapper64 *l, const uint64_t *d_s, const uint64_t *d_e, uint64_t n, cudaStream_t stream) {
@@ -637,6 +649,69 @@ void find_emit64(const lapper64 *l, const uint64_t *d_qs, const uint64_t *d_qe, 
     LAPPER_CUDA_CHECK(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------ narrowing
+// A Lapper<u64, T> -- the README's `usize` -- whose coordinates all fit 32 bits (every genome does) is served by the u32
+// engine's tables and kernels: the sorted arrays are narrowed once into a u32 index (positions and tie order are those
+// of this handle: lapper_from_sorted_dev keeps the order it is given), and a batch's queries are narrowed on the way in:
+//     stop'  = min(stop, 2^32 - 2)
+//     start' = start == u64::MAX ? u32::MAX : min(start, 2^32 - 2)
+// With every coordinate <= 2^32 - 3 each comparison the reference makes (start_i < stop, stop_i <= start resp.
+// stop_i > start; src/lib.rs:140-142, :611-618) has the same outcome on the narrowed query, and `start + 1` wraps for
+// start' = u32::MAX exactly as it does for start = u64::MAX (:614).  Counts are u64 either way, positions u32.
+// The u64 arrays stay: the set operations, insert, depth and the seek cursor work on them.
+std::atomic<int> g_narrow_mode{1};  // 0 = never, 1 = from the first batch of kNarrowMinBatch queries on, 2 = always
+constexpr uint64_t kNarrowMaxCoord = 0xFFFFFFFDull;
+constexpr uint64_t kNarrowMinBatch = 4096;
+
+__global__ void __launch_bounds__(kT) narrow_index_kernel(const uint64_t *__restrict__ S, const uint64_t *__restrict__ Eiv,
+                                                          const uint64_t *__restrict__ E, uint64_t n, uint32_t *__restrict__ s,
+                                                          uint32_t *__restrict__ eiv, uint32_t *__restrict__ e) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        s[i] = (uint32_t)S[i], eiv[i] = (uint32_t)Eiv[i], e[i] = (uint32_t)E[i];
+}
+
+__global__ void __launch_bounds__(kT) narrow_queries_kernel(const uint64_t *__restrict__ qs, const uint64_t *__restrict__ qe,
+                                                            uint64_t nq, uint32_t *__restrict__ a, uint32_t *__restrict__ b) {
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t x = qs[j], y = qe[j];
+        a[j] = x == ~0ull ? 0xFFFFFFFFu : (uint32_t)min(x, (uint64_t)0xFFFFFFFEull);
+        b[j] = (uint32_t)min(y, (uint64_t)0xFFFFFFFEull);
+    }
+}
+
+// the u32 engine of this handle, or nullptr when the batch takes the 64-bit kernels
+lapper_t *narrow_of(const lapper64 *l, uint64_t nq, cudaStream_t stream) {
+    const int mode = g_narrow_mode.load(std::memory_order_relaxed);
+    if (mode == 0 || l->n == 0 || l->n >= 0xFFFFFFF0ull || l->max_coord > kNarrowMaxCoord) return nullptr;
+    lapper_t *h = l->narrow.load(std::memory_order_acquire);
+    if (h) return h;
+    if (mode == 1 && nq < kNarrowMinBatch) return nullptr;
+    std::lock_guard<std::mutex> guard(l->narrow_mu);
+    h = l->narrow.load(std::memory_order_acquire);
+    if (h) return h;
+    Scratch<uint32_t> s(l->n, stream), eiv(l->n, stream), e(l->n, stream);
+    narrow_index_kernel<<<capped(l->n), kT, 0, stream>>>(l->S, l->Eiv, l->E, l->n, s.p, eiv.p, e.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    const int rc = lapper_from_sorted_dev(s.p, eiv.p, e.p, l->perm, l->n, l->overlaps_merged ? 1 : 0, l->device, 0, stream, &h);
+    if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
+    l->narrow.store(h, std::memory_order_release);
+    return h;
+}
+
+void drop_narrow(lapper64 *l) {
+    lapper_t *h = l->narrow.exchange(nullptr, std::memory_order_acq_rel);
+    if (h) lapper_free(h);
+}
+
+struct NarrowQueries {
+    Scratch<uint32_t> a, b;
+    NarrowQueries(const uint64_t *d_qs, const uint64_t *d_qe, uint64_t nq, cudaStream_t stream) : a(nq, stream), b(nq, stream) {
+        if (nq == 0) return;
+        narrow_queries_kernel<<<capped(nq), kT, 0, stream>>>(d_qs, d_qe, nq, a.p, b.p);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+    }
+};
+
 void check64(const lapper64 *l) { LAPPER_REQUIRE(l != nullptr, "null lapper64 handle"); }
 
 }  // namespace
@@ -701,6 +776,7 @@ void lapper64_free(lapper64_t *l) {
     int prev = -1;
     cudaGetDevice(&prev);
     cudaSetDevice(l->device);
+    drop_narrow(l);
     free_arrays(l, nullptr);
     cudaStreamSynchronize(nullptr);
     if (prev >= 0) cudaSetDevice(prev);
@@ -743,6 +819,12 @@ int lapper64_count_batch_dev(const lapper64_t *l, const uint64_t *d_q_start, con
             LAPPER_CUDA_CHECK(cudaMemsetAsync(d_counts_out, 0, nq * 8, (cudaStream_t)stream));
             return;
         }
+        if (lapper_t *h = narrow_of(l, nq, (cudaStream_t)stream)) {
+            NarrowQueries q(d_q_start, d_q_stop, nq, (cudaStream_t)stream);
+            const int rc = lapper_count_batch_u32_dev64(h, q.a.p, q.b.p, nq, d_counts_out, stream);
+            if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
+            return;
+        }
         g_query_launches++, count64_kernel<<<capped(nq), kT, 0, (cudaStream_t)stream>>>(view_of(l), d_q_start, d_q_stop, nq, d_counts_out);
         LAPPER_CUDA_CHECK(cudaGetLastError());
     });
@@ -775,6 +857,12 @@ int lapper64_find_batch_dev(const lapper64_t *l, const uint64_t *d_q_start, cons
         DeviceGuard dg(l->device);
         cudaStream_t s = (cudaStream_t)stream;
         *total_out = 0;
+        if (lapper_t *h = narrow_of(l, nq, s)) {
+            NarrowQueries q(d_q_start, d_q_stop, nq, s);
+            const int rc = lapper_find_batch_u32_dev(h, q.a.p, q.b.p, nq, d_offsets, d_indices, indices_capacity, total_out, stream);
+            if (rc != LAPPER_OK) throw Error(rc, last_error_slot());  // (LAPPER_ERR_CAPACITY included: same contract)
+            return;
+        }
         find_offsets64(l, d_q_start, d_q_stop, nq, d_offsets, s);
         if (d_indices) find_emit64(l, d_q_start, d_q_stop, nq, d_offsets, d_indices, indices_capacity, s);
         uint64_t total = 0;
@@ -799,6 +887,13 @@ int lapper64_find_batch(const lapper64_t *l, const uint64_t *q_start, const uint
         if (nq) {
             LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqs.p, q_start, nq * 8, cudaMemcpyHostToDevice, st.s));
             LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqe.p, q_stop, nq * 8, cudaMemcpyHostToDevice, st.s));
+        }
+        if (lapper_t *h = narrow_of(l, nq, st.s)) {
+            NarrowQueries q(dqs.p, dqe.p, nq, st.s);
+            dqs.release(), dqe.release();
+            const int rc = lapper_find_batch_u32_devq(h, q.a.p, q.b.p, nq, st.s, out);
+            if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
+            return;
         }
         std::unique_ptr<lapper_result_t> r(new lapper_result_t());
         r->device = l->device;
@@ -875,10 +970,11 @@ int lapper64_merge_overlaps(lapper64_t *l) {
             cudaStreamSynchronize(st.s);
             throw;
         }
+        drop_narrow(l);
         free_arrays(l, st.s);
         l->n = next.n;
         l->S = next.S, l->Eiv = next.Eiv, l->E = next.E, l->P = next.P, l->perm = next.perm;
-        l->max_len = next.max_len, l->has_inverted = next.has_inverted;
+        l->max_len = next.max_len, l->has_inverted = next.has_inverted, l->max_coord = next.max_coord;
         l->overlaps_merged = true;
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
     });
@@ -949,10 +1045,11 @@ int lapper64_insert(lapper64_t *l, uint64_t start, uint64_t stop, uint64_t *inpu
             cudaStreamSynchronize(st.s);
             throw;
         }
+        drop_narrow(l);
         free_arrays(l, st.s);
         l->n = next.n;
         l->S = next.S, l->Eiv = next.Eiv, l->E = next.E, l->P = next.P, l->perm = next.perm;
-        l->max_len = next.max_len, l->has_inverted = next.has_inverted;
+        l->max_len = next.max_len, l->has_inverted = next.has_inverted, l->max_coord = next.max_coord;
         l->next_input_id = id + 1;
         l->cov_is_some = false;      // src/lib.rs:271
         l->overlaps_merged = false;  // src/lib.rs:272
@@ -1043,5 +1140,11 @@ int lapper64_depth(const lapper64_t *l, uint64_t *n_out, uint64_t **starts_out, 
         *starts_out = hs, *stops_out = he, *depth_out = hd;  // freed with lapper_host_free
     });
 }
+
+/* which engine answers this handle's batches: 1 = the u32 engine is built (coordinates fit 32 bits), 0 = the 64-bit kernels */
+int lapper64_is_narrow(const lapper64_t *l) { return l && l->narrow.load(std::memory_order_acquire) != nullptr; }
+
+/* tests: 0 = never narrow, 1 = from the first batch of 4096 queries on (default), 2 = always; returns the old mode */
+int lapper64_debug_set_narrow_mode(int mode) { return g_narrow_mode.exchange(std::min(std::max(mode, 0), 2)); }
 
 }  // extern "C"

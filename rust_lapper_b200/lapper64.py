@@ -80,6 +80,11 @@ class Lapper64:
         return bool(self._lib.lapper64_overlaps_merged(self._h))
 
     @property
+    def is_narrow(self) -> bool:
+        """True once this handle's batches are answered by the u32 engine (every coordinate fits 32 bits)."""
+        return bool(_ffi.lib().lapper64_is_narrow(self._h))
+
+    @property
     def has_inverted(self) -> bool:
         return bool(self._lib.lapper64_has_inverted(self._h))
 

@@ -103,6 +103,12 @@ def draw_queries(rng, bits, U, s):
         m = min(nq, 4)
         a[:m] = np.array([0, top, top, 0], dtype=dt)[:m]
         b[:m] = np.array([0, top, 0, top], dtype=dt)[:m]
+        if bits == 64 and nq > 40:  # coordinates around 2^32: where a narrowed u64 set clamps its queries
+            t32 = (1 << 32) - 1
+            pts = np.array([t32 - 3, t32 - 2, t32 - 1, t32, t32 + 1, 1 << 33, top - 1, top], dtype=dt)
+            k = rng.integers(4, nq, 32)
+            a[k] = pts[rng.integers(0, pts.size, 32)]
+            b[k] = pts[rng.integers(0, pts.size, 32)]
     return a, b, order
 
 
@@ -122,6 +128,11 @@ def check_case(rng, bits, case_id, verbose=False):
         cpu = lapper_oracle.OracleLapper(starts=s.astype(np.uint32), stops=e.astype(np.uint32))
         qs, qe = qs.astype(np.uint32), qe.astype(np.uint32)
     else:
+        # which engine answers a u64 set whose coordinates fit 32 bits: the 64-bit kernels, the default policy (u32
+        # engine from the first large batch on), or the u32 engine from the start
+        mode = int(rng.choice([0, 1, 2, 2]))
+        _ffi.lib().lapper64_debug_set_narrow_mode(mode)
+        desc += f" narrow_mode={mode}"
         gpu = Lapper64(starts=s, stops=e)
         cpu = lapper_oracle.OracleLapper(starts=s, stops=e, coord_bits=64)
     want_c = cpu.count_batch(qs, qe, 4)

@@ -276,3 +276,148 @@ def test_find_one_call_device_api_u64(oracle64):
         assert int(t.value) == total
     finally:
         lib.lapper64_free(h)
+
+
+# ---------------------------------------------------------------------------------------------- narrowing
+# A u64 set whose coordinates fit 32 bits is answered by the u32 engine (csrc/engine64.cu, "narrowing"): same oracle
+# (I = u64), same bits, whichever engine runs.
+@pytest.fixture
+def narrow_mode():
+    from rust_lapper_b200 import _ffi
+
+    lib = _ffi.lib()
+    old = []
+
+    def set_mode(m):
+        old.append(lib.lapper64_debug_set_narrow_mode(m))
+
+    yield set_mode
+    if old:
+        lib.lapper64_debug_set_narrow_mode(old[0])
+
+
+@pytest.mark.parametrize("mode", [0, 2], ids=["wide", "narrow"])
+@pytest.mark.parametrize("check", rs.CORE_CHECKS + [rs.check_depth], ids=lambda f: f.__name__)
+def test_reference_known_answers_u64_either_engine(make, narrow_mode, mode, check):
+    narrow_mode(mode)
+    check(make)
+
+
+def _special_queries(rng, universe, nq, qlen):
+    qs = rng.integers(0, universe + universe // 8, nq, dtype=np.uint64)
+    qe = qs + rng.integers(0, max(qlen, 2), nq, dtype=np.uint64)
+    k = rng.choice(nq, nq // 10, replace=False)
+    qe[k] = qs[k] - rng.integers(0, 3, k.size, dtype=np.uint64).clip(max=qs[k])  # empty and inverted
+    top32 = (1 << 32) - 1
+    pts = np.array([0, 1, top32 - 3, top32 - 2, top32 - 1, top32, top32 + 1, 1 << 40, U64_MAX - 1, U64_MAX], dtype=np.uint64)
+    a, b = np.meshgrid(pts, pts)
+    m = a.size
+    qs[:m], qe[:m] = a.reshape(-1), b.reshape(-1)
+    return qs, qe
+
+
+@pytest.mark.parametrize("n,universe,max_len,top", [
+    (1, 1000, 50, None),
+    (3000, 200_000, 300, None),
+    (200_000, 3_000_000_000, 5000, None),
+    (200_000, 3_000_000_000, 5000, (1 << 32) - 3),   # an interval that ends at the largest coordinate that still narrows
+    (50_000, 1 << 20, 1 << 8, None),                  # duplicates and ties
+])
+def test_narrow_engine_matches_the_u64_oracle(oracle64, narrow_mode, n, universe, max_len, top):
+    from rust_lapper_b200 import Lapper64
+
+    narrow_mode(2)
+    rng = np.random.default_rng(n ^ 0x5EED)
+    s, e = _random_set(rng, n, universe, max_len, 0.0)
+    if top is not None:
+        s[0], e[0] = top - 7, top
+    gpu, cpu = Lapper64(starts=s, stops=e), oracle64(starts=s, stops=e)
+    qs, qe = _special_queries(rng, universe, 30_000, max_len)
+    _same(gpu, cpu, qs, qe)
+    assert gpu.is_narrow
+    o = np.argsort(qs, kind="stable")
+    _same(gpu, cpu, qs[o], np.maximum.accumulate(qe[o]))
+    # the set operations and the structure still come from the u64 arrays
+    gs, ge, gp = gpu.intervals_soa()
+    cs, ce, cv = cpu.intervals_soa()
+    assert np.array_equal(gs, cs) and np.array_equal(ge, ce) and np.array_equal(gp, cv)
+    assert gpu.cov() == cpu.cov()
+    # merge_overlaps drops the u32 index; the next batch rebuilds it over the merged set
+    gpu.merge_overlaps(), cpu.merge_overlaps()
+    assert not gpu.is_narrow
+    _same(gpu, cpu, qs, qe)
+    assert gpu.is_narrow
+    # insert beyond 32 bits: the handle goes back to the 64-bit kernels for good
+    gpu.insert(1 << 33, (1 << 33) + 10), cpu.insert(1 << 33, (1 << 33) + 10)
+    _same(gpu, cpu, qs, qe)
+    assert not gpu.is_narrow
+
+
+def test_narrow_boundary_and_default_policy(oracle64, narrow_mode):
+    from rust_lapper_b200 import Lapper64
+
+    rng = np.random.default_rng(99)
+    s, e = _random_set(rng, 5000, 1_000_000, 400, 0.0)
+    qs, qe = _special_queries(rng, 1_000_000, 30_000, 400)
+    # default policy: small batches stay on the 64-bit kernels, the first batch of >= 4096 queries builds the u32 index
+    gpu, cpu = Lapper64(starts=s, stops=e), oracle64(starts=s, stops=e)
+    _same(gpu, cpu, qs[:1000], qe[:1000])
+    assert not gpu.is_narrow
+    _same(gpu, cpu, qs, qe)
+    assert gpu.is_narrow
+    _same(gpu, cpu, qs[:1000], qe[:1000])  # small batches use it once it exists
+    # one coordinate above 2^32 - 3: never narrowed (b' = 2^32 - 2 could no longer stand in for every larger stop)
+    narrow_mode(2)
+    for top, narrows in (((1 << 32) - 3, True), ((1 << 32) - 2, False), ((1 << 32) - 1, False), (1 << 32, False)):
+        s2, e2 = s.copy(), e.copy()
+        s2[0], e2[0] = top - 3, top
+        gpu, cpu = Lapper64(starts=s2, stops=e2), oracle64(starts=s2, stops=e2)
+        _same(gpu, cpu, qs, qe)
+        assert gpu.is_narrow == narrows, top
+    # inverted intervals narrow too (count / find have no precondition)
+    s3, e3 = s.copy(), e.copy()
+    s3[:50], e3[:50] = e[:50] + np.uint64(5), s[:50]
+    gpu, cpu = Lapper64(starts=s3, stops=e3), oracle64(starts=s3, stops=e3)
+    assert gpu.has_inverted
+    _same(gpu, cpu, qs, qe)
+    assert gpu.is_narrow
+
+
+def test_narrow_one_call_device_api(oracle64, narrow_mode):
+    """lapper64_find_batch_dev / lapper64_count_batch_dev on a narrowed handle: same capacity protocol, same bits"""
+    import ctypes as C
+
+    import torch
+
+    from rust_lapper_b200 import Lapper64, _ffi
+
+    narrow_mode(2)
+    lib = _ffi.lib()
+    rng = np.random.default_rng(5)
+    s, e = _random_set(rng, 100_000, 50_000_000, 2000, 0.0)
+    gpu, cpu = Lapper64(starts=s, stops=e), oracle64(starts=s, stops=e)
+    qs, qe = _special_queries(rng, 50_000_000, 100_000, 500)
+    wo, wi = cpu.find_batch(qs, qe, 4)
+    total = int(wo[-1])
+    dev = torch.device("cuda", 0)
+    dq_s = torch.from_numpy(qs.view(np.int64)).to(dev)
+    dq_e = torch.from_numpy(qe.view(np.int64)).to(dev)
+    d_off = torch.zeros(qs.size + 1, dtype=torch.int64, device=dev)
+    d_cnt = torch.zeros(qs.size, dtype=torch.int64, device=dev)
+    vp = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _ffi.check(lib.lapper64_count_batch_dev(gpu._h, vp(dq_s), vp(dq_e), qs.size, vp(d_cnt), sp))
+    torch.cuda.synchronize()
+    assert np.array_equal(d_cnt.cpu().numpy().view(np.uint64), cpu.count_batch(qs, qe, 4))
+    tot = C.c_uint64(0)
+    # too small a buffer: LAPPER_ERR_CAPACITY with complete offsets and total
+    d_idx = torch.zeros(max(total // 2, 1), dtype=torch.int32, device=dev)
+    rc = lib.lapper64_find_batch_dev(gpu._h, vp(dq_s), vp(dq_e), qs.size, vp(d_off), vp(d_idx), d_idx.numel(), C.byref(tot), sp)
+    assert rc == _ffi.ERR_CAPACITY and int(tot.value) == total
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint64), wo)
+    d_idx = torch.zeros(total + 5, dtype=torch.int32, device=dev)
+    _ffi.check(lib.lapper64_find_batch_dev(gpu._h, vp(dq_s), vp(dq_e), qs.size, vp(d_off), vp(d_idx), d_idx.numel(), C.byref(tot), sp))
+    assert int(tot.value) == total
+    assert np.array_equal(d_off.cpu().numpy().view(np.uint64), wo)
+    assert np.array_equal(d_idx[:total].cpu().numpy().view(np.uint32), wi)
+    assert gpu.is_narrow
