@@ -452,6 +452,7 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = world * nq * args.steps / (total_ms * 1e-3)
     checksum = int(counts.to(torch.int64).sum().item())
+    cx.headline_checksum = checksum
 
     # per-launch distribution (each launch separately timed) for the roofline of the one kernel
     per_launch = []
@@ -1177,7 +1178,38 @@ def run_extras(cx, n, nq):
         "published_reference": "README.md:73-76: find 4.78125 s (1,469,068,763 hits, unseeded data), count 15.625 ms (timer floor), unstated CPU",
     }
     lib.lapper_free(h1)
-    del idx1, off1
+    del idx1, off1, ta, tb, c1
+    torch.cuda.empty_cache()
+
+    # Lapper<u64, T> (the README's usize) on the cfg-2 shape: the coordinates fit 32 bits, so the u32 engine answers
+    # (narrowed index, queries clamped on the way in); the 64-bit kernels (bisection) timed beside it on a tenth
+    nq64 = min(nq, 100_000_000)
+    iv_s, iv_e = synth.intervals_uniform(SEED_IV, n, UNIVERSE, 50, 5000, device=dev)
+    s64 = (iv_s.to(torch.int64) & 0xFFFFFFFF).contiguous()
+    e64 = (iv_e.to(torch.int64) & 0xFFFFFFFF).contiguous()
+    del iv_s, iv_e
+    h64 = C.c_void_p(0)
+    _ffi.check(lib.lapper64_build_dev(_vp(s64), _vp(e64), n, dev.index, sp, C.byref(h64)))
+    del s64, e64
+    rq_s, rq_e = synth.queries_fixed_len(SEED_Q, nq64, UNIVERSE, QLEN, device=dev)
+    q64s = (rq_s.to(torch.int64) & 0xFFFFFFFF).contiguous()
+    q64e = (rq_e.to(torch.int64) & 0xFFFFFFFF).contiguous()
+    c64 = torch.empty(nq64, dtype=torch.int64, device=dev)
+    ms_n = timed(lambda: _ffi.check(lib.lapper64_count_batch_dev(h64, _vp(q64s), _vp(q64e), nq64, _vp(c64), sp)), 5)
+    narrow = bool(lib.lapper64_is_narrow(h64))
+    sum_n = int(c64.sum().item())
+    old_mode = lib.lapper64_debug_set_narrow_mode(0)
+    nqw = nq64 // 10
+    ms_w = timed(lambda: _ffi.check(lib.lapper64_count_batch_dev(h64, _vp(q64s), _vp(q64e), nqw, _vp(c64), sp)), 3)
+    lib.lapper64_debug_set_narrow_mode(old_mode)
+    out["u64_coordinates_cfg2"] = {
+        "count_random_ms": ms_n, "queries": nq64, "queries_per_s": nq64 / (ms_n * 1e-3), "answered_by_u32_engine": narrow,
+        "counts_sum": sum_n, "equals_u32_headline_checksum": (sum_n == cx.headline_checksum) if nq64 == nq else None,
+        "wide_kernels_ms": ms_w, "wide_kernels_queries": nqw, "wide_kernels_queries_per_s": nqw / (ms_w * 1e-3),
+        "note": "lapper64_count_batch_dev, u64 queries and u64 counts on the device; 28 B/query instead of 12: the narrowing pass "
+                "reads 16 B and writes 8 B per query in front of the u32 kernel",
+    }
+    lib.lapper64_free(h64)
     return out
 
 

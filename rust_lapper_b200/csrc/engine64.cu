@@ -836,15 +836,33 @@ int lapper64_count_batch(const lapper64_t *l, const uint64_t *q_start, const uin
         LAPPER_REQUIRE(nq == 0 || (q_start && q_stop && counts_out), "count_batch: null pointer");
         if (nq == 0) return;
         DeviceGuard dg(l->device);
-        OwnedStream st;
-        Scratch<uint64_t> dqs(nq, st.s), dqe(nq, st.s), dout(nq, st.s);
-        LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqs.p, q_start, nq * 8, cudaMemcpyHostToDevice, st.s));
-        LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqe.p, q_stop, nq * 8, cudaMemcpyHostToDevice, st.s));
-        const int rc = lapper64_count_batch_dev(l, dqs.p, dqe.p, nq, dout.p, st.s);
-        if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
-        LAPPER_CUDA_CHECK(cudaMemcpyAsync(counts_out, dout.p, nq * 8, cudaMemcpyDeviceToHost, st.s));
-        dqs.release(), dqe.release(), dout.release();
-        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+        // chunks of 4 M queries on three streams: chunk k's counts go out while chunk k+1 is counted and chunk k+2's
+        // queries come in (as the u32 engine's host path does; pinned buffers give the link's full rate both ways)
+        constexpr int kSlots = 3;
+        const uint64_t chunk = std::min<uint64_t>(nq, 1ull << 22);
+        const int used = (int)std::min<uint64_t>(kSlots, div_up(nq, chunk));
+        OwnedStream st[1];  // slot 0; the other slots' streams only for batches of several chunks
+        std::unique_ptr<OwnedStream> more[kSlots];
+        cudaStream_t ss[kSlots] = {st[0].s, nullptr, nullptr};
+        for (int s = 1; s < used; s++) more[s].reset(new OwnedStream()), ss[s] = more[s]->s;
+        Scratch<uint64_t> dqs[kSlots], dqe[kSlots], dout[kSlots];
+        for (int s = 0; s < used; s++) dqs[s].alloc(chunk, ss[s]), dqe[s].alloc(chunk, ss[s]), dout[s].alloc(chunk, ss[s]);
+        uint64_t done = 0;
+        for (int i = 0; done < nq; i++) {
+            const int s = i % kSlots;
+            const uint64_t m = std::min(chunk, nq - done);
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqs[s].p, q_start + done, m * 8, cudaMemcpyHostToDevice, ss[s]));
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqe[s].p, q_stop + done, m * 8, cudaMemcpyHostToDevice, ss[s]));
+            // (a batch is not split between the two engines: the first chunk decides, see narrow_of)
+            const int rc = lapper64_count_batch_dev(l, dqs[s].p, dqe[s].p, m, dout[s].p, ss[s]);
+            if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(counts_out + done, dout[s].p, m * 8, cudaMemcpyDeviceToHost, ss[s]));
+            done += m;
+        }
+        for (int s = 0; s < used; s++) {
+            dqs[s].release(), dqe[s].release(), dout[s].release();
+            LAPPER_CUDA_CHECK(cudaStreamSynchronize(ss[s]));
+        }
     });
 }
 

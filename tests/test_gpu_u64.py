@@ -421,3 +421,23 @@ def test_narrow_one_call_device_api(oracle64, narrow_mode):
     assert np.array_equal(d_off.cpu().numpy().view(np.uint64), wo)
     assert np.array_equal(d_idx[:total].cpu().numpy().view(np.uint32), wi)
     assert gpu.is_narrow
+
+
+@pytest.mark.parametrize("mode", [0, 1], ids=["wide", "default"])
+def test_host_count_in_several_chunks_u64(oracle64, narrow_mode, mode):
+    """lapper64_count_batch pipelines batches beyond 4 M queries in chunks (H2D | count | D2H on three streams)"""
+    from rust_lapper_b200 import Lapper64
+
+    narrow_mode(mode)
+    rng = np.random.default_rng(31)
+    sh = np.uint64(0 if mode else 1 << 36)
+    s, e = _random_set(rng, 100_000, 50_000_000, 3000, 0.0)
+    s, e = s + sh, e + sh
+    gpu, cpu = Lapper64(starts=s, stops=e), oracle64(starts=s, stops=e)
+    nq = 9_000_001
+    qs = rng.integers(0, 55_000_000, nq, dtype=np.uint64) + sh
+    qe = qs + rng.integers(0, 600, nq, dtype=np.uint64)
+    qs[-3:] = [0, U64_MAX, 1 << 32]
+    qe[-3:] = [U64_MAX, U64_MAX, 1 << 33]
+    assert np.array_equal(gpu.count_batch(qs, qe), cpu.count_batch(qs, qe, 8))
+    assert gpu.is_narrow == bool(mode)
