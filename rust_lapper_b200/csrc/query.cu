@@ -709,10 +709,46 @@ __device__ unsigned long long g_emit_stats[8];  // chunks, fast, staged-slow, un
 #else
 #define EMIT_STAT(i, v) do { } while (0)
 #endif
-constexpr int kEmitQ = 2;  // queries per lane: one candidate union serves 64 consecutive queries
 constexpr uint32_t kHeavyHits = 256;  // a query with at least this many hits gets a warp of its own (find_heavy_kernel)
 
-__global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kernel(FindView f, const uint32_t *__restrict__ qs,
+__device__ __forceinline__ uint32_t smem_lower_bound(const uint32_t *a, uint32_t n, uint32_t key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < key)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// Two shapes of the per-warp kernel, both launched, one working (decided on the device from the batch's total, which
+// every warp reads from offsets[nq]: no host round trip, like the count kernel's two builds):
+//   sparse (< kDenseHitsPerQuery hits per query on average): two queries per lane share one candidate union of at most
+//       64 intervals, 6 KB of shared memory per warp, four CTAs per SM -- queries without locality, whose lanes emit on
+//       their own, need the occupancy, not the shared memory;
+//   dense (cfg 5: 50 M intervals, 43 hits per query, every query brings 2 - 3 new intervals): one query per lane (a
+//       second one would add more new candidates than it shares), up to 256 candidates and 2048 staged positions per
+//       warp, 12 KB per warp, two CTAs per SM.
+template <int kQ_, int kCand_, int kWords_, int kMinCtas_, bool kDense_>
+struct FillShape {
+    static constexpr int kQ = kQ_;                       // queries per lane
+    static constexpr int kCand = kCand_;                 // candidates a warp can sweep cooperatively
+    static constexpr int kWords = kWords_;               // u32 words of shared memory per warp
+    static constexpr int kStage = kWords_ - 4 * kCand_;  // output slots staged per warp
+    static constexpr int kMinCtas = kMinCtas_;
+    static constexpr bool kDense = kDense_;
+    static_assert(3 * kCand_ <= kWords_ - 4 * kCand_, "the raw candidate list lives in the head of the stage");
+    static_assert((kWords_ - 4 * kCand_) % 4 == 0, "the sorted list is 16-byte aligned");
+};
+using FillSparse = FillShape<2, kEmitCand, kEmitWarpWords, LAPPER_EMIT_MIN_CTAS, false>;
+using FillDense = FillShape<1, 256, 3072, 2, true>;
+constexpr uint64_t kDenseHitsPerQuery = 20;
+static_assert(FillSparse::kStage == kEmitStage, "");
+
+template <typename Shape>
+__global__ void __launch_bounds__(kThreads, Shape::kMinCtas) find_fill_kernel(FindView f, const uint32_t *__restrict__ qs,
                                                              const uint32_t *__restrict__ qe, uint64_t nq,
                                                              const uint64_t *__restrict__ offsets,
                                                              uint32_t *__restrict__ indices,
@@ -721,13 +757,15 @@ __global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kern
                                                              const uint32_t *__restrict__ tile_list,
                                                              const unsigned int *__restrict__ tile_count,
                                                              unsigned int *__restrict__ heavy_admitted, uint32_t heavy_max_admitted) {
+    constexpr int kEmitQ = Shape::kQ, kEmitCand = Shape::kCand, kEmitStage = Shape::kStage, kEmitWarpWords = Shape::kWords;
+    if ((offsets[nq] / kDenseHitsPerQuery >= nq) != Shape::kDense) return;  // the other shape's batch (uniform over the grid)
     const HeavyList heavy = {heavy_list, heavy_count, heavy_admitted, heavy_max_admitted};
-    __shared__ __align__(16) uint32_t smem_all[kThreads / 32][kEmitWarpWords];
+    extern __shared__ __align__(16) uint32_t smem_all[];
     const uint32_t lane = threadIdx.x & 31u;
-    uint32_t *const stage = smem_all[threadIdx.x >> 5];       // kEmitStage output slots ...
+    uint32_t *const stage = smem_all + (threadIdx.x >> 5) * kEmitWarpWords;  // kEmitStage output slots ...
     uint4 *const sorted = reinterpret_cast<uint4 *>(stage + kEmitStage);  // ... then kEmitCand x (start, stop, position, -)
     const uint64_t nwarps = (uint64_t)gridDim.x * (kThreads / 32);
-    // with a tile list (the tiles find_fill_tile_kernel left over) the chunks are the 16 chunks of each listed tile
+    // with a tile list (the tiles find_fill_tile_kernel left over) the chunks are the 16 (32) chunks of each listed tile
     constexpr uint32_t kChunksPerTile = kFindTile / (32 * kEmitQ);
     const uint64_t nchunks = tile_list ? (uint64_t)*tile_count * kChunksPerTile : div_up(nq, 32 * kEmitQ);
     for (uint64_t ci = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); ci < nchunks; ci += nwarps) {
@@ -821,13 +859,14 @@ __global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kern
         // start, and most of the intervals starting down there end before it (stop <= amin)
         uint32_t *const raw = stage;
         uint32_t Tk = 0;  // candidates kept (warp-uniform)
+        uint32_t kc[4] = {0, 0, 0, 0};  // ... per class (warp-uniform)
         bool fits = staged && T <= kEmitRawMax;
         if (fits) {
             for (uint32_t i0 = 0; i0 < T; i0 += 32) {
                 const uint32_t i = i0 + lane;
-                uint32_t g = 0, cs = 0, ce = 0;
+                uint32_t g = 0, cs = 0, ce = 0, c = 0;
                 if (i < T) {
-                    uint32_t c = 0, base = 0;  // class of candidate i and the index of that class's first candidate
+                    uint32_t base = 0;  // class of candidate i and the index of that class's first candidate
                     if (i >= cnt[0]) {
                         c = 1, base = cnt[0];
                         if (i >= base + cnt[1]) {
@@ -849,6 +888,8 @@ __global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kern
                     raw[2 * kEmitCand + pos] = ce;
                 }
                 Tk += __popc(km);
+#pragma unroll
+                for (uint32_t cc = 0; cc < 4; cc++) kc[cc] += __popc(__ballot_sync(0xFFFFFFFFu, keep && c == cc));
             }
             fits = Tk <= (uint32_t)kEmitCand;
         }
@@ -858,11 +899,25 @@ __global__ void __launch_bounds__(kThreads, LAPPER_EMIT_MIN_CTAS) find_fill_kern
             EMIT_STAT(5, Tk);
             T = Tk;
             __syncwarp();
-            // merged order = rank of the global position among all candidates (positions are distinct)
+            // merged order = rank of the global position among all candidates (positions are distinct): the kept list
+            // is class-major and ascending within a class, so a candidate's rank is its index in its own class plus
+            // one binary search per other class
             for (uint32_t i = lane; i < T; i += 32) {
+                uint32_t c = 0, k = i;
+                if (k >= kc[0]) {
+                    c = 1, k -= kc[0];
+                    if (k >= kc[1]) {
+                        c = 2, k -= kc[1];
+                        if (k >= kc[2]) c = 3, k -= kc[2];
+                    }
+                }
                 const uint32_t g = raw[i];
-                uint32_t rank = 0;
-                for (uint32_t x = 0; x < T; x++) rank += (raw[x] < g);
+                uint32_t rank = k;
+                if (c != 0) rank += smem_lower_bound(raw, kc[0], g);
+                if (c != 1) rank += smem_lower_bound(raw + kc[0], kc[1], g);
+                if (c != 2) rank += smem_lower_bound(raw + kc[0] + kc[1], kc[2], g);
+                if (c != 3) rank += smem_lower_bound(raw + kc[0] + kc[1] + kc[2], kc[3], g);
+                LAPPER_CHECK(rank < T);
                 sorted[rank] = make_uint4(raw[kEmitCand + i], raw[2 * kEmitCand + i], g, 0u);
             }
             __syncwarp();
@@ -958,18 +1013,6 @@ constexpr int kTSmemWords = 4 * kTCand + kTW * kTWarpWords + kTRelWords + kTCtlW
 static_assert(3 * kTCand <= kTW * kTWarpWords, "the raw candidate list aliases the warps' areas");
 static_assert(kTQPT == 4 || kTQPT == 8, "tile prologue: 4 or 8 queries per thread");
 static_assert(kTW <= 8, "ctl[16 + warp] and ctl[24 + warp]");
-
-__device__ __forceinline__ uint32_t smem_lower_bound(const uint32_t *a, uint32_t n, uint32_t key) {
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (a[mid] < key)
-            lo = mid + 1;
-        else
-            hi = mid;
-    }
-    return lo;
-}
 
 // The fused form (kFromCounts, lapper_find_batch_u32_dev): the tile's offsets do not exist yet -- the kernel derives them
 // from the count pass's u32 counts and the scanned tile sums (one block scan per tile, which it needs anyway for its
@@ -1852,6 +1895,30 @@ void launch_rebase_offsets(const uint64_t *in, uint64_t *out, uint64_t count, ui
 }
 
 namespace {
+// the per-warp emit kernel in its two shapes (one of them works, see FillShape)
+void launch_fill_shapes(const FindView &f, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, const uint64_t *d_offsets,
+                        uint32_t *d_indices, uint32_t *heavy, unsigned int *heavy_count, const uint32_t *tile_list,
+                        const unsigned int *tile_count, unsigned int *admitted, uint32_t max_admitted, cudaStream_t stream) {
+    constexpr size_t kSparseBytes = (size_t)(kThreads / 32) * FillSparse::kWords * sizeof(uint32_t);
+    constexpr size_t kDenseBytes = (size_t)(kThreads / 32) * FillDense::kWords * sizeof(uint32_t);
+    static std::atomic<bool> prepared[64];
+    int dev = 0;
+    LAPPER_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !prepared[dev].load(std::memory_order_acquire)) {
+        LAPPER_CUDA_CHECK(cudaFuncSetAttribute(find_fill_kernel<FillSparse>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSparseBytes));
+        LAPPER_CUDA_CHECK(cudaFuncSetAttribute(find_fill_kernel<FillDense>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDenseBytes));
+        prepared[dev].store(true, std::memory_order_release);
+    }
+    const uint32_t grid_s = capped_grid(nq, kThreads, FillSparse::kMinCtas * 8);
+    const uint32_t grid_d = capped_grid(nq, kThreads, FillDense::kMinCtas * 8);
+    g_query_launches++, find_fill_kernel<FillSparse><<<grid_s, kThreads, kSparseBytes, stream>>>(
+        f, d_qs, d_qe, nq, d_offsets, d_indices, heavy, heavy_count, tile_list, tile_count, admitted, max_admitted);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    g_query_launches++, find_fill_kernel<FillDense><<<grid_d, kThreads, kDenseBytes, stream>>>(
+        f, d_qs, d_qe, nq, d_offsets, d_indices, heavy, heavy_count, tile_list, tile_count, admitted, max_admitted);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+}
+
 // the emit kernels over offsets that exist (tc == nullptr) or that the tile kernel derives from the counts (fused form)
 void launch_emit(const FindView &f, const uint32_t *d_qs, const uint32_t *d_qe, uint64_t nq, uint64_t *d_offsets,
                  uint32_t *d_indices, uint64_t heavy_bound, const TileCounts *tc, bool tiled, cudaStream_t stream) {
@@ -1864,7 +1931,6 @@ void launch_emit(const FindView &f, const uint32_t *d_qs, const uint32_t *d_qe, 
     Scratch<uint32_t> fallback(ntiles, stream);
     Scratch<unsigned int> counters(4, stream);  // heavy queries, next heavy query, fallback tiles, admitted long-window queries
     LAPPER_CUDA_CHECK(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned int), stream));
-    const uint32_t grid = capped_grid(nq, kThreads, LAPPER_EMIT_MIN_CTAS * 8);
     if (tiled) {
         // tile form first; the tiles it cannot take (no locality) are left to the per-warp kernel
         // once per device: all of the SM's L1/shared array as shared memory, so that LAPPER_TILE_CTAS tiles are resident
@@ -1890,13 +1956,12 @@ void launch_emit(const FindView &f, const uint32_t *d_qs, const uint32_t *d_qe, 
             g_query_launches++, find_fill_tile_kernel<false><<<tgrid, kTT, kTSmemWords * sizeof(uint32_t), stream>>>(
                 f, d_qs, d_qe, nq, d_offsets, TileCounts{}, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2, counters.p + 3, max_admitted);
         LAPPER_CUDA_CHECK(cudaGetLastError());
-        g_query_launches++, find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p,
-                                                        fallback.p, counters.p + 2, counters.p + 3, max_admitted);
+        launch_fill_shapes(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, fallback.p, counters.p + 2, counters.p + 3,
+                           max_admitted, stream);
     } else {
-        g_query_launches++, find_fill_kernel<<<grid, kThreads, 0, stream>>>(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, nullptr,
-                                                        nullptr, counters.p + 3, max_admitted);
+        launch_fill_shapes(f, d_qs, d_qe, nq, d_offsets, d_indices, heavy.p, counters.p, nullptr, nullptr, counters.p + 3, max_admitted,
+                           stream);
     }
-    LAPPER_CUDA_CHECK(cudaGetLastError());
     // persistent warps; exits at once when the list is empty (it may also hold light queries with long windows)
     g_query_launches++, find_heavy_kernel<<<sm_count() * 8, kThreads, 0, stream>>>(f, d_qs, d_qe, d_offsets, d_indices, heavy.p, counters.p, counters.p + 1);
     LAPPER_CUDA_CHECK(cudaGetLastError());

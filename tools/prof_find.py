@@ -14,7 +14,10 @@ reps = int(os.environ.get("REPS", 3))
 order = os.environ.get("ORDER", "sorted")
 dev = torch.device("cuda", 0)
 lib = _ffi.lib()
-s, e = synth.intervals_gene_exon(44, n, synth.GRCH38, device=dev)
+if os.environ.get("GEN", "gene_exon") == "uniform":  # the cfg-5 shape: GEN=uniform N_IV=50000000 NQ=20000000
+    s, e = synth.intervals_uniform(42, n, synth.GRCH38, 50, 5000, device=dev)
+else:
+    s, e = synth.intervals_gene_exon(44, n, synth.GRCH38, device=dev)
 sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 h = C.c_void_p(0)
 _ffi.check(lib.lapper_build_u32_dev(C.c_void_p(s.data_ptr()), C.c_void_p(e.data_ptr()), n, 0, 0, sp, C.byref(h)))
