@@ -32,19 +32,80 @@ inline void check(int rc) {
     if (rc != LAPPER_OK) throw Error(rc, lapper_last_error());
 }
 
+// The C entry points behind each coordinate type (src/lib.rs:88-100: `I: PrimInt + Unsigned`): u32 -> lapper_*_u32,
+// u64 (the README's usize) -> lapper64_*.
+namespace detail {
+template <typename I>
+struct Abi;
+template <>
+struct Abi<uint32_t> {
+    using handle = lapper_t;
+    static int build(const uint32_t *s, const uint32_t *e, uint64_t n, int dev, uint32_t flags, handle **out) {
+        return lapper_build_u32_ex(s, e, n, dev, flags, out);
+    }
+    static void release(handle *h) { lapper_free(h); }
+    static uint64_t len(const handle *h) { return lapper_len(h); }
+    static uint32_t max_len(const handle *h) { return lapper_max_len(h); }
+    static bool overlaps_merged(const handle *h) { return lapper_overlaps_merged(h) != 0; }
+    static int get_intervals(const handle *h, uint32_t *s, uint32_t *e, uint32_t *p) { return lapper_get_intervals(h, s, e, p); }
+    static int count_batch(const handle *h, const uint32_t *a, const uint32_t *b, uint64_t nq, uint64_t *out) {
+        return lapper_count_batch_u32(h, a, b, nq, out);
+    }
+    static int find_batch(const handle *h, const uint32_t *a, const uint32_t *b, uint64_t nq, lapper_result_t **out) {
+        return lapper_find_batch_u32(h, a, b, nq, out);
+    }
+    static int seek_cursor(const handle *h, uint32_t start, uint64_t *c) { return lapper_seek_cursor(h, start, c); }
+    static int insert(handle *h, uint32_t s, uint32_t e, uint64_t *pos) { return lapper_insert_u32(h, s, e, pos); }
+    static int merge_overlaps(handle *h) { return lapper_merge_overlaps(h); }
+    static int cov(const handle *h, uint32_t *c) { return lapper_cov(h, c); }
+    static int set_cov(handle *h, uint32_t *c) { return lapper_set_cov(h, c); }
+    static int union_and_intersect(const handle *a, const handle *b, uint32_t *u, uint32_t *i) {
+        return lapper_union_and_intersect(a, b, u, i);
+    }
+    static int depth(const handle *h, uint64_t *n, uint32_t **s, uint32_t **e, uint32_t **d) { return lapper_depth(h, n, s, e, d); }
+};
+template <>
+struct Abi<uint64_t> {
+    using handle = lapper64_t;
+    static int build(const uint64_t *s, const uint64_t *e, uint64_t n, int dev, uint32_t, handle **out) {
+        return lapper64_build(s, e, n, dev, out);  // (the build flags shape the u32 tables only)
+    }
+    static void release(handle *h) { lapper64_free(h); }
+    static uint64_t len(const handle *h) { return lapper64_len(h); }
+    static uint64_t max_len(const handle *h) { return lapper64_max_len(h); }
+    static bool overlaps_merged(const handle *h) { return lapper64_overlaps_merged(h) != 0; }
+    static int get_intervals(const handle *h, uint64_t *s, uint64_t *e, uint32_t *p) { return lapper64_get_intervals(h, s, e, p); }
+    static int count_batch(const handle *h, const uint64_t *a, const uint64_t *b, uint64_t nq, uint64_t *out) {
+        return lapper64_count_batch(h, a, b, nq, out);
+    }
+    static int find_batch(const handle *h, const uint64_t *a, const uint64_t *b, uint64_t nq, lapper_result_t **out) {
+        return lapper64_find_batch(h, a, b, nq, out);
+    }
+    static int seek_cursor(const handle *h, uint64_t start, uint64_t *c) { return lapper64_seek_cursor(h, start, c); }
+    static int insert(handle *h, uint64_t s, uint64_t e, uint64_t *pos) { return lapper64_insert(h, s, e, pos); }
+    static int merge_overlaps(handle *h) { return lapper64_merge_overlaps(h); }
+    static int cov(const handle *h, uint64_t *c) { return lapper64_cov(h, c); }
+    static int set_cov(handle *h, uint64_t *c) { return lapper64_set_cov(h, c); }
+    static int union_and_intersect(const handle *a, const handle *b, uint64_t *u, uint64_t *i) {
+        return lapper64_union_and_intersect(a, b, u, i);
+    }
+    static int depth(const handle *h, uint64_t *n, uint64_t **s, uint64_t **e, uint32_t **d) { return lapper64_depth(h, n, s, e, d); }
+};
+}  // namespace detail
+
 // src/lib.rs:88-100
-template <typename T>
+template <typename T, typename I = uint32_t>
 struct Interval {
-    uint32_t start;
-    uint32_t stop;
+    I start;
+    I stop;
     T val;
     // src/lib.rs:130-136
-    uint32_t intersect(const Interval &o) const {
-        const uint32_t hi = stop < o.stop ? stop : o.stop, lo = start > o.start ? start : o.start;
+    I intersect(const Interval &o) const {
+        const I hi = stop < o.stop ? stop : o.stop, lo = start > o.start ? start : o.start;
         return hi >= lo ? hi - lo : 0;
     }
     // src/lib.rs:138-142
-    bool overlap(uint32_t s, uint32_t e) const { return start < e && stop > s; }
+    bool overlap(I s, I e) const { return start < e && stop > s; }
     // src/lib.rs:171-180: equality ignores val
     bool operator==(const Interval &o) const { return start == o.start && stop == o.stop; }
 };
@@ -54,41 +115,46 @@ struct Csr {
     std::vector<uint32_t> indices;  // positions in Lapper::intervals, iterator order per query
 };
 
-template <typename T>
+// Lapper<I, T> (src/lib.rs:102-123); the coordinate type is the SECOND parameter here so that Lapper<T> stays the
+// u32 form the reference's own tests and benches use (benches/lapper_benchmark.rs:13)
+template <typename T, typename I = uint32_t>
 class Lapper {
-  public:
-    std::vector<Interval<T>> intervals;  // sorted by (start, stop), stable  (src/lib.rs:112)
+    using A = detail::Abi<I>;
 
-    explicit Lapper(std::vector<Interval<T>> ivs, int device = 0, uint32_t flags = LAPPER_BUILD_DEFAULT) {
-        std::vector<uint32_t> s(ivs.size()), e(ivs.size());
+  public:
+    using Iv = Interval<T, I>;
+    std::vector<Iv> intervals;  // sorted by (start, stop), stable  (src/lib.rs:112)
+
+    explicit Lapper(std::vector<Iv> ivs, int device = 0, uint32_t flags = LAPPER_BUILD_DEFAULT) {
+        std::vector<I> s(ivs.size()), e(ivs.size());
         for (size_t i = 0; i < ivs.size(); i++) s[i] = ivs[i].start, e[i] = ivs[i].stop;
-        check(lapper_build_u32_ex(s.data(), e.data(), ivs.size(), device, flags, &h_));
+        check(A::build(s.data(), e.data(), ivs.size(), device, flags, &h_));
         input_ = std::move(ivs);
         refresh();
     }
-    ~Lapper() { lapper_free(h_); }
+    ~Lapper() { A::release(h_); }
     Lapper(const Lapper &) = delete;
     Lapper &operator=(const Lapper &) = delete;
 
     size_t len() const { return intervals.size(); }       // src/lib.rs:284-287
     bool is_empty() const { return intervals.empty(); }   // src/lib.rs:296-299
-    uint32_t max_len() const { return lapper_max_len(h_); }
-    bool overlaps_merged() const { return lapper_overlaps_merged(h_) != 0; }
-    const lapper_t *handle() const { return h_; }
-    typename std::vector<Interval<T>>::const_iterator begin() const { return intervals.begin(); }  // iter(), :353-359
-    typename std::vector<Interval<T>>::const_iterator end() const { return intervals.end(); }
+    I max_len() const { return A::max_len(h_); }
+    bool overlaps_merged() const { return A::overlaps_merged(h_); }
+    const typename A::handle *handle() const { return h_; }
+    typename std::vector<Iv>::const_iterator begin() const { return intervals.begin(); }  // iter(), :353-359
+    typename std::vector<Iv>::const_iterator end() const { return intervals.end(); }
 
     // batch entry points
-    std::vector<uint64_t> count_batch(const std::vector<uint32_t> &qs, const std::vector<uint32_t> &qe) const {
+    std::vector<uint64_t> count_batch(const std::vector<I> &qs, const std::vector<I> &qe) const {
         if (qs.size() != qe.size()) throw Error(LAPPER_ERR_INVALID_ARG, "count_batch: q_start and q_stop differ in length");
         std::vector<uint64_t> out(qs.size());
-        check(lapper_count_batch_u32(h_, qs.data(), qe.data(), qs.size(), out.data()));
+        check(A::count_batch(h_, qs.data(), qe.data(), qs.size(), out.data()));
         return out;
     }
-    Csr find_batch(const std::vector<uint32_t> &qs, const std::vector<uint32_t> &qe) const {
+    Csr find_batch(const std::vector<I> &qs, const std::vector<I> &qe) const {
         if (qs.size() != qe.size()) throw Error(LAPPER_ERR_INVALID_ARG, "find_batch: q_start and q_stop differ in length");
         lapper_result_t *r = nullptr;
-        check(lapper_find_batch_u32(h_, qs.data(), qe.data(), qs.size(), &r));
+        check(A::find_batch(h_, qs.data(), qe.data(), qs.size(), &r));
         Csr c;
         c.offsets.resize(qs.size() + 1);
         c.indices.resize(lapper_result_total(r));
@@ -99,76 +165,78 @@ class Lapper {
     }
 
     // per-query API of the reference
-    uint64_t count(uint32_t start, uint32_t stop) const { return count_batch({start}, {stop})[0]; }
-    std::vector<const Interval<T> *> find(uint32_t start, uint32_t stop) const {
-        std::vector<const Interval<T> *> out;
+    uint64_t count(I start, I stop) const { return count_batch({start}, {stop})[0]; }
+    std::vector<const Iv *> find(I start, I stop) const {
+        std::vector<const Iv *> out;
         for (uint32_t i : find_batch({start}, {stop}).indices) out.push_back(&intervals[i]);
         return out;
     }
-    std::vector<const Interval<T> *> seek(uint32_t start, uint32_t stop, size_t *cursor) const {
+    std::vector<const Iv *> seek(I start, I stop, size_t *cursor) const {
         uint64_t c = *cursor;
-        check(lapper_seek_cursor(h_, start, &c));  // the reference's cursor update, src/lib.rs:658-671
+        check(A::seek_cursor(h_, start, &c));  // the reference's cursor update, src/lib.rs:658-671
         *cursor = (size_t)c;
-        std::vector<const Interval<T> *> out;
+        std::vector<const Iv *> out;
         for (uint32_t i : find_batch({start}, {stop}).indices)
             if (i >= c) out.push_back(&intervals[i]);  // IterFind starts at the cursor
         return out;
     }
 
     // src/lib.rs:260-273 (O(n), like the reference)
-    void insert(const Interval<T> &elem) {
+    void insert(const Iv &elem) {
         uint64_t pos = 0;
-        check(lapper_insert_u32(h_, elem.start, elem.stop, &pos));
+        check(A::insert(h_, elem.start, elem.stop, &pos));
         if (input_.size() <= pos) input_.resize(pos + 1, elem);
         input_[pos] = elem;
         refresh();
     }
     void merge_overlaps() {
-        check(lapper_merge_overlaps(h_));
+        check(A::merge_overlaps(h_));
         refresh();
     }
-    uint32_t cov() const {
-        uint32_t c = 0;
-        check(lapper_cov(h_, &c));
+    I cov() const {
+        I c = 0;
+        check(A::cov(h_, &c));
         return c;
     }
-    uint32_t set_cov() {
-        uint32_t c = 0;
-        check(lapper_set_cov(h_, &c));
+    I set_cov() {
+        I c = 0;
+        check(A::set_cov(h_, &c));
         return c;
     }
-    std::pair<uint32_t, uint32_t> union_and_intersect(const Lapper &other) const {
-        uint32_t u = 0, i = 0;
-        check(lapper_union_and_intersect(h_, other.h_, &u, &i));
+    std::pair<I, I> union_and_intersect(const Lapper &other) const {
+        I u = 0, i = 0;
+        check(A::union_and_intersect(h_, other.h_, &u, &i));
         return {u, i};
     }
     // depth() / IterDepth (src/lib.rs:576-598, :720-784): runs of equal coverage depth, val = the depth
-    std::vector<Interval<uint32_t>> depth() const {
+    std::vector<Interval<uint32_t, I>> depth() const {
         uint64_t n = 0;
-        uint32_t *s = nullptr, *e = nullptr, *d = nullptr;
-        check(lapper_depth(h_, &n, &s, &e, &d));
-        std::vector<Interval<uint32_t>> out;
-        for (uint64_t i = 0; i < n; i++) out.push_back(Interval<uint32_t>{s[i], e[i], d[i]});
+        I *s = nullptr, *e = nullptr;
+        uint32_t *d = nullptr;
+        check(A::depth(h_, &n, &s, &e, &d));
+        std::vector<Interval<uint32_t, I>> out;
+        for (uint64_t i = 0; i < n; i++) out.push_back(Interval<uint32_t, I>{s[i], e[i], d[i]});
         lapper_host_free(s);
         lapper_host_free(e);
         lapper_host_free(d);
         return out;
     }
-    uint32_t intersect(const Lapper &o) const { return union_and_intersect(o).second; }
-    uint32_t union_(const Lapper &o) const { return union_and_intersect(o).first; }
+    I intersect(const Lapper &o) const { return union_and_intersect(o).second; }
+    I union_(const Lapper &o) const { return union_and_intersect(o).first; }
 
   private:
     // rebuild `intervals` from the engine's sorted order; vals follow through perm
     void refresh() {
-        const size_t n = lapper_len(h_);
-        std::vector<uint32_t> s(n), e(n), p(n);
-        check(lapper_get_intervals(h_, s.data(), e.data(), p.data()));
+        const size_t n = A::len(h_);
+        std::vector<I> s(n), e(n);
+        std::vector<uint32_t> p(n);
+        check(A::get_intervals(h_, s.data(), e.data(), p.data()));
         intervals.clear();
         intervals.reserve(n);
-        for (size_t i = 0; i < n; i++) intervals.push_back(Interval<T>{s[i], e[i], input_[p[i]].val});
+        for (size_t i = 0; i < n; i++) intervals.push_back(Iv{s[i], e[i], input_[p[i]].val});
     }
-    lapper_t *h_ = nullptr;
-    std::vector<Interval<T>> input_;
+    typename A::handle *h_ = nullptr;
+    std::vector<Iv> input_;
 };
 
 }  // namespace lapper_b200

@@ -768,24 +768,59 @@ __global__ void __launch_bounds__(kThreads, Shape::kMinCtas) find_fill_kernel(Fi
     // with a tile list (the tiles find_fill_tile_kernel left over) the chunks are the 16 (32) chunks of each listed tile
     constexpr uint32_t kChunksPerTile = kFindTile / (32 * kEmitQ);
     const uint64_t nchunks = tile_list ? (uint64_t)*tile_count * kChunksPerTile : div_up(nq, 32 * kEmitQ);
-    for (uint64_t ci = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); ci < nchunks; ci += nwarps) {
+    // A chunk's inputs: the offsets of its queries (and the one after each), the queries, the offset after the chunk.
+    // The dense shape loads them one chunk ahead (the warp's next chunk, while this one is swept): two of the five
+    // dependent memory round trips of a chunk (offsets -> queries -> directory -> class starts -> candidates) leave the
+    // critical path.  The sparse shape has no registers to spare for that (64 at four CTAs per SM) and loads the
+    // queries only where there are hits.
+    struct ChunkIn {
+        uint64_t jbase, o0[kEmitQ], o1[kEmitQ], wend;
+        uint32_t a[kEmitQ], b[kEmitQ];
+    };
+    const auto fetch = [&](uint64_t ci, ChunkIn &in) {
         const uint64_t chunk = tile_list ? (uint64_t)tile_list[ci / kChunksPerTile] * kChunksPerTile + ci % kChunksPerTile : ci;
-        // lane's q-th query is chunk*64 + q*32 + lane: consecutive lanes hold consecutive queries
+        // lane's q-th query is chunk*32*kEmitQ + q*32 + lane: consecutive lanes hold consecutive queries
+        in.jbase = chunk * (32 * kEmitQ);
+        if (in.jbase >= nq) return;
+        const uint64_t jend = min(in.jbase + 32 * kEmitQ, nq);  // one past the chunk's last query
+#pragma unroll
+        for (int q = 0; q < kEmitQ; q++) {
+            const uint64_t j = in.jbase + q * 32 + lane;
+            const bool live = j < nq;
+            in.o0[q] = live ? offsets[j] : 0;
+            if (Shape::kDense) {
+                in.o1[q] = live ? offsets[j + 1] : 0;
+                in.a[q] = live ? ld_stream_u32(qs + j) : 0xFFFFFFFFu;
+                in.b[q] = live ? ld_stream_u32(qe + j) : 0u;
+            } else {
+                // offsets[j + 1] is the next lane's o0, except for lane 31 / the last query
+                in.o1[q] = __shfl_down_sync(0xFFFFFFFFu, in.o0[q], 1);
+                if (live && (lane == 31 || j + 1 == nq)) in.o1[q] = offsets[j + 1];
+                if (!live) in.o0[q] = in.o1[q] = 0;
+            }
+        }
+        in.wend = offsets[jend];  // same address for the whole warp: one broadcast load
+    };
+    const uint64_t ci0 = (uint64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+    ChunkIn cur, nxt;
+    if (Shape::kDense && ci0 < nchunks) fetch(ci0, nxt);
+    for (uint64_t ci = ci0; ci < nchunks; ci += nwarps) {
+        if (Shape::kDense) {
+            cur = nxt;
+            if (ci + nwarps < nchunks) fetch(ci + nwarps, nxt);
+        } else {
+            fetch(ci, cur);
+        }
+        const uint64_t jbase = cur.jbase;
+        if (jbase >= nq) continue;
         uint64_t o0[kEmitQ], o1[kEmitQ];
         uint32_t a[kEmitQ], b[kEmitQ];
         bool mine[kEmitQ];
-        const uint64_t jbase = chunk * (32 * kEmitQ);
-        if (jbase >= nq) continue;
-        const uint64_t jend = min(jbase + 32 * kEmitQ, nq);  // one past the chunk's last query
 #pragma unroll
         for (int q = 0; q < kEmitQ; q++) {
             const uint64_t j = jbase + q * 32 + lane;
             const bool live = j < nq;
-            o0[q] = live ? offsets[j] : 0;
-            // offsets[j + 1] is the next lane's o0, except for lane 31 / the last query
-            o1[q] = __shfl_down_sync(0xFFFFFFFFu, o0[q], 1);
-            if (live && (lane == 31 || j + 1 == nq)) o1[q] = offsets[j + 1];
-            if (!live) o0[q] = o1[q] = 0;
+            o0[q] = cur.o0[q], o1[q] = cur.o1[q];
             mine[q] = live && o1[q] > o0[q];
             if (mine[q] && o1[q] - o0[q] >= kHeavyHits) {
                 // too many hits for one lane: hand the query to find_heavy_kernel (a warp per query)
@@ -794,12 +829,12 @@ __global__ void __launch_bounds__(kThreads, Shape::kMinCtas) find_fill_kernel(Fi
             }
             a[q] = 0xFFFFFFFFu, b[q] = 0;
             if (mine[q]) {
-                a[q] = ld_stream_u32(qs + j);
-                b[q] = ld_stream_u32(qe + j);
+                a[q] = Shape::kDense ? cur.a[q] : ld_stream_u32(qs + j);
+                b[q] = Shape::kDense ? cur.b[q] : ld_stream_u32(qe + j);
             }
         }
         const uint64_t wbase = __shfl_sync(0xFFFFFFFFu, o0[0], 0);
-        const uint64_t wend = offsets[jend];  // same address for the whole warp: one broadcast load
+        const uint64_t wend = cur.wend;
         const uint64_t wtotal = wend - wbase;
         EMIT_STAT(0, 1);
         if (wtotal == 0) { EMIT_STAT(7, 1); continue; }
@@ -862,34 +897,43 @@ __global__ void __launch_bounds__(kThreads, Shape::kMinCtas) find_fill_kernel(Fi
         uint32_t kc[4] = {0, 0, 0, 0};  // ... per class (warp-uniform)
         bool fits = staged && T <= kEmitRawMax;
         if (fits) {
-            for (uint32_t i0 = 0; i0 < T; i0 += 32) {
-                const uint32_t i = i0 + lane;
-                uint32_t g = 0, cs = 0, ce = 0, c = 0;
-                if (i < T) {
-                    uint32_t base = 0;  // class of candidate i and the index of that class's first candidate
-                    if (i >= cnt[0]) {
-                        c = 1, base = cnt[0];
-                        if (i >= base + cnt[1]) {
-                            c = 2, base += cnt[1];
-                            if (i >= base + cnt[2]) c = 3, base += cnt[2];
-                        }
-                    }
-                    const uint32_t p = f.cls_off[c] + lo[c] + (i - base);
-                    ce = __ldg(f.ce + p);  // three independent loads
-                    g = __ldg(f.cg + p);
-                    cs = __ldg(f.cs + p);
-                }
-                const bool keep = i < T && ce > amin;
-                const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-                const uint32_t pos = Tk + __popc(km & ((1u << lane) - 1u));
-                if (keep && pos < (uint32_t)kEmitCand) {
-                    raw[pos] = g;
-                    raw[kEmitCand + pos] = cs;
-                    raw[2 * kEmitCand + pos] = ce;
-                }
-                Tk += __popc(km);
+            // (dense shape: the loads of four rounds are issued together -- one memory round trip instead of four)
+            constexpr int kU = Shape::kDense ? 4 : 1;
+            for (uint32_t i0 = 0; i0 < T; i0 += 32 * kU) {
+                uint32_t g[kU], cs[kU], ce[kU], c[kU];
 #pragma unroll
-                for (uint32_t cc = 0; cc < 4; cc++) kc[cc] += __popc(__ballot_sync(0xFFFFFFFFu, keep && c == cc));
+                for (int u = 0; u < kU; u++) {
+                    const uint32_t i = i0 + 32 * u + lane;
+                    g[u] = cs[u] = ce[u] = c[u] = 0;
+                    if (i < T) {
+                        uint32_t base = 0;  // class of candidate i and the index of that class's first candidate
+                        if (i >= cnt[0]) {
+                            c[u] = 1, base = cnt[0];
+                            if (i >= base + cnt[1]) {
+                                c[u] = 2, base += cnt[1];
+                                if (i >= base + cnt[2]) c[u] = 3, base += cnt[2];
+                            }
+                        }
+                        const uint32_t p = f.cls_off[c[u]] + lo[c[u]] + (i - base);
+                        ce[u] = __ldg(f.ce + p);  // three independent loads
+                        g[u] = __ldg(f.cg + p);
+                        cs[u] = __ldg(f.cs + p);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < kU; u++) {
+                    const bool keep = i0 + 32 * u + lane < T && ce[u] > amin;
+                    const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                    const uint32_t pos = Tk + __popc(km & ((1u << lane) - 1u));
+                    if (keep && pos < (uint32_t)kEmitCand) {
+                        raw[pos] = g[u];
+                        raw[kEmitCand + pos] = cs[u];
+                        raw[2 * kEmitCand + pos] = ce[u];
+                    }
+                    Tk += __popc(km);
+#pragma unroll
+                    for (uint32_t cc = 0; cc < 4; cc++) kc[cc] += __popc(__ballot_sync(0xFFFFFFFFu, keep && c[u] == cc));
+                }
             }
             fits = Tk <= (uint32_t)kEmitCand;
         }
@@ -902,37 +946,81 @@ __global__ void __launch_bounds__(kThreads, Shape::kMinCtas) find_fill_kernel(Fi
             // merged order = rank of the global position among all candidates (positions are distinct): the kept list
             // is class-major and ascending within a class, so a candidate's rank is its index in its own class plus
             // one binary search per other class
-            for (uint32_t i = lane; i < T; i += 32) {
-                uint32_t c = 0, k = i;
-                if (k >= kc[0]) {
-                    c = 1, k -= kc[0];
-                    if (k >= kc[1]) {
-                        c = 2, k -= kc[1];
-                        if (k >= kc[2]) c = 3, k -= kc[2];
+            // (kR candidates per lane side by side, every search in the same number of power-of-two steps: the
+            // shared-memory loads of a step are independent of one another)
+            constexpr int kR = Shape::kDense ? 4 : 2;
+            for (uint32_t i0 = 0; i0 < T; i0 += 32 * kR) {
+                uint32_t g[kR], k[kR], c[kR], rank[kR];
+#pragma unroll
+                for (int u = 0; u < kR; u++) {
+                    const uint32_t i = min(i0 + 32 * u + lane, T - 1);
+                    c[u] = 0, k[u] = i;
+                    if (k[u] >= kc[0]) {
+                        c[u] = 1, k[u] -= kc[0];
+                        if (k[u] >= kc[1]) {
+                            c[u] = 2, k[u] -= kc[1];
+                            if (k[u] >= kc[2]) c[u] = 3, k[u] -= kc[2];
+                        }
+                    }
+                    g[u] = raw[i];
+                    rank[u] = k[u];
+                }
+                uint32_t base = 0;
+#pragma unroll
+                for (uint32_t cc = 0; cc < 4; cc++) {
+                    const uint32_t n = kc[cc];
+                    if (n) {  // (warp-uniform)
+                        uint32_t pos[kR];
+#pragma unroll
+                        for (int u = 0; u < kR; u++) pos[u] = 0;
+                        for (uint32_t step = 1u << (31 - __clz(n)); step; step >>= 1) {
+#pragma unroll
+                            for (int u = 0; u < kR; u++)
+                                if (pos[u] + step <= n && raw[base + pos[u] + step - 1] < g[u]) pos[u] += step;
+                        }
+#pragma unroll
+                        for (int u = 0; u < kR; u++)
+                            if (c[u] != cc) rank[u] += pos[u];
+                    }
+                    base += n;
+                }
+#pragma unroll
+                for (int u = 0; u < kR; u++) {
+                    const uint32_t i = i0 + 32 * u + lane;
+                    if (i < T) {
+                        LAPPER_CHECK(rank[u] < T);
+                        sorted[rank[u]] = make_uint4(raw[kEmitCand + i], raw[2 * kEmitCand + i], g[u], 0u);
                     }
                 }
-                const uint32_t g = raw[i];
-                uint32_t rank = k;
-                if (c != 0) rank += smem_lower_bound(raw, kc[0], g);
-                if (c != 1) rank += smem_lower_bound(raw + kc[0], kc[1], g);
-                if (c != 2) rank += smem_lower_bound(raw + kc[0] + kc[1], kc[2], g);
-                if (c != 3) rank += smem_lower_bound(raw + kc[0] + kc[1] + kc[2], kc[3], g);
-                LAPPER_CHECK(rank < T);
-                sorted[rank] = make_uint4(raw[kEmitCand + i], raw[2 * kEmitCand + i], g, 0u);
             }
             __syncwarp();
             // every lane sweeps the sorted candidates for its own queries (broadcast reads)
-            uint32_t *wp[kEmitQ];
+            // (write cursors as shared-memory addresses, predicated store + predicated add in inline PTX: five
+            // instructions per candidate and query instead of the seven the compiler's own form spends)
+            uint32_t wp[kEmitQ];
 #pragma unroll
-            for (int q = 0; q < kEmitQ; q++) wp[q] = stage + pad + (uint32_t)(o0[q] - wbase);
+            for (int q = 0; q < kEmitQ; q++) wp[q] = (uint32_t)__cvta_generic_to_shared(stage + pad + (uint32_t)(o0[q] - wbase));
             for (uint32_t x = 0; x < T; x++) {
                 const uint4 c = sorted[x];  // one broadcast LDS.128: (start, stop, position)
 #pragma unroll
-                for (int q = 0; q < kEmitQ; q++)
-                    if (c.x < b[q] && c.y > a[q]) {  // src/lib.rs:140-142
-                        LAPPER_CHECK(wp[q] >= stage + pad && wp[q] < stage + pad + wtotal);
-                        *wp[q]++ = c.z;
+                for (int q = 0; q < kEmitQ; q++) {
+#ifdef LAPPER_DEBUG_CHECKS
+                    if (c.x < b[q] && c.y > a[q]) {
+                        const uint32_t lo_a = (uint32_t)__cvta_generic_to_shared(stage + pad);
+                        LAPPER_CHECK(wp[q] >= lo_a && wp[q] < lo_a + 4u * (uint32_t)wtotal);
                     }
+#endif
+                    // src/lib.rs:140-142: start_i < q_stop && stop_i > q_start
+                    asm volatile(
+                        "{ .reg .pred p;\n"
+                        "  setp.lt.u32 p, %2, %3;\n"
+                        "  setp.gt.and.u32 p, %4, %5, p;\n"
+                        "  @p st.shared.u32 [%0], %1;\n"
+                        "  @p add.u32 %0, %0, 4; }"
+                        : "+r"(wp[q])
+                        : "r"(c.z), "r"(c.x), "r"(b[q]), "r"(c.y), "r"(a[q])
+                        : "memory");
+                }
             }
             __syncwarp();
         } else if (staged) {

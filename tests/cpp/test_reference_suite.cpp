@@ -7,8 +7,6 @@
 #include "lapper_b200.hpp"
 
 using lapper_b200::Interval;
-using lapper_b200::Lapper;
-typedef Interval<uint32_t> Iv;
 
 static int failures = 0;
 #define CHECK(cond)                                                      \
@@ -19,25 +17,36 @@ static int failures = 0;
         }                                                                \
     } while (0)
 
-static std::vector<Iv> step_by(uint32_t lo, uint32_t hi, uint32_t step, uint32_t len) {
-    std::vector<Iv> v;
-    for (uint32_t x = lo; x < hi; x += step) v.push_back(Iv{x, x + len, 0});
-    return v;
-}
-static std::vector<Iv> nonoverlapping() { return step_by(0, 100, 20, 10); }  // :857-867
-static std::vector<Iv> overlapping() { return step_by(0, 100, 10, 15); }     // :869-879
-static std::vector<Iv> badlapper() {                                         // :881-895
-    return {{70, 120, 0}, {10, 15, 1}, {10, 15, 2}, {12, 15, 3}, {14, 16, 4}, {40, 45, 5},
-            {50, 55, 6},  {60, 65, 7}, {68, 71, 8}, {70, 75, 9}};
-}
-static bool same(const std::vector<const Iv *> &got, const std::vector<Iv> &want) {
-    if (got.size() != want.size()) return false;
-    for (size_t i = 0; i < got.size(); i++)
-        if (!(*got[i] == want[i])) return false;
-    return true;
-}
+// The suite runs once per coordinate type: I = u32 (the reference's own tests and benches) and I = u64 (the README's
+// usize; these coordinates fit 32 bits, so batches of >= 4096 queries would be narrowed -- single queries are not).
+template <typename I>
+struct Suite {
+    typedef Interval<uint32_t, I> Iv;
+    template <typename T>
+    using Lapper = lapper_b200::Lapper<T, I>;
 
-int main() {
+    static std::vector<Iv> step_by(I lo, I hi, I step, I len) {
+        std::vector<Iv> v;
+        for (I x = lo; x < hi; x += step) v.push_back(Iv{x, x + len, 0});
+        return v;
+    }
+    static std::vector<Iv> nonoverlapping() { return step_by(0, 100, 20, 10); }  // :857-867
+    static std::vector<Iv> overlapping() { return step_by(0, 100, 10, 15); }     // :869-879
+    static std::vector<Iv> badlapper() {                                         // :881-895
+        return {{70, 120, 0}, {10, 15, 1}, {10, 15, 2}, {12, 15, 3}, {14, 16, 4}, {40, 45, 5},
+                {50, 55, 6},  {60, 65, 7}, {68, 71, 8}, {70, 75, 9}};
+    }
+    static bool same(const std::vector<const Iv *> &got, const std::vector<Iv> &want) {
+        if (got.size() != want.size()) return false;
+        for (size_t i = 0; i < got.size(); i++)
+            if (!(*got[i] == want[i])) return false;
+        return true;
+    }
+    static void run();
+};
+
+template <typename I>
+void Suite<I>::run() {
     {  // test_query_stop_interval_start / test_query_start_interval_stop  :1023-1039
         Lapper<uint32_t> lapper(nonoverlapping());
         size_t cursor = 0;
@@ -49,7 +58,7 @@ int main() {
     }
     {  // the four overlap shapes  :1043-1099
         Lapper<uint32_t> lapper(nonoverlapping());
-        const uint32_t qs[4][2] = {{15, 25}, {25, 35}, {22, 27}, {15, 35}};
+        const I qs[4][2] = {{15, 25}, {25, 35}, {22, 27}, {15, 35}};
         for (auto &q : qs) {
             size_t cursor = 0;
             const Iv expected{20, 30, 0};
@@ -82,7 +91,7 @@ int main() {
     }
     {  // test_lapper_cov  :1168-1178
         Lapper<uint32_t> lapper(badlapper());
-        const uint32_t before = lapper.cov();
+        const I before = lapper.cov();
         lapper.merge_overlaps();
         CHECK(before == lapper.cov() && before == 73);
         Lapper<uint32_t> l2(nonoverlapping());
@@ -98,14 +107,14 @@ int main() {
     {  // test_union_and_intersect  :1203-1240
         Lapper<uint32_t> l1({{70, 120, 0}, {10, 15, 0}, {12, 15, 0}, {14, 16, 0}, {68, 71, 0}});
         Lapper<uint32_t> l2({{10, 15, 0}, {40, 45, 0}, {50, 55, 0}, {60, 65, 0}, {70, 75, 0}});
-        CHECK(l1.union_and_intersect(l2) == std::make_pair(73u, 10u));
-        CHECK(l2.union_and_intersect(l1) == std::make_pair(73u, 10u));
+        CHECK(l1.union_and_intersect(l2) == std::make_pair((I)73, (I)10));
+        CHECK(l2.union_and_intersect(l1) == std::make_pair((I)73, (I)10));
         l1.merge_overlaps();
         l1.set_cov();
         l2.merge_overlaps();
         l2.set_cov();
-        CHECK(l1.union_and_intersect(l2) == std::make_pair(73u, 10u));
-        CHECK(l2.union_and_intersect(l1) == std::make_pair(73u, 10u));
+        CHECK(l1.union_and_intersect(l2) == std::make_pair((I)73, (I)10));
+        CHECK(l2.union_and_intersect(l1) == std::make_pair((I)73, (I)10));
     }
     {  // test_find_overlaps_in_large_intervals  :1243-1276
         Lapper<uint32_t> lapper({{0, 8, 0}, {1, 10, 0}, {2, 5, 0}, {3, 8, 0}, {4, 7, 0}, {5, 8, 0}, {8, 8, 0}, {9, 11, 0},
@@ -140,14 +149,14 @@ int main() {
         CHECK(Lapper<uint32_t>(step_by(0, 20, 5, 10)).cov() == 25);
         Lapper<uint32_t> ex(badlapper()), other({{5, 15, 0}, {48, 80, 0}});
         ex.merge_overlaps();
-        CHECK(ex.union_and_intersect(other) == std::make_pair(88u, 27u));
+        CHECK(ex.union_and_intersect(other) == std::make_pair((I)88, (I)27));
     }
     {  // test_depth_sanity / test_depth_hard  :1279-1313
         Lapper<uint32_t> l1({{0, 10, 0}, {5, 10, 0}});
         auto d = l1.depth();
-        CHECK(d.size() == 2 && d[0] == (Interval<uint32_t>{0, 5, 1}) && d[0].val == 1 && d[1] == (Interval<uint32_t>{5, 10, 2}) && d[1].val == 2);
+        CHECK(d.size() == 2 && d[0] == (Iv{0, 5, 1}) && d[0].val == 1 && d[1] == (Iv{5, 10, 2}) && d[1].val == 2);
         Lapper<uint32_t> l2({{1, 10, 0}, {2, 5, 0}, {3, 8, 0}, {3, 8, 0}, {3, 8, 0}, {5, 8, 0}, {9, 11, 0}});
-        const uint32_t want[6][3] = {{1, 2, 1}, {2, 3, 2}, {3, 8, 5}, {8, 9, 1}, {9, 10, 2}, {10, 11, 1}};
+        const I want[6][3] = {{1, 2, 1}, {2, 3, 2}, {3, 8, 5}, {8, 9, 1}, {9, 10, 2}, {10, 11, 1}};
         auto d2 = l2.depth();
         CHECK(d2.size() == 6);
         for (size_t i = 0; i < 6 && i < d2.size(); i++)
@@ -164,6 +173,13 @@ int main() {
         CHECK(a.intervals.size() == b.intervals.size() && a.max_len() == b.max_len());
         for (size_t i = 0; i < a.intervals.size() && i < b.intervals.size(); i++) CHECK(a.intervals[i] == b.intervals[i]);
     }
+}
+
+int main() {
+    Suite<uint32_t>::run();
+    const int f32 = failures;
+    Suite<uint64_t>::run();
+    std::printf("I = u32: %d failures, I = u64: %d failures\n", f32, failures - f32);
     std::printf(failures ? "%d FAILED\n" : "all reference tests passed (C++ facade)\n", failures);
     return failures ? 1 : 0;
 }
