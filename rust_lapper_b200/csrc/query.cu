@@ -850,150 +850,196 @@ __global__ void __launch_bounds__(kThreads, Shape::kMinCtas) find_fill_kernel(Fi
         for (int q = 1; q < kEmitQ; q++) amin = min(amin, a[q]), bmax = max(bmax, b[q]);
         amin = __reduce_min_sync(0xFFFFFFFFu, amin);
         bmax = __reduce_max_sync(0xFFFFFFFFu, bmax);
-        // eight class bounds (4 classes x {window start, window end}), four lanes each: the directory gives a
-        // rank range of at most 16 class starts, which the four lanes probe with independent loads (one memory
-        // round trip instead of a serial walk)
-        uint32_t r = 0;
-        {
-            const int c = (int)((lane >> 2) & 3u);
-            const uint32_t sub = lane & 3u;
-            const bool on = c < (int)f.ncls;
-            const uint32_t key = (lane >> 4) ? bmax : (amin >= f.cls_maxlen[c] ? amin - f.cls_maxlen[c] : 0u);
-            const uint32_t *cs = f.cs + f.cls_off[c];
-            uint32_t r0 = 0, hi = 0, cnt = 0;
-            if (on) {
-                const uint32_t B = min(key >> f.cls_shift, f.cls_nb);
-                r0 = dir_get(__ldg(f.dir + B), c);
-                hi = B < f.cls_nb ? dir_get(__ldg(f.dir + B + 1), c) : r0;
-                if (hi - r0 <= 16u) {
-                    uint32_t v[4];
+        // Dense shape, first choice: the candidates straight from the single sorted vector -- the reference's own window
+        // [lower_bound(amin - max_len), lower_bound(bmax)) (src/lib.rs:632-635) -- when that window is short (sets
+        // without long intervals: cfg 5).  It is in position order already: no class directory, no merge of class
+        // lists, two loads per entry instead of three.
+        uint32_t T = 0, Tk = 0;  // candidates found / kept (warp-uniform)
+        bool fits = false, single = false;
+        if (Shape::kDense && staged && amin != 0xFFFFFFFFu) {
+            uint32_t rr = 0;
+            if (lane == 0) rr = rank_lb_starts(f, bmax);
+            if (lane == 1) rr = rank_lb_starts(f, amin >= f.max_len ? amin - f.max_len : 0u);
+            const uint32_t whi = __shfl_sync(0xFFFFFFFFu, rr, 0), wlo = __shfl_sync(0xFFFFFFFFu, rr, 1);
+            const uint32_t n1 = whi > wlo ? whi - wlo : 0u;
+            if (n1 <= kEmitRawMax) {
+                single = true;
+                T = n1;
+                for (uint32_t i0 = 0; i0 < n1; i0 += 128) {
+                    uint32_t cs[4], ce[4];
 #pragma unroll
-                    for (uint32_t t = 0; t < 4; t++) {
-                        const uint32_t i = r0 + sub * 4 + t;
-                        v[t] = i < hi ? __ldg(cs + i) : 0xFFFFFFFFu;
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t i = i0 + 32 * u + lane;
+                        cs[u] = ce[u] = 0;
+                        if (i < n1) {
+                            ce[u] = __ldg(f.Eiv + wlo + i);
+                            cs[u] = __ldg(f.S + wlo + i);
+                        }
                     }
 #pragma unroll
-                    for (uint32_t t = 0; t < 4; t++) cnt += (r0 + sub * 4 + t < hi) && (v[t] < key);
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t i = i0 + 32 * u + lane;
+                        const bool keep = i < n1 && ce[u] > amin;
+                        const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                        const uint32_t pos = Tk + __popc(km & ((1u << lane) - 1u));
+                        if (keep && pos < (uint32_t)kEmitCand) sorted[pos] = make_uint4(cs[u], ce[u], wlo + i, 0u);
+                        Tk += __popc(km);
+                    }
                 }
+                fits = Tk <= (uint32_t)kEmitCand;
+                if (fits) T = Tk;
+                __syncwarp();
             }
-            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1);
-            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
-            r = r0 + cnt;
-            if (on && hi - r0 > 16u) r = lower_bound_u32(cs, r0, hi, key);
         }
-        uint32_t lo[4], cnt[4], T = 0;
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            lo[c] = __shfl_sync(0xFFFFFFFFu, r, 4 * c);
-            const uint32_t hi = __shfl_sync(0xFFFFFFFFu, r, 16 + 4 * c);
-            cnt[c] = hi > lo[c] ? hi - lo[c] : 0u;
-            T += cnt[c];
-        }
-        // raw candidates (class-major) into the head of the stage area, which is still unused -- but only those
-        // that can overlap some query of the chunk at all: a class window reaches maxlen_c below the smallest query
-        // start, and most of the intervals starting down there end before it (stop <= amin)
-        uint32_t *const raw = stage;
-        uint32_t Tk = 0;  // candidates kept (warp-uniform)
-        uint32_t kc[4] = {0, 0, 0, 0};  // ... per class (warp-uniform)
-        bool fits = staged && T <= kEmitRawMax;
-        if (fits) {
-            // (dense shape: the loads of four rounds are issued together -- one memory round trip instead of four)
-            constexpr int kU = Shape::kDense ? 4 : 1;
-            for (uint32_t i0 = 0; i0 < T; i0 += 32 * kU) {
-                uint32_t g[kU], cs[kU], ce[kU], c[kU];
-#pragma unroll
-                for (int u = 0; u < kU; u++) {
-                    const uint32_t i = i0 + 32 * u + lane;
-                    g[u] = cs[u] = ce[u] = c[u] = 0;
-                    if (i < T) {
-                        uint32_t base = 0;  // class of candidate i and the index of that class's first candidate
-                        if (i >= cnt[0]) {
-                            c[u] = 1, base = cnt[0];
-                            if (i >= base + cnt[1]) {
-                                c[u] = 2, base += cnt[1];
-                                if (i >= base + cnt[2]) c[u] = 3, base += cnt[2];
+        if (!single) {
+            // eight class bounds (4 classes x {window start, window end}), four lanes each: the directory gives a
+            // rank range of at most 16 class starts, which the four lanes probe with independent loads (one memory
+            // round trip instead of a serial walk)
+            uint32_t r = 0;
+            {
+                const int c = (int)((lane >> 2) & 3u);
+                const uint32_t sub = lane & 3u;
+                const bool on = c < (int)f.ncls;
+                const uint32_t key = (lane >> 4) ? bmax : (amin >= f.cls_maxlen[c] ? amin - f.cls_maxlen[c] : 0u);
+                const uint32_t *cs = f.cs + f.cls_off[c];
+                uint32_t r0 = 0, hi = 0, cnt = 0;
+                if (on) {
+                    const uint32_t B = min(key >> f.cls_shift, f.cls_nb);
+                    r0 = dir_get(__ldg(f.dir + B), c);
+                    hi = B < f.cls_nb ? dir_get(__ldg(f.dir + B + 1), c) : r0;
+                    if (hi - r0 <= 16u) {
+                        uint32_t v[4];
+    #pragma unroll
+                        for (uint32_t t = 0; t < 4; t++) {
+                            const uint32_t i = r0 + sub * 4 + t;
+                            v[t] = i < hi ? __ldg(cs + i) : 0xFFFFFFFFu;
+                        }
+    #pragma unroll
+                        for (uint32_t t = 0; t < 4; t++) cnt += (r0 + sub * 4 + t < hi) && (v[t] < key);
+                    }
+                }
+                cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 1);
+                cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, 2);
+                r = r0 + cnt;
+                if (on && hi - r0 > 16u) r = lower_bound_u32(cs, r0, hi, key);
+            }
+            uint32_t lo[4], cnt[4];
+            T = 0;
+    #pragma unroll
+            for (int c = 0; c < 4; c++) {
+                lo[c] = __shfl_sync(0xFFFFFFFFu, r, 4 * c);
+                const uint32_t hi = __shfl_sync(0xFFFFFFFFu, r, 16 + 4 * c);
+                cnt[c] = hi > lo[c] ? hi - lo[c] : 0u;
+                T += cnt[c];
+            }
+            // raw candidates (class-major) into the head of the stage area, which is still unused -- but only those
+            // that can overlap some query of the chunk at all: a class window reaches maxlen_c below the smallest query
+            // start, and most of the intervals starting down there end before it (stop <= amin)
+            uint32_t *const raw = stage;
+            Tk = 0;
+            uint32_t kc[4] = {0, 0, 0, 0};  // ... per class (warp-uniform)
+            fits = staged && T <= kEmitRawMax;
+            if (fits) {
+                // (dense shape: the loads of four rounds are issued together -- one memory round trip instead of four)
+                constexpr int kU = Shape::kDense ? 4 : 1;
+                for (uint32_t i0 = 0; i0 < T; i0 += 32 * kU) {
+                    uint32_t g[kU], cs[kU], ce[kU], c[kU];
+    #pragma unroll
+                    for (int u = 0; u < kU; u++) {
+                        const uint32_t i = i0 + 32 * u + lane;
+                        g[u] = cs[u] = ce[u] = c[u] = 0;
+                        if (i < T) {
+                            uint32_t base = 0;  // class of candidate i and the index of that class's first candidate
+                            if (i >= cnt[0]) {
+                                c[u] = 1, base = cnt[0];
+                                if (i >= base + cnt[1]) {
+                                    c[u] = 2, base += cnt[1];
+                                    if (i >= base + cnt[2]) c[u] = 3, base += cnt[2];
+                                }
+                            }
+                            const uint32_t p = f.cls_off[c[u]] + lo[c[u]] + (i - base);
+                            ce[u] = __ldg(f.ce + p);  // three independent loads
+                            g[u] = __ldg(f.cg + p);
+                            cs[u] = __ldg(f.cs + p);
+                        }
+                    }
+    #pragma unroll
+                    for (int u = 0; u < kU; u++) {
+                        const bool keep = i0 + 32 * u + lane < T && ce[u] > amin;
+                        const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
+                        const uint32_t pos = Tk + __popc(km & ((1u << lane) - 1u));
+                        if (keep && pos < (uint32_t)kEmitCand) {
+                            raw[pos] = g[u];
+                            raw[kEmitCand + pos] = cs[u];
+                            raw[2 * kEmitCand + pos] = ce[u];
+                        }
+                        Tk += __popc(km);
+    #pragma unroll
+                        for (uint32_t cc = 0; cc < 4; cc++) kc[cc] += __popc(__ballot_sync(0xFFFFFFFFu, keep && c[u] == cc));
+                    }
+                }
+                fits = Tk <= (uint32_t)kEmitCand;
+            }
+            EMIT_STAT(4, T);
+            if (fits) {
+                T = Tk;
+                __syncwarp();
+                // merged order = rank of the global position among all candidates (positions are distinct): the kept list
+                // is class-major and ascending within a class, so a candidate's rank is its index in its own class plus
+                // one binary search per other class
+                // (kR candidates per lane side by side, every search in the same number of power-of-two steps: the
+                // shared-memory loads of a step are independent of one another)
+                constexpr int kR = Shape::kDense ? 4 : 2;
+                for (uint32_t i0 = 0; i0 < T; i0 += 32 * kR) {
+                    uint32_t g[kR], k[kR], c[kR], rank[kR];
+    #pragma unroll
+                    for (int u = 0; u < kR; u++) {
+                        const uint32_t i = min(i0 + 32 * u + lane, T - 1);
+                        c[u] = 0, k[u] = i;
+                        if (k[u] >= kc[0]) {
+                            c[u] = 1, k[u] -= kc[0];
+                            if (k[u] >= kc[1]) {
+                                c[u] = 2, k[u] -= kc[1];
+                                if (k[u] >= kc[2]) c[u] = 3, k[u] -= kc[2];
                             }
                         }
-                        const uint32_t p = f.cls_off[c[u]] + lo[c[u]] + (i - base);
-                        ce[u] = __ldg(f.ce + p);  // three independent loads
-                        g[u] = __ldg(f.cg + p);
-                        cs[u] = __ldg(f.cs + p);
+                        g[u] = raw[i];
+                        rank[u] = k[u];
+                    }
+                    uint32_t base = 0;
+    #pragma unroll
+                    for (uint32_t cc = 0; cc < 4; cc++) {
+                        const uint32_t n = kc[cc];
+                        if (n) {  // (warp-uniform)
+                            uint32_t pos[kR];
+    #pragma unroll
+                            for (int u = 0; u < kR; u++) pos[u] = 0;
+                            for (uint32_t step = 1u << (31 - __clz(n)); step; step >>= 1) {
+    #pragma unroll
+                                for (int u = 0; u < kR; u++)
+                                    if (pos[u] + step <= n && raw[base + pos[u] + step - 1] < g[u]) pos[u] += step;
+                            }
+    #pragma unroll
+                            for (int u = 0; u < kR; u++)
+                                if (c[u] != cc) rank[u] += pos[u];
+                        }
+                        base += n;
+                    }
+    #pragma unroll
+                    for (int u = 0; u < kR; u++) {
+                        const uint32_t i = i0 + 32 * u + lane;
+                        if (i < T) {
+                            LAPPER_CHECK(rank[u] < T);
+                            sorted[rank[u]] = make_uint4(raw[kEmitCand + i], raw[2 * kEmitCand + i], g[u], 0u);
+                        }
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < kU; u++) {
-                    const bool keep = i0 + 32 * u + lane < T && ce[u] > amin;
-                    const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
-                    const uint32_t pos = Tk + __popc(km & ((1u << lane) - 1u));
-                    if (keep && pos < (uint32_t)kEmitCand) {
-                        raw[pos] = g[u];
-                        raw[kEmitCand + pos] = cs[u];
-                        raw[2 * kEmitCand + pos] = ce[u];
-                    }
-                    Tk += __popc(km);
-#pragma unroll
-                    for (uint32_t cc = 0; cc < 4; cc++) kc[cc] += __popc(__ballot_sync(0xFFFFFFFFu, keep && c[u] == cc));
-                }
+                __syncwarp();
             }
-            fits = Tk <= (uint32_t)kEmitCand;
         }
-        EMIT_STAT(4, T);
         if (fits) {
             EMIT_STAT(1, 1);
             EMIT_STAT(5, Tk);
-            T = Tk;
-            __syncwarp();
-            // merged order = rank of the global position among all candidates (positions are distinct): the kept list
-            // is class-major and ascending within a class, so a candidate's rank is its index in its own class plus
-            // one binary search per other class
-            // (kR candidates per lane side by side, every search in the same number of power-of-two steps: the
-            // shared-memory loads of a step are independent of one another)
-            constexpr int kR = Shape::kDense ? 4 : 2;
-            for (uint32_t i0 = 0; i0 < T; i0 += 32 * kR) {
-                uint32_t g[kR], k[kR], c[kR], rank[kR];
-#pragma unroll
-                for (int u = 0; u < kR; u++) {
-                    const uint32_t i = min(i0 + 32 * u + lane, T - 1);
-                    c[u] = 0, k[u] = i;
-                    if (k[u] >= kc[0]) {
-                        c[u] = 1, k[u] -= kc[0];
-                        if (k[u] >= kc[1]) {
-                            c[u] = 2, k[u] -= kc[1];
-                            if (k[u] >= kc[2]) c[u] = 3, k[u] -= kc[2];
-                        }
-                    }
-                    g[u] = raw[i];
-                    rank[u] = k[u];
-                }
-                uint32_t base = 0;
-#pragma unroll
-                for (uint32_t cc = 0; cc < 4; cc++) {
-                    const uint32_t n = kc[cc];
-                    if (n) {  // (warp-uniform)
-                        uint32_t pos[kR];
-#pragma unroll
-                        for (int u = 0; u < kR; u++) pos[u] = 0;
-                        for (uint32_t step = 1u << (31 - __clz(n)); step; step >>= 1) {
-#pragma unroll
-                            for (int u = 0; u < kR; u++)
-                                if (pos[u] + step <= n && raw[base + pos[u] + step - 1] < g[u]) pos[u] += step;
-                        }
-#pragma unroll
-                        for (int u = 0; u < kR; u++)
-                            if (c[u] != cc) rank[u] += pos[u];
-                    }
-                    base += n;
-                }
-#pragma unroll
-                for (int u = 0; u < kR; u++) {
-                    const uint32_t i = i0 + 32 * u + lane;
-                    if (i < T) {
-                        LAPPER_CHECK(rank[u] < T);
-                        sorted[rank[u]] = make_uint4(raw[kEmitCand + i], raw[2 * kEmitCand + i], g[u], 0u);
-                    }
-                }
-            }
-            __syncwarp();
             // every lane sweeps the sorted candidates for its own queries (broadcast reads)
             // (write cursors as shared-memory addresses, predicated store + predicated add in inline PTX: five
             // instructions per candidate and query instead of the seven the compiler's own form spends)
