@@ -46,6 +46,7 @@ struct lapper64 {
     // The u32 engine over the same sorted intervals (see "narrowing" below): built on the first batch that is worth it
     // when every coordinate fits, dropped by insert / merge_overlaps.
     mutable std::atomic<lapper_t *> narrow{nullptr};
+    mutable std::atomic<bool> narrow_failed{false};  // building it failed once (memory): the 64-bit kernels answer from then on
     mutable std::mutex narrow_mu;
 };
 
@@ -683,22 +684,33 @@ __global__ void __launch_bounds__(kT) narrow_queries_kernel(const uint64_t *__re
 lapper_t *narrow_of(const lapper64 *l, uint64_t nq, cudaStream_t stream) {
     const int mode = g_narrow_mode.load(std::memory_order_relaxed);
     if (mode == 0 || l->n == 0 || l->n >= 0xFFFFFFF0ull || l->max_coord > kNarrowMaxCoord) return nullptr;
+    if (l->narrow_failed.load(std::memory_order_relaxed)) return nullptr;
     lapper_t *h = l->narrow.load(std::memory_order_acquire);
     if (h) return h;
     if (mode == 1 && nq < kNarrowMinBatch) return nullptr;
     std::lock_guard<std::mutex> guard(l->narrow_mu);
     h = l->narrow.load(std::memory_order_acquire);
     if (h) return h;
-    Scratch<uint32_t> s(l->n, stream), eiv(l->n, stream), e(l->n, stream);
-    narrow_index_kernel<<<capped(l->n), kT, 0, stream>>>(l->S, l->Eiv, l->E, l->n, s.p, eiv.p, e.p);
-    LAPPER_CUDA_CHECK(cudaGetLastError());
-    const int rc = lapper_from_sorted_dev(s.p, eiv.p, e.p, l->perm, l->n, l->overlaps_merged ? 1 : 0, l->device, 0, stream, &h);
-    if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
+    // The u32 index is an accelerator, not a requirement: if it cannot be built (about 50 bytes per interval on top of
+    // the u64 arrays), the batch and every later one go to the 64-bit kernels.
+    try {
+        Scratch<uint32_t> s(l->n, stream), eiv(l->n, stream), e(l->n, stream);
+        narrow_index_kernel<<<capped(l->n), kT, 0, stream>>>(l->S, l->Eiv, l->E, l->n, s.p, eiv.p, e.p);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        const int rc = lapper_from_sorted_dev(s.p, eiv.p, e.p, l->perm, l->n, l->overlaps_merged ? 1 : 0, l->device, 0, stream, &h);
+        if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
+    } catch (const Error &err) {
+        if (err.code != LAPPER_ERR_OOM) throw;
+        cudaGetLastError();
+        l->narrow_failed.store(true, std::memory_order_relaxed);
+        return nullptr;
+    }
     l->narrow.store(h, std::memory_order_release);
     return h;
 }
 
 void drop_narrow(lapper64 *l) {
+    l->narrow_failed.store(false, std::memory_order_relaxed);
     lapper_t *h = l->narrow.exchange(nullptr, std::memory_order_acq_rel);
     if (h) lapper_free(h);
 }
