@@ -1048,6 +1048,8 @@ def group_selfcheck(cx):
                     "count_equal": bool(np.array_equal(want_c, got_c)),
                     "find_equal": bool(np.array_equal(want_o, got_o) and np.array_equal(want_i, got_i)),
                     "hits": int(want_o[-1]),
+                    "note": "rank 0 alone drives every GPU of the box through lapper_group_*; replicate_ms includes creating this "
+                            "process's CUDA context and memory pool on each peer (about 0.4 s per GPU, once per process)",
                 }
                 grp.close()
                 lap.close()
