@@ -1437,6 +1437,13 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
         }
         __syncthreads();  // cand complete; the raw list (aliasing the warps' areas) is dead
         // ---- 5. groups of kTG consecutive queries, kTQL per lane
+#ifdef LAPPER_TILE_XFROM
+        // Where the filter below starts: the round of the tile list in which the warp's previous group kept its first
+        // candidate.  Everything before that candidate starts before it (the list is in start order), so the previous
+        // group dropped it for ending at or before ITS smallest start, and a group whose smallest start is no smaller
+        // drops it again.  (Start-sorted batches: the groups' smallest starts ascend.)
+        uint32_t xfrom = 0, prev_gamin = 0;
+#endif
         for (uint32_t gq = warp * kTG; gq < nqt; gq += kTW * kTG) {
             const uint32_t gq_end = min(gq + kTG, nqt);
             const uint32_t gbase = rel[gq];
@@ -1464,7 +1471,13 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
             // the group's candidates: tile candidates that start before its largest stop and end after its smallest
             // start, in order (the tile list is ordered by position, i.e. by start: stop at the first round past gbmax)
             uint32_t T = 0;
+#ifdef LAPPER_TILE_XFROM
+            if (gamin < prev_gamin) xfrom = 0;
+            prev_gamin = gamin;
+            for (uint32_t x0 = xfrom; x0 < K; x0 += 32) {
+#else
             for (uint32_t x0 = 0; x0 < K; x0 += 32) {
+#endif
                 const uint32_t x = x0 + lane;
                 uint4 c = make_uint4(0xFFFFFFFFu, 0u, 0u, 0u);
                 if (x < K) c = cand[x];
@@ -1472,6 +1485,9 @@ __global__ void __launch_bounds__(kTT, LAPPER_TILE_CTAS) find_fill_tile_kernel(F
                 const uint32_t km = __ballot_sync(0xFFFFFFFFu, keep);
                 const uint32_t pos = T + __popc(km & ((1u << lane) - 1u));
                 if (keep && pos < (uint32_t)kEmitCand) wlist[pos] = c;
+#ifdef LAPPER_TILE_XFROM
+                if (T == 0 && km) xfrom = x0;
+#endif
                 T += __popc(km);
                 if (__all_sync(0xFFFFFFFFu, c.x >= gbmax)) break;
             }
