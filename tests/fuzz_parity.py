@@ -9,7 +9,9 @@ inverted intervals, coordinates up to the top of the type), the build flags (aut
 table forced, no tables), the query batch (size around the kernels' tile / run / threshold boundaries; random, sorted,
 sorted-by-start-only, block-shuffled; fixed or random length; empty, inverted and MAX-coordinate queries mixed in), and
 checks count_batch (u64 and c32), find_batch (CSR byte-equal), find_batch_into (capacity protocol) and, now and then,
-merge_overlaps / cov.  Prints one line per failure with everything needed to replay it, and a summary."""
+merge_overlaps / cov, union_and_intersect against a second random set, depth, the seek cursor protocol, insert.  u64
+cases also draw which engine answers a set that fits 32 bits (the 64-bit kernels / the default policy / the u32 engine
+from the first batch on).  Prints one line per failure with everything needed to replay it, and a summary."""
 import argparse
 import sys
 import time
@@ -164,6 +166,48 @@ def check_case(rng, bits, case_id, verbose=False):
             t = gpu.find_batch_into(qs, qe, off, idx)
             if t != int(wo[-1]) or not (np.array_equal(off, wo) and np.array_equal(idx, wi)):
                 return f"find_batch_into differs: {desc}"
+    # the rest of the API now and then, on sets small enough for the per-call oracle: union_and_intersect against a
+    # second random set, depth, the seek cursor protocol over a sorted batch, insert (positions, perm, max_len)
+    if not inverted and 0 < s.size <= 20_000 and rng.random() < 0.25:
+        s2, e2, _, inv2 = draw_intervals(rng, bits)
+        if not inv2 and 0 < s2.size <= 5000:
+            if bits == 32:
+                g2 = Lapper(starts=s2.astype(np.uint32), stops=e2.astype(np.uint32))
+                c2 = lapper_oracle.OracleLapper(starts=s2.astype(np.uint32), stops=e2.astype(np.uint32))
+            else:
+                g2 = Lapper64(starts=s2, stops=e2)
+                c2 = lapper_oracle.OracleLapper(starts=s2, stops=e2, coord_bits=64)
+            if gpu.union_and_intersect(g2) != cpu.union_and_intersect(c2) or g2.union_and_intersect(gpu) != c2.union_and_intersect(cpu):
+                return f"union_and_intersect differs (second set n={s2.size}): {desc}"
+        if s.size <= 5000:
+            # (the reference's depth iterator walks the merged intervals coordinate by coordinate, src/lib.rs:744-784, and so
+            # does the oracle: only sets that cover little)
+            if cpu.cov() <= 100_000 and gpu.depth() != cpu.depth():
+                return f"depth differs: {desc}"
+            o = np.argsort(qs[:300], kind="stable")
+            cg, cc = [0], [0]
+            for j in o.tolist():
+                if gpu.seek_idx(int(qs[j]), int(qe[j]), cg) != cpu.seek_idx(int(qs[j]), int(qe[j]), cc) or cg != cc:
+                    return f"seek differs at query {j}: {desc}"
+    if 0 < s.size <= 5000 and rng.random() < 0.2:
+        top = (1 << bits) - 1
+        for i in range(4):
+            k = int(rng.integers(0, s.size))
+            a = int(s[k]) if rng.random() < 0.5 else int(rng.integers(0, min(top, 2 * U + 10), dtype=np.uint64))
+            b = min(top, a + int(rng.integers(0, 500)))
+            gpu.insert(a, b), cpu.insert(a, b, s.size + i)  # (the oracle's val = the input position the engine hands out)
+        gs, ge, gp = gpu.intervals_soa()
+        cs, ce, cv = cpu.intervals_soa()
+        if not (np.array_equal(gs, cs) and np.array_equal(ge, ce) and gpu.max_len == cpu.max_len and np.array_equal(gpu.stops, cpu.stops)):
+            return f"insert differs: {desc}"
+        if not np.array_equal(gpu.count_batch(qs, qe), cpu.count_batch(qs, qe, 4)):
+            return f"count_batch after insert differs: {desc}"
+        wo, wi = cpu.find_batch(qs, qe, 4)
+        if int(wo[-1]) < 60_000_000:
+            go, gi = gpu.find_batch(qs, qe)
+            if not (np.array_equal(go, wo) and np.array_equal(gi, wi)):
+                return f"find_batch after insert differs: {desc}"
+        inverted = bool((ge < gs).any())
     if not inverted and s.size and rng.random() < 0.3:
         if gpu.cov() != cpu.cov():
             return f"cov differs: {desc}"
