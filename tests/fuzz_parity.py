@@ -21,7 +21,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle import lapper_oracle  # noqa: E402
-from rust_lapper_b200 import Lapper, Lapper64, LapperError, _ffi  # noqa: E402
+from rust_lapper_b200 import Lapper, Lapper64, LapperError, LapperGroup, _ffi  # noqa: E402
 
 
 def draw_intervals(rng, bits):
@@ -166,6 +166,17 @@ def check_case(rng, bits, case_id, verbose=False):
             t = gpu.find_batch_into(qs, qe, off, idx)
             if t != int(wo[-1]) or not (np.array_equal(off, wo) and np.array_equal(idx, wi)):
                 return f"find_batch_into differs: {desc}"
+    if bits == 32 and s.size and rng.random() < 0.05 and int(wo[-1]) < 60_000_000:
+        # replica group on this GPU (three replicas of the handle; the batch is cut into three shards)
+        grp = LapperGroup(gpu, [0, 0, 0])
+        try:
+            if not np.array_equal(grp.count_batch(qs, qe), want_c):
+                return f"group count_batch differs: {desc}"
+            go, gi = grp.find_batch(qs, qe)
+            if not (np.array_equal(go, wo) and np.array_equal(gi, wi)):
+                return f"group find_batch differs: {desc}"
+        finally:
+            grp.close()
     # the rest of the API now and then, on sets small enough for the per-call oracle: union_and_intersect against a
     # second random set, depth, the seek cursor protocol over a sorted batch, insert (positions, perm, max_len)
     if not inverted and 0 < s.size <= 20_000 and rng.random() < 0.25:
