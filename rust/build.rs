@@ -13,7 +13,8 @@ fn main() {
     println!("cargo:rustc-link-search=native={}", libdir.display());
     println!("cargo:rustc-link-lib=dylib=lapper_b200");
     println!("cargo:rustc-link-arg=-Wl,-rpath,{}", libdir.display());
-    for f in ["api.cu", "build.cu", "query.cu", "setops.cu", "index.cuh", "common.cuh"] {
+    for f in ["api.cu", "build.cu", "query.cu", "count_sorted.cu", "setops.cu", "engine64.cu", "index.cuh", "common.cuh",
+              "packed_sector.cuh", "query_views.cuh", "abi_common.cuh"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
 }

@@ -204,3 +204,117 @@ impl<'a, T: Eq + Clone + Send + Sync> IntoIterator for &'a Lapper<T> {
 impl<T: Eq + Clone + Send + Sync> Drop for Lapper<T> {
     fn drop(&mut self) { unsafe { lapper_free(self.h) } }
 }
+
+/// `Lapper<usize, T>` -- the coordinate type of the reference's README examples -- over `lapper64_*`
+/// (include/lapper_b200.h).  Sets whose coordinates fit 32 bits are answered by the u32 engine inside the library
+/// (narrowing, csrc/engine64.cu); nothing changes for the caller.  UNVERIFIED like the rest of this file.
+pub mod wide {
+    use super::{check, lapper_result_copy, lapper_result_free, lapper_result_total, LapperResult};
+    use std::os::raw::c_int;
+
+    #[repr(C)]
+    pub struct Lapper64Handle {
+        _private: [u8; 0],
+    }
+    extern "C" {
+        fn lapper64_build(starts: *const u64, stops: *const u64, n: u64, device: c_int, out: *mut *mut Lapper64Handle) -> c_int;
+        fn lapper64_free(l: *mut Lapper64Handle);
+        fn lapper64_len(l: *const Lapper64Handle) -> u64;
+        fn lapper64_max_len(l: *const Lapper64Handle) -> u64;
+        fn lapper64_get_intervals(l: *const Lapper64Handle, s: *mut u64, e: *mut u64, perm: *mut u32) -> c_int;
+        fn lapper64_count_batch(l: *const Lapper64Handle, qs: *const u64, qe: *const u64, nq: u64, out: *mut u64) -> c_int;
+        fn lapper64_find_batch(l: *const Lapper64Handle, qs: *const u64, qe: *const u64, nq: u64, out: *mut *mut LapperResult) -> c_int;
+        fn lapper64_merge_overlaps(l: *mut Lapper64Handle) -> c_int;
+        fn lapper64_cov(l: *const Lapper64Handle, out: *mut u64) -> c_int;
+        fn lapper64_union_and_intersect(a: *const Lapper64Handle, b: *const Lapper64Handle, u: *mut u64, i: *mut u64) -> c_int;
+        fn lapper64_insert(l: *mut Lapper64Handle, start: u64, stop: u64, input_position_out: *mut u64) -> c_int;
+        fn lapper64_seek_cursor(l: *const Lapper64Handle, start: u64, cursor: *mut u64) -> c_int;
+    }
+
+    #[derive(Debug, Clone)]
+    pub struct Interval<T: Eq + Clone + Send + Sync> {
+        pub start: usize,
+        pub stop: usize,
+        pub val: T,
+    }
+
+    pub struct Lapper<T: Eq + Clone + Send + Sync> {
+        pub intervals: Vec<Interval<T>>,
+        input: Vec<Interval<T>>,
+        h: *mut Lapper64Handle,
+    }
+    unsafe impl<T: Eq + Clone + Send + Sync> Send for Lapper<T> {}
+    unsafe impl<T: Eq + Clone + Send + Sync> Sync for Lapper<T> {}
+
+    impl<T: Eq + Clone + Send + Sync> Lapper<T> {
+        pub fn new(intervals: Vec<Interval<T>>) -> Self {
+            let s: Vec<u64> = intervals.iter().map(|x| x.start as u64).collect();
+            let e: Vec<u64> = intervals.iter().map(|x| x.stop as u64).collect();
+            let mut h = std::ptr::null_mut();
+            check(unsafe { lapper64_build(s.as_ptr(), e.as_ptr(), s.len() as u64, 0, &mut h) });
+            let mut l = Lapper { intervals: vec![], input: intervals, h };
+            l.refresh();
+            l
+        }
+        fn refresh(&mut self) {
+            let n = unsafe { lapper64_len(self.h) } as usize;
+            let (mut s, mut e, mut p) = (vec![0u64; n], vec![0u64; n], vec![0u32; n]);
+            check(unsafe { lapper64_get_intervals(self.h, s.as_mut_ptr(), e.as_mut_ptr(), p.as_mut_ptr()) });
+            self.intervals = (0..n)
+                .map(|i| Interval { start: s[i] as usize, stop: e[i] as usize, val: self.input[p[i] as usize].val.clone() })
+                .collect();
+        }
+        pub fn len(&self) -> usize { self.intervals.len() }
+        pub fn is_empty(&self) -> bool { self.intervals.is_empty() }
+        pub fn max_len(&self) -> usize { unsafe { lapper64_max_len(self.h) as usize } }
+        pub fn count_batch(&self, qs: &[u64], qe: &[u64]) -> Vec<u64> {
+            assert_eq!(qs.len(), qe.len());
+            let mut out = vec![0u64; qs.len()];
+            check(unsafe { lapper64_count_batch(self.h, qs.as_ptr(), qe.as_ptr(), qs.len() as u64, out.as_mut_ptr()) });
+            out
+        }
+        pub fn find_batch(&self, qs: &[u64], qe: &[u64]) -> (Vec<u64>, Vec<u32>) {
+            assert_eq!(qs.len(), qe.len());
+            let mut r = std::ptr::null_mut();
+            check(unsafe { lapper64_find_batch(self.h, qs.as_ptr(), qe.as_ptr(), qs.len() as u64, &mut r) });
+            let total = unsafe { lapper_result_total(r) } as usize;
+            let (mut off, mut idx) = (vec![0u64; qs.len() + 1], vec![0u32; total]);
+            let rc = unsafe { lapper_result_copy(r, off.as_mut_ptr(), idx.as_mut_ptr()) };
+            unsafe { lapper_result_free(r) };
+            check(rc);
+            (off, idx)
+        }
+        pub fn count(&self, start: usize, stop: usize) -> usize { self.count_batch(&[start as u64], &[stop as u64])[0] as usize }
+        pub fn find(&self, start: usize, stop: usize) -> impl Iterator<Item = &Interval<T>> {
+            let (_, idx) = self.find_batch(&[start as u64], &[stop as u64]);
+            idx.into_iter().map(move |i| &self.intervals[i as usize])
+        }
+        pub fn seek<'a>(&'a self, start: usize, stop: usize, cursor: &mut usize) -> impl Iterator<Item = &'a Interval<T>> {
+            let mut c = *cursor as u64;
+            check(unsafe { lapper64_seek_cursor(self.h, start as u64, &mut c) });
+            *cursor = c as usize;
+            let (_, idx) = self.find_batch(&[start as u64], &[stop as u64]);
+            idx.into_iter().filter(move |&i| i as u64 >= c).map(move |i| &self.intervals[i as usize])
+        }
+        pub fn insert(&mut self, elem: Interval<T>) {
+            let mut pos = 0u64;
+            check(unsafe { lapper64_insert(self.h, elem.start as u64, elem.stop as u64, &mut pos) });
+            debug_assert_eq!(pos as usize, self.input.len());
+            self.input.push(elem);
+            self.refresh();
+        }
+        pub fn merge_overlaps(&mut self) {
+            check(unsafe { lapper64_merge_overlaps(self.h) });
+            self.refresh();
+        }
+        pub fn cov(&self) -> usize { let mut c = 0u64; check(unsafe { lapper64_cov(self.h, &mut c) }); c as usize }
+        pub fn union_and_intersect(&self, other: &Self) -> (usize, usize) {
+            let (mut u, mut i) = (0u64, 0u64);
+            check(unsafe { lapper64_union_and_intersect(self.h, other.h, &mut u, &mut i) });
+            (u as usize, i as usize)
+        }
+    }
+    impl<T: Eq + Clone + Send + Sync> Drop for Lapper<T> {
+        fn drop(&mut self) { unsafe { lapper64_free(self.h) } }
+    }
+}
