@@ -191,10 +191,10 @@ int lapper_insert_u32(lapper_t *l, uint32_t start, uint32_t stop, uint64_t *inpu
 /* ---- Lapper::merge_overlaps (src/lib.rs:361-416): prefix-max scan, run heads, compaction; rebuilds
  *      starts / stops / max_len; sets overlaps_merged iff the lapper is non-empty.  The query tables of the merged set
  *      are built on its first count / find.
- *      DEVIATION: LAPPER_ERR_PRECONDITION if some interval has stop < start.  The reference's loop (comparisons and
- *      checked_sub only) is well defined for such sets; the prefix-max closed form used here is not, so the call is
- *      refused rather than answered differently.  (cov, union_and_intersect and depth refuse the same sets because
- *      the reference itself overflows on them.) */
+ *      Sets in which some interval has stop < start: the reference's loop (comparisons and checked_sub only) is well
+ *      defined for them but is not a prefix-max scan; the engine then runs the loop literally on one warp (about 10 ns
+ *      per interval; csrc/merge_sequential.cuh) -- same result as the reference.  (cov, union_and_intersect and depth
+ *      refuse such sets with LAPPER_ERR_PRECONDITION because the reference itself overflows on them.) */
 int lapper_merge_overlaps(lapper_t *l);
 /* ---- Lapper::cov / set_cov (src/lib.rs:310-350) */
 int lapper_cov(const lapper_t *l, uint32_t *cov_out);

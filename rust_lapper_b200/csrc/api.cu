@@ -840,17 +840,23 @@ int lapper_merge_overlaps(lapper_t *l) {
     return guarded([&] {
         check_handle(l);
         if (l->ix.n == 0) return;  // src/lib.rs:366: nothing happens without a first interval
-        need_valid_intervals(l, "merge_overlaps");
         DeviceGuard dg(l->device);
         StreamOwner st;
         IndexBuilder b(st.s);
+        // (sets with stop < start: the reference's loop is well defined for them -- comparisons only -- and
+        // compute_merged runs it literally, setops.cu / merge_sequential.cuh)
+        const bool inverted = l->ix.has_inverted;
         const uint64_t m = compute_merged(l->ix, &b.ix.starts, &b.ix.stops_by_iv, &b.ix.perm, st.s);
         b.ix.n = m;
         b.ix.bytes = 3 * 4 * std::max<uint64_t>(m, 1);
         // runs are disjoint and ascending: their stops are already the sorted `stops` (src/lib.rs:396-406 sorts
-        // them again, a no-op)
+        // them again, a no-op) -- unless a run kept an inverted interval's stop: sort then
         b.ix.stops_sorted = pool_alloc<uint32_t>(m, b.ix.bytes, st.s);
         LAPPER_CUDA_CHECK(cudaMemcpyAsync(b.ix.stops_sorted, b.ix.stops_by_iv, m * 4, cudaMemcpyDeviceToDevice, st.s));
+        if (inverted && m > 1) {
+            Scratch<uint32_t> tmp(m, st.s);
+            launch_sort_u32(b.ix.stops_sorted, tmp.p, m, st.s);
+        }
         finish_index_core(b.ix, st.s);  // max_len of the runs (src/lib.rs:408-415); the query tables follow on first use
         b.commit(l);
         l->overlaps_merged = true;  // src/lib.rs:382; the cached cov is left alone like the reference

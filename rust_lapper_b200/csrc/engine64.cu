@@ -27,6 +27,7 @@
 
 #include "abi_common.cuh"
 #include "index.cuh"
+#include "merge_sequential.cuh"
 
 struct lapper64 {
     int device = 0;
@@ -604,6 +605,23 @@ struct Merged64 {
 
 void merged_of(const lapper64 *l, Merged64 &out, cudaStream_t stream) {
     if (l->n == 0) return;
+    if (l->has_inverted) {
+        // some stop < start: the reference's own loop, one warp (merge_sequential.cuh)
+        Scratch<unsigned long long> d_m(1, stream);
+        merge_sequential_kernel<uint64_t, false><<<1, 32, 0, stream>>>(l->S, l->Eiv, l->perm, l->n, nullptr, nullptr, nullptr, d_m.p);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        unsigned long long m = 0;
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(&m, d_m.p, 8, cudaMemcpyDeviceToHost, stream));
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+        uint64_t bytes = 0;
+        out.m = m;
+        out.s = pool_alloc<uint64_t>(m, bytes, stream);
+        out.e = pool_alloc<uint64_t>(m, bytes, stream);
+        out.perm = pool_alloc<uint32_t>(m, bytes, stream);
+        merge_sequential_kernel<uint64_t, true><<<1, 32, 0, stream>>>(l->S, l->Eiv, l->perm, l->n, out.s, out.e, out.perm, nullptr);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        return;
+    }
     const uint64_t n = l->n, ntiles = div_up(n, kTile64);
     const Head64 flags{l->S, l->P};
     Scratch<uint64_t> agg(ntiles, stream), d_total(1, stream);
@@ -977,10 +995,10 @@ int lapper64_set_cov(lapper64_t *l, uint64_t *cov_out) {
 int lapper64_merge_overlaps(lapper64_t *l) {
     return guarded_call([&] {
         check64(l);
-        need_valid(l, "merge_overlaps");
         if (l->n == 0) return;  // src/lib.rs:366: overlaps_merged is set only when there is a first interval
         DeviceGuard dg(l->device);
         OwnedStream st;
+        const bool inverted = l->has_inverted;  // (merged_of runs the reference's loop literally for such sets)
         Merged64 mg(st.s);
         merged_of(l, mg, st.s);
         // the new index is completed aside and swapped in only when nothing can fail any more
@@ -994,6 +1012,10 @@ int lapper64_merge_overlaps(lapper64_t *l) {
             // the merged runs are disjoint and ascending: their stops are sorted, and the prefix max is the stops themselves
             next.E = pool_alloc<uint64_t>(next.n, bytes, st.s);
             LAPPER_CUDA_CHECK(cudaMemcpyAsync(next.E, next.Eiv, next.n * 8, cudaMemcpyDeviceToDevice, st.s));
+            if (inverted && next.n > 1) {  // a run may have kept an inverted interval's stop: `stops` has to be sorted (:396-406)
+                Scratch<uint64_t> tmp(next.n, st.s);
+                launch_sort_u64(next.E, tmp.p, next.n, st.s);
+            }
             finish_from_sorted(&next, st.s);
         } catch (...) {
             free_arrays(&next, st.s);

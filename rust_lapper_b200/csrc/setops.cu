@@ -11,6 +11,7 @@
 #include <algorithm>
 
 #include "index.cuh"
+#include "merge_sequential.cuh"
 
 namespace lap {
 
@@ -380,6 +381,26 @@ uint64_t compute_merged(const DeviceIndex &ix, uint32_t **m_starts, uint32_t **m
                         cudaStream_t stream) {
     *m_starts = *m_stops = *m_perm = nullptr;
     if (ix.n == 0) return 0;
+    if (ix.has_inverted) {
+        // some stop < start: the reference's own loop, one warp (merge_sequential.cuh)
+        Scratch<unsigned long long> d_m(1, stream);
+        merge_sequential_kernel<uint32_t, false><<<1, 32, 0, stream>>>(ix.starts, ix.stops_by_iv, ix.perm, ix.n, nullptr, nullptr,
+                                                                      nullptr, d_m.p);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        unsigned long long m = 0;
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(&m, d_m.p, 8, cudaMemcpyDeviceToHost, stream));
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+        DevArrays out(stream);
+        out.alloc(m);
+        merge_sequential_kernel<uint32_t, true><<<1, 32, 0, stream>>>(ix.starts, ix.stops_by_iv, ix.perm, ix.n, out.s, out.e, out.perm,
+                                                                     nullptr);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        *m_starts = out.s;
+        *m_stops = out.e;
+        *m_perm = out.perm;
+        out.s = out.e = out.perm = nullptr;
+        return m;
+    }
     // the run count is needed before the outputs can be sized: count heads first
     Scratch<uint32_t> d_total(1, stream);
     const uint64_t n = ix.n;

@@ -314,10 +314,42 @@ def test_merge_large_and_precondition(oracle):
     assert np.array_equal(A.intervals_soa()[0], cA.intervals_soa()[0])
     assert np.array_equal(A.intervals_soa()[1], cA.intervals_soa()[1])
     assert np.array_equal(A.intervals_soa()[2], cA.intervals_soa()[2])
+    # sets with stop < start: merge_overlaps follows the reference's loop (comparisons only, src/lib.rs:361-416);
+    # cov still refuses (the reference's arithmetic overflows there)
     bad = Lapper([(10, 5), (1, 2)])
     with pytest.raises(LapperError) as ei:
-        bad.merge_overlaps()
+        bad.cov()
     assert ei.value.code == _ffi.ERR_PRECONDITION
+    bad.merge_overlaps()
+    cbad = oracle.OracleLapper([(10, 5), (1, 2)])
+    cbad.merge_overlaps()
+    assert bad.intervals == cbad.intervals and bad.overlaps_merged
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_merge_overlaps_with_inverted_intervals(oracle, seed):
+    """The reference's stack loop on sets where some stop < start: a run that opens with such an interval restarts its
+    running stop BELOW stops seen earlier, so the prefix-max form does not apply; the engine runs the loop literally."""
+    rng = np.random.default_rng(seed)
+    n = [500, 30_000, 200_000][seed - 1]
+    s = rng.integers(0, 20 * n, n).astype(np.uint32)
+    e = s + rng.integers(0, 60, n).astype(np.uint32)
+    k = rng.choice(n, n // 25, replace=False)
+    s[k], e[k] = e[k] + np.uint32(1 + seed), s[k]
+    A, cA = _both(oracle, s, e)
+    assert A.has_inverted
+    qs = rng.integers(0, 20 * n, 50_000).astype(np.uint32)
+    qe = qs + rng.integers(0, 100, qs.size).astype(np.uint32)
+    _assert_same_queries(A, cA, qs, qe)
+    A.merge_overlaps(), cA.merge_overlaps()
+    gs, ge, gp = A.intervals_soa()
+    cs, ce, cv = cA.intervals_soa()
+    assert np.array_equal(gs, cs) and np.array_equal(ge, ce) and np.array_equal(gp, cv)
+    assert np.array_equal(A.stops, cA.stops) and A.max_len == cA.max_len and A.overlaps_merged
+    _assert_same_queries(A, cA, qs, qe)
+    A.merge_overlaps(), cA.merge_overlaps()  # again, on the merged set (which may still hold inverted runs)
+    assert np.array_equal(A.intervals_soa()[0], cA.intervals_soa()[0]) and np.array_equal(A.intervals_soa()[1], cA.intervals_soa()[1])
+    _assert_same_queries(A, cA, qs, qe)
 
 
 def test_seek_cursor_protocol(oracle):

@@ -168,7 +168,7 @@ def test_coordinates_at_the_ends_of_u64(oracle64):
 
 
 def test_inverted_intervals_u64(oracle64):
-    """count and find have no precondition on the intervals (src/lib.rs:610-639); cov / merge / union refuse"""
+    """count, find and merge_overlaps have no precondition on the intervals (src/lib.rs:361-416, :610-639); cov / union refuse"""
     from rust_lapper_b200 import Lapper64, LapperError, _ffi
 
     rng = np.random.default_rng(3)
@@ -179,10 +179,16 @@ def test_inverted_intervals_u64(oracle64):
     assert gpu.has_inverted
     qs = rng.integers(0, 1 << 42, 20_000, dtype=np.uint64)
     _same(gpu, cpu, qs, qs + rng.integers(0, 1 << 29, qs.size, dtype=np.uint64))
-    for call in (gpu.cov, gpu.merge_overlaps):
-        with pytest.raises(LapperError) as ei:
-            call()
-        assert ei.value.code == _ffi.ERR_PRECONDITION
+    with pytest.raises(LapperError) as ei:
+        gpu.cov()
+    assert ei.value.code == _ffi.ERR_PRECONDITION
+    # merge_overlaps follows the reference's loop (comparisons only) on such sets
+    gpu.merge_overlaps(), cpu.merge_overlaps()
+    gs, ge, gp = gpu.intervals_soa()
+    cs, ce, cv = cpu.intervals_soa()
+    assert np.array_equal(gs, cs) and np.array_equal(ge, ce) and np.array_equal(gp, cv)
+    assert np.array_equal(gpu.stops, cpu.stops) and gpu.max_len == cpu.max_len
+    _same(gpu, cpu, qs, qs + rng.integers(0, 1 << 29, qs.size, dtype=np.uint64))
 
 
 def test_empty_u64():
