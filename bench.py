@@ -1100,6 +1100,23 @@ def run_extras(cx, n, nq):
     out["count_sorted_queries"] = {"queries_per_s": nq / (ms * 1e-3), "ms": ms, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
     del qs, qe
 
+    # longer reads, random order: the default packed table (margin for 150-bp queries) and the table after
+    # lapper_tune_query_length (margin covering the announced length); the handle is tuned back afterwards
+    longer = {}
+    for ql in (250, 400):
+        lq_s, lq_e = synth.queries_fixed_len(SEED_Q + ql, nq, UNIVERSE, ql, device=dev)
+        ms_d = timed(lambda: _ffi.check(lib.lapper_count_batch_u32_dev(h, _vp(lq_s), _vp(lq_e), nq, _vp(counts), sp)), 5)
+        sum_d = int(counts.to(torch.int64).sum().item())
+        _ffi.check(lib.lapper_tune_query_length(h, ql))
+        ms_t = timed(lambda: _ffi.check(lib.lapper_count_batch_u32_dev(h, _vp(lq_s), _vp(lq_e), nq, _vp(counts), sp)), 5)
+        sum_t = int(counts.to(torch.int64).sum().item())
+        _ffi.check(lib.lapper_tune_query_length(h, 0))
+        longer[f"{ql}bp"] = {"default_table_ms": ms_d, "tuned_table_ms": ms_t, "tuned_queries_per_s": nq / (ms_t * 1e-3),
+                             "same_counts": sum_d == sum_t}
+        del lq_s, lq_e
+    out["count_random_longer_queries"] = dict(longer, note="lapper_tune_query_length(h, len): the packed count table rebuilt with a "
+                                              "margin that covers the announced query length; 100 M random-order queries per launch")
+
     # variant C: random-order queries INCLUDING an on-device sort by start, the count
     # on the sorted order, and the un-permute of the results.  The sort here is torch.sort (a library call) used
     # only to quantify this alternative -- the engine itself never pre-sorts, because this is slower than

@@ -63,6 +63,7 @@ struct Abi<uint32_t> {
         return lapper_union_and_intersect(a, b, u, i);
     }
     static int depth(const handle *h, uint64_t *n, uint32_t **s, uint32_t **e, uint32_t **d) { return lapper_depth(h, n, s, e, d); }
+    static int tune_query_length(handle *h, uint32_t len) { return lapper_tune_query_length(h, len); }
 };
 template <>
 struct Abi<uint64_t> {
@@ -90,6 +91,7 @@ struct Abi<uint64_t> {
         return lapper64_union_and_intersect(a, b, u, i);
     }
     static int depth(const handle *h, uint64_t *n, uint64_t **s, uint64_t **e, uint32_t **d) { return lapper64_depth(h, n, s, e, d); }
+    static int tune_query_length(handle *h, uint32_t len) { return lapper64_tune_query_length(h, len); }
 };
 }  // namespace detail
 
@@ -143,6 +145,9 @@ class Lapper {
     const typename A::handle *handle() const { return h_; }
     typename std::vector<Iv>::const_iterator begin() const { return intervals.begin(); }  // iter(), :353-359
     typename std::vector<Iv>::const_iterator end() const { return intervals.end(); }
+
+    // optional: announce the typical query length (stop - start) so that the packed count table's margin covers it
+    void tune_query_length(uint32_t typical_query_len) { check(A::tune_query_length(h_, typical_query_len)); }
 
     // batch entry points
     std::vector<uint64_t> count_batch(const std::vector<I> &qs, const std::vector<I> &qe) const {

@@ -71,6 +71,7 @@ SIGNATURES = {
     "lapper_bucket_shift": (_u32, [_vp]),
     "lapper_index_bytes": (_u64, [_vp]),
     "lapper_packed_table_info": (_int, [_vp, C.POINTER(_u32), C.POINTER(_u64), C.POINTER(_u64)]),
+    "lapper_tune_query_length": (_int, [_vp, _u32]),
     "lapper_get_intervals": (_int, [_vp, _vp, _vp, _vp]),
     "lapper_get_starts": (_int, [_vp, _vp]),
     "lapper_get_stops": (_int, [_vp, _vp]),
@@ -134,6 +135,7 @@ SIGNATURES = {
     "lapper64_seek_cursor": (_int, [_vp, _u64, C.POINTER(_u64)]),
     "lapper64_depth": (_int, [_vp, C.POINTER(_u64), _pvp, _pvp, _pvp]),
     "lapper64_is_narrow": (_int, [_vp]),
+    "lapper64_tune_query_length": (_int, [_vp, _u32]),
     "lapper64_debug_set_narrow_mode": (_int, [_int]),
     "lapper_host_free_pinned": (None, [_vp]),
 }

@@ -134,6 +134,7 @@ struct IndexBuilder {
     }
     // replaces l's index (the old arrays are returned to the pool in stream order)
     void commit(lapper_t *l) {
+        ix.query_len_hint = l->ix.query_len_hint;  // (the announced query length outlives merge_overlaps / insert)
         free_index(l->ix, stream);
         l->ix = ix;
         l->tables_flag.store(ix.tables_ready, std::memory_order_release);
@@ -864,6 +865,17 @@ int lapper_merge_overlaps(lapper_t *l) {
     });
 }
 
+int lapper_tune_query_length(lapper_t *l, uint32_t typical_query_len) {
+    return guarded([&] {
+        check_handle(l);
+        DeviceGuard dg(l->device);
+        StreamOwner st;
+        l->ix.query_len_hint = typical_query_len;
+        rebuild_packed_table(l->ix, l->build_flags, st.s);  // (not built yet -- after merge / insert: the lazy build reads the hint)
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
+    });
+}
+
 int lapper_cov(const lapper_t *l, uint32_t *cov_out) {
     return guarded([&] {
         check_handle(l);
@@ -998,6 +1010,13 @@ int lapper_replicate(const lapper_t *l, const int *devices, int g, lapper_group_
                 rep->cov_is_some = l->cov_is_some;
                 rep->cov = l->cov;
                 rep->next_input_id = l->next_input_id;
+                if (l->ix.query_len_hint) {
+                    rc = lapper_tune_query_length(rep, l->ix.query_len_hint);
+                    if (rc != LAPPER_OK) {
+                        lapper_free(rep);
+                        throw Error(rc, g_last_error);
+                    }
+                }
                 grp->replicas.push_back(rep);
             }
         } catch (...) {

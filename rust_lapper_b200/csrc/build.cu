@@ -379,10 +379,15 @@ bool choose_shift(uint64_t n, uint32_t max_coord, uint32_t flags, uint32_t &shif
 //     smaller), or neither does and the packed table saves second DRAM accesses (its margin covers longer queries
 //     than the sector table's w / 4).
 constexpr uint32_t kDenseMinMargin = 160;
+constexpr uint32_t kQueryLenHintMax = 640;  // longer queries leave too few lanes for the bucket itself: default margin
 bool choose_dense_shape(uint64_t n, uint32_t max_coord, uint32_t flags, uint64_t sector_table_bytes, uint32_t sector_margin,
-                        uint32_t &w_out, uint32_t &m_out) {
+                        uint32_t query_len_hint, uint32_t &w_out, uint32_t &m_out) {
     if (flags & LAPPER_BUILD_NO_DENSE) return false;
     uint32_t min_margin = kDenseMinMargin;
+    // a caller that announced its query length (lapper_tune_query_length) gets a margin that covers it: measured at
+    // the cfg-2 shape, random order, per 100 M queries: 250 bp 0.942 -> 0.740 ms, 400 bp 1.345 -> 0.839 ms (and 150 bp
+    // 0.688 -> 0.743 / 0.837 ms with those wider margins, which is why the default stays where it is)
+    if (query_len_hint && query_len_hint <= kQueryLenHintMax) min_margin = std::max(min_margin, query_len_hint + 20);
     if (const char *env = std::getenv("LAPPER_DENSE_MIN_MARGIN")) min_margin = (uint32_t)atoi(env);  // experiments
     const auto margin_for = [&](uint32_t w) { return std::min(std::max(w / 8, std::min(min_margin, (3 * w) / 4)), 2047u - w); };
     const uint32_t forced = (flags >> 16) & 0xFFFu;
@@ -590,6 +595,41 @@ void finish_index_core(DeviceIndex &ix, cudaStream_t stream) {
     ix.max_coord = std::max(ix.stats.last_start, ix.stats.last_stop);
 }
 
+// the packed count table next to an existing sector table (ix.buckets): shape from choose_dense_shape
+static void build_packed_table(DeviceIndex &ix, uint32_t flags, cudaStream_t stream) {
+    uint32_t dw = 0, dm = 0;
+    if (!choose_dense_shape(ix.n, ix.max_coord, flags, (ix.nbuckets + 1 + ix.npool) * sizeof(Sector), ix.margin, ix.query_len_hint, dw, dm))
+        return;
+    Scratch<unsigned long long> d_over(1, stream);
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(d_over.p, 0, 8, stream));
+    const PackedParams pp = packed_params(dw, ix.max_coord, dm);
+    ix.dense_w = pp.w;
+    ix.dense_m = pp.m;
+    ix.dense_magic = pp.magic;
+    ix.dense_nb = pp.nb;
+    ix.dense = pool_alloc<Sector>(ix.dense_nb + 1, ix.bytes, stream);
+    fill_dense_kernel<<<grid_for(ix.dense_nb + 1), kThreads, 0, stream>>>(ix.starts, ix.stops_sorted, (uint32_t)ix.n, pp, ix.dense, d_over.p);
+    LAPPER_CUDA_CHECK(cudaGetLastError());
+    unsigned long long nover = 0;
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(&nover, d_over.p, 8, cudaMemcpyDeviceToHost, stream));
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+    ix.dense_overflow = nover;
+}
+
+void rebuild_packed_table(DeviceIndex &ix, uint32_t flags, cudaStream_t stream) {
+    if (!ix.tables_ready || !ix.buckets || ix.n == 0) return;  // (tables not built yet: build_query_tables will read the hint)
+    if (ix.dense) {
+        ix.bytes -= (ix.dense_nb + 1) * sizeof(Sector);
+        pool_free(ix.dense, stream);
+    }
+    ix.dense = nullptr;
+    ix.dense_nb = 0;
+    ix.dense_w = ix.dense_m = ix.dense_magic = 0;
+    ix.dense_overflow = 0;
+    build_packed_table(ix, flags, stream);
+    LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
 void build_query_tables(DeviceIndex &ix, uint32_t flags, cudaStream_t stream) {
     const uint64_t n = ix.n;
     if (ix.tables_ready) return;
@@ -635,22 +675,7 @@ void build_query_tables(DeviceIndex &ix, uint32_t flags, cudaStream_t stream) {
                     ix.starts, ix.stops_sorted, (uint32_t)n, shift, ix.nbuckets, ix.buckets, ix.pool);
                 LAPPER_CUDA_CHECK(cudaGetLastError());
             }
-            uint32_t dw = 0, dm = 0;
-            if (choose_dense_shape(n, ix.max_coord, flags, (ix.nbuckets + 1 + ix.npool) * sizeof(Sector), ix.margin, dw, dm)) {
-                const PackedParams pp = packed_params(dw, ix.max_coord, dm);
-                ix.dense_w = pp.w;
-                ix.dense_m = pp.m;
-                ix.dense_magic = pp.magic;
-                ix.dense_nb = pp.nb;
-                ix.dense = pool_alloc<Sector>(ix.dense_nb + 1, ix.bytes, stream);
-                fill_dense_kernel<<<grid_for(ix.dense_nb + 1), kThreads, 0, stream>>>(
-                    ix.starts, ix.stops_sorted, (uint32_t)n, pp, ix.dense, d_counters.p + 1);
-                LAPPER_CUDA_CHECK(cudaGetLastError());
-                unsigned long long nover = 0;
-                LAPPER_CUDA_CHECK(cudaMemcpyAsync(&nover, d_counters.p + 1, 8, cudaMemcpyDeviceToHost, stream));
-                LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
-                ix.dense_overflow = nover;
-            }
+            build_packed_table(ix, flags, stream);
         }
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));  // the tables are complete when tables_ready says so
         ix.tables_ready = true;

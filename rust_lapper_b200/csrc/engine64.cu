@@ -44,6 +44,7 @@ struct lapper64 {
     uint64_t cov = 0;
     uint64_t next_input_id = 0;  // input position handed to the next inserted interval
     uint64_t max_coord = 0;      // largest start or stop
+    uint32_t query_len_hint = 0; // lapper64_tune_query_length: handed to the u32 engine of a narrowed set
     // The u32 engine over the same sorted intervals (see "narrowing" below): built on the first batch that is worth it
     // when every coordinate fits, dropped by insert / merge_overlaps.
     mutable std::atomic<lapper_t *> narrow{nullptr};
@@ -717,6 +718,11 @@ lapper_t *narrow_of(const lapper64 *l, uint64_t nq, cudaStream_t stream) {
         LAPPER_CUDA_CHECK(cudaGetLastError());
         const int rc = lapper_from_sorted_dev(s.p, eiv.p, e.p, l->perm, l->n, l->overlaps_merged ? 1 : 0, l->device, 0, stream, &h);
         if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
+        if (l->query_len_hint && lapper_tune_query_length(h, l->query_len_hint) != LAPPER_OK) {
+            lapper_free(h);
+            h = nullptr;
+            throw Error(LAPPER_ERR_OOM, last_error_slot());
+        }
     } catch (const Error &err) {
         if (err.code != LAPPER_ERR_OOM) throw;
         cudaGetLastError();
@@ -1190,6 +1196,18 @@ int lapper64_depth(const lapper64_t *l, uint64_t *n_out, uint64_t **starts_out, 
         }
         *n_out = nr;
         *starts_out = hs, *stops_out = he, *depth_out = hd;  // freed with lapper_host_free
+    });
+}
+
+/* lapper_tune_query_length for a u64 handle: takes effect where the u32 engine answers (narrowed sets) */
+int lapper64_tune_query_length(lapper64_t *l, uint32_t typical_query_len) {
+    return guarded_call([&] {
+        check64(l);
+        l->query_len_hint = typical_query_len;
+        if (lapper_t *h = l->narrow.load(std::memory_order_acquire)) {
+            const int rc = lapper_tune_query_length(h, typical_query_len);
+            if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
+        }
     });
 }
 

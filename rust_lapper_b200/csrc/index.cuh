@@ -72,6 +72,7 @@ struct DeviceIndex {
     uint32_t dense_w = 0, dense_m = 0;
     uint32_t dense_magic = 0;  // ceil(2^32 / dense_w)
     uint64_t dense_overflow = 0;  // sectors that did not fit (their queries fall back)
+    uint32_t query_len_hint = 0;  // typical query length the caller announced (lapper_tune_query_length): the packed table's margin covers it
     uint32_t shift = 0xFFFFFFFFu;
     uint32_t max_len = 0;
     uint32_t max_coord = 0;
@@ -146,6 +147,8 @@ void build_index_from_unsorted(DeviceIndex &ix, const uint32_t *d_starts, const 
 // packed table); sets ix.tables_ready.
 void finish_index_core(DeviceIndex &ix, cudaStream_t stream);
 void build_query_tables(DeviceIndex &ix, uint32_t flags, cudaStream_t stream);
+// (re)builds the packed count table alone, for the current ix.query_len_hint (the other tables must exist)
+void rebuild_packed_table(DeviceIndex &ix, uint32_t flags, cudaStream_t stream);
 // every array of the index goes back to the library pool, stream-ordered on `stream`
 void free_index(DeviceIndex &ix, cudaStream_t stream);
 // index memory: stream-ordered allocations from the library pool (common.cuh) -- a rebuilt index reuses the

@@ -125,6 +125,11 @@ class Lapper:
         k = int(self._lib.lapper_bucket_shift(self._h))
         return None if k == 0xFFFFFFFF else k
 
+    def tune_query_length(self, typical_query_len: int) -> None:
+        """Announce the typical query length (stop - start): the packed count table is rebuilt with a margin that covers
+        it (faster random-order `count` for queries longer than 150-bp reads; results never change)."""
+        _ffi.check(self._lib.lapper_tune_query_length(self._h, int(typical_query_len)))
+
     @property
     def packed_table(self) -> Optional[Tuple[int, int, int]]:
         """(bucket width, sectors, overflowed sectors) of the packed table, None when it was not built."""

@@ -79,6 +79,10 @@ class Lapper64:
     def overlaps_merged(self) -> bool:
         return bool(self._lib.lapper64_overlaps_merged(self._h))
 
+    def tune_query_length(self, typical_query_len: int) -> None:
+        """see Lapper.tune_query_length; takes effect where the u32 engine answers (coordinates that fit 32 bits)"""
+        _ffi.check(self._lib.lapper64_tune_query_length(self._h, int(typical_query_len)))
+
     @property
     def is_narrow(self) -> bool:
         """True once this handle's batches are answered by the u32 engine (every coordinate fits 32 bits)."""

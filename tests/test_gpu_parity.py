@@ -680,3 +680,40 @@ def test_find_batch_guesses_the_result_size_from_the_previous_batch(oracle):
         go, gi = gpu.find_batch(qs, qe)
         co, ci = cpu.find_batch(qs, qe, 4)
         assert np.array_equal(go, co) and np.array_equal(gi, ci)
+
+
+@pytest.mark.parametrize("qlen", [250, 400, 640, 5000])
+def test_tune_query_length_changes_the_table_not_the_answers(oracle, qlen):
+    """lapper_tune_query_length: the packed table is rebuilt with a margin that covers the announced query length
+    (a hint beyond 640 keeps the default margin); counts and CSR stay those of the oracle; the setting survives
+    merge_overlaps and insert and is copied to replicas"""
+    from rust_lapper_b200 import Lapper, LapperGroup, synth
+
+    s, e = synth.intervals_uniform(5, 400_000, 120_000_000, 50, 5000)
+    gpu = Lapper(starts=s, stops=e, flags=8)  # (the packed table is only built next to large sector tables: force it)
+    cpu = oracle.OracleLapper(starts=s, stops=e)
+    before = gpu.packed_table
+    rng = np.random.default_rng(qlen)
+    qs = rng.integers(0, 120_000_000, 300_000).astype(np.uint32)
+    qe = qs + rng.integers(max(1, qlen - 30), qlen + 1, qs.size).astype(np.uint32)
+    want = cpu.count_batch(qs, qe, 8)
+    assert np.array_equal(gpu.count_batch(qs, qe), want)
+    gpu.tune_query_length(qlen)
+    after = gpu.packed_table
+    assert after is not None
+    if qlen <= 640:
+        assert after[0] < before[0], "a wider margin leaves a narrower bucket"
+    else:
+        assert after == before
+    assert np.array_equal(gpu.count_batch(qs, qe), want)
+    o = np.argsort(qs, kind="stable")
+    _assert_same_queries(gpu, cpu, qs[o][:50_000], qe[o][:50_000])
+    grp = LapperGroup(gpu, [0, 0])
+    assert np.array_equal(grp.count_batch(qs, qe), want)
+    grp.close()
+    gpu.insert(77, 99), cpu.insert(77, 99, len(s))
+    assert np.array_equal(gpu.count_batch(qs, qe), cpu.count_batch(qs, qe, 8))
+    if qlen <= 640:
+        assert gpu.packed_table[0] < before[0], "the tables rebuilt after insert keep the announced length"
+    gpu.merge_overlaps(), cpu.merge_overlaps()
+    assert np.array_equal(gpu.count_batch(qs, qe), cpu.count_batch(qs, qe, 8))
