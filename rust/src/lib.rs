@@ -40,6 +40,7 @@ extern "C" {
                                   indices: *mut u32, capacity: u64, total: *mut u64) -> c_int;
     fn lapper_get_cached_state(l: *const LapperHandle, cov_is_some: *mut c_int, cov: *mut u32, overlaps_merged: *mut c_int) -> c_int;
     fn lapper_restore_cached_state(l: *mut LapperHandle, cov_is_some: c_int, cov: u32, overlaps_merged: c_int) -> c_int;
+    fn lapper_tune_query_length(l: *mut LapperHandle, typical_query_len: u32) -> c_int;
 }
 
 fn check(rc: c_int) {
@@ -86,6 +87,9 @@ impl<T: Eq + Clone + Send + Sync> Lapper<T> {
         check(unsafe { lapper_get_intervals(self.h, s.as_mut_ptr(), e.as_mut_ptr(), p.as_mut_ptr()) });
         self.intervals = (0..n).map(|i| Interval { start: s[i], stop: e[i], val: self.input[p[i] as usize].val.clone() }).collect();
     }
+    /// Not in the reference: announce the typical query length so that random-order `count` stays on its
+    /// one-sector path for reads longer than 150 bp (results never change).
+    pub fn tune_query_length(&mut self, typical_query_len: u32) { check(unsafe { lapper_tune_query_length(self.h, typical_query_len) }) }
     pub fn len(&self) -> usize { self.intervals.len() }
     pub fn is_empty(&self) -> bool { self.intervals.is_empty() }
     pub fn max_len(&self) -> u32 { unsafe { lapper_max_len(self.h) } }
