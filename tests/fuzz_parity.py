@@ -129,6 +129,10 @@ def check_case(rng, bits, case_id, verbose=False):
             raise
         cpu = lapper_oracle.OracleLapper(starts=s.astype(np.uint32), stops=e.astype(np.uint32))
         qs, qe = qs.astype(np.uint32), qe.astype(np.uint32)
+        if rng.random() < 0.2:  # an announced query length reshapes the packed table, never the answers
+            ql = int(rng.choice([0, 1, 37, 150, 300, 640, 641, 5000]))
+            gpu.tune_query_length(ql)
+            desc += f" tuned={ql}"
     else:
         # which engine answers a u64 set whose coordinates fit 32 bits: the 64-bit kernels, the default policy (u32
         # engine from the first large batch on), or the u32 engine from the start
