@@ -1100,6 +1100,27 @@ def run_extras(cx, n, nq):
     out["count_sorted_queries"] = {"queries_per_s": nq / (ms * 1e-3), "ms": ms, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
     del qs, qe
 
+    # the headline batch from PAGEABLE host arrays (what a Vec<u32> / numpy caller passes): the library stages it through
+    # its own pinned buffers with a few copy threads (api.cu count_host_staged)
+    import numpy as np
+
+    pq_s, pq_e = synth.queries_fixed_len(SEED_Q, nq, UNIVERSE, QLEN)  # numpy, pageable
+    p_out = np.zeros(nq, np.uint32)
+    npp = lambda a: a.ctypes.data_as(C.c_void_p)  # noqa: E731
+    _ffi.check(lib.lapper_count_batch_u32_c32(h, npp(pq_s), npp(pq_e), nq, npp(p_out)))
+    t0 = time.perf_counter()
+    for _ in range(2):
+        _ffi.check(lib.lapper_count_batch_u32_c32(h, npp(pq_s), npp(pq_e), nq, npp(p_out)))
+    pg_s = (time.perf_counter() - t0) / 2
+    out["e2e_pageable_host_buffers"] = {
+        "ms": 1e3 * pg_s, "queries_per_s": nq / pg_s, "counts_sum": int(p_out.sum(dtype=np.uint64)),
+        "equals_headline_checksum": int(p_out.sum(dtype=np.uint64)) == cx.headline_checksum,
+        "copy_threads": int(os.environ.get("LAPPER_HOST_COPY_THREADS", 4)),
+        "note": "lapper_count_batch_u32_c32 with unpinned numpy arrays; the driver's own pageable path (LAPPER_HOST_COPY_THREADS=0) "
+                "takes 94 ms for the same call on the bench boxes, pinned buffers 17 ms (the `e2e` block)",
+    }
+    del pq_s, pq_e, p_out
+
     # longer reads, random order: the default packed table (margin for 150-bp queries) and the table after
     # lapper_tune_query_length (margin covering the announced length); the handle is tuned back afterwards
     longer = {}

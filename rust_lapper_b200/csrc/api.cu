@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
@@ -142,6 +143,138 @@ struct IndexBuilder {
     }
 };
 
+// ---- pageable callers.  A Vec<u32> / numpy array / std::vector is pageable memory: cudaMemcpyAsync from it runs at
+// 11 GB/s in and 22 GB/s out on the bench boxes (the driver stages it through its own small pinned buffers, one
+// thread), against 55 GB/s for pinned memory (tools/mb_pageable.py).  For large batches the library does the staging
+// itself: pinned staging buffers (cached for the life of the process), filled and drained by a few host threads
+// (memcpy at ~15 GB/s each), with the copies of chunk k+1 and k-1 running beside the kernel of chunk k.
+bool host_pointer_is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+int host_copy_threads() {
+    static const int n = [] {
+        const char *e = std::getenv("LAPPER_HOST_COPY_THREADS");
+        const int hw = (int)std::thread::hardware_concurrency();
+        return std::min(std::max(e ? atoi(e) : 4, 0), std::max(hw, 1));  // 0: leave pageable buffers to the driver
+    }();
+    return n;
+}
+
+// memcpy in host_copy_threads() slices (the calling thread takes the last one)
+void parallel_memcpy(void *dst, const void *src, size_t bytes) {
+    const int nt = bytes < (4u << 20) ? 1 : host_copy_threads();
+    if (nt <= 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t slice = ((bytes / nt) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    th.reserve(nt - 1);
+    size_t off = 0;
+    for (int i = 0; i < nt - 1 && off + slice < bytes; i++, off += slice)
+        th.emplace_back([=] { std::memcpy((char *)dst + off, (const char *)src + off, slice); });
+    std::memcpy((char *)dst + off, (const char *)src + off, bytes - off);
+    for (auto &x : th) x.join();
+}
+
+// pinned staging buffers, kept for the life of the process (cudaHostAlloc pins pages at a few GB/s: not per call)
+struct PinnedCache {
+    std::mutex mu;
+    std::vector<std::pair<void *, size_t>> free_list;
+    void *get(size_t bytes, size_t &got) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            for (size_t i = 0; i < free_list.size(); i++)
+                if (free_list[i].second >= bytes) {
+                    void *p = free_list[i].first;
+                    got = free_list[i].second;
+                    free_list.erase(free_list.begin() + i);
+                    return p;
+                }
+        }
+        void *p = nullptr;
+        LAPPER_CUDA_CHECK(cudaHostAlloc(&p, bytes, cudaHostAllocPortable));
+        got = bytes;
+        return p;
+    }
+    void put(void *p, size_t bytes) {
+        std::lock_guard<std::mutex> g(mu);
+        free_list.emplace_back(p, bytes);
+    }
+};
+PinnedCache &pinned_cache() {
+    static PinnedCache *c = new PinnedCache();  // (never destroyed: the driver may be gone at static destruction time)
+    return *c;
+}
+struct PinnedBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+    PinnedBuf() = default;
+    explicit PinnedBuf(size_t n) { p = pinned_cache().get(n, bytes); }
+    ~PinnedBuf() {
+        if (p) pinned_cache().put(p, bytes);
+    }
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    PinnedBuf(PinnedBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; }
+};
+
+constexpr uint64_t kStagedMinQueries = 4ull << 20;  // below this the driver's own pageable path is as good
+
+// count_host for pageable buffers: chunks of 4 M queries, three slots; per chunk the host threads copy the queries into
+// the slot's pinned buffers, the stream does H2D | count | D2H into the slot's pinned output, and the counts of the
+// chunk that used the slot before are copied out to the caller first.
+template <typename OutT>
+void count_host_staged(const lapper_t *l, const uint32_t *qs, const uint32_t *qe, uint64_t nq, OutT *out) {
+    constexpr int kSlots = 3;
+    const uint64_t chunk = std::min<uint64_t>(nq, 1ull << 22);
+    const int used = (int)std::min<uint64_t>(kSlots, div_up(nq, chunk));
+    StreamOwner st[kSlots];
+    ensure_tables(l, st[0].s);
+    Scratch<uint32_t> d_qs[kSlots], d_qe[kSlots];
+    Scratch<OutT> d_out[kSlots];
+    std::vector<PinnedBuf> h_qs, h_qe, h_out;
+    uint64_t pending_lo[kSlots] = {}, pending_m[kSlots] = {};  // the chunk whose counts sit in the slot's pinned output
+    for (int s = 0; s < used; s++) {
+        d_qs[s].alloc(chunk, st[s].s), d_qe[s].alloc(chunk, st[s].s), d_out[s].alloc(chunk, st[s].s);
+        h_qs.emplace_back(chunk * 4), h_qe.emplace_back(chunk * 4), h_out.emplace_back(chunk * sizeof(OutT));
+    }
+    const auto drain = [&](int s) {
+        if (!pending_m[s]) return;
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st[s].s));
+        parallel_memcpy(out + pending_lo[s], h_out[s].p, pending_m[s] * sizeof(OutT));
+        pending_m[s] = 0;
+    };
+    uint64_t done = 0;
+    for (int i = 0; done < nq; i++) {
+        const int s = i % kSlots;
+        const uint64_t m = std::min(chunk, nq - done);
+        drain(s);  // (also: the slot's H2D of its previous chunk has finished, its pinned inputs are free)
+        parallel_memcpy(h_qs[s].p, qs + done, m * 4);
+        parallel_memcpy(h_qe[s].p, qe + done, m * 4);
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(d_qs[s].p, h_qs[s].p, m * 4, cudaMemcpyHostToDevice, st[s].s));
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(d_qe[s].p, h_qe[s].p, m * 4, cudaMemcpyHostToDevice, st[s].s));
+        if (sizeof(OutT) == 8)
+            launch_count(l->ix, d_qs[s].p, d_qe[s].p, m, nullptr, reinterpret_cast<uint64_t *>(d_out[s].p), st[s].s);
+        else
+            launch_count(l->ix, d_qs[s].p, d_qe[s].p, m, reinterpret_cast<uint32_t *>(d_out[s].p), nullptr, st[s].s);
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(h_out[s].p, d_out[s].p, m * sizeof(OutT), cudaMemcpyDeviceToHost, st[s].s));
+        pending_lo[s] = done, pending_m[s] = m;
+        done += m;
+    }
+    for (int k = 0; k < kSlots; k++) drain((int)((div_up(nq, chunk) + k) % kSlots));  // oldest chunk first; empty slots are no-ops
+    for (int s = 0; s < used; s++) {
+        d_qs[s].release(), d_qe[s].release(), d_out[s].release();
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st[s].s));
+    }
+}
+
 // chunked host <-> device pipeline for count: three slots, each its own stream, so the H2D of chunk
 // i+1, the kernel of chunk i and the D2H of chunk i-1 overlap (PCIe is full duplex).
 template <typename OutT>
@@ -150,6 +283,10 @@ void count_host(const lapper_t *l, const uint32_t *qs, const uint32_t *qe, uint6
     if (nq == 0) return;
     LAPPER_REQUIRE(qs && qe && out, "count_batch: null pointer");
     DeviceGuard dg(l->device);
+    if (nq >= kStagedMinQueries && host_copy_threads() > 0 && !(host_pointer_is_pinned(qs) && host_pointer_is_pinned(qe) && host_pointer_is_pinned(out))) {
+        count_host_staged<OutT>(l, qs, qe, nq, out);
+        return;
+    }
     constexpr int kSlots = 3;
     // 8 M queries per chunk: measured best of 2^20 .. 2^25 (20.0 / 18.0 / 17.1 / 16.8 / 17.0 / 18.0 ms per 100 M queries)
     const uint64_t chunk = std::min<uint64_t>(nq, 1ull << 23);

@@ -717,3 +717,20 @@ def test_tune_query_length_changes_the_table_not_the_answers(oracle, qlen):
         assert gpu.packed_table[0] < before[0], "the tables rebuilt after insert keep the announced length"
     gpu.merge_overlaps(), cpu.merge_overlaps()
     assert np.array_equal(gpu.count_batch(qs, qe), cpu.count_batch(qs, qe, 8))
+
+
+@pytest.mark.parametrize("nq", [(4 << 20), (4 << 20) + 1, 13_000_003])
+def test_host_count_from_pageable_arrays_staged(oracle, nq):
+    """count_batch from pageable host arrays (numpy, Vec<u32>) of >= 4 Mi queries goes through the library's own pinned
+    staging buffers and copy threads (api.cu count_host_staged): same counts, u64 and u32 outputs, ragged last chunk"""
+    from rust_lapper_b200 import synth
+
+    s, e = synth.intervals_uniform(9, 200_000, 80_000_000, 50, 5000)
+    gpu, cpu = _both(oracle, s, e)
+    rng = np.random.default_rng(nq & 0xFFFF)
+    qs = rng.integers(0, 80_000_000, nq, dtype=np.uint64).astype(np.uint32)
+    qe = qs + rng.integers(0, 300, nq).astype(np.uint32)
+    want = cpu.count_batch(qs, qe, 8)
+    assert np.array_equal(gpu.count_batch(qs, qe), want)
+    assert np.array_equal(gpu.count_batch_c32(qs, qe), want.astype(np.uint32))
+    assert np.array_equal(gpu.count_batch(qs, qe), want)  # again: the staging buffers come back from the cache
