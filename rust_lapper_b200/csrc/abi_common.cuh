@@ -10,6 +10,11 @@
 namespace lap {
 
 std::string &last_error_slot();  // api.cu: the calling thread's last error text
+// api.cu: copies between device memory and (possibly pageable) host memory; large pageable transfers are staged through
+// the library's pinned buffers by copy threads.  copy_to_host is synchronous; copy_to_device is stream-ordered for
+// pinned / small sources and returns after the data has left the caller's memory either way.
+void copy_to_host(void *h_dst, const void *d_src, size_t bytes);
+void copy_to_device(void *d_dst, const void *h_src, size_t bytes, cudaStream_t stream);
 void require_device_index(int device);  // api.cu: throws LAPPER_ERR_NO_DEVICE / LAPPER_ERR_INVALID_ARG
 
 template <typename F>

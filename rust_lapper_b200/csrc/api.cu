@@ -225,6 +225,57 @@ struct PinnedBuf {
     PinnedBuf(PinnedBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; }
 };
 
+}  // namespace
+namespace lap {
+// One-directional copies between device memory and PAGEABLE host memory, staged through two pinned buffers: while the
+// copy threads move piece k between the caller's memory and one buffer, the DMA engine moves piece k+1 through the
+// other.  Synchronous (returns when the data is in place); small or pinned transfers take plain cudaMemcpy.
+constexpr size_t kStagePiece = 32u << 20;
+void copy_to_host(void *h_dst, const void *d_src, size_t bytes) {
+    if (bytes < 2 * kStagePiece || host_copy_threads() == 0 || host_pointer_is_pinned(h_dst)) {
+        LAPPER_CUDA_CHECK(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+        return;
+    }
+    StreamOwner st;
+    PinnedBuf buf[2] = {PinnedBuf(kStagePiece), PinnedBuf(kStagePiece)};
+    const size_t npieces = (bytes + kStagePiece - 1) / kStagePiece;
+    const auto piece_bytes = [&](size_t k) { return std::min(kStagePiece, bytes - k * kStagePiece); };
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(buf[0].p, d_src, piece_bytes(0), cudaMemcpyDeviceToHost, st.s));
+    for (size_t k = 0; k < npieces; k++) {
+        LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));  // piece k has arrived in buf[k & 1]
+        if (k + 1 < npieces)
+            LAPPER_CUDA_CHECK(cudaMemcpyAsync(buf[(k + 1) & 1].p, (const char *)d_src + (k + 1) * kStagePiece, piece_bytes(k + 1),
+                                              cudaMemcpyDeviceToHost, st.s));
+        parallel_memcpy((char *)h_dst + k * kStagePiece, buf[k & 1].p, piece_bytes(k));
+    }
+}
+void copy_to_device(void *d_dst, const void *h_src, size_t bytes, cudaStream_t stream) {
+    if (bytes < 2 * kStagePiece || host_copy_threads() == 0 || host_pointer_is_pinned(h_src)) {
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, stream));
+        return;
+    }
+    PinnedBuf buf[2] = {PinnedBuf(kStagePiece), PinnedBuf(kStagePiece)};
+    cudaEvent_t done[2];
+    LAPPER_CUDA_CHECK(cudaEventCreateWithFlags(&done[0], cudaEventDisableTiming));
+    LAPPER_CUDA_CHECK(cudaEventCreateWithFlags(&done[1], cudaEventDisableTiming));
+    const size_t npieces = (bytes + kStagePiece - 1) / kStagePiece;
+    cudaError_t err = cudaSuccess;
+    for (size_t k = 0; k < npieces && err == cudaSuccess; k++) {
+        const size_t b = std::min(kStagePiece, bytes - k * kStagePiece);
+        if (k >= 2) err = cudaEventSynchronize(done[k & 1]);  // the buffer's previous piece has left it
+        if (err != cudaSuccess) break;
+        parallel_memcpy(buf[k & 1].p, (const char *)h_src + k * kStagePiece, b);
+        err = cudaMemcpyAsync((char *)d_dst + k * kStagePiece, buf[k & 1].p, b, cudaMemcpyHostToDevice, stream);
+        if (err == cudaSuccess) err = cudaEventRecord(done[k & 1], stream);
+    }
+    if (err == cudaSuccess) err = cudaStreamSynchronize(stream);  // the staging buffers go back to the cache on return
+    cudaEventDestroy(done[0]);
+    cudaEventDestroy(done[1]);
+    LAPPER_CUDA_CHECK(err);
+}
+
+}  // namespace lap
+namespace {
 constexpr uint64_t kStagedMinQueries = 4ull << 20;  // below this the driver's own pageable path is as good
 
 // count_host for pageable buffers: chunks of 4 M queries, three slots; per chunk the host threads copy the queries into
@@ -804,8 +855,8 @@ int lapper_find_batch_u32(const lapper_t *l, const uint32_t *q_start, const uint
         StreamOwner st;
         Scratch<uint32_t> d_qs(nq, st.s), d_qe(nq, st.s);
         if (nq) {
-            LAPPER_CUDA_CHECK(cudaMemcpyAsync(d_qs.p, q_start, nq * 4, cudaMemcpyHostToDevice, st.s));
-            LAPPER_CUDA_CHECK(cudaMemcpyAsync(d_qe.p, q_stop, nq * 4, cudaMemcpyHostToDevice, st.s));
+            copy_to_device(d_qs.p, q_start, nq * 4, st.s);
+            copy_to_device(d_qe.p, q_stop, nq * 4, st.s);
         }
         *out = find_on_device(l, d_qs.p, d_qe.p, nq, st.s);
         d_qs.release();
@@ -837,10 +888,9 @@ int lapper_result_copy(const lapper_result_t *r, uint64_t *offsets_out, uint32_t
     return guarded([&] {
         LAPPER_REQUIRE(r, "null result");
         DeviceGuard dg(r->device);
-        if (offsets_out)
-            LAPPER_CUDA_CHECK(cudaMemcpy(offsets_out, r->d_offsets, (r->nq + 1) * 8, cudaMemcpyDeviceToHost));
-        if (indices_out && r->total)
-            LAPPER_CUDA_CHECK(cudaMemcpy(indices_out, r->d_indices, r->total * 4, cudaMemcpyDeviceToHost));
+        // (pageable destinations of some size go through the library's pinned staging buffers: copy_to_host)
+        if (offsets_out) copy_to_host(offsets_out, r->d_offsets, (r->nq + 1) * 8);
+        if (indices_out && r->total) copy_to_host(indices_out, r->d_indices, r->total * 4);
     });
 }
 

@@ -939,8 +939,8 @@ int lapper64_find_batch(const lapper64_t *l, const uint64_t *q_start, const uint
         OwnedStream st;
         Scratch<uint64_t> dqs(nq, st.s), dqe(nq, st.s);
         if (nq) {
-            LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqs.p, q_start, nq * 8, cudaMemcpyHostToDevice, st.s));
-            LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqe.p, q_stop, nq * 8, cudaMemcpyHostToDevice, st.s));
+            copy_to_device(dqs.p, q_start, nq * 8, st.s);
+            copy_to_device(dqe.p, q_stop, nq * 8, st.s);
         }
         if (lapper_t *h = narrow_of(l, nq, st.s)) {
             NarrowQueries q(dqs.p, dqe.p, nq, st.s);

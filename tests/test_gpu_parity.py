@@ -734,3 +734,21 @@ def test_host_count_from_pageable_arrays_staged(oracle, nq):
     assert np.array_equal(gpu.count_batch(qs, qe), want)
     assert np.array_equal(gpu.count_batch_c32(qs, qe), want.astype(np.uint32))
     assert np.array_equal(gpu.count_batch(qs, qe), want)  # again: the staging buffers come back from the cache
+
+
+def test_find_batch_with_pageable_arrays_beyond_the_staging_piece(oracle):
+    """find_batch from / into pageable numpy arrays of more than 64 MB each: the query upload and lapper_result_copy go
+    through the library's pinned staging buffers in 32 MB pieces (api.cu copy_to_device / copy_to_host)"""
+    from rust_lapper_b200 import synth
+
+    s, e = synth.intervals_uniform(11, 100_000, 200_000_000, 500, 4000)
+    gpu, cpu = _both(oracle, s, e)
+    rng = np.random.default_rng(12)
+    nq = 17_000_001
+    qs = np.sort(rng.integers(0, 200_000_000, nq, dtype=np.uint64)).astype(np.uint32)
+    qe = qs + np.uint32(150)
+    go, gi = gpu.find_batch(qs, qe)
+    wo, wi = cpu.find_batch(qs, qe, 8)
+    assert gi.nbytes > (64 << 20) and go.nbytes > (64 << 20)
+    assert np.array_equal(go, wo)
+    assert np.array_equal(gi, wi)
