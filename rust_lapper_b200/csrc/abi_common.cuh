@@ -15,6 +15,20 @@ std::string &last_error_slot();  // api.cu: the calling thread's last error text
 // pinned / small sources and returns after the data has left the caller's memory either way.
 void copy_to_host(void *h_dst, const void *d_src, size_t bytes);
 void copy_to_device(void *d_dst, const void *h_src, size_t bytes, cudaStream_t stream);
+// the pieces of that staging, for the host pipelines that overlap it with kernels (count_host_staged and its u64 twin)
+bool host_pointer_is_pinned(const void *p);
+int host_copy_threads();  // LAPPER_HOST_COPY_THREADS (default 4; 0 = leave pageable buffers to the driver)
+void parallel_memcpy(void *dst, const void *src, size_t bytes);
+struct PinnedBuf {  // a pinned staging buffer from the process-wide cache (returned to it on destruction)
+    void *p = nullptr;
+    size_t bytes = 0;
+    PinnedBuf() = default;
+    explicit PinnedBuf(size_t n);
+    ~PinnedBuf();
+    PinnedBuf(const PinnedBuf &) = delete;
+    PinnedBuf &operator=(const PinnedBuf &) = delete;
+    PinnedBuf(PinnedBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; }
+};
 void require_device_index(int device);  // api.cu: throws LAPPER_ERR_NO_DEVICE / LAPPER_ERR_INVALID_ARG
 
 template <typename F>

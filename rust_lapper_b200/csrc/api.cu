@@ -143,6 +143,8 @@ struct IndexBuilder {
     }
 };
 
+}  // namespace
+namespace lap {
 // ---- pageable callers.  A Vec<u32> / numpy array / std::vector is pageable memory: cudaMemcpyAsync from it runs at
 // 11 GB/s in and 22 GB/s out on the bench boxes (the driver stages it through its own small pinned buffers, one
 // thread), against 55 GB/s for pinned memory (tools/mb_pageable.py).  For large batches the library does the staging
@@ -212,21 +214,11 @@ PinnedCache &pinned_cache() {
     static PinnedCache *c = new PinnedCache();  // (never destroyed: the driver may be gone at static destruction time)
     return *c;
 }
-struct PinnedBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-    PinnedBuf() = default;
-    explicit PinnedBuf(size_t n) { p = pinned_cache().get(n, bytes); }
-    ~PinnedBuf() {
-        if (p) pinned_cache().put(p, bytes);
-    }
-    PinnedBuf(const PinnedBuf &) = delete;
-    PinnedBuf &operator=(const PinnedBuf &) = delete;
-    PinnedBuf(PinnedBuf &&o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; }
-};
+PinnedBuf::PinnedBuf(size_t n) { p = pinned_cache().get(n, bytes); }
+PinnedBuf::~PinnedBuf() {
+    if (p) pinned_cache().put(p, bytes);
+}
 
-}  // namespace
-namespace lap {
 // One-directional copies between device memory and PAGEABLE host memory, staged through two pinned buffers: while the
 // copy threads move piece k between the caller's memory and one buffer, the DMA engine moves piece k+1 through the
 // other.  Synchronous (returns when the data is in place); small or pinned transfers take plain cudaMemcpy.

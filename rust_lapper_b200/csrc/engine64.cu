@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <memory>
 #include <mutex>
+#include <vector>
 
 #include "abi_common.cuh"
 #include "index.cuh"
@@ -877,6 +878,46 @@ int lapper64_count_batch(const lapper64_t *l, const uint64_t *q_start, const uin
         constexpr int kSlots = 3;
         const uint64_t chunk = std::min<uint64_t>(nq, 1ull << 22);
         const int used = (int)std::min<uint64_t>(kSlots, div_up(nq, chunk));
+        if (nq >= (4ull << 20) && host_copy_threads() > 0 &&
+            !(host_pointer_is_pinned(q_start) && host_pointer_is_pinned(q_stop) && host_pointer_is_pinned(counts_out))) {
+            // pageable buffers (a Vec<usize>): the same pipeline through the library's pinned staging buffers, filled and
+            // drained by the copy threads (api.cu count_host_staged is the u32 twin)
+            OwnedStream sst[kSlots];
+            Scratch<uint64_t> dqs[kSlots], dqe[kSlots], dout[kSlots];
+            std::vector<PinnedBuf> hqs, hqe, hout;
+            uint64_t pending_lo[kSlots] = {}, pending_m[kSlots] = {};
+            for (int s = 0; s < used; s++) {
+                dqs[s].alloc(chunk, sst[s].s), dqe[s].alloc(chunk, sst[s].s), dout[s].alloc(chunk, sst[s].s);
+                hqs.emplace_back(chunk * 8), hqe.emplace_back(chunk * 8), hout.emplace_back(chunk * 8);
+            }
+            const auto drain = [&](int s) {
+                if (!pending_m[s]) return;
+                LAPPER_CUDA_CHECK(cudaStreamSynchronize(sst[s].s));
+                parallel_memcpy(counts_out + pending_lo[s], hout[s].p, pending_m[s] * 8);
+                pending_m[s] = 0;
+            };
+            uint64_t done = 0;
+            for (int i = 0; done < nq; i++) {
+                const int s = i % kSlots;
+                const uint64_t m = std::min(chunk, nq - done);
+                drain(s);
+                parallel_memcpy(hqs[s].p, q_start + done, m * 8);
+                parallel_memcpy(hqe[s].p, q_stop + done, m * 8);
+                LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqs[s].p, hqs[s].p, m * 8, cudaMemcpyHostToDevice, sst[s].s));
+                LAPPER_CUDA_CHECK(cudaMemcpyAsync(dqe[s].p, hqe[s].p, m * 8, cudaMemcpyHostToDevice, sst[s].s));
+                const int rc = lapper64_count_batch_dev(l, dqs[s].p, dqe[s].p, m, dout[s].p, sst[s].s);
+                if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
+                LAPPER_CUDA_CHECK(cudaMemcpyAsync(hout[s].p, dout[s].p, m * 8, cudaMemcpyDeviceToHost, sst[s].s));
+                pending_lo[s] = done, pending_m[s] = m;
+                done += m;
+            }
+            for (int k = 0; k < kSlots; k++) drain((int)((div_up(nq, chunk) + k) % kSlots));  // oldest chunk first
+            for (int s = 0; s < used; s++) {
+                dqs[s].release(), dqe[s].release(), dout[s].release();
+                LAPPER_CUDA_CHECK(cudaStreamSynchronize(sst[s].s));
+            }
+            return;
+        }
         OwnedStream st[1];  // slot 0; the other slots' streams only for batches of several chunks
         std::unique_ptr<OwnedStream> more[kSlots];
         cudaStream_t ss[kSlots] = {st[0].s, nullptr, nullptr};
