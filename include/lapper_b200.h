@@ -292,6 +292,10 @@ int lapper64_find_batch_dev(const lapper64_t *l, const uint64_t *d_q_start, cons
 /* cov / set_cov (src/lib.rs:310-350), merge_overlaps (:361-416), union_and_intersect (:512-559) */
 int lapper64_cov(const lapper64_t *l, uint64_t *cov_out);
 int lapper64_set_cov(lapper64_t *l, uint64_t *cov_out);
+/* `cov: Option<I>` and `overlaps_merged` as they are / restored (the contracts of lapper_get_cached_state and
+ * lapper_restore_cached_state): what `with_serde` (src/lib.rs:85-86) needs for a Lapper<u64 | usize, T> */
+int lapper64_get_cached_state(const lapper64_t *l, int *cov_is_some_out, uint64_t *cov_out, int *overlaps_merged_out);
+int lapper64_restore_cached_state(lapper64_t *l, int cov_is_some, uint64_t cov, int overlaps_merged);
 int lapper64_merge_overlaps(lapper64_t *l);
 int lapper64_union_and_intersect(const lapper64_t *a, const lapper64_t *b, uint64_t *union_out, uint64_t *intersect_out);
 /* insert (src/lib.rs:260-273), the seek cursor (:658-671) and depth (:576-598, :720-784; arrays freed with

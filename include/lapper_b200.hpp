@@ -9,14 +9,17 @@
 //   merge_overlaps(), cov(), set_cov()            :361-416, :310-324
 //   union_and_intersect / intersect / union_      :512-559
 //   count_batch / find_batch                      new batch entry points (CSR)
+//   to_bincode() / from_bincode()                 the `with_serde` feature     :85-86, :111-122, test :1387-1409
 //
 // `val: T` stays on the host; the engine returns positions into the sorted `intervals` vector.
 // Errors: the reference panics; this facade throws lapper_b200::Error carrying the ABI status code.
 #pragma once
 
 #include <cstdint>
+#include <cstring>
 #include <stdexcept>
 #include <string>
+#include <type_traits>
 #include <utility>
 #include <vector>
 
@@ -64,6 +67,9 @@ struct Abi<uint32_t> {
     }
     static int depth(const handle *h, uint64_t *n, uint32_t **s, uint32_t **e, uint32_t **d) { return lapper_depth(h, n, s, e, d); }
     static int tune_query_length(handle *h, uint32_t len) { return lapper_tune_query_length(h, len); }
+    static int get_sorted_stops(const handle *h, uint32_t *out) { return lapper_get_stops(h, out); }
+    static int get_cached_state(const handle *h, int *some, uint32_t *cov, int *merged) { return lapper_get_cached_state(h, some, cov, merged); }
+    static int restore_cached_state(handle *h, int some, uint32_t cov, int merged) { return lapper_restore_cached_state(h, some, cov, merged); }
 };
 template <>
 struct Abi<uint64_t> {
@@ -92,10 +98,53 @@ struct Abi<uint64_t> {
     }
     static int depth(const handle *h, uint64_t *n, uint64_t **s, uint64_t **e, uint32_t **d) { return lapper64_depth(h, n, s, e, d); }
     static int tune_query_length(handle *h, uint32_t len) { return lapper64_tune_query_length(h, len); }
+    static int get_sorted_stops(const handle *h, uint64_t *out) { return lapper64_get_sorted_stops(h, out); }
+    static int get_cached_state(const handle *h, int *some, uint64_t *cov, int *merged) { return lapper64_get_cached_state(h, some, cov, merged); }
+    static int restore_cached_state(handle *h, int some, uint64_t cov, int merged) { return lapper64_restore_cached_state(h, some, cov, merged); }
 };
 }  // namespace detail
 
 // src/lib.rs:88-100
+// bincode 1.3 with default options (Cargo.lock pins 1.3.3): little-endian fixed-width integers, `Vec<X>` = u64 length
+// + elements, `usize` = u64, `Option<X>` = one tag byte + X, `bool` = one byte, structs = their fields in order.
+// (Host code; a little-endian host is assumed, as everywhere CUDA runs.)
+namespace bincode {
+template <typename X>
+inline void put(std::vector<uint8_t> &out, X x) {
+    static_assert(std::is_arithmetic<X>::value, "bincode: integer, bool or float fields only");
+    uint8_t b[sizeof(X)];
+    std::memcpy(b, &x, sizeof(X));
+    out.insert(out.end(), b, b + sizeof(X));
+}
+template <>
+inline void put<bool>(std::vector<uint8_t> &out, bool x) { out.push_back(x ? 1 : 0); }
+struct Reader {
+    const uint8_t *p, *end;
+    template <typename X>
+    X take() {
+        static_assert(std::is_arithmetic<X>::value, "bincode: integer, bool or float fields only");
+        if ((size_t)(end - p) < sizeof(X)) throw Error(LAPPER_ERR_INVALID_ARG, "bincode: unexpected end of input");
+        X x;
+        std::memcpy(&x, p, sizeof(X));
+        p += sizeof(X);
+        return x;
+    }
+    uint8_t tag(const char *what) {  // Option tag / bool: 0 or 1, anything else is malformed
+        const uint8_t t = take<uint8_t>();
+        if (t > 1) throw Error(LAPPER_ERR_INVALID_ARG, what);
+        return t;
+    }
+    // a Vec length, checked against the bytes that are left (elem_size bytes per element)
+    uint64_t vec_len(size_t elem_size) {
+        const uint64_t n = take<uint64_t>();
+        if (n > (uint64_t)(end - p) / (elem_size ? elem_size : 1)) throw Error(LAPPER_ERR_INVALID_ARG, "bincode: unexpected end of input");
+        return n;
+    }
+};
+template <>
+inline bool Reader::take<bool>() { return tag("bincode: invalid bool") != 0; }
+}  // namespace bincode
+
 template <typename T, typename I = uint32_t>
 struct Interval {
     I start;
@@ -134,9 +183,12 @@ class Lapper {
         input_ = std::move(ivs);
         refresh();
     }
-    ~Lapper() { A::release(h_); }
+    ~Lapper() {
+        if (h_) A::release(h_);
+    }
     Lapper(const Lapper &) = delete;
     Lapper &operator=(const Lapper &) = delete;
+    Lapper(Lapper &&o) noexcept : intervals(std::move(o.intervals)), h_(o.h_), input_(std::move(o.input_)) { o.h_ = nullptr; }
 
     size_t len() const { return intervals.size(); }       // src/lib.rs:284-287
     bool is_empty() const { return intervals.empty(); }   // src/lib.rs:296-299
@@ -228,6 +280,60 @@ class Lapper {
     }
     I intersect(const Lapper &o) const { return union_and_intersect(o).second; }
     I union_(const Lapper &o) const { return union_and_intersect(o).first; }
+
+    // ---- the `with_serde` feature (src/lib.rs:85-86): bincode::serialize(&lapper) / bincode::deserialize, fields in
+    // the order of src/lib.rs:111-122.  T: an integer, bool or float type.
+    std::vector<uint8_t> to_bincode() const {
+        const size_t n = intervals.size();
+        std::vector<I> stops(n);
+        check(A::get_sorted_stops(h_, stops.data()));
+        int some = 0, merged = 0;
+        I cv = 0;
+        check(A::get_cached_state(h_, &some, &cv, &merged));
+        std::vector<uint8_t> out;
+        out.reserve(8 + n * (2 * sizeof(I) + sizeof(T)) + 2 * (8 + n * sizeof(I)) + 2 * sizeof(I) + 2);
+        bincode::put<uint64_t>(out, n);  // intervals: Vec<Interval<I, T>>
+        for (const Iv &iv : intervals) bincode::put<I>(out, iv.start), bincode::put<I>(out, iv.stop), bincode::put<T>(out, iv.val);
+        bincode::put<uint64_t>(out, n);  // starts: Vec<I>
+        for (const Iv &iv : intervals) bincode::put<I>(out, iv.start);
+        bincode::put<uint64_t>(out, n);  // stops: Vec<I> (sorted on their own)
+        for (const I e : stops) bincode::put<I>(out, e);
+        bincode::put<I>(out, max_len());
+        bincode::put<uint8_t>(out, some ? 1 : 0);  // cov: Option<I>
+        if (some) bincode::put<I>(out, cv);
+        bincode::put<bool>(out, merged != 0);
+        return out;
+    }
+    // The index is derived data: it is rebuilt from `intervals` and the serialised starts / stops / max_len are checked
+    // against it; cov and overlaps_merged are restored as they were.  Malformed input throws Error(INVALID_ARG).
+    static Lapper from_bincode(const uint8_t *data, size_t len, int device = 0) {
+        bincode::Reader r{data, data + len};
+        const uint64_t n = r.vec_len(2 * sizeof(I) + sizeof(T));
+        std::vector<Iv> ivs;
+        ivs.reserve(n);
+        for (uint64_t i = 0; i < n; i++) {
+            const I s = r.template take<I>(), e = r.template take<I>();
+            ivs.push_back(Iv{s, e, r.template take<T>()});
+        }
+        std::vector<I> starts(r.vec_len(sizeof(I)));
+        for (I &x : starts) x = r.template take<I>();
+        std::vector<I> stops(r.vec_len(sizeof(I)));
+        for (I &x : stops) x = r.template take<I>();
+        const I max_len = r.template take<I>();
+        const bool some = r.tag("bincode: invalid Option tag") != 0;
+        const I cv = some ? r.template take<I>() : I(0);
+        const bool merged = r.template take<bool>();
+        if (r.p != r.end) throw Error(LAPPER_ERR_INVALID_ARG, "bincode: trailing bytes");
+        Lapper lap(std::move(ivs), device);
+        std::vector<I> have(lap.intervals.size());
+        check(A::get_sorted_stops(lap.h_, have.data()));
+        bool same = starts.size() == lap.intervals.size() && have == stops && lap.max_len() == max_len;
+        for (size_t i = 0; same && i < starts.size(); i++) same = starts[i] == lap.intervals[i].start;
+        if (!same) throw Error(LAPPER_ERR_INVALID_ARG, "bincode: serialised starts / stops / max_len do not belong to the serialised intervals");
+        check(A::restore_cached_state(lap.h_, some ? 1 : 0, cv, merged ? 1 : 0));
+        return lap;
+    }
+    static Lapper from_bincode(const std::vector<uint8_t> &buf, int device = 0) { return from_bincode(buf.data(), buf.size(), device); }
 
   private:
     // rebuild `intervals` from the engine's sorted order; vals follow through perm

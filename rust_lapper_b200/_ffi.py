@@ -129,6 +129,8 @@ SIGNATURES = {
     "lapper64_find_batch_dev": (_int, [_vp, _vp, _vp, _u64, _vp, _vp, _u64, C.POINTER(_u64), _vp]),
     "lapper64_cov": (_int, [_vp, C.POINTER(_u64)]),
     "lapper64_set_cov": (_int, [_vp, C.POINTER(_u64)]),
+    "lapper64_get_cached_state": (_int, [_vp, C.POINTER(_int), C.POINTER(_u64), C.POINTER(_int)]),
+    "lapper64_restore_cached_state": (_int, [_vp, _int, _u64, _int]),
     "lapper64_merge_overlaps": (_int, [_vp]),
     "lapper64_union_and_intersect": (_int, [_vp, _vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "lapper64_insert": (_int, [_vp, _u64, _u64, C.POINTER(_u64)]),

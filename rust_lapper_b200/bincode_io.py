@@ -9,7 +9,8 @@ their fields in declaration order.  The fields of `Lapper` (src/lib.rs:111-122):
     starts: Vec<I>, stops: Vec<I>, max_len: I, cov: Option<I>, overlaps_merged: bool
 
 `coord` names I ("u32", "u64"/"usize", "u16", "u8"), `val` names T (an integer type or "bool").  The codec works on a
-plain dict, so it is testable without a GPU; `dumps` / `loads` connect it to a `Lapper` handle.  There is no Rust
+plain dict, so it is testable without a GPU; `dumps` / `loads` connect it to a `Lapper` / `Lapper64` handle
+(include/lapper_b200.hpp carries the same codec for the C++ facade: `to_bincode` / `from_bincode`).  There is no Rust
 toolchain in this image, so the byte layout is pinned by the format description above, not by bytes the crate wrote.
 """
 from __future__ import annotations
@@ -82,31 +83,59 @@ def decode(buf: bytes, coord: str = "u32", val: str = "u32") -> Dict[str, Any]:
     return state
 
 
+def _is_wide(lapper) -> bool:
+    from .lapper64 import Lapper64
+
+    return isinstance(lapper, Lapper64)
+
+
 def dumps(lapper, coord: str = "u32", val: str = "u32", default_val: Any = 0) -> bytes:
-    """`bincode::serialize(&lapper)` for a b200 `Lapper` (vals come from the host-side list; `default_val` without one)."""
+    """`bincode::serialize(&lapper)` for a b200 `Lapper` or `Lapper64` (vals come from the host-side list;
+    `default_val` without one).  A coordinate that does not fit `coord` is an error, as it could not exist in a
+    `Lapper<coord, T>`."""
     lib = _ffi.lib()
     s, e, perm = lapper.intervals_soa()
     vals = lapper._vals
     ivs = [(int(a), int(b), default_val if vals is None else vals[int(p)]) for a, b, p in zip(s.tolist(), e.tolist(), perm.tolist())]
-    some, cov, merged = C.c_int(0), C.c_uint32(0), C.c_int(0)
-    _ffi.check(lib.lapper_get_cached_state(lapper.handle, C.byref(some), C.byref(cov), C.byref(merged)))
-    return encode({"intervals": ivs, "starts": lapper.starts, "stops": lapper.stops, "max_len": lapper.max_len,
-                   "cov": int(cov.value) if some.value else None, "overlaps_merged": bool(merged.value)}, coord, val)
+    some, merged = C.c_int(0), C.c_int(0)
+    if _is_wide(lapper):
+        cov = C.c_uint64(0)
+        _ffi.check(lib.lapper64_get_cached_state(lapper._h, C.byref(some), C.byref(cov), C.byref(merged)))
+    else:
+        cov = C.c_uint32(0)
+        _ffi.check(lib.lapper_get_cached_state(lapper.handle, C.byref(some), C.byref(cov), C.byref(merged)))
+    try:
+        return encode({"intervals": ivs, "starts": lapper.starts, "stops": lapper.stops, "max_len": lapper.max_len,
+                       "cov": int(cov.value) if some.value else None, "overlaps_merged": bool(merged.value)}, coord, val)
+    except struct.error as err:
+        raise ValueError(f"value does not fit the serialised type ({coord} coordinates, {val} vals): {err}") from None
 
 
-def loads(buf: bytes, coord: str = "u32", val: str = "u32", device: int = 0):
-    """`bincode::deserialize::<Lapper<I, T>>` into a b200 `Lapper` (coordinates must fit u32).  The index is rebuilt
-    from `intervals` -- it is derived data -- and checked against the serialised `starts` / `stops` / `max_len`."""
+def loads(buf: bytes, coord: str = "u32", val: str = "u32", device: int = 0, engine: str = "auto"):
+    """`bincode::deserialize::<Lapper<I, T>>` into a b200 handle.  `engine`: "u32" -> `Lapper`, "u64" -> `Lapper64`,
+    "auto" -> `Lapper` when every coordinate fits 32 bits (any width of `coord`), else `Lapper64`.  The index is
+    rebuilt from `intervals` -- it is derived data -- and checked against the serialised `starts` / `stops` /
+    `max_len`."""
     from .lapper import Lapper
+    from .lapper64 import Lapper64
 
+    if engine not in ("auto", "u32", "u64"):
+        raise ValueError("engine must be 'auto', 'u32' or 'u64'")
     st = decode(buf, coord, val)
     ivs = st["intervals"]
-    if any(a > 0xFFFFFFFF or b > 0xFFFFFFFF for a, b, _ in ivs):
-        raise ValueError("coordinates beyond u32 are not supported by this engine")
-    lap = Lapper(starts=[a for a, _, _ in ivs], stops=[b for _, b, _ in ivs], vals=[v for _, _, v in ivs], device=device)
-    if not (np.array_equal(lap.starts, np.asarray(st["starts"], dtype=np.uint32))
-            and np.array_equal(lap.stops, np.asarray(st["stops"], dtype=np.uint32)) and lap.max_len == st["max_len"]):
+    beyond = any(a > 0xFFFFFFFF or b > 0xFFFFFFFF for a, b, _ in ivs)
+    if engine == "u32" and beyond:
+        raise ValueError("coordinates beyond u32 are not supported by the u32 engine")
+    wide = engine == "u64" or (engine == "auto" and beyond)
+    cls, dt = (Lapper64, np.uint64) if wide else (Lapper, np.uint32)
+    lap = cls(starts=np.array([a for a, _, _ in ivs], dtype=dt), stops=np.array([b for _, b, _ in ivs], dtype=dt),
+              vals=[v for _, _, v in ivs], device=device)
+    if not (np.array_equal(lap.starts, np.asarray(st["starts"], dtype=dt))
+            and np.array_equal(lap.stops, np.asarray(st["stops"], dtype=dt)) and lap.max_len == st["max_len"]):
         raise ValueError("serialised starts / stops / max_len do not belong to the serialised intervals")
-    _ffi.check(_ffi.lib().lapper_restore_cached_state(lap.handle, 0 if st["cov"] is None else 1, st["cov"] or 0,
-                                                       1 if st["overlaps_merged"] else 0))
+    some, cov, merged = 0 if st["cov"] is None else 1, st["cov"] or 0, 1 if st["overlaps_merged"] else 0
+    if wide:
+        _ffi.check(_ffi.lib().lapper64_restore_cached_state(lap._h, some, cov, merged))
+    else:
+        _ffi.check(_ffi.lib().lapper_restore_cached_state(lap.handle, some, cov, merged))
     return lap

@@ -1039,6 +1039,25 @@ int lapper64_set_cov(lapper64_t *l, uint64_t *cov_out) {
     });
 }
 
+/* the cached fields of src/lib.rs:119-122 (`cov: Option<I>`, `overlaps_merged`), for (de)serialisation */
+int lapper64_get_cached_state(const lapper64_t *l, int *cov_is_some_out, uint64_t *cov_out, int *overlaps_merged_out) {
+    return guarded_call([&] {
+        check64(l);
+        if (cov_is_some_out) *cov_is_some_out = l->cov_is_some ? 1 : 0;
+        if (cov_out) *cov_out = l->cov_is_some ? l->cov : 0u;
+        if (overlaps_merged_out) *overlaps_merged_out = l->overlaps_merged ? 1 : 0;
+    });
+}
+
+int lapper64_restore_cached_state(lapper64_t *l, int cov_is_some, uint64_t cov, int overlaps_merged) {
+    return guarded_call([&] {
+        check64(l);
+        l->cov_is_some = cov_is_some != 0;
+        l->cov = cov_is_some ? cov : 0u;
+        l->overlaps_merged = overlaps_merged != 0;
+    });
+}
+
 int lapper64_merge_overlaps(lapper64_t *l) {
     return guarded_call([&] {
         check64(l);

@@ -173,6 +173,49 @@ void Suite<I>::run() {
         CHECK(a.intervals.size() == b.intervals.size() && a.max_len() == b.max_len());
         for (size_t i = 0; i < a.intervals.size() && i < b.intervals.size(); i++) CHECK(a.intervals[i] == b.intervals[i]);
     }
+    {  // serde_test  :1387-1409 (the `with_serde` feature): bincode round trip, then the same find / count
+        Lapper<uint32_t> lapper({{25264912, 25264986, 0}, {27273024, 27273065, 0}, {27440273, 27440318, 0}, {27488033, 27488125, 0},
+                                 {27938410, 27938470, 0}, {27959118, 27959171, 0}, {28866309, 33141404, 0}});
+        const std::vector<uint8_t> serialized = lapper.to_bincode();
+        Lapper<uint32_t> deserialized = Lapper<uint32_t>::from_bincode(serialized);
+        CHECK(same(deserialized.find(28974798, 33141355), {{28866309, 33141404, 0}}));
+        CHECK(deserialized.count(28974798, 33141355) == 1);
+        CHECK(deserialized.to_bincode() == serialized);
+        // layout, field by field (bincode 1.3 defaults): Lapper<I, u32> { intervals: [(5, 9, 7), (6, 20, 8)], starts: [5, 6],
+        // stops: [9, 20], max_len: 14, cov: Some(15), overlaps_merged: false }
+        Lapper<uint32_t> two({{6, 20, 8}, {5, 9, 7}});
+        CHECK(two.set_cov() == 15);
+        std::vector<uint8_t> want;
+        auto le = [&want](uint64_t x, size_t w) { for (size_t i = 0; i < w; i++) want.push_back((uint8_t)(x >> (8 * i))); };
+        const size_t W = sizeof(I);
+        le(2, 8), le(5, W), le(9, W), le(7, 4), le(6, W), le(20, W), le(8, 4);
+        le(2, 8), le(5, W), le(6, W), le(2, 8), le(9, W), le(20, W), le(14, W), le(1, 1), le(15, W), le(0, 1);
+        CHECK(two.to_bincode() == want);
+        // the cached fields survive: cov: Option<I> and overlaps_merged (src/lib.rs:119-122)
+        Lapper<uint32_t> bad(badlapper());
+        bad.set_cov();
+        bad.merge_overlaps();
+        Lapper<uint32_t> again = Lapper<uint32_t>::from_bincode(bad.to_bincode());
+        CHECK(again.overlaps_merged() && again.cov() == bad.cov() && again.len() == 5);
+        for (size_t i = 0; i < again.len() && i < bad.len(); i++) CHECK(again.intervals[i] == bad.intervals[i] && again.intervals[i].val == bad.intervals[i].val);
+        // malformed input is an error, not a crash: truncated, trailing byte, bad Option tag, bad bool, absurd length
+        std::vector<std::vector<uint8_t>> broken;
+        broken.push_back(std::vector<uint8_t>(want.begin(), want.end() - 1));
+        broken.push_back(want), broken.back().push_back(0);
+        broken.push_back(want), broken.back()[want.size() - 2 - W] = 2;
+        broken.push_back(want), broken.back().back() = 7;
+        broken.push_back(std::vector<uint8_t>(8, 0xFF));
+        broken.push_back(want), broken.back()[8] ^= 1;  // intervals[0].start no longer matches starts[0]
+        for (const auto &b : broken) {
+            bool threw = false;
+            try {
+                Lapper<uint32_t>::from_bincode(b);
+            } catch (const lapper_b200::Error &e) {
+                threw = e.code == LAPPER_ERR_INVALID_ARG;
+            }
+            CHECK(threw);
+        }
+    }
 }
 
 int main() {

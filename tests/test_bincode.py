@@ -74,3 +74,30 @@ def test_reference_serde_test_through_the_engine():
     assert again.overlaps_merged and again.cov() == lapper.cov() and again.intervals == lapper.intervals
     state = bincode_io.decode(bincode_io.dumps(lapper, "u32", "u32"), "u32", "u32")
     assert state["cov"] == lapper.cov() and state["overlaps_merged"] is True
+
+
+@pytest.mark.gpu
+def test_serde_through_the_u64_engine():
+    """Lapper<usize, u32> with coordinates beyond 32 bits: `loads` picks the u64 engine, cached fields survive."""
+    from rust_lapper_b200 import Lapper64
+
+    big = 1 << 40
+    data = [(big + a, big + b, v) for a, b, v in SERDE_TEST_DATA]
+    lapper = Lapper64(data)
+    raw = bincode_io.dumps(lapper, coord="usize", val="u32")
+    with pytest.raises(ValueError):
+        bincode_io.dumps(lapper, coord="u32", val="u32")               # no Lapper<u32, _> can hold these
+    with pytest.raises(ValueError):
+        bincode_io.loads(raw, coord="usize", val="u32", engine="u32")
+    back = bincode_io.loads(raw, coord="usize", val="u32")
+    assert isinstance(back, Lapper64)
+    assert back.find(big + 28974798, big + 33141355) == [(big + 28866309, big + 33141404)]
+    assert back.count(big + 28974798, big + 33141355) == 1
+    lapper.set_cov()
+    lapper.merge_overlaps()
+    again = bincode_io.loads(bincode_io.dumps(lapper, "u64", "u32"), "u64", "u32")
+    assert again.overlaps_merged and again.cov() == lapper.cov() and again.intervals == lapper.intervals
+    # a set that fits 32 bits loads into the u32 engine unless the u64 one is asked for
+    small = bincode_io.dumps(Lapper64(SERDE_TEST_DATA), coord="usize", val="u32")
+    assert not isinstance(bincode_io.loads(small, "usize", "u32"), Lapper64)
+    assert isinstance(bincode_io.loads(small, "usize", "u32", engine="u64"), Lapper64)
