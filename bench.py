@@ -1230,6 +1230,13 @@ def run_extras(cx, n, nq):
     del iv_s, iv_e
     h64 = C.c_void_p(0)
     _ffi.check(lib.lapper64_build_dev(_vp(s64), _vp(e64), n, dev.index, sp, C.byref(h64)))
+    # the same set translated by 2^40 (timestamps rather than a genome): beyond 32 bits, but the span fits, so the u32
+    # engine answers on coordinates relative to the smallest one (csrc/engine64.cu, "rebased form")
+    shift64 = 1 << 40
+    s64 += shift64
+    e64 += shift64
+    h64r = C.c_void_p(0)
+    _ffi.check(lib.lapper64_build_dev(_vp(s64), _vp(e64), n, dev.index, sp, C.byref(h64r)))
     del s64, e64
     rq_s, rq_e = synth.queries_fixed_len(SEED_Q, nq64, UNIVERSE, QLEN, device=dev)
     q64s = (rq_s.to(torch.int64) & 0xFFFFFFFF).contiguous()
@@ -1242,10 +1249,18 @@ def run_extras(cx, n, nq):
     nqw = nq64 // 10
     ms_w = timed(lambda: _ffi.check(lib.lapper64_count_batch_dev(h64, _vp(q64s), _vp(q64e), nqw, _vp(c64), sp)), 3)
     lib.lapper64_debug_set_narrow_mode(old_mode)
+    q64s += shift64
+    q64e += shift64
+    ms_r = timed(lambda: _ffi.check(lib.lapper64_count_batch_dev(h64r, _vp(q64s), _vp(q64e), nq64, _vp(c64), sp)), 5)
+    rebased = bool(lib.lapper64_is_narrow(h64r))
+    sum_r = int(c64.sum().item())
+    lib.lapper64_free(h64r)
     out["u64_coordinates_cfg2"] = {
         "count_random_ms": ms_n, "queries": nq64, "queries_per_s": nq64 / (ms_n * 1e-3), "answered_by_u32_engine": narrow,
         "counts_sum": sum_n, "equals_u32_headline_checksum": (sum_n == cx.headline_checksum) if nq64 == nq else None,
         "wide_kernels_ms": ms_w, "wide_kernels_queries": nqw, "wide_kernels_queries_per_s": nqw / (ms_w * 1e-3),
+        "translated_by_2^40": {"count_random_ms": ms_r, "queries_per_s": nq64 / (ms_r * 1e-3), "answered_by_u32_engine": rebased,
+                               "same_counts_sum": sum_r == sum_n},
         "note": "lapper64_count_batch_dev, u64 queries and u64 counts on the device; 28 B/query instead of 12: the narrowing pass "
                 "reads 16 B and writes 8 B per query in front of the u32 kernel",
     }

@@ -306,6 +306,8 @@ int lapper64_depth(const lapper64_t *l, uint64_t *n_out, uint64_t **starts_out, 
 /* Narrowing: a u64 set whose coordinates all fit 32 bits (<= 2^32 - 3) has its count / find batches answered by the
  * u32 engine's tables and kernels (same results bit for bit: csrc/engine64.cu, "narrowing"); the u32 index is built on
  * the first batch of >= 4096 queries and dropped by insert / merge_overlaps.  lapper64_is_narrow: 1 once it exists.
+ * Sets beyond 32 bits whose span fits (max - min <= 2^32 - 4, e.g. timestamps) are answered the same way on coordinates
+ * relative to their smallest one ("rebased form").
  * lapper64_debug_set_narrow_mode (tests): 0 = never, 1 = default, 2 = from the first batch on; returns the old mode. */
 int lapper64_is_narrow(const lapper64_t *l);
 /* lapper_tune_query_length for a u64 handle (takes effect where the u32 engine answers) */

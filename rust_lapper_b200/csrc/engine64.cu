@@ -45,10 +45,12 @@ struct lapper64 {
     uint64_t cov = 0;
     uint64_t next_input_id = 0;  // input position handed to the next inserted interval
     uint64_t max_coord = 0;      // largest start or stop
+    uint64_t min_coord = 0;      // smallest start or stop
     uint32_t query_len_hint = 0; // lapper64_tune_query_length: handed to the u32 engine of a narrowed set
     // The u32 engine over the same sorted intervals (see "narrowing" below): built on the first batch that is worth it
     // when every coordinate fits, dropped by insert / merge_overlaps.
     mutable std::atomic<lapper_t *> narrow{nullptr};
+    mutable uint64_t narrow_base = 0, narrow_add = 0, narrow_top = 0xFFFFFFFEull;  // the coordinate map of `narrow` (NarrowMap)
     mutable std::atomic<bool> narrow_failed{false};  // building it failed once (memory): the 64-bit kernels answer from then on
     mutable std::mutex narrow_mu;
 };
@@ -98,26 +100,29 @@ __global__ void gather64_kernel(uint64_t *__restrict__ out, const uint64_t *__re
     if (i < n) out[i] = in[idx[i]];
 }
 // max_len with checked_sub -> 0 (src/lib.rs:218-227), the inverted flag and the largest coordinate;
-// out[0] = max_len, out[1] = inverted, out[2] = max(start, stop)
+// out[0] = max_len, out[1] = inverted, out[2] = max(start, stop), out[3] = ~min(start, stop)
 __global__ void __launch_bounds__(kT) stats64_kernel(const uint64_t *__restrict__ s, const uint64_t *__restrict__ e, uint64_t n,
                                                      unsigned long long *__restrict__ out) {
-    unsigned long long mx = 0, inv = 0, top = 0;
+    unsigned long long mx = 0, inv = 0, top = 0, nlow = 0;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t a = s[i], b = e[i];
         mx = max(mx, (unsigned long long)(b > a ? b - a : 0ull));
         inv |= (b < a) ? 1ull : 0ull;
         top = max(top, (unsigned long long)max(a, b));
+        nlow = max(nlow, (unsigned long long)~min(a, b));
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o));
         inv |= __shfl_xor_sync(0xFFFFFFFFu, inv, o);
         top = max(top, __shfl_xor_sync(0xFFFFFFFFu, top, o));
+        nlow = max(nlow, __shfl_xor_sync(0xFFFFFFFFu, nlow, o));
     }
     if ((threadIdx.x & 31) == 0) {
         if (mx) atomicMax(out, mx);
         if (inv) atomicOr(out + 1, 1ull);
         if (top) atomicMax(out + 2, top);
+        if (nlow) atomicMax(out + 3, nlow);
     }
 }
 
@@ -542,20 +547,21 @@ void free_arrays(lapper64 *l, cudaStream_t stream) {
 // max_len, inverted flag and prefix max from the sorted arrays (S, Eiv set; P allocated here)
 void finish_from_sorted(lapper64 *l, cudaStream_t stream) {
     uint64_t bytes = 0;
-    l->max_len = 0, l->has_inverted = false, l->max_coord = 0;
+    l->max_len = 0, l->has_inverted = false, l->max_coord = 0, l->min_coord = 0;
     if (l->n == 0) return;
     l->P = pool_alloc<uint64_t>(l->n, bytes, stream);
-    Scratch<unsigned long long> st(3, stream);
-    LAPPER_CUDA_CHECK(cudaMemsetAsync(st.p, 0, 24, stream));
+    Scratch<unsigned long long> st(4, stream);
+    LAPPER_CUDA_CHECK(cudaMemsetAsync(st.p, 0, 32, stream));
     stats64_kernel<<<capped(l->n), kT, 0, stream>>>(l->S, l->Eiv, l->n, st.p);
     LAPPER_CUDA_CHECK(cudaGetLastError());
     scan64<Max64>(Load64{l->Eiv}, l->n, StoreIncl{l->P}, nullptr, stream);
-    unsigned long long h[3] = {0, 0, 0};
-    LAPPER_CUDA_CHECK(cudaMemcpyAsync(h, st.p, 24, cudaMemcpyDeviceToHost, stream));
+    unsigned long long h[4] = {0, 0, 0, 0};
+    LAPPER_CUDA_CHECK(cudaMemcpyAsync(h, st.p, 32, cudaMemcpyDeviceToHost, stream));
     LAPPER_CUDA_CHECK(cudaStreamSynchronize(stream));
     l->max_len = h[0];
     l->has_inverted = h[1] != 0;
     l->max_coord = h[2];
+    l->min_coord = ~h[3];
 }
 
 void build_from_device(lapper64 *l, const uint64_t *d_s, const uint64_t *d_e, uint64_t n, cudaStream_t stream) {
@@ -680,30 +686,62 @@ void find_emit64(const lapper64 *l, const uint64_t *d_qs, const uint64_t *d_qe, 
 // stop_i > start; src/lib.rs:140-142, :611-618) has the same outcome on the narrowed query, and `start + 1` wraps for
 // start' = u32::MAX exactly as it does for start = u64::MAX (:614).  Counts are u64 either way, positions u32.
 // The u64 arrays stay: the set operations, insert, depth and the seek cursor work on them.
+//
+// Rebased form: a set with coordinates beyond 32 bits whose SPAN fits (max - min <= 2^32 - 4: nanosecond timestamps
+// within four seconds, microseconds within 71 minutes, seconds at any epoch) is narrowed relative to its smallest
+// coordinate.  With base = min, R = max - min:   x' = x - base + 1 for the set's coordinates (1 .. R + 1), and for a
+// query coordinate q:   q' = 0 if q < base,   q - base + 1 if q - base <= R,   R + 2 beyond;   start' = u32::MAX for
+// start = u64::MAX as above.  The map is monotone and sends "below every coordinate" / "above every coordinate" to
+// values below / above every narrowed coordinate, so x < q, x <= q and x > q keep their outcomes for every x in the set.
 std::atomic<int> g_narrow_mode{1};  // 0 = never, 1 = from the first batch of kNarrowMinBatch queries on, 2 = always
 constexpr uint64_t kNarrowMaxCoord = 0xFFFFFFFDull;
+constexpr uint64_t kNarrowMaxSpan = 0xFFFFFFFCull;
 constexpr uint64_t kNarrowMinBatch = 4096;
+
+// q' = q < base ? 0 : min(q - base + add, top); plain form: base = 0, add = 0, top = 2^32 - 2
+struct NarrowMap {
+    uint64_t base, add, top;
+    __host__ __device__ uint32_t operator()(uint64_t q) const {
+        if (q < base) return 0u;
+        const uint64_t d = q - base;
+        return (uint32_t)(d >= top - add ? top : d + add);
+    }
+};
+
+// the map of a set, or false when neither form applies
+bool narrow_map_of(const lapper64 *l, NarrowMap &m) {
+    if (l->max_coord <= kNarrowMaxCoord) {
+        m = NarrowMap{0, 0, 0xFFFFFFFEull};
+        return true;
+    }
+    if (l->max_coord - l->min_coord <= kNarrowMaxSpan) {
+        m = NarrowMap{l->min_coord, 1, l->max_coord - l->min_coord + 2};
+        return true;
+    }
+    return false;
+}
 
 __global__ void __launch_bounds__(kT) narrow_index_kernel(const uint64_t *__restrict__ S, const uint64_t *__restrict__ Eiv,
                                                           const uint64_t *__restrict__ E, uint64_t n, uint32_t *__restrict__ s,
-                                                          uint32_t *__restrict__ eiv, uint32_t *__restrict__ e) {
+                                                          uint32_t *__restrict__ eiv, uint32_t *__restrict__ e, NarrowMap m) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-        s[i] = (uint32_t)S[i], eiv[i] = (uint32_t)Eiv[i], e[i] = (uint32_t)E[i];
+        s[i] = m(S[i]), eiv[i] = m(Eiv[i]), e[i] = m(E[i]);
 }
 
 __global__ void __launch_bounds__(kT) narrow_queries_kernel(const uint64_t *__restrict__ qs, const uint64_t *__restrict__ qe,
-                                                            uint64_t nq, uint32_t *__restrict__ a, uint32_t *__restrict__ b) {
+                                                            uint64_t nq, uint32_t *__restrict__ a, uint32_t *__restrict__ b, NarrowMap m) {
     for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j < nq; j += (uint64_t)gridDim.x * blockDim.x) {
         const uint64_t x = qs[j], y = qe[j];
-        a[j] = x == ~0ull ? 0xFFFFFFFFu : (uint32_t)min(x, (uint64_t)0xFFFFFFFEull);
-        b[j] = (uint32_t)min(y, (uint64_t)0xFFFFFFFEull);
+        a[j] = x == ~0ull ? 0xFFFFFFFFu : m(x);
+        b[j] = m(y);
     }
 }
 
 // the u32 engine of this handle, or nullptr when the batch takes the 64-bit kernels
 lapper_t *narrow_of(const lapper64 *l, uint64_t nq, cudaStream_t stream) {
     const int mode = g_narrow_mode.load(std::memory_order_relaxed);
-    if (mode == 0 || l->n == 0 || l->n >= 0xFFFFFFF0ull || l->max_coord > kNarrowMaxCoord) return nullptr;
+    NarrowMap m;
+    if (mode == 0 || l->n == 0 || l->n >= 0xFFFFFFF0ull || !narrow_map_of(l, m)) return nullptr;
     if (l->narrow_failed.load(std::memory_order_relaxed)) return nullptr;
     lapper_t *h = l->narrow.load(std::memory_order_acquire);
     if (h) return h;
@@ -715,7 +753,7 @@ lapper_t *narrow_of(const lapper64 *l, uint64_t nq, cudaStream_t stream) {
     // the u64 arrays), the batch and every later one go to the 64-bit kernels.
     try {
         Scratch<uint32_t> s(l->n, stream), eiv(l->n, stream), e(l->n, stream);
-        narrow_index_kernel<<<capped(l->n), kT, 0, stream>>>(l->S, l->Eiv, l->E, l->n, s.p, eiv.p, e.p);
+        narrow_index_kernel<<<capped(l->n), kT, 0, stream>>>(l->S, l->Eiv, l->E, l->n, s.p, eiv.p, e.p, m);
         LAPPER_CUDA_CHECK(cudaGetLastError());
         const int rc = lapper_from_sorted_dev(s.p, eiv.p, e.p, l->perm, l->n, l->overlaps_merged ? 1 : 0, l->device, 0, stream, &h);
         if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
@@ -730,6 +768,7 @@ lapper_t *narrow_of(const lapper64 *l, uint64_t nq, cudaStream_t stream) {
         l->narrow_failed.store(true, std::memory_order_relaxed);
         return nullptr;
     }
+    l->narrow_base = m.base, l->narrow_add = m.add, l->narrow_top = m.top;  // (published by the release store below)
     l->narrow.store(h, std::memory_order_release);
     return h;
 }
@@ -742,9 +781,10 @@ void drop_narrow(lapper64 *l) {
 
 struct NarrowQueries {
     Scratch<uint32_t> a, b;
-    NarrowQueries(const uint64_t *d_qs, const uint64_t *d_qe, uint64_t nq, cudaStream_t stream) : a(nq, stream), b(nq, stream) {
+    NarrowQueries(const lapper64 *l, const uint64_t *d_qs, const uint64_t *d_qe, uint64_t nq, cudaStream_t stream) : a(nq, stream), b(nq, stream) {
         if (nq == 0) return;
-        narrow_queries_kernel<<<capped(nq), kT, 0, stream>>>(d_qs, d_qe, nq, a.p, b.p);
+        const NarrowMap m{l->narrow_base, l->narrow_add, l->narrow_top};  // read after the acquire load of l->narrow
+        narrow_queries_kernel<<<capped(nq), kT, 0, stream>>>(d_qs, d_qe, nq, a.p, b.p, m);
         LAPPER_CUDA_CHECK(cudaGetLastError());
     }
 };
@@ -857,7 +897,7 @@ int lapper64_count_batch_dev(const lapper64_t *l, const uint64_t *d_q_start, con
             return;
         }
         if (lapper_t *h = narrow_of(l, nq, (cudaStream_t)stream)) {
-            NarrowQueries q(d_q_start, d_q_stop, nq, (cudaStream_t)stream);
+            NarrowQueries q(l, d_q_start, d_q_stop, nq, (cudaStream_t)stream);
             const int rc = lapper_count_batch_u32_dev64(h, q.a.p, q.b.p, nq, d_counts_out, stream);
             if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
             return;
@@ -953,7 +993,7 @@ int lapper64_find_batch_dev(const lapper64_t *l, const uint64_t *d_q_start, cons
         cudaStream_t s = (cudaStream_t)stream;
         *total_out = 0;
         if (lapper_t *h = narrow_of(l, nq, s)) {
-            NarrowQueries q(d_q_start, d_q_stop, nq, s);
+            NarrowQueries q(l, d_q_start, d_q_stop, nq, s);
             const int rc = lapper_find_batch_u32_dev(h, q.a.p, q.b.p, nq, d_offsets, d_indices, indices_capacity, total_out, stream);
             if (rc != LAPPER_OK) throw Error(rc, last_error_slot());  // (LAPPER_ERR_CAPACITY included: same contract)
             return;
@@ -984,7 +1024,7 @@ int lapper64_find_batch(const lapper64_t *l, const uint64_t *q_start, const uint
             copy_to_device(dqe.p, q_stop, nq * 8, st.s);
         }
         if (lapper_t *h = narrow_of(l, nq, st.s)) {
-            NarrowQueries q(dqs.p, dqe.p, nq, st.s);
+            NarrowQueries q(l, dqs.p, dqe.p, nq, st.s);
             dqs.release(), dqe.release();
             const int rc = lapper_find_batch_u32_devq(h, q.a.p, q.b.p, nq, st.s, out);
             if (rc != LAPPER_OK) throw Error(rc, last_error_slot());
@@ -1092,7 +1132,7 @@ int lapper64_merge_overlaps(lapper64_t *l) {
         free_arrays(l, st.s);
         l->n = next.n;
         l->S = next.S, l->Eiv = next.Eiv, l->E = next.E, l->P = next.P, l->perm = next.perm;
-        l->max_len = next.max_len, l->has_inverted = next.has_inverted, l->max_coord = next.max_coord;
+        l->max_len = next.max_len, l->has_inverted = next.has_inverted, l->max_coord = next.max_coord, l->min_coord = next.min_coord;
         l->overlaps_merged = true;
         LAPPER_CUDA_CHECK(cudaStreamSynchronize(st.s));
     });
@@ -1167,7 +1207,7 @@ int lapper64_insert(lapper64_t *l, uint64_t start, uint64_t stop, uint64_t *inpu
         free_arrays(l, st.s);
         l->n = next.n;
         l->S = next.S, l->Eiv = next.Eiv, l->E = next.E, l->P = next.P, l->perm = next.perm;
-        l->max_len = next.max_len, l->has_inverted = next.has_inverted, l->max_coord = next.max_coord;
+        l->max_len = next.max_len, l->has_inverted = next.has_inverted, l->max_coord = next.max_coord, l->min_coord = next.min_coord;
         l->next_input_id = id + 1;
         l->cov_is_some = false;      // src/lib.rs:271
         l->overlaps_merged = false;  // src/lib.rs:272

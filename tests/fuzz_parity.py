@@ -139,6 +139,22 @@ def check_case(rng, bits, case_id, verbose=False):
         mode = int(rng.choice([0, 1, 2, 2]))
         _ffi.lib().lapper64_debug_set_narrow_mode(mode)
         desc += f" narrow_mode={mode}"
+        top = (1 << 64) - 1
+        hi = int(max(s.max(), e.max())) if s.size else top
+        if top - hi > (1 << 33) and rng.random() < 0.35:
+            # the whole case translated beyond 32 bits (now and then right up to u64::MAX): a set whose span still fits
+            # 32 bits is answered by the u32 engine on rebased coordinates (csrc/engine64.cu, "rebased form")
+            off = top - hi if rng.random() < 0.2 else int(rng.integers(1 << 32, min(top - hi, 1 << 63), dtype=np.uint64))
+            s, e = s + np.uint64(off), e + np.uint64(off)
+            qs = np.minimum(qs.astype(object) + off, top).astype(np.uint64)
+            qe = np.minimum(qe.astype(object) + off, top).astype(np.uint64)
+            lo, hi = int(min(s.min(), e.min())), int(max(s.max(), e.max()))
+            if qs.size > 40:
+                pts = np.array([0, 1, lo - 1, lo, lo + 1, hi - 1, hi, min(hi + 1, top), top - 1, top], dtype=np.uint64)
+                k = rng.integers(4, qs.size, 32)
+                qs[k] = pts[rng.integers(0, pts.size, 32)]
+                qe[k] = pts[rng.integers(0, pts.size, 32)]
+            desc += f" shifted_by={off}"
         gpu = Lapper64(starts=s, stops=e)
         cpu = lapper_oracle.OracleLapper(starts=s, stops=e, coord_bits=64)
     want_c = cpu.count_batch(qs, qe, 4)
@@ -246,11 +262,12 @@ def main():
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--case", type=int, default=None, help="replay one case_seed verbosely")
+    ap.add_argument("--u64-share", type=float, default=0.3, help="share of the cases drawn for the u64 engine")
     args = ap.parse_args()
     if args.case is not None:
         _ffi.lib().lapper_debug_set_sorted_min_queries(32 * 1024)
         rng = np.random.default_rng(args.case)
-        bits = 64 if rng.random() < 0.3 else 32
+        bits = 64 if rng.random() < args.u64_share else 32
         print(check_case(rng, bits, 0, verbose=True))
         return
     lib = _ffi.lib()
@@ -262,7 +279,7 @@ def main():
     while time.time() - t0 < args.seconds:
         case_seed = args.seed * 1_000_003 + case_id
         rng = np.random.default_rng(case_seed)
-        bits = 64 if rng.random() < 0.3 else 32
+        bits = 64 if rng.random() < args.u64_share else 32
         try:
             msg = check_case(rng, bits, case_id)
         except Exception as ex:  # noqa: BLE001

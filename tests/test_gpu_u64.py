@@ -372,11 +372,13 @@ def test_narrow_boundary_and_default_policy(oracle64, narrow_mode):
     _same(gpu, cpu, qs, qe)
     assert gpu.is_narrow
     _same(gpu, cpu, qs[:1000], qe[:1000])  # small batches use it once it exists
-    # one coordinate above 2^32 - 3: never narrowed (b' = 2^32 - 2 could no longer stand in for every larger stop)
+    # a set that starts at 0 with one coordinate above 2^32 - 3: never narrowed (b' = 2^32 - 2 could no longer stand in
+    # for every larger stop, and the span is too wide for the rebased form)
     narrow_mode(2)
     for top, narrows in (((1 << 32) - 3, True), ((1 << 32) - 2, False), ((1 << 32) - 1, False), (1 << 32, False)):
         s2, e2 = s.copy(), e.copy()
         s2[0], e2[0] = top - 3, top
+        s2[1], e2[1] = 0, 5
         gpu, cpu = Lapper64(starts=s2, stops=e2), oracle64(starts=s2, stops=e2)
         _same(gpu, cpu, qs, qe)
         assert gpu.is_narrow == narrows, top
@@ -387,6 +389,48 @@ def test_narrow_boundary_and_default_policy(oracle64, narrow_mode):
     assert gpu.has_inverted
     _same(gpu, cpu, qs, qe)
     assert gpu.is_narrow
+
+
+@pytest.mark.parametrize("place", ["2^40", "2^63", "top"])
+@pytest.mark.parametrize("span,narrows", [(5_000_000, True), ((1 << 32) - 4, True), ((1 << 32) - 3, False)])
+def test_rebased_narrowing_matches_the_u64_oracle(oracle64, narrow_mode, place, span, narrows):
+    """Coordinates beyond 32 bits whose span fits: the u32 engine answers on coordinates relative to the smallest one
+    (csrc/engine64.cu, "rebased form"); one coordinate more of span and the 64-bit kernels answer.  Same bits either way."""
+    from rust_lapper_b200 import Lapper64
+
+    narrow_mode(2)
+    rng = np.random.default_rng(span % 1000 + len(place))
+    base = {"2^40": 1 << 40, "2^63": (1 << 63) - 12345, "top": U64_MAX - span}[place]
+    n = 60_000
+    rel_s = rng.integers(0, span - 3010, n, dtype=np.uint64)
+    rel_e = rel_s + rng.integers(0, 3000, n, dtype=np.uint64)
+    rel_s[0], rel_e[0] = 0, 7                 # the smallest coordinate: the base of the map
+    rel_s[1], rel_e[1] = span - 9, span       # the largest one
+    rel_s[2:40], rel_e[2:40] = rel_e[2:40] + np.uint64(3), rel_s[2:40].copy()   # a few inverted intervals
+    s, e = rel_s + np.uint64(base), rel_e + np.uint64(base)
+    gpu, cpu = Lapper64(starts=s, stops=e), oracle64(starts=s, stops=e)
+    nq = 40_000
+    qs = np.uint64(base) + rng.integers(0, span, nq, dtype=np.uint64)
+    qe = np.minimum(qs.astype(object) + rng.integers(0, 5000, nq).astype(object), U64_MAX).astype(np.uint64)
+    k = rng.choice(nq, nq // 10, replace=False)
+    qe[k] = qs[k] - rng.integers(0, 3, k.size, dtype=np.uint64)   # empty and inverted queries
+    hi = base + span
+    pts = np.array([0, 1, (1 << 32) - 1, base - 1, base, base + 1, base + 7, hi - 9, hi - 1, hi, min(hi + 1, U64_MAX),
+                    min(hi + (1 << 33), U64_MAX), U64_MAX - 1, U64_MAX], dtype=np.uint64)
+    a, b = np.meshgrid(pts, pts)
+    qs[:a.size], qe[:a.size] = a.reshape(-1), b.reshape(-1)
+    _same(gpu, cpu, qs, qe)
+    assert gpu.is_narrow == narrows
+    o = np.argsort(qs, kind="stable")
+    _same(gpu, cpu, qs[o], np.maximum.accumulate(qe[o]))
+    # structure and set operations come from the u64 arrays
+    assert gpu.max_len == cpu.max_len and np.array_equal(gpu.stops, cpu.stops)
+    # an insert below the base moves it: the u32 index is dropped and rebuilt on the new base (or not at all)
+    lo = base - 1000
+    gpu.insert(lo, lo + 10), cpu.insert(lo, lo + 10)
+    assert not gpu.is_narrow
+    _same(gpu, cpu, qs, qe)
+    assert gpu.is_narrow == (span + 1000 <= (1 << 32) - 4)
 
 
 def test_narrow_one_call_device_api(oracle64, narrow_mode):
