@@ -900,10 +900,19 @@ def bench_cfg5(cx):
         _ffi.check(lib.lapper_build_u32_dev(_vp(s5), _vp(e5), n5, cx.local_rank, 0, cx.sp, C.byref(hh)))
         return hh
 
-    handles = []
-    ms_build, h5 = wall(lambda: handles.append(build5()) or handles[-1])
-    for hh in handles[:-1]:
-        lib.lapper_free(hh)
+    # best of 3, the previous index freed first so that the library's pool hands the same memory out again (with the
+    # earlier handles kept alive every build grew the pool by another 2.7 GB inside the timed region)
+    best5, h5 = None, None
+    for _ in range(3):
+        if h5 is not None:
+            lib.lapper_free(h5)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        h5 = build5()
+        torch.cuda.synchronize()
+        dt5 = time.perf_counter() - t0
+        best5 = dt5 if best5 is None else min(best5, dt5)
+    ms_build = cx.max_over_ranks(best5 * 1e3)
 
     # ---- count: this rank's shard of the 1 B random-order queries, generated on the device in pieces
     qs = torch.empty(m, dtype=torch.int32, device=dev)
