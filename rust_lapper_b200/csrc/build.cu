@@ -116,10 +116,45 @@ __global__ void __launch_bounds__(kThreads) rs_scatter_kernel(const K *__restric
     }
 }
 
+// Small sets (a per-chromosome or per-contig Lapper of a few thousand intervals is the reference's everyday use): the
+// radix sort's 24 launches per 64-bit sort are all overhead there.  Every CTA keeps ALL keys in shared memory and ranks
+// 128 of them by counting: rank_i = #{j < i : k_j <= k_i} + #{j > i : k_j < k_i} -- stable, like the radix passes, so
+// ties keep input order (src/lib.rs:201: `intervals.sort()` is stable).  Out of place, copied back by the caller.
+constexpr uint32_t kSmallSortMax = 4096, kSmallSortThreads = 128;
+inline bool small_sort_disabled() {  // LAPPER_NO_SMALL_SORT=1: the radix passes for every size (A/B, tests of the passes on tiny sets)
+    static const bool off = [] {
+        const char *e = std::getenv("LAPPER_NO_SMALL_SORT");
+        return e && *e && *e != '0';
+    }();
+    return off;
+}
+template <typename K, bool kHasVal>
+__global__ void __launch_bounds__(kSmallSortThreads) small_sort_kernel(const K *__restrict__ kin, const uint32_t *__restrict__ vin,
+                                                                      K *__restrict__ kout, uint32_t *__restrict__ vout, uint32_t n) {
+    __shared__ K sk[kSmallSortMax];
+    for (uint32_t j = threadIdx.x; j < n; j += kSmallSortThreads) sk[j] = kin[j];
+    __syncthreads();
+    const uint32_t i = blockIdx.x * kSmallSortThreads + threadIdx.x;
+    if (i >= n) return;
+    const K me = sk[i];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < i; j++) rank += sk[j] <= me;       // (the lanes of a warp read the same word: a broadcast)
+    for (uint32_t j = i + 1; j < n; j++) rank += sk[j] < me;
+    kout[rank] = me;
+    if (kHasVal) vout[rank] = vin[i];
+}
+
 // Sorts n keys (and their u32 payloads) by bits [0, nbits) of the key.  `keys`/`vals` hold the input and,
 // on return, the output (nbits is a multiple of 16, so the ping-pong ends where it started).
 template <typename K, bool kHasVal>
 void radix_sort(K *keys, K *keys_tmp, uint32_t *vals, uint32_t *vals_tmp, uint64_t n, int nbits, cudaStream_t stream) {
+    if (n <= kSmallSortMax && nbits == (int)(8 * sizeof(K)) && !small_sort_disabled()) {
+        small_sort_kernel<K, kHasVal><<<(uint32_t)div_up(n, kSmallSortThreads), kSmallSortThreads, 0, stream>>>(keys, vals, keys_tmp, vals_tmp, (uint32_t)n);
+        LAPPER_CUDA_CHECK(cudaGetLastError());
+        LAPPER_CUDA_CHECK(cudaMemcpyAsync(keys, keys_tmp, n * sizeof(K), cudaMemcpyDeviceToDevice, stream));
+        if (kHasVal) LAPPER_CUDA_CHECK(cudaMemcpyAsync(vals, vals_tmp, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream));
+        return;
+    }
     const uint32_t nblocks = (uint32_t)div_up(n, kRsTile);
     Scratch<uint32_t> hist((uint64_t)256 * nblocks, stream);
     K *kin = keys, *kout = keys_tmp;
