@@ -2,8 +2,11 @@
 // exception -> status code boundary, the per-thread error text behind lapper_last_error(), device checks.
 #pragma once
 
+#include <cstdlib>
 #include <new>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 
@@ -51,11 +54,44 @@ int guarded_call(F &&f) {
     }
 }
 
+// A non-blocking stream for the duration of one call.  Creating and destroying one costs about as much as the rest of a
+// single-query call, so every host thread keeps the streams it has used (per device) and hands them out again: a
+// call's stream is still its own (nothing else runs on it until the call returns it), and work left on it by a call
+// that threw is simply ordered before the next call's.  The per-thread lists are never destroyed (the driver may be
+// gone by the time thread-locals are).
+struct StreamCache {
+    std::vector<std::pair<int, cudaStream_t>> free_list;
+};
+inline StreamCache &stream_cache() {
+    static thread_local StreamCache *c = new StreamCache();
+    return *c;
+}
+inline bool stream_cache_enabled() {  // LAPPER_NO_STREAM_CACHE=1: a fresh stream per call, destroyed at its end
+    static const bool on = [] {
+        const char *e = std::getenv("LAPPER_NO_STREAM_CACHE");
+        return !(e && *e && *e != '0');
+    }();
+    return on;
+}
 struct OwnedStream {
     cudaStream_t s = nullptr;
-    OwnedStream() { LAPPER_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
+    int device = 0;
+    OwnedStream() {
+        LAPPER_CUDA_CHECK(cudaGetDevice(&device));
+        auto &fl = stream_cache().free_list;
+        for (size_t i = stream_cache_enabled() ? fl.size() : 0; i-- > 0;)
+            if (fl[i].first == device) {
+                s = fl[i].second;
+                fl.erase(fl.begin() + (long)i);
+                return;
+            }
+        LAPPER_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    }
     ~OwnedStream() {
-        if (s) cudaStreamDestroy(s);
+        if (s && stream_cache_enabled())
+            stream_cache().free_list.emplace_back(device, s);
+        else if (s)
+            cudaStreamDestroy(s);
     }
     OwnedStream(const OwnedStream &) = delete;
     OwnedStream &operator=(const OwnedStream &) = delete;

@@ -96,13 +96,7 @@ void require_device(int device) {
         throw Error(LAPPER_ERR_INVALID_ARG, "device index out of range: " + std::to_string(device));
 }
 
-struct StreamOwner {
-    cudaStream_t s = nullptr;
-    StreamOwner() { LAPPER_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)); }
-    ~StreamOwner() {
-        if (s) cudaStreamDestroy(s);
-    }
-};
+using StreamOwner = OwnedStream;  // abi_common.cuh: per-thread cache of the streams calls run on
 
 void check_handle(const lapper_t *l) { LAPPER_REQUIRE(l != nullptr, "null lapper handle"); }
 
