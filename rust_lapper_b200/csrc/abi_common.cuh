@@ -3,6 +3,7 @@
 #pragma once
 
 #include <cstdlib>
+#include <mutex>
 #include <new>
 #include <string>
 #include <utility>
@@ -54,16 +55,31 @@ int guarded_call(F &&f) {
     }
 }
 
-// A non-blocking stream for the duration of one call.  Creating and destroying one costs about as much as the rest of a
-// single-query call, so every host thread keeps the streams it has used (per device) and hands them out again: a
-// call's stream is still its own (nothing else runs on it until the call returns it), and work left on it by a call
-// that threw is simply ordered before the next call's.  The per-thread lists are never destroyed (the driver may be
-// gone by the time thread-locals are).
+// A non-blocking stream for the duration of one call.  Creating and destroying one costs about 100 us here -- several
+// times the rest of a single-query call -- so the process keeps the streams its calls have used (per device) and hands
+// them out again: a call's stream is still its own (nothing else runs on it until the call returns it), and work left
+// on it by a call that threw is simply ordered before the next call's.  One list for all host threads (the replica
+// groups run every call on fresh threads); never destroyed (the driver may be gone by static destruction time).
 struct StreamCache {
+    std::mutex mu;
     std::vector<std::pair<int, cudaStream_t>> free_list;
+    cudaStream_t get(int device) {
+        std::lock_guard<std::mutex> g(mu);
+        for (size_t i = free_list.size(); i-- > 0;)
+            if (free_list[i].first == device) {
+                cudaStream_t s = free_list[i].second;
+                free_list.erase(free_list.begin() + (long)i);
+                return s;
+            }
+        return nullptr;
+    }
+    void put(int device, cudaStream_t s) {
+        std::lock_guard<std::mutex> g(mu);
+        free_list.emplace_back(device, s);
+    }
 };
 inline StreamCache &stream_cache() {
-    static thread_local StreamCache *c = new StreamCache();
+    static StreamCache *c = new StreamCache();
     return *c;
 }
 inline bool stream_cache_enabled() {  // LAPPER_NO_STREAM_CACHE=1: a fresh stream per call, destroyed at its end
@@ -78,18 +94,12 @@ struct OwnedStream {
     int device = 0;
     OwnedStream() {
         LAPPER_CUDA_CHECK(cudaGetDevice(&device));
-        auto &fl = stream_cache().free_list;
-        for (size_t i = stream_cache_enabled() ? fl.size() : 0; i-- > 0;)
-            if (fl[i].first == device) {
-                s = fl[i].second;
-                fl.erase(fl.begin() + (long)i);
-                return;
-            }
-        LAPPER_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        if (stream_cache_enabled()) s = stream_cache().get(device);
+        if (!s) LAPPER_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     }
     ~OwnedStream() {
         if (s && stream_cache_enabled())
-            stream_cache().free_list.emplace_back(device, s);
+            stream_cache().put(device, s);
         else if (s)
             cudaStreamDestroy(s);
     }
