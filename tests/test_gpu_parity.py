@@ -45,6 +45,27 @@ def test_random_small(oracle, seed, flags):
         _assert_same_queries(gpu, cpu, qs, qe)
 
 
+@pytest.mark.parametrize("n", [2, 127, 128, 129, 4095, 4096, 4097, 9000])
+def test_sorted_structure_around_the_small_sort_limit(oracle, n):
+    """csrc/build.cu sorts sets of <= 4096 intervals by rank counting in shared memory (128 keys per CTA) and larger ones
+    by radix passes: both stable (src/lib.rs:201), so the sorted vector, `perm` and the private `stops` are the oracle's on
+    either side of the limit -- with many duplicates of (start, stop) and of start alone, and inverted intervals."""
+    rng = np.random.default_rng(n)
+    s = rng.integers(0, max(n // 6, 2), n).astype(np.uint32) * np.uint32(1000)
+    e = s + rng.integers(0, 3, n).astype(np.uint32) * np.uint32(700)
+    s[::5], e[::5] = 0xFFFFFF00, 0xFFFFFFFF                    # one large key many times over
+    k = rng.random(n) < 0.05
+    s[k], e[k] = e[k].copy(), s[k].copy()                      # inverted where e != s
+    gpu, cpu = _both(oracle, s, e, FLAGS["auto"])
+    gs, ge, gp = gpu.intervals_soa()
+    cs, ce, cv = cpu.intervals_soa()
+    assert np.array_equal(gs, cs) and np.array_equal(ge, ce) and np.array_equal(gp, cv)
+    assert np.array_equal(gpu.starts, cpu.starts) and np.array_equal(gpu.stops, cpu.stops) and gpu.max_len == cpu.max_len
+    near = s[rng.integers(0, n, 2000)].astype(np.int64) + rng.integers(-1500, 1500, 2000)
+    qs = np.concatenate([np.clip(near, 0, 0xFFFFFFFF), rng.integers(0, 0xFFFFFFFF, 1000)]).astype(np.uint32)
+    _assert_same_queries(gpu, cpu, qs, qs + np.uint32(900))
+
+
 @pytest.mark.parametrize("flags", ["auto", "plain"])
 def test_inverted_intervals_and_queries(oracle, flags):
     rng = np.random.default_rng(11)
