@@ -233,6 +233,9 @@ pub mod wide {
         fn lapper64_union_and_intersect(a: *const Lapper64Handle, b: *const Lapper64Handle, u: *mut u64, i: *mut u64) -> c_int;
         fn lapper64_insert(l: *mut Lapper64Handle, start: u64, stop: u64, input_position_out: *mut u64) -> c_int;
         fn lapper64_seek_cursor(l: *const Lapper64Handle, start: u64, cursor: *mut u64) -> c_int;
+        fn lapper64_set_cov(l: *mut Lapper64Handle, out: *mut u64) -> c_int;
+        fn lapper64_get_cached_state(l: *const Lapper64Handle, cov_is_some: *mut c_int, cov: *mut u64, overlaps_merged: *mut c_int) -> c_int;
+        fn lapper64_restore_cached_state(l: *mut Lapper64Handle, cov_is_some: c_int, cov: u64, overlaps_merged: c_int) -> c_int;
     }
 
     #[derive(Debug, Clone)]
@@ -316,6 +319,17 @@ pub mod wide {
             let (mut u, mut i) = (0u64, 0u64);
             check(unsafe { lapper64_union_and_intersect(self.h, other.h, &mut u, &mut i) });
             (u as usize, i as usize)
+        }
+        pub fn set_cov(&mut self) -> usize { let mut c = 0u64; check(unsafe { lapper64_set_cov(self.h, &mut c) }); c as usize }
+        /// `with_serde` for `Lapper<usize, T>`: see `cached_state` / `restore_cached_state` of the u32 form above;
+        /// include/lapper_b200.hpp (`to_bincode` / `from_bincode`) is the exercised implementation of the layout.
+        pub fn cached_state(&self) -> (Option<usize>, bool) {
+            let (mut some, mut cov, mut merged) = (0, 0u64, 0);
+            check(unsafe { lapper64_get_cached_state(self.h, &mut some, &mut cov, &mut merged) });
+            (if some != 0 { Some(cov as usize) } else { None }, merged != 0)
+        }
+        pub fn restore_cached_state(&mut self, cov: Option<usize>, overlaps_merged: bool) {
+            check(unsafe { lapper64_restore_cached_state(self.h, cov.is_some() as c_int, cov.unwrap_or(0) as u64, overlaps_merged as c_int) });
         }
     }
     impl<T: Eq + Clone + Send + Sync> Drop for Lapper<T> {
