@@ -113,3 +113,34 @@ def test_python_mirror_rejects_out_of_range_coordinates():
     for bad in ([-1, 3], [1 << 32], np.array([2**40], dtype=np.int64), [1.5]):
         with pytest.raises(ValueError):
             _u32(bad)
+
+
+def test_header_is_plain_c_and_links_from_a_c_program(lib, tmp_path):
+    """The boundary is a C ABI: include/lapper_b200.h compiles as strict C99 (no C++ in the signatures) and a C program
+    links against the library and gets status codes, not exceptions (here: no device / null arguments)."""
+    import subprocess
+
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "lapper_b200.h"\n'
+        "int main(void) {\n"
+        "    lapper_t *h = 0;\n"
+        "    lapper64_t *w = 0;\n"
+        "    uint32_t s[2] = {1, 5}, e[2] = {4, 9};\n"
+        "    uint64_t s64[2] = {1, 5}, e64[2] = {4, 9};\n"
+        "    int devices = -1;\n"
+        "    if (lapper_version() <= 0 || lapper_device_count(&devices) != LAPPER_OK) return 1;\n"
+        "    if (lapper_build_u32(s, e, 2, 0, 0) == LAPPER_OK) return 2;         /* null output handle */\n"
+        "    if (devices == 0 && lapper_build_u32(s, e, 2, 0, &h) != LAPPER_ERR_NO_DEVICE) return 3;\n"
+        "    if (devices == 0 && lapper64_build(s64, e64, 2, 0, &w) != LAPPER_ERR_NO_DEVICE) return 4;\n"
+        '    printf("%d %s\\n", devices, lapper_last_error());\n'
+        "    lapper_free(h);\n"
+        "    lapper64_free(w);\n"
+        "    return 0;\n"
+        "}\n")
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "rust_lapper_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           str(src), "-L", libdir, "-llapper_b200", f"-Wl,-rpath,{libdir}", "-o", str(exe)])
+    res = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
