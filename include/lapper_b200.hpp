@@ -17,6 +17,8 @@
 
 #include <cstdint>
 #include <cstring>
+#include <initializer_list>
+#include <limits>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -36,7 +38,7 @@ inline void check(int rc) {
 }
 
 // The C entry points behind each coordinate type (src/lib.rs:88-100: `I: PrimInt + Unsigned`): u32 -> lapper_*_u32,
-// u64 (the README's usize) -> lapper64_*.
+// u64 (the README's usize) -> lapper64_*, u8 / u16 -> widened into the u32 entry points.
 namespace detail {
 template <typename I>
 struct Abi;
@@ -102,6 +104,99 @@ struct Abi<uint64_t> {
     static int get_cached_state(const handle *h, int *some, uint64_t *cov, int *merged) { return lapper64_get_cached_state(h, some, cov, merged); }
     static int restore_cached_state(handle *h, int some, uint64_t cov, int merged) { return lapper64_restore_cached_state(h, some, cov, merged); }
 };
+// Coordinate types narrower than 32 bits (u8, u16) widen losslessly into the u32 engine.  The one place where the width
+// of I shows in the reference's arithmetic is `start + 1` in count (src/lib.rs:614), which wraps to 0 for start = I::MAX
+// (release builds): the engine does the same for u32::MAX, so that is what such a start is widened to.  (find has no
+// hit for it either way: no stop exceeds I::MAX.)  Results narrow back without loss: every coordinate, max_len and cov
+// of a valid set fit I.
+template <typename I>
+struct WidenAbi {
+    using handle = lapper_t;
+    using B = Abi<uint32_t>;
+    static constexpr I kMax = std::numeric_limits<I>::max();
+    static std::vector<uint32_t> widen(const I *x, uint64_t n, bool as_query_start = false) {
+        std::vector<uint32_t> w(n);
+        for (uint64_t i = 0; i < n; i++) w[i] = (as_query_start && x[i] == kMax) ? 0xFFFFFFFFu : (uint32_t)x[i];
+        return w;
+    }
+    static int build(const I *s, const I *e, uint64_t n, int dev, uint32_t flags, handle **out) {
+        return B::build(widen(s, n).data(), widen(e, n).data(), n, dev, flags, out);
+    }
+    static void release(handle *h) { B::release(h); }
+    static uint64_t len(const handle *h) { return B::len(h); }
+    static I max_len(const handle *h) { return (I)B::max_len(h); }
+    static bool overlaps_merged(const handle *h) { return B::overlaps_merged(h); }
+    static int get_intervals(const handle *h, I *s, I *e, uint32_t *p) {
+        const uint64_t n = B::len(h);
+        std::vector<uint32_t> ws(n), we(n);
+        const int rc = B::get_intervals(h, ws.data(), we.data(), p);
+        for (uint64_t i = 0; i < n; i++) s[i] = (I)ws[i], e[i] = (I)we[i];
+        return rc;
+    }
+    static int count_batch(const handle *h, const I *a, const I *b, uint64_t nq, uint64_t *out) {
+        return B::count_batch(h, widen(a, nq, true).data(), widen(b, nq).data(), nq, out);
+    }
+    static int find_batch(const handle *h, const I *a, const I *b, uint64_t nq, lapper_result_t **out) {
+        return B::find_batch(h, widen(a, nq, true).data(), widen(b, nq).data(), nq, out);
+    }
+    static int seek_cursor(const handle *h, I start, uint64_t *c) { return B::seek_cursor(h, (uint32_t)start, c); }
+    static int insert(handle *h, I s, I e, uint64_t *pos) { return B::insert(h, (uint32_t)s, (uint32_t)e, pos); }
+    static int merge_overlaps(handle *h) { return B::merge_overlaps(h); }
+    static int cov(const handle *h, I *c) {
+        uint32_t w = 0;
+        const int rc = B::cov(h, &w);
+        if (c) *c = (I)w;
+        return rc;
+    }
+    static int set_cov(handle *h, I *c) {
+        uint32_t w = 0;
+        const int rc = B::set_cov(h, &w);
+        if (c) *c = (I)w;
+        return rc;
+    }
+    static int union_and_intersect(const handle *a, const handle *b, I *u, I *i) {
+        uint32_t wu = 0, wi = 0;
+        const int rc = B::union_and_intersect(a, b, &wu, &wi);
+        *u = (I)wu, *i = (I)wi;
+        return rc;
+    }
+    // the library's u32 arrays narrowed in place (front to back: element i is read before bytes it shares are written)
+    static int depth(const handle *h, uint64_t *n, I **s, I **e, uint32_t **d) {
+        uint32_t *ws = nullptr, *we = nullptr;
+        const int rc = B::depth(h, n, &ws, &we, d);
+        if (rc != LAPPER_OK) return rc;
+        for (uint32_t *arr : {ws, we}) {
+            unsigned char *bytes = reinterpret_cast<unsigned char *>(arr);  // (byte accesses: no aliasing assumptions)
+            for (uint64_t i = 0; i < *n; i++) {
+                uint32_t w;
+                std::memcpy(&w, bytes + 4 * i, 4);
+                const I v = (I)w;
+                std::memcpy(bytes + sizeof(I) * i, &v, sizeof(I));
+            }
+        }
+        *s = reinterpret_cast<I *>(ws), *e = reinterpret_cast<I *>(we);
+        return rc;
+    }
+    static int tune_query_length(handle *h, uint32_t len) { return B::tune_query_length(h, len); }
+    static int get_sorted_stops(const handle *h, I *out) {
+        const uint64_t n = B::len(h);
+        std::vector<uint32_t> w(n);
+        const int rc = B::get_sorted_stops(h, w.data());
+        for (uint64_t i = 0; i < n; i++) out[i] = (I)w[i];
+        return rc;
+    }
+    static int get_cached_state(const handle *h, int *some, I *cov, int *merged) {
+        uint32_t w = 0;
+        const int rc = B::get_cached_state(h, some, &w, merged);
+        if (cov) *cov = (I)w;
+        return rc;
+    }
+    static int restore_cached_state(handle *h, int some, I cov, int merged) { return B::restore_cached_state(h, some, (uint32_t)cov, merged); }
+};
+template <>
+struct Abi<uint16_t> : WidenAbi<uint16_t> {};
+template <>
+struct Abi<uint8_t> : WidenAbi<uint8_t> {};
 }  // namespace detail
 
 // src/lib.rs:88-100

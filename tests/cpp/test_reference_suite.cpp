@@ -2,6 +2,7 @@
 // include/lapper_b200.hpp -- they read like the originals.  Needs a B200 to run; compiles anywhere.
 #include <cstdio>
 #include <cstdlib>
+#include <limits>
 #include <vector>
 
 #include "lapper_b200.hpp"
@@ -218,11 +219,61 @@ void Suite<I>::run() {
     }
 }
 
+// Coordinate types narrower than 32 bits (`I: PrimInt + Unsigned`, src/lib.rs:88-100): the reference's small vectors
+// through Lapper<u32, u8> / Lapper<u32, u16>, which widen into the u32 engine.
+template <typename I>
+static void small_coordinate_types() {
+    typedef Interval<uint32_t, I> Iv;
+    typedef lapper_b200::Lapper<uint32_t, I> L;
+    const I top = std::numeric_limits<I>::max();
+    auto step_by = [](I lo, I hi, I step, I len) {
+        std::vector<Iv> v;
+        for (unsigned x = lo; x < hi; x += step) v.push_back(Iv{(I)x, (I)(x + len), 0});
+        return v;
+    };
+    L non(step_by(0, 100, 20, 10)), over(step_by(0, 100, 10, 15));
+    size_t cursor = 0;
+    CHECK(non.find(15, 20).empty() && non.count(15, 20) == 0 && non.seek(15, 20, &cursor).empty());   // :1023-1039
+    CHECK(non.find(15, 25).size() == 1 && non.find(15, 25)[0]->start == 20 && non.count(15, 25) == 1);  // :1043-1056
+    CHECK(over.find(8, 20).size() == 2 && over.count(8, 20) == 2 && over.find(8, 20)[1]->start == 10);  // :1102-1121
+    CHECK(non.cov() == 50 && non.max_len() == 10);
+    L bad({{70, 120, 0}, {10, 15, 1}, {10, 15, 2}, {12, 15, 3}, {14, 16, 4}, {40, 45, 5}, {50, 55, 6}, {60, 65, 7}, {68, 71, 8}, {70, 75, 9}});
+    CHECK(bad.cov() == 73);
+    L other({{5, 15, 0}, {48, 80, 0}});
+    bad.merge_overlaps();                                                                           // :1124-1138
+    CHECK(bad.len() == 5 && bad.intervals[0] == (Iv{10, 16, 0}) && bad.intervals[4] == (Iv{68, 120, 0}) && bad.intervals[0].val == 1);
+    CHECK(bad.union_and_intersect(other) == std::make_pair((I)88, (I)27));                         // examples/ex1.rs:107-121
+    auto d = L({{0, 10, 0}, {5, 10, 0}}).depth();                                                   // :1279-1290
+    CHECK(d.size() == 2 && d[0].start == 0 && d[0].stop == 5 && d[0].val == 1 && d[1].start == 5 && d[1].stop == 10 && d[1].val == 2);
+    // the top of the type: `start + 1` wraps to 0 for start = I::MAX (src/lib.rs:614, release builds), exactly as it
+    // does in a Lapper<u32, _> for u32::MAX -- same set at the top of u32, same answers
+    L hi({{(I)(top - 9), top, 0}, {(I)(top - 4), (I)(top - 1), 0}, {3, top, 0}});
+    lapper_b200::Lapper<uint32_t, uint32_t> hi32({{0xFFFFFFFFu - 9, 0xFFFFFFFFu, 0}, {0xFFFFFFFFu - 4, 0xFFFFFFFFu - 1, 0}, {3, 0xFFFFFFFFu, 0}});
+    for (unsigned a = 0; a <= 9; a++)
+        for (unsigned b = 0; b <= 9; b++) {
+            const I qa = (I)(top - a), qb = (I)(top - b);
+            CHECK(hi.count(qa, qb) == hi32.count(0xFFFFFFFFu - a, 0xFFFFFFFFu - b));
+            CHECK(hi.find(qa, qb).size() == hi32.find(0xFFFFFFFFu - a, 0xFFFFFFFFu - b).size());
+        }
+    // with_serde: the fields are as wide as I
+    const std::vector<uint8_t> raw = over.to_bincode();
+    CHECK(raw.size() == 8 + 10 * (2 * sizeof(I) + 4) + 2 * (8 + 10 * sizeof(I)) + sizeof(I) + 1 + 1);
+    L back = L::from_bincode(raw);
+    CHECK(back.to_bincode() == raw && back.count(8, 20) == 2);
+    // insert keeps the reference's positions
+    L ins({{0, 5, 1}, {6, 10, 2}});
+    ins.insert(Iv{0, 20, 5});
+    CHECK(ins.len() == 3 && ins.find(1, 3).size() == 2 && ins.find(1, 3)[1]->val == 5);
+}
+
 int main() {
     Suite<uint32_t>::run();
     const int f32 = failures;
     Suite<uint64_t>::run();
-    std::printf("I = u32: %d failures, I = u64: %d failures\n", f32, failures - f32);
+    const int f64 = failures;
+    small_coordinate_types<uint16_t>();
+    small_coordinate_types<uint8_t>();
+    std::printf("I = u32: %d failures, I = u64: %d failures, I = u16 / u8: %d failures\n", f32, f64 - f32, failures - f64);
     std::printf(failures ? "%d FAILED\n" : "all reference tests passed (C++ facade)\n", failures);
     return failures ? 1 : 0;
 }
